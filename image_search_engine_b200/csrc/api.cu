@@ -1,0 +1,106 @@
+// Context, error plumbing and the host-side sequential-RNG helpers of libise.
+#include <random>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+
+static thread_local std::string g_last_error;
+
+void ise_set_error(const std::string& msg) { g_last_error = msg; }
+
+ISE_EXPORT int ise_version(void) { return ISE_VERSION; }
+
+ISE_EXPORT const char* ise_last_error(void) { return g_last_error.c_str(); }
+
+ISE_EXPORT int ise_ctx_create(int device, ise_ctx** out) {
+    ISE_CHECK_ARG(out != nullptr);
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        ISE_FAIL(std::string("no CUDA device visible (there is no CPU fallback): ") + cudaGetErrorString(e));
+    ISE_CHECK_ARG(device >= 0 && device < ndev);
+    cudaDeviceProp prop;
+    ISE_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        ISE_FAIL("libise is built for sm_100a (B200) only; device is sm_" + std::to_string(prop.major) +
+                 std::to_string(prop.minor));
+    DeviceGuard g(device);
+    ise_ctx* ctx = new ise_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->cc_major = prop.major;
+    ctx->cc_minor = prop.minor;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    ctx->encode_tiled = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ctx->encode_tiled, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || ctx->encode_tiled == nullptr) {
+        delete ctx;
+        ISE_FAIL("cuTensorMapEncodeTiled not available from the driver");
+    }
+    *out = ctx;
+    return 0;
+}
+
+ISE_EXPORT void ise_ctx_destroy(ise_ctx* ctx) { delete ctx; }
+
+ISE_EXPORT int ise_ctx_sm_count(const ise_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+// faiss/utils/random.cpp rand_perm: perm = iota; for i in [0, n-1): swap(perm[i], perm[i + mt() % (n - i)]).
+// Entry i is final after step i, so the first m entries need m steps; displaced slots are kept sparse.
+ISE_EXPORT int ise_rand_perm_prefix(int64_t n, int64_t seed, int64_t m, int64_t* out) {
+    ISE_CHECK_ARG(n >= 0 && m >= 0 && m <= n && (out != nullptr || m == 0));
+    std::mt19937 mt((unsigned int)seed);
+    int64_t steps = std::min<int64_t>(m, std::max<int64_t>(n - 1, 0));
+    if (m * 4 >= n) {
+        std::vector<int64_t> perm((size_t)n);
+        for (int64_t i = 0; i < n; i++) perm[(size_t)i] = i;
+        for (int64_t i = 0; i < steps; i++) {
+            int64_t j = i + (int64_t)(mt() % (uint64_t)(n - i));
+            std::swap(perm[(size_t)i], perm[(size_t)j]);
+        }
+        for (int64_t i = 0; i < m; i++) out[i] = perm[(size_t)i];
+        return 0;
+    }
+    std::unordered_map<int64_t, int64_t> moved;
+    moved.reserve((size_t)steps * 2);
+    auto get = [&](int64_t p) {
+        auto it = moved.find(p);
+        return it == moved.end() ? p : it->second;
+    };
+    for (int64_t i = 0; i < steps; i++) {
+        int64_t j = i + (int64_t)(mt() % (uint64_t)(n - i));
+        int64_t vi = get(i), vj = get(j);
+        moved[j] = vi;
+        out[i] = vj;
+    }
+    for (int64_t i = steps; i < m; i++) out[i] = get(i);
+    return 0;
+}
+
+// faiss/Clustering.cpp split_clusters(): the RNG stream is consumed one draw per probed donor, so the
+// plan is inherently sequential; it only runs when an iteration produced empty clusters.
+ISE_EXPORT int ise_split_plan(float* hassign, int64_t k, int64_t n, int32_t* pairs, int32_t* nsplit) {
+    ISE_CHECK_ARG(hassign != nullptr && pairs != nullptr && nsplit != nullptr && k > 0 && n > k);
+    std::mt19937 mt(1234);
+    int32_t ns = 0;
+    const float denom = (float)(n - k);
+    for (int64_t ci = 0; ci < k; ci++) {
+        if (hassign[ci] != 0) continue;
+        int64_t cj = 0;
+        for (;; cj = (cj + 1) % k) {
+            float p = (float)((hassign[cj] - 1.0) / denom);
+            float r = mt() / float(mt.max());
+            if (r < p) break;
+        }
+        pairs[2 * ns] = (int32_t)ci;
+        pairs[2 * ns + 1] = (int32_t)cj;
+        hassign[ci] = hassign[cj] / 2;
+        hassign[cj] -= hassign[ci];
+        ns++;
+    }
+    *nsplit = ns;
+    return 0;
+}

@@ -1,0 +1,92 @@
+// Shared host/device helpers for libise (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/ise.h"
+
+#define ISE_EXPORT extern "C" __attribute__((visibility("default")))
+
+struct ise_ctx {
+    int device;
+    int sm_count;
+    int cc_major, cc_minor;
+    size_t smem_optin;
+    // cuTensorMapEncodeTiled resolved through the runtime (no link-time libcuda dependency)
+    void* encode_tiled;
+};
+
+void ise_set_error(const std::string& msg);
+
+#define ISE_FAIL(msg)                                                                  \
+    do {                                                                               \
+        ise_set_error(std::string(__func__) + ": " + (msg));                           \
+        return 1;                                                                      \
+    } while (0)
+
+#define ISE_CHECK_ARG(cond)                                                            \
+    do {                                                                               \
+        if (!(cond)) ISE_FAIL(std::string("invalid argument: ") + #cond);              \
+    } while (0)
+
+#define ISE_CUDA(expr)                                                                 \
+    do {                                                                               \
+        cudaError_t _e = (expr);                                                       \
+        if (_e != cudaSuccess)                                                         \
+            ISE_FAIL(std::string(#expr) + " -> " + cudaGetErrorString(_e));            \
+    } while (0)
+
+#define ISE_LAUNCH_CHECK()                                                             \
+    do {                                                                               \
+        cudaError_t _e = cudaGetLastError();                                           \
+        if (_e != cudaSuccess)                                                         \
+            ISE_FAIL(std::string("kernel launch -> ") + cudaGetErrorString(_e));       \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        ok = cudaGetDevice(&prev) == cudaSuccess;
+        if (ok && prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// meta layout shared by prepare.cu and gemm_select.cu
+enum { META_SCALE = 0, META_INV_SCALE = 1, META_LO_NONZERO = 2, META_ABSMAX = 3 };
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Canonical ordering shared by every selection kernel: `better(a, b)` is true when candidate a
+// must precede b.  LARGEST: bigger score first; ties by smaller id; id < 0 (padding) loses ties.
+template <bool LARGEST>
+__device__ __forceinline__ bool cand_better(float va, int64_t ia, float vb, int64_t ib) {
+    if (va != vb) return LARGEST ? (va > vb) : (va < vb);
+    if (ia < 0) return false;
+    if (ib < 0) return true;
+    return ia < ib;
+}
+
+#endif  // __CUDACC__

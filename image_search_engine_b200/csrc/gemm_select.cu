@@ -1,0 +1,505 @@
+// Fused distance contraction + selection on the Blackwell tensor cores.
+//
+//   rows  A : m x d   (descriptors for k-means assign / quantisation, queries for kNN)
+//   cols  B : n x d   (centroids, database vectors)
+//   out     : per row the topk best columns under inner product or squared L2
+//
+// The m x n score matrix only ever exists as 128 x 256 FP32 accumulator tiles in TMEM.
+// A persistent, warp-specialised CTA (one per SM) runs three roles:
+//   warp 0   TMA producer : cp.async.bulk.tensor loads of the FP16 hi/lo planes (128B swizzle)
+//   warp 1   MMA issuer   : tcgen05.mma kind::f16, split products hi*hi + hi*lo + lo*hi into one
+//                           TMEM accumulator (2 accumulators x 256 columns, double buffered)
+//   warps 4-7 epilogue    : tcgen05.ld the accumulator, per-row running top-1 / top-k in registers
+//                           or thread-local lists while the next tile's MMAs run
+// Replaces Faiss knn_inner_product / knn_L2sqr (sgemm + result handler) behind
+// reference call sites kmeans_faiss.py:41,49 and engine.py:55.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+#include "topk_list.cuh"
+
+namespace gs {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 256;
+constexpr int BLOCK_K = 64;  // fp16 elements = one 128-byte swizzle span
+constexpr int UMMA_K = 16;
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
+constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;  // 32 KiB
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+constexpr int NUM_EPI_THREADS = 128;
+constexpr int TMEM_COLS = 512;  // 2 accumulator stages x BLOCK_N fp32 columns
+constexpr int AUX_BYTES = 4096;
+constexpr int SMEM_LIMIT = 232448;  // 227 KiB opt-in per CTA on sm_100
+
+__host__ __device__ constexpr int stage_bytes(int pa, int pb) { return pa * A_TILE_BYTES + pb * B_TILE_BYTES; }
+__host__ __device__ constexpr int num_stages(int pa, int pb) {
+    int s = (SMEM_LIMIT - AUX_BYTES - 1024) / stage_bytes(pa, pb);
+    return s > 6 ? 6 : s;
+}
+
+struct Params {
+    int64_t m, n;
+    int d;
+    int n_mtiles;         // ceil(m / 128)
+    int n_ntiles;         // ceil(n / 256)
+    int tiles_per_split;  // N tiles handled by one work item
+    int n_splits;
+    int topk;
+    int64_t id_base;
+    const float* a_meta;
+    const float* b_meta;
+    const float* a_norms;
+    const float* b_norms;
+    float* out_val;    // [n_splits, m, topk]
+    int64_t* out_idx;  // [n_splits, m, topk]
+};
+
+struct Aux {  // lives after the stage ring in dynamic shared memory
+    uint64_t full[8];
+    uint64_t empty[8];
+    uint64_t tmem_full[2];
+    uint64_t tmem_empty[2];
+    uint32_t tmem_base;
+    uint32_t pad_[3];
+    float bnorm[2][BLOCK_N];
+};
+static_assert(sizeof(Aux) <= AUX_BYTES, "aux area too small");
+
+// KSEL: 1 = running top-1 in registers, otherwise capacity of the thread-local list
+template <int PA, int PB, bool L2, int KSEL>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                   const Params p) {
+    constexpr int STAGES = num_stages(PA, PB);
+    constexpr int STAGE_BYTES = stage_bytes(PA, PB);
+    static_assert(STAGES >= 2 && STAGES <= 8, "pipeline depth");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    Aux* aux = reinterpret_cast<Aux*>(smem + STAGES * STAGE_BYTES);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tm_a_hi);
+        ptx::prefetch_tensormap(&tm_b_hi);
+        if (PA == 2) ptx::prefetch_tensormap(&tm_a_lo);
+        if (PB == 2) ptx::prefetch_tensormap(&tm_b_lo);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            ptx::mbar_init(&aux->full[i], 1);
+            ptx::mbar_init(&aux->empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&aux->tmem_full[i], 1);
+            ptx::mbar_init(&aux->tmem_empty[i], NUM_EPI_THREADS);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) ptx::tmem_alloc(&aux->tmem_base, TMEM_COLS);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = aux->tmem_base;
+
+    const int num_kb = (p.d + BLOCK_K - 1) / BLOCK_K;
+    const int total_work = p.n_mtiles * p.n_splits;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const int split = w / p.n_mtiles, mt = w - split * p.n_mtiles;
+                const int nt0 = split * p.tiles_per_split;
+                const int nt1 = min(nt0 + p.tiles_per_split, p.n_ntiles);
+                for (int nt = nt0; nt < nt1; ++nt) {
+                    for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                        const int s = it % STAGES;
+                        const uint32_t ph = (it / STAGES) & 1;
+                        ptx::mbar_wait(&aux->empty[s], ph ^ 1);
+                        uint8_t* st = smem + s * STAGE_BYTES;
+                        ptx::mbar_arrive_expect_tx(&aux->full[s], STAGE_BYTES);
+                        ptx::tma_load_2d(st, &tm_a_hi, &aux->full[s], kb * BLOCK_K, mt * BLOCK_M);
+                        if (PA == 2)
+                            ptx::tma_load_2d(st + A_TILE_BYTES, &tm_a_lo, &aux->full[s], kb * BLOCK_K, mt * BLOCK_M);
+                        ptx::tma_load_2d(st + PA * A_TILE_BYTES, &tm_b_hi, &aux->full[s], kb * BLOCK_K,
+                                         nt * BLOCK_N);
+                        if (PB == 2)
+                            ptx::tma_load_2d(st + PA * A_TILE_BYTES + B_TILE_BYTES, &tm_b_lo, &aux->full[s],
+                                             kb * BLOCK_K, nt * BLOCK_N);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_f16_f32(BLOCK_M, BLOCK_N);
+            const uint32_t smem_base = ptx::smem_u32(smem);
+            uint32_t it = 0, tile = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const int split = w / p.n_mtiles;
+                const int nt0 = split * p.tiles_per_split;
+                const int nt1 = min(nt0 + p.tiles_per_split, p.n_ntiles);
+                for (int nt = nt0; nt < nt1; ++nt, ++tile) {
+                    const int as = tile & 1;
+                    const uint32_t aph = (tile >> 1) & 1;
+                    ptx::mbar_wait(&aux->tmem_empty[as], aph ^ 1);
+                    ptx::tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+                    for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                        const int s = it % STAGES;
+                        const uint32_t ph = (it / STAGES) & 1;
+                        ptx::mbar_wait(&aux->full[s], ph);
+                        ptx::tc_fence_after();
+                        const uint32_t st = smem_base + s * STAGE_BYTES;
+                        const uint64_t da_hi = ptx::make_smem_desc_sw128(st);
+                        const uint64_t da_lo = ptx::make_smem_desc_sw128(st + A_TILE_BYTES);
+                        const uint64_t db_hi = ptx::make_smem_desc_sw128(st + PA * A_TILE_BYTES);
+                        const uint64_t db_lo = ptx::make_smem_desc_sw128(st + PA * A_TILE_BYTES + B_TILE_BYTES);
+                        const int rem = p.d - kb * BLOCK_K;
+                        const int ksteps = rem >= BLOCK_K ? BLOCK_K / UMMA_K : (rem + UMMA_K - 1) / UMMA_K;
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            // advancing 16 fp16 = 32 bytes inside the 128B swizzle span: +2 in the >>4 address
+                            const uint64_t koff = (uint64_t)(ks * ((UMMA_K * 2) >> 4));
+                            ptx::umma_f16_ss(tmem_d, da_hi + koff, db_hi + koff, idesc, (kb | ks) != 0);
+                            if (PB == 2) ptx::umma_f16_ss(tmem_d, da_hi + koff, db_lo + koff, idesc, 1);
+                            if (PA == 2) ptx::umma_f16_ss(tmem_d, da_lo + koff, db_hi + koff, idesc, 1);
+                        }
+                        ptx::umma_commit(&aux->empty[s]);  // frees the smem stage when these MMAs retire
+                    }
+                    ptx::umma_commit(&aux->tmem_full[as]);  // accumulator complete -> epilogue
+                }
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ===================== epilogue: selection =====================
+        const int q = warp & 3;  // TMEM lane quadrant this warp may read
+        const int et = threadIdx.x - EPI_WARP0 * 32;
+        const float inv = p.a_meta[META_INV_SCALE] * p.b_meta[META_INV_SCALE];
+        const float two_inv = 2.f * inv;
+        uint32_t tile = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            const int split = w / p.n_mtiles, mt = w - split * p.n_mtiles;
+            const int nt0 = split * p.tiles_per_split;
+            const int nt1 = min(nt0 + p.tiles_per_split, p.n_ntiles);
+            const int64_t row = (int64_t)mt * BLOCK_M + q * 32 + lane;
+
+            float best = -CUDART_INF_F;
+            int best_id = -1;
+            TopKList<(KSEL > 1 ? KSEL : 1)> list;
+            if (KSEL > 1) list.init(p.topk);
+
+            for (int nt = nt0; nt < nt1; ++nt, ++tile) {
+                const int as = tile & 1;
+                const uint32_t aph = (tile >> 1) & 1;
+                const int col0 = nt * BLOCK_N;
+                const int ncols = (int)min((int64_t)BLOCK_N, p.n - col0);
+                if (L2) {
+                    for (int c = et; c < BLOCK_N; c += NUM_EPI_THREADS)
+                        aux->bnorm[as][c] = (c < ncols) ? __ldg(p.b_norms + col0 + c) : 0.f;
+                    asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_THREADS) : "memory");
+                }
+                ptx::mbar_wait(&aux->tmem_full[as], aph);
+                ptx::tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N;
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N; c += 32) {
+                    if (c >= ncols) break;
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32b_x32(taddr + c, r);
+                    ptx::tmem_ld_wait();
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        v[j] = __uint_as_float(r[j]);
+                        // maximise 2<a,b> - |b|^2  ==  minimise |a|^2 + |b|^2 - 2<a,b>
+                        if (L2) v[j] = fmaf(v[j], two_inv, -aux->bnorm[as][c + j]);
+                    }
+                    if (c + 32 > ncols) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (c + j >= ncols) v[j] = -CUDART_INF_F;
+                    }
+                    float mx = v[0];
+#pragma unroll
+                    for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
+                    if (KSEL == 1) {
+                        if (mx > best) {  // strict: an equal score in a later column never replaces
+                            best = mx;
+                            int jj = 31;
+#pragma unroll
+                            for (int j = 30; j >= 0; --j)
+                                if (v[j] == mx) jj = j;  // lowest column among equals
+                            best_id = col0 + c + jj;
+                        }
+                    } else {
+                        if (mx > list.thr) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (v[j] > list.thr) list.insert(v[j], col0 + c + j);
+                        }
+                    }
+                }
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(&aux->tmem_empty[as]);
+            }
+
+            if (row < p.m) {
+                const float an = L2 ? __ldg(p.a_norms + row) : 0.f;
+                float* ov = p.out_val + ((int64_t)split * p.m + row) * p.topk;
+                int64_t* oi = p.out_idx + ((int64_t)split * p.m + row) * p.topk;
+                if (KSEL == 1) {
+                    if (best_id >= 0) {
+                        ov[0] = L2 ? fmaxf(an - best, 0.f) : best * inv;
+                        oi[0] = p.id_base + best_id;
+                    } else {
+                        ov[0] = L2 ? 3.402823466e+38f : -3.402823466e+38f;
+                        oi[0] = -1;
+                    }
+                } else {
+#pragma unroll 1
+                    for (int j = 0; j < p.topk; ++j) {
+                        if (list.id[j] >= 0) {
+                            ov[j] = L2 ? fmaxf(an - list.v[j], 0.f) : list.v[j] * inv;
+                            oi[j] = p.id_base + list.id[j];
+                        } else {
+                            ov[j] = L2 ? 3.402823466e+38f : -3.402823466e+38f;
+                            oi[j] = -1;
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// merge of g sorted lists per row: one warp per row, each lane owns lists lane, lane+32, ...
+// ------------------------------------------------------------------------------------------
+constexpr int MERGE_MAX_LISTS_PER_LANE = 8;
+
+template <bool LARGEST>
+__global__ void topk_merge_kernel(const float* __restrict__ vparts, const int64_t* __restrict__ iparts, int g,
+                                  int64_t m, int topk, float* __restrict__ out_val, int64_t* __restrict__ out_idx) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= m) return;
+    int ptr[MERGE_MAX_LISTS_PER_LANE];
+#pragma unroll
+    for (int t = 0; t < MERGE_MAX_LISTS_PER_LANE; ++t) ptr[t] = 0;
+    const float worst = LARGEST ? -3.402823466e+38f : 3.402823466e+38f;
+    for (int j = 0; j < topk; ++j) {
+        float bv = worst;
+        int64_t bi = -1;
+        int bt = -1;
+#pragma unroll
+        for (int t = 0; t < MERGE_MAX_LISTS_PER_LANE; ++t) {
+            const int l = lane + 32 * t;
+            if (l < g && ptr[t] < topk) {
+                const int64_t off = ((int64_t)l * m + row) * topk + ptr[t];
+                const float cv = vparts[off];
+                const int64_t ci = iparts[off];
+                if (ci >= 0 && (bt < 0 || cand_better<LARGEST>(cv, ci, bv, bi))) {
+                    bv = cv; bi = ci; bt = t;
+                }
+            }
+        }
+        // warp arg-best on (value, id)
+        float wv = bv;
+        int64_t wi = bi;
+        int wl = bt >= 0 ? lane : -1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
+            const int64_t oi = __shfl_xor_sync(0xffffffffu, wi, o);
+            const int ol = __shfl_xor_sync(0xffffffffu, wl, o);
+            const bool take = (ol >= 0) && (wl < 0 || cand_better<LARGEST>(ov, oi, wv, wi));
+            if (take) { wv = ov; wi = oi; wl = ol; }
+        }
+        if (wl == lane && bt >= 0) {
+#pragma unroll
+            for (int t = 0; t < MERGE_MAX_LISTS_PER_LANE; ++t)
+                if (t == bt) ptr[t]++;
+        }
+        if (lane == 0) {
+            out_val[row * topk + j] = (wl >= 0) ? wv : worst;
+            out_idx[row * topk + j] = (wl >= 0) ? wi : -1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_plane_map(const ise_ctx* ctx, CUtensorMap* map, const void* base, int64_t rows, int d, int64_t ld,
+                          int box_rows) {
+    EncodeTiledFn fn = (EncodeTiledFn)ctx->encode_tiled;
+    cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        ise_set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+        return 1;
+    }
+    return 0;
+}
+
+struct Plan {
+    int n_mtiles, n_ntiles, tiles_per_split, n_splits;
+};
+
+static Plan make_plan(const ise_ctx* ctx, int64_t m, int64_t n) {
+    Plan pl;
+    pl.n_mtiles = (int)ceil_div64(m, BLOCK_M);
+    pl.n_ntiles = (int)std::max<int64_t>(1, ceil_div64(n, BLOCK_N));
+    // enough work items for ~4 waves of the persistent grid, but never less than 8 column tiles per
+    // item (a fresh item restarts its selection threshold) and at most 256 partial lists per row
+    int64_t want = ceil_div64((int64_t)4 * ctx->sm_count, std::max(1, pl.n_mtiles));
+    int64_t max_by_tiles = std::max<int64_t>(1, pl.n_ntiles / 8);
+    int64_t s_hi = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(2 * want, max_by_tiles), 256));
+    // pick the split count with the smallest makespan = waves x column tiles per item
+    int64_t best_s = 1, best_cost = -1;
+    for (int64_t s = 1; s <= s_hi; ++s) {
+        const int64_t tps = ceil_div64(pl.n_ntiles, s);
+        const int64_t ns = ceil_div64(pl.n_ntiles, tps);
+        const int64_t waves = ceil_div64((int64_t)pl.n_mtiles * ns, ctx->sm_count);
+        const int64_t cost = waves * tps;
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_s = ns; }
+    }
+    pl.tiles_per_split = (int)ceil_div64(pl.n_ntiles, best_s);
+    pl.n_splits = (int)ceil_div64(pl.n_ntiles, pl.tiles_per_split);
+    return pl;
+}
+
+template <int PA, int PB, bool L2, int KSEL>
+static int launch(const ise_ctx* ctx, const CUtensorMap* maps, const Params& p, cudaStream_t st) {
+    auto kern = gemm_select_kernel<PA, PB, L2, KSEL>;
+    const int smem = num_stages(PA, PB) * stage_bytes(PA, PB) + AUX_BYTES + 1024;
+    ISE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int total = p.n_mtiles * p.n_splits;
+    const int grid = std::min(total, ctx->sm_count);
+    kern<<<grid, NUM_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+    ISE_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int PA, int PB, bool L2>
+static int dispatch_k(const ise_ctx* ctx, const CUtensorMap* maps, const Params& p, cudaStream_t st) {
+    if (p.topk == 1) return launch<PA, PB, L2, 1>(ctx, maps, p, st);
+    if (p.topk <= 32) return launch<PA, PB, L2, 32>(ctx, maps, p, st);
+    return launch<PA, PB, L2, 128>(ctx, maps, p, st);
+}
+
+template <int PA, int PB>
+static int dispatch_metric(const ise_ctx* ctx, const CUtensorMap* maps, const Params& p, int metric,
+                           cudaStream_t st) {
+    return metric == ISE_METRIC_L2 ? dispatch_k<PA, PB, true>(ctx, maps, p, st)
+                                   : dispatch_k<PA, PB, false>(ctx, maps, p, st);
+}
+
+}  // namespace gs
+
+ISE_EXPORT size_t ise_gemm_select_workspace_bytes(ise_ctx* ctx, int64_t m, int64_t n, int d, int topk) {
+    if (!ctx || m <= 0 || topk <= 0) return 0;
+    gs::Plan pl = gs::make_plan(ctx, m, n);
+    if (pl.n_splits <= 1) return 0;
+    return (size_t)pl.n_splits * (size_t)m * (size_t)topk * (sizeof(float) + sizeof(int64_t)) + 256;
+}
+
+ISE_EXPORT int ise_topk_merge(ise_ctx* ctx, const float* val_parts, const int64_t* idx_parts, int g, int64_t m,
+                              int topk, int metric, float* out_val, int64_t* out_idx, void* stream) {
+    ISE_CHECK_ARG(ctx && g >= 1 && g <= 32 * gs::MERGE_MAX_LISTS_PER_LANE && m >= 0 && topk >= 1);
+    if (m == 0) return 0;
+    ISE_CHECK_ARG(val_parts && idx_parts && out_val && out_idx);
+    DeviceGuard guard(ctx->device);
+    const int warps = 8;
+    const int grid = (int)ceil_div64(m, warps);
+    if (metric == ISE_METRIC_IP)
+        gs::topk_merge_kernel<true><<<grid, warps * 32, 0, (cudaStream_t)stream>>>(val_parts, idx_parts, g, m, topk,
+                                                                                  out_val, out_idx);
+    else
+        gs::topk_merge_kernel<false><<<grid, warps * 32, 0, (cudaStream_t)stream>>>(val_parts, idx_parts, g, m, topk,
+                                                                                   out_val, out_idx);
+    ISE_LAUNCH_CHECK();
+    return 0;
+}
+
+ISE_EXPORT int ise_gemm_select(ise_ctx* ctx, const void* a_hi, const void* a_lo, int64_t lda, const float* a_meta,
+                               const float* a_norms, const void* b_hi, const void* b_lo, int64_t ldb,
+                               const float* b_meta, const float* b_norms, int64_t m, int64_t n, int d, int metric,
+                               int topk, int64_t id_base, float* out_val, int64_t* out_idx, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+    ISE_CHECK_ARG(ctx != nullptr);
+    ISE_CHECK_ARG(metric == ISE_METRIC_IP || metric == ISE_METRIC_L2);
+    ISE_CHECK_ARG(m >= 0 && n >= 0 && d > 0 && topk >= 1 && topk <= 128);
+    ISE_CHECK_ARG(n < (int64_t)1 << 31 && m < (int64_t)1 << 31);
+    if (m == 0) return 0;
+    ISE_CHECK_ARG(a_hi && b_hi && a_meta && b_meta && out_val && out_idx);
+    ISE_CHECK_ARG(lda >= d && ldb >= d && lda % 8 == 0 && ldb % 8 == 0);
+    ISE_CHECK_ARG((reinterpret_cast<uintptr_t>(a_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(b_hi) & 15) == 0);
+    if (metric == ISE_METRIC_L2) ISE_CHECK_ARG(a_norms && b_norms);
+    ISE_CHECK_ARG(n > 0);  // an empty index is handled by the caller (Faiss pads with -1)
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+
+    gs::Plan pl = gs::make_plan(ctx, m, n);
+    gs::Params p;
+    p.m = m; p.n = n; p.d = d;
+    p.n_mtiles = pl.n_mtiles; p.n_ntiles = pl.n_ntiles;
+    p.tiles_per_split = pl.tiles_per_split; p.n_splits = pl.n_splits;
+    p.topk = topk; p.id_base = id_base;
+    p.a_meta = a_meta; p.b_meta = b_meta; p.a_norms = a_norms; p.b_norms = b_norms;
+    float* wv = nullptr;
+    int64_t* wi = nullptr;
+    if (pl.n_splits > 1) {
+        const size_t need = ise_gemm_select_workspace_bytes(ctx, m, n, d, topk);
+        if (!workspace || workspace_bytes < need) ISE_FAIL("workspace too small: need " + std::to_string(need));
+        const size_t cnt = (size_t)pl.n_splits * (size_t)m * (size_t)topk;
+        wi = reinterpret_cast<int64_t*>(workspace);  // int64 first keeps both arrays aligned
+        wv = reinterpret_cast<float*>(wi + cnt);
+        p.out_val = wv; p.out_idx = wi;
+    } else {
+        p.out_val = out_val; p.out_idx = out_idx;
+    }
+
+    const int pa = a_lo ? 2 : 1, pb = b_lo ? 2 : 1;
+    CUtensorMap maps[4];
+    if (gs::make_plane_map(ctx, &maps[0], a_hi, m, d, lda, gs::BLOCK_M)) return 1;
+    if (gs::make_plane_map(ctx, &maps[1], a_lo ? a_lo : a_hi, m, d, lda, gs::BLOCK_M)) return 1;
+    if (gs::make_plane_map(ctx, &maps[2], b_hi, n, d, ldb, gs::BLOCK_N)) return 1;
+    if (gs::make_plane_map(ctx, &maps[3], b_lo ? b_lo : b_hi, n, d, ldb, gs::BLOCK_N)) return 1;
+
+    int rc;
+    if (pa == 1 && pb == 1) rc = gs::dispatch_metric<1, 1>(ctx, maps, p, metric, st);
+    else if (pa == 1 && pb == 2) rc = gs::dispatch_metric<1, 2>(ctx, maps, p, metric, st);
+    else if (pa == 2 && pb == 2) rc = gs::dispatch_metric<2, 2>(ctx, maps, p, metric, st);
+    else ISE_FAIL("a_lo without b_lo is not supported: pass a zero b_lo plane");
+    if (rc) return rc;
+    if (pl.n_splits > 1)
+        return ise_topk_merge(ctx, wv, wi, pl.n_splits, m, topk, metric, out_val, out_idx, stream);
+    return 0;
+}

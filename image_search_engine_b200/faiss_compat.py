@@ -1,0 +1,417 @@
+"""B200-resident drop-in for the slice of the ``faiss`` module the reference calls.
+
+Same names and call contracts as faiss (IndexFlatIP / IndexFlatL2 / Kmeans / normalize_L2 /
+read_index / write_index), so the reference's own ``kmeans_faiss.py``, ``utils.py``,
+``bag_of_visual_words.py`` and ``engine.py`` run unmodified on top of it
+(``sys.modules["faiss"] = image_search_engine_b200.faiss_compat`` -- see INTEGRATION.md).
+
+Reference call sites (under /root/reference/backend):
+  kmeans_faiss.py:29-44,49   utils.py:300-327   engine.py:53-55,116,131
+  bag_of_visual_words.py:187,194,213   siamese/test_index.py:53-54
+
+Inputs may be NumPy arrays (host: copied to the GPU, results returned as NumPy with
+Faiss's shapes/dtypes) or CUDA tensors (zero-copy, results returned as CUDA tensors).
+All arithmetic runs in libise kernels; there is no CPU path.
+"""
+from __future__ import annotations
+
+import struct
+import threading
+import time
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import METRIC_IP, METRIC_L2, IseError
+
+METRIC_INNER_PRODUCT = METRIC_IP
+# METRIC_L2 imported above keeps faiss's value (1)
+
+# faiss/utils/distances.cpp: below this many queries Faiss skips the BLAS expansion
+distance_compute_blas_threshold = 20
+
+_FLT_MAX = float(np.finfo(np.float32).max)
+
+
+def _as_host_f32(x) -> np.ndarray:
+    a = np.asarray(x)  # shares memory with np.matrix
+    if a.ndim != 2:
+        raise AssertionError("expected a 2-D array")
+    return a
+
+
+def _to_device(x, dtype=torch.float32) -> tuple[torch.Tensor, bool]:
+    """Returns (cuda tensor [n, d], input_was_torch_cuda)."""
+    dev = ops.require_cuda()
+    if isinstance(x, torch.Tensor):
+        if x.dim() != 2:
+            raise AssertionError("expected a 2-D tensor")
+        if x.is_cuda:
+            t = x if x.dtype in (torch.float32, torch.uint8) else x.to(torch.float32)
+            return (t if t.stride(1) == 1 else t.contiguous()), True
+        t = x
+    else:
+        a = _as_host_f32(x)
+        if a.dtype == np.uint8:
+            pass  # ORB / BRISK bytes travel as bytes; the float32 cast happens on the device
+        elif a.dtype != np.float32:
+            a = a.astype(np.float32)
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    if t.dtype not in (torch.float32, torch.uint8):
+        t = t.to(torch.float32)
+    return t.to(dev, non_blocking=True), False
+
+
+def normalize_L2(x) -> None:
+    """faiss.normalize_L2: in place on the caller's buffer (utils.py:303 relies on that)."""
+    if isinstance(x, torch.Tensor) and x.is_cuda:
+        ops.normalize_l2_(x)
+        return
+    a = np.asarray(x)
+    if a.dtype != np.float32 or a.ndim != 2 or not a.flags.c_contiguous:
+        raise TypeError("normalize_L2 needs a C-contiguous float32 2-D array")
+    dev = ops.require_cuda()
+    t = torch.from_numpy(a).to(dev)
+    ops.normalize_l2_(t)
+    a[...] = t.cpu().numpy()
+
+
+class IndexFlat:
+    """Flat (exhaustive) index whose vectors live in HBM."""
+
+    def __init__(self, d: int, metric: int = METRIC_L2):
+        self.d = int(d)
+        self.metric_type = int(metric)
+        self.metric_arg = 0.0
+        self.is_trained = True
+        self.verbose = False
+        self._chunks: list[torch.Tensor] = []
+        self._ntotal = 0
+        self._xb: torch.Tensor | None = None
+        self._op: ops.Operand | None = None
+        self._lock = threading.Lock()
+
+    # ---- storage ----
+    @property
+    def ntotal(self) -> int:
+        return self._ntotal
+
+    def add(self, x) -> None:
+        t, _ = _to_device(x)
+        if t.shape[1] != self.d:
+            raise AssertionError(f"add: expected (n, {self.d}) array")
+        if t.dtype != torch.float32:
+            t = t.to(torch.float32)
+        with self._lock:
+            self._chunks.append(t.clone() if isinstance(x, torch.Tensor) and x.is_cuda else t)
+            self._ntotal += t.shape[0]
+            self._xb = None
+            self._op = None
+
+    def train(self, x) -> None:
+        pass
+
+    def reset(self) -> None:
+        with self._lock:
+            self._chunks, self._ntotal, self._xb, self._op = [], 0, None, None
+
+    def _database(self) -> torch.Tensor:
+        with self._lock:
+            if self._xb is None:
+                if not self._chunks:
+                    dev = ops.require_cuda()
+                    self._xb = torch.zeros((0, self.d), dtype=torch.float32, device=dev)
+                elif len(self._chunks) == 1:
+                    self._xb = self._chunks[0]
+                else:
+                    self._xb = torch.cat(self._chunks, dim=0)
+                    self._chunks = [self._xb]
+            return self._xb
+
+    def _operand(self) -> ops.Operand:
+        xb = self._database()
+        with self._lock:
+            if self._op is None:
+                self._op = ops.prepare_operand(xb)
+            return self._op
+
+    # ---- search ----
+    def search(self, x, k: int):
+        k = int(k)
+        if k <= 0:
+            raise AssertionError("k must be positive")
+        q, was_cuda = _to_device(x)
+        if q.shape[1] != self.d:
+            raise AssertionError(f"search: expected (n, {self.d}) array")
+        D, I = self._search_device(q, k)
+        if was_cuda:
+            return D, I
+        return D.cpu().numpy(), I.cpu().numpy()
+
+    def _search_device(self, q: torch.Tensor, k: int):
+        nq = q.shape[0]
+        largest = self.metric_type == METRIC_INNER_PRODUCT
+        pad = -_FLT_MAX if largest else _FLT_MAX
+        if self._ntotal == 0 or nq == 0:
+            D = torch.full((nq, k), pad, dtype=torch.float32, device=q.device)
+            I = torch.full((nq, k), -1, dtype=torch.int64, device=q.device)
+            return D, I
+        kk = min(k, ops.MAX_TOPK)
+        if k > ops.MAX_TOPK and self._ntotal > ops.MAX_TOPK:
+            raise IseError(f"k = {k} exceeds the fused-selection limit of {ops.MAX_TOPK}")
+        if nq < distance_compute_blas_threshold:
+            qf = q if q.dtype == torch.float32 else q.to(torch.float32)
+            D, I = ops.flat_search_exact(qf.contiguous(), self._database(), self.metric_type, kk)
+        else:
+            b = self._operand()
+            a = ops.prepare_operand(q)
+            D, I = ops.gemm_select(a, b, self.metric_type, kk)
+        if kk < k:
+            Dp = torch.full((nq, k), pad, dtype=torch.float32, device=q.device)
+            Ip = torch.full((nq, k), -1, dtype=torch.int64, device=q.device)
+            Dp[:, :kk], Ip[:, :kk] = D, I
+            D, I = Dp, Ip
+        return D, I
+
+    def assign(self, x, k: int = 1):
+        return self.search(x, k)[1]
+
+    def reconstruct(self, i: int) -> np.ndarray:
+        return self._database()[int(i)].cpu().numpy()
+
+    def reconstruct_n(self, i0: int = 0, ni: int = -1) -> np.ndarray:
+        if ni < 0:
+            ni = self._ntotal - i0
+        return self._database()[i0:i0 + ni].cpu().numpy()
+
+    def __repr__(self):
+        name = "IndexFlatIP" if self.metric_type == METRIC_INNER_PRODUCT else "IndexFlatL2"
+        return f"<image_search_engine_b200.{name} d={self.d} ntotal={self.ntotal} (HBM resident)>"
+
+    # joblib/pickle: persist like faiss.serialize_index would (host copy of the vectors)
+    def __getstate__(self):
+        return {"d": self.d, "metric_type": self.metric_type, "xb": self.reconstruct_n()}
+
+    def __setstate__(self, st):
+        self.__init__(st["d"], st["metric_type"])
+        if st["xb"].shape[0]:
+            self.add(st["xb"])
+
+
+class IndexFlatIP(IndexFlat):
+    def __init__(self, d: int, metric: int = METRIC_INNER_PRODUCT):
+        super().__init__(d, METRIC_INNER_PRODUCT)
+
+
+class IndexFlatL2(IndexFlat):
+    def __init__(self, d: int, metric: int = METRIC_L2):
+        super().__init__(d, METRIC_L2)
+
+
+class IndexIVFPQ:
+    """utils.py:311-325 ("cell-probe") -- off every default path; outside the hot-path scope."""
+
+    def __init__(self, *a, **kw):
+        raise NotImplementedError("IndexIVFPQ ('cell-probe') is not part of the B200 retrieval core")
+
+
+# ------------------------------------------------------------------------------------------
+# flat index file format (faiss/impl/index_write.cpp), so existing models/*.faiss files open
+# ------------------------------------------------------------------------------------------
+def write_index(index: IndexFlat, fname) -> None:
+    xb = index.reconstruct_n() if index.ntotal else np.zeros((0, index.d), np.float32)
+    fourcc = b"IxFI" if index.metric_type == METRIC_INNER_PRODUCT else b"IxF2"
+    with open(str(fname), "wb") as f:
+        f.write(fourcc)
+        f.write(struct.pack("<i", index.d))
+        f.write(struct.pack("<q", index.ntotal))
+        f.write(struct.pack("<q", 1 << 20))
+        f.write(struct.pack("<q", 1 << 20))
+        f.write(struct.pack("<B", 1))
+        f.write(struct.pack("<i", index.metric_type))
+        if index.metric_type > 1:
+            f.write(struct.pack("<f", index.metric_arg))
+        f.write(struct.pack("<Q", index.ntotal * index.d))
+        f.write(np.ascontiguousarray(xb, dtype="<f4").tobytes())
+
+
+def read_index(fname) -> IndexFlat:
+    with open(str(fname), "rb") as f:
+        fourcc = f.read(4)
+        if fourcc not in (b"IxFI", b"IxF2", b"IxFl"):
+            raise RuntimeError(f"unsupported index type {fourcc!r}: only flat indexes are on the hot path")
+        (d,) = struct.unpack("<i", f.read(4))
+        (ntotal,) = struct.unpack("<q", f.read(8))
+        f.read(16)
+        f.read(1)
+        (metric,) = struct.unpack("<i", f.read(4))
+        if metric > 1:
+            f.read(4)
+        (count,) = struct.unpack("<Q", f.read(8))
+        if count != ntotal * d:
+            raise RuntimeError("corrupt flat index payload")
+        xb = np.frombuffer(f.read(count * 4), dtype="<f4").reshape(ntotal, d)
+    idx = IndexFlatIP(d) if metric == METRIC_INNER_PRODUCT else IndexFlatL2(d)
+    if ntotal:
+        idx.add(xb)
+    return idx
+
+
+# ------------------------------------------------------------------------------------------
+# k-means (faiss/Clustering.cpp + python/extra_wrappers.py Kmeans)
+# ------------------------------------------------------------------------------------------
+class ClusteringParameters:
+    def __init__(self):
+        self.niter = 25
+        self.nredo = 1
+        self.verbose = False
+        self.spherical = False
+        self.int_centroids = False
+        self.update_index = False
+        self.frozen_centroids = False
+        self.min_points_per_centroid = 39
+        self.max_points_per_centroid = 256
+        self.seed = 1234
+        self.decode_block_size = 32768
+
+
+class Kmeans:
+    """faiss.Kmeans with the Lloyd iterations on the B200.
+
+    Per iteration: centroid planes (prepare) -> fused assign (tcgen05 contraction + argmax) ->
+    scatter-add update -> [allreduce hook for sharded training] -> mean / split-empty / renorm.
+    ``allreduce`` (optional) is called with the [k*d + k] float32 sum|count buffer and the [1]
+    float64 objective; image_search_engine_b200.parallel plugs NCCL in there.
+    """
+
+    def __init__(self, d, k, **kwargs):
+        self.d = int(d)
+        self.k = int(k)
+        self.cp = ClusteringParameters()
+        for key, v in kwargs.items():
+            if key == "gpu":
+                continue  # everything already runs on the GPU
+            getattr(self.cp, key)
+            setattr(self.cp, key, v)
+        self.centroids = None
+        self.obj = None
+        self.iteration_stats = None
+        self.index = None
+        # sharded-training hooks (set by parallel.ShardedKmeans)
+        self.allreduce = None
+        self.n_global = None
+        self.trace = None  # optional list: per-iteration device snapshots for lock-step tests
+
+    # -- helpers --
+    def _post_process(self, cent: torch.Tensor):
+        if self.cp.spherical:
+            ops.normalize_l2_(cent)
+        if self.cp.int_centroids:
+            raise NotImplementedError("int_centroids is never set by the reference")
+
+    def train(self, x, weights=None, init_centroids=None):
+        if weights is not None:
+            raise NotImplementedError("weights are never passed by the reference")
+        cp, d, k = self.cp, self.d, self.k
+        xd, _ = _to_device(x)
+        n = xd.shape[0]
+        assert xd.shape[1] == d
+        n_glob = int(self.n_global) if self.n_global is not None else n
+        if n_glob < k:
+            raise RuntimeError("Number of training points (%d) should be at least as large as number of "
+                               "clusters (%d)" % (n_glob, k))
+        if xd.dtype == torch.float32 and not bool(torch.isfinite(xd).all()):
+            raise RuntimeError("input contains NaN's or Inf's")
+        t0 = time.time()
+        sharded = self.allreduce is not None
+        if not sharded and n > k * cp.max_points_per_centroid:
+            nsub = k * cp.max_points_per_centroid
+            perm = ops.rand_perm_prefix(n, cp.seed, nsub)
+            xd = xd.index_select(0, torch.from_numpy(perm).to(xd.device))
+            n = n_glob = nsub
+        metric = METRIC_INNER_PRODUCT if cp.spherical else METRIC_L2
+        self.index = IndexFlatIP(d) if cp.spherical else IndexFlatL2(d)
+        if n_glob == k and not sharded:
+            cent = xd.to(torch.float32).clone()
+            self.centroids = cent.cpu().numpy()
+            self.iteration_stats = [dict(obj=0.0, time=0.0, time_search=0.0, imbalance_factor=1.0, nsplit=0)]
+            self.obj = np.array([0.0])
+            self.index.add(cent)
+            return 0.0
+
+        a_op = ops.prepare_operand(xd)
+        dev = xd.device
+        if init_centroids is not None:
+            ic = np.ascontiguousarray(init_centroids, dtype=np.float32)
+            assert ic.shape[1] == d
+            ic = ic[:k]
+        else:
+            ic = np.zeros((0, d), np.float32)
+        n_input = ic.shape[0]
+        lower_is_better = not cp.spherical
+        best_obj = float("inf") if lower_is_better else float("-inf")
+        best_cent, best_stats = None, []
+        stats: list[dict] = []
+        accum = torch.empty((k * d + k,), dtype=torch.float32, device=dev)
+        sums, counts = accum[: k * d].view(k, d), accum[k * d:]
+        objbuf = torch.zeros((1,), dtype=torch.float64, device=dev)
+        n_empty = torch.zeros((1,), dtype=torch.int32, device=dev)
+        cent = torch.empty((k, d), dtype=torch.float32, device=dev)
+        t_search = 0.0
+        for redo in range(cp.nredo):
+            if n_input:
+                cent[:n_input] = torch.from_numpy(ic).to(dev)
+            if n_input < k:
+                cent[n_input:] = self._initial_rows(xd, n, n_glob, cp.seed + 1 + redo * 15486557, n_input, k)
+            self._post_process(cent)
+            obj = 0.0
+            for it in range(cp.niter):
+                b_op = ops.prepare_operand(cent, keep_lo=True)
+                dis, assign = ops.gemm_select(a_op, b_op, metric, 1)
+                accum.zero_()
+                objbuf.zero_()
+                ops.kmeans_accumulate(xd, assign, dis, sums, counts, objbuf)
+                if sharded:
+                    self.allreduce(accum, objbuf)
+                if self.trace is not None:
+                    self.trace.append(dict(redo=redo, it=it, centroids_in=cent.clone(), assign=assign.clone(),
+                                           dis=dis.clone()))
+                ops.kmeans_mean(sums, counts, cent, n_empty)
+                obj = float(objbuf.item())          # one tiny sync per iteration
+                nsplit = 0
+                if int(n_empty.item()) > 0:
+                    pairs, _ = ops.split_plan(counts.cpu().numpy(), n_glob)
+                    nsplit = pairs.shape[0]
+                    ops.kmeans_apply_splits(cent, torch.from_numpy(pairs).to(dev))
+                cs = counts.double()
+                imb = float((cs * cs).sum() * k / (cs.sum() ** 2)) if cp.verbose else float("nan")
+                stats.append(dict(obj=obj, time=time.time() - t0, time_search=t_search, imbalance_factor=imb,
+                                  nsplit=nsplit))
+                self._post_process(cent)
+                if self.trace is not None:
+                    self.trace[-1]["centroids_out"] = cent.clone()
+                    self.trace[-1]["nsplit"] = nsplit
+            if cp.nredo > 1:
+                if (lower_is_better and obj < best_obj) or (not lower_is_better and obj > best_obj):
+                    best_cent, best_stats, best_obj = cent.clone(), list(stats), obj
+        if cp.nredo > 1:
+            cent, stats = best_cent, best_stats
+        self.index.add(cent)
+        self.centroids = cent.cpu().numpy().reshape(k, d)
+        self.iteration_stats = stats
+        self.obj = np.array([s["obj"] for s in stats])
+        return self.obj[-1] if self.obj.size else 0.0
+
+    def _initial_rows(self, xd, n, n_glob, seed, n_input, k):
+        """centroids[i] = x[perm[i]] for i in [n_input, k) with perm = rand_perm(nx, seed)."""
+        perm = ops.rand_perm_prefix(n_glob, seed, k)[n_input:k]
+        if self.allreduce is None:
+            return xd.index_select(0, torch.from_numpy(perm).to(xd.device)).to(torch.float32)
+        # sharded: rows live on different ranks; parallel.ShardedKmeans provides the gather
+        return self.gather_rows(perm)
+
+    def assign(self, x):
+        assert self.centroids is not None, "should train before assigning"
+        D, I = self.index.search(x, 1)
+        return D.ravel(), I.ravel()

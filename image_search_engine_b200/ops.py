@@ -1,0 +1,264 @@
+"""Tensor-level wrappers over the C ABI (include/ise.h).
+
+PyTorch is plumbing here: it owns device memory and streams; every arithmetic step
+of the hot path is a libise kernel.  All functions take CUDA tensors and launch on
+``torch.cuda.current_stream()``.  Nothing falls back to torch math or the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (DTYPE_F32, DTYPE_U8, HIST_BINCOUNT, HIST_NUMPY_COMPAT, METRIC_IP, METRIC_L2, OUT_F32,
+                   OUT_F64, IseError)
+
+MAX_TOPK = 128
+
+# kernel-launch counter (bench.py reports it as gpu_launches)
+_launches = 0
+_launch_lock = threading.Lock()
+
+
+def _count(n: int = 1):
+    global _launches
+    with _launch_lock:
+        _launches += n
+
+
+def launches() -> int:
+    return _launches
+
+
+def _ptr(t: torch.Tensor | None):
+    return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev(t: torch.Tensor) -> int:
+    if not t.is_cuda:
+        raise IseError("libise operates on CUDA tensors only (no CPU fallback)")
+    return t.device.index if t.device.index is not None else torch.cuda.current_device()
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise IseError("no CUDA device: image_search_engine_b200 needs a B200 (sm_100a); there is no CPU fallback")
+    _lib.ctx(torch.cuda.current_device())
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+# ------------------------------------------------------------------------------------------
+# host helpers (sequential Faiss RNG semantics)
+# ------------------------------------------------------------------------------------------
+def rand_perm_prefix(n: int, seed: int, m: int) -> np.ndarray:
+    out = np.empty(int(m), dtype=np.int64)
+    _lib.check(_lib.load().ise_rand_perm_prefix(int(n), int(seed), int(m), out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def split_plan(hassign: np.ndarray, n: int) -> tuple[np.ndarray, np.ndarray]:
+    """Returns (pairs int32 [nsplit, 2], updated hassign)."""
+    h = np.ascontiguousarray(hassign, dtype=np.float32).copy()
+    k = h.shape[0]
+    pairs = np.empty(2 * k, dtype=np.int32)
+    ns = C.c_int32(0)
+    _lib.check(_lib.load().ise_split_plan(h.ctypes.data_as(C.c_void_p), k, int(n),
+                                          pairs.ctypes.data_as(C.c_void_p), C.byref(ns)))
+    return pairs[: 2 * ns.value].reshape(-1, 2).copy(), h
+
+
+# ------------------------------------------------------------------------------------------
+# operands
+# ------------------------------------------------------------------------------------------
+@dataclass
+class Operand:
+    """FP16 hi/lo planes + FP32 norms of a row-major matrix, ready for gemm_select."""
+    hi: torch.Tensor          # [n, ldp] float16
+    lo: torch.Tensor | None   # [n, ldp] float16 (None when the source is exactly representable)
+    norms: torch.Tensor       # [n] float32 sum of squares
+    meta: torch.Tensor        # [4] float32: scale, 1/scale, lo_nonzero, absmax
+    n: int
+    d: int
+    ldp: int
+
+
+def prepare_operand(x: torch.Tensor, *, keep_lo: bool | None = None) -> Operand:
+    """x: [n, d] float32 or uint8 CUDA tensor (row-major, last dim contiguous).
+
+    keep_lo=None reads the lo_nonzero flag back (one tiny D2H sync) and drops the lo plane when
+    the data is exactly representable in one FP16 plane (e.g. ORB / SIFT integer descriptors);
+    keep_lo=True/False skips the readback.
+    """
+    if x.dim() != 2:
+        raise IseError("prepare_operand expects a 2-D tensor")
+    if x.dtype == torch.float32:
+        dt = DTYPE_F32
+    elif x.dtype == torch.uint8:
+        dt = DTYPE_U8
+    else:
+        raise IseError(f"unsupported descriptor dtype {x.dtype}; use float32 or uint8")
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    dev = _dev(x)
+    n, d = x.shape
+    ldp = (d + 7) // 8 * 8
+    hi = torch.empty((n, ldp), dtype=torch.float16, device=x.device)
+    want_lo = dt == DTYPE_F32 and keep_lo is not False
+    lo = torch.empty((n, ldp), dtype=torch.float16, device=x.device) if want_lo else None
+    norms = torch.empty((n,), dtype=torch.float32, device=x.device)
+    meta = torch.empty((4,), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().ise_prepare_planes(
+        _lib.ctx(dev), _ptr(x), dt, n, d, x.stride(0) if n > 0 else d, _ptr(hi), _ptr(lo), ldp, _ptr(norms),
+        _ptr(meta), _stream()))
+    _count(2 if dt == DTYPE_F32 else 1)
+    if want_lo and keep_lo is None and n > 0:
+        if float(meta[2].item()) == 0.0:
+            lo = None
+    return Operand(hi, lo, norms, meta, n, d, ldp)
+
+
+def normalize_l2_(x: torch.Tensor) -> torch.Tensor:
+    if x.dtype != torch.float32 or x.dim() != 2 or not x.is_contiguous():
+        raise IseError("normalize_L2 needs a contiguous float32 2-D tensor")
+    _lib.check(_lib.load().ise_normalize_l2(_lib.ctx(_dev(x)), _ptr(x), x.shape[0], x.shape[1], _stream()))
+    _count()
+    return x
+
+
+# ------------------------------------------------------------------------------------------
+# fused contraction + selection
+# ------------------------------------------------------------------------------------------
+def gemm_select(a: Operand, b: Operand, metric: int, topk: int, id_base: int = 0):
+    """Top-k columns of b for every row of a.  Returns (val float32 [m, k], idx int64 [m, k])."""
+    if a.d != b.d:
+        raise IseError(f"dimension mismatch {a.d} vs {b.d}")
+    if not 1 <= topk <= MAX_TOPK:
+        raise IseError(f"topk must be in [1, {MAX_TOPK}]")
+    if b.n == 0:
+        raise IseError("empty column operand")
+    dev = _dev(a.hi)
+    lib, ctx = _lib.load(), _lib.ctx(dev)
+    val = torch.empty((a.n, topk), dtype=torch.float32, device=a.hi.device)
+    idx = torch.empty((a.n, topk), dtype=torch.int64, device=a.hi.device)
+    if a.n == 0:
+        return val, idx
+    a_lo, b_lo = a.lo, b.lo
+    if a_lo is not None and b_lo is None:  # kernel has no (2,1) variant: give b an all-zero lo plane
+        b_lo = torch.zeros_like(b.hi)
+    ws_bytes = lib.ise_gemm_select_workspace_bytes(ctx, a.n, b.n, a.d, topk)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=a.hi.device) if ws_bytes else None
+    _lib.check(lib.ise_gemm_select(
+        ctx, _ptr(a.hi), _ptr(a_lo), a.ldp, _ptr(a.meta), _ptr(a.norms),
+        _ptr(b.hi), _ptr(b_lo), b.ldp, _ptr(b.meta), _ptr(b.norms),
+        a.n, b.n, a.d, int(metric), int(topk), int(id_base), _ptr(val), _ptr(idx), _ptr(ws), ws_bytes, _stream()))
+    _count(2 if ws_bytes else 1)
+    return val, idx
+
+
+def flat_search_exact(q: torch.Tensor, db: torch.Tensor, metric: int, topk: int, id_base: int = 0):
+    """Exact FP32 CUDA-core search (Faiss's n < 20 path)."""
+    if q.dtype != torch.float32 or db.dtype != torch.float32 or not q.is_contiguous() or not db.is_contiguous():
+        raise IseError("flat_search_exact needs contiguous float32 tensors")
+    if not 1 <= topk <= MAX_TOPK:
+        raise IseError(f"topk must be in [1, {MAX_TOPK}]")
+    dev = _dev(q)
+    lib, ctx = _lib.load(), _lib.ctx(dev)
+    nq, d = q.shape
+    nb = db.shape[0]
+    val = torch.empty((nq, topk), dtype=torch.float32, device=q.device)
+    idx = torch.empty((nq, topk), dtype=torch.int64, device=q.device)
+    if nq == 0:
+        return val, idx
+    ws_bytes = lib.ise_flat_search_exact_workspace_bytes(ctx, nq, nb, topk)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=q.device)
+    _lib.check(lib.ise_flat_search_exact(ctx, _ptr(q), nq, _ptr(db), nb, d, int(metric), int(topk), int(id_base),
+                                         _ptr(val), _ptr(idx), _ptr(ws), ws_bytes, _stream()))
+    _count(3)
+    return val, idx
+
+
+def topk_merge(val_parts: torch.Tensor, idx_parts: torch.Tensor, metric: int):
+    """[g, m, k] sorted partial lists -> ([m, k], [m, k])."""
+    g, m, k = val_parts.shape
+    val_parts = val_parts.contiguous()
+    idx_parts = idx_parts.contiguous()
+    val = torch.empty((m, k), dtype=torch.float32, device=val_parts.device)
+    idx = torch.empty((m, k), dtype=torch.int64, device=val_parts.device)
+    _lib.check(_lib.load().ise_topk_merge(_lib.ctx(_dev(val_parts)), _ptr(val_parts), _ptr(idx_parts), g, m, k,
+                                          int(metric), _ptr(val), _ptr(idx), _stream()))
+    _count()
+    return val, idx
+
+
+# ------------------------------------------------------------------------------------------
+# k-means update
+# ------------------------------------------------------------------------------------------
+def kmeans_accumulate(x: torch.Tensor, assign: torch.Tensor, dis: torch.Tensor | None, sums: torch.Tensor,
+                      counts: torch.Tensor, obj: torch.Tensor | None):
+    dt = DTYPE_F32 if x.dtype == torch.float32 else DTYPE_U8
+    if x.dtype not in (torch.float32, torch.uint8):
+        raise IseError("kmeans_accumulate: float32 or uint8 rows")
+    n, d = x.shape
+    assign = assign.reshape(-1)
+    if dis is not None:
+        dis = dis.reshape(-1)
+    _lib.check(_lib.load().ise_kmeans_accumulate(
+        _lib.ctx(_dev(x)), _ptr(x), dt, n, d, x.stride(0) if n > 0 else d, _ptr(assign), _ptr(dis), _ptr(sums),
+        _ptr(counts), _ptr(obj), _stream()))
+    _count()
+
+
+def kmeans_mean(sums: torch.Tensor, counts: torch.Tensor, centroids: torch.Tensor, n_empty: torch.Tensor):
+    k, d = centroids.shape
+    _lib.check(_lib.load().ise_kmeans_mean(_lib.ctx(_dev(sums)), _ptr(sums), _ptr(counts), k, d, _ptr(centroids),
+                                           _ptr(n_empty), _stream()))
+    _count()
+
+
+def kmeans_apply_splits(centroids: torch.Tensor, pairs: torch.Tensor):
+    k, d = centroids.shape
+    ns = pairs.shape[0]
+    _lib.check(_lib.load().ise_kmeans_apply_splits(_lib.ctx(_dev(centroids)), _ptr(centroids), k, d, _ptr(pairs),
+                                                   ns, _stream()))
+    _count()
+
+
+# ------------------------------------------------------------------------------------------
+# BoVW histogram / Okapi
+# ------------------------------------------------------------------------------------------
+def bovw_histogram(words: torch.Tensor, img_offsets: torch.Tensor, k: int, *, mode: int = HIST_NUMPY_COMPAT,
+                   out_dtype: torch.dtype = torch.float64, okapi: bool = False, k1: float = 1.0, k2: float = 1.0,
+                   b: float = 0.75) -> torch.Tensor:
+    if words.dtype != torch.int64 or img_offsets.dtype != torch.int64:
+        raise IseError("bovw_histogram: words and img_offsets must be int64")
+    words = words.reshape(-1).contiguous()
+    n_img = img_offsets.numel() - 1
+    od = OUT_F64 if out_dtype == torch.float64 else OUT_F32
+    if out_dtype not in (torch.float32, torch.float64):
+        raise IseError("bovw_histogram: float32 or float64 output")
+    out = torch.empty((n_img, k), dtype=out_dtype, device=words.device)
+    _lib.check(_lib.load().ise_bovw_histogram(
+        _lib.ctx(_dev(img_offsets)), _ptr(words), _ptr(img_offsets), n_img, int(k), int(mode), od, _ptr(out),
+        1 if okapi else 0, float(k1), float(k2), float(b), _stream()))
+    _count()
+    return out
+
+
+def okapi_tf_(h: torch.Tensor, k1: float = 1.0, k2: float = 1.0, b: float = 0.75, avgdl: float = -1.0):
+    if h.dtype not in (torch.float32, torch.float64) or h.dim() != 2 or not h.is_contiguous():
+        raise IseError("okapi_tf_: contiguous float32/float64 matrix")
+    n_img, k = h.shape
+    od = OUT_F64 if h.dtype == torch.float64 else OUT_F32
+    ws = torch.empty((n_img + 1,), dtype=torch.float64, device=h.device)
+    _lib.check(_lib.load().ise_okapi_tf(_lib.ctx(_dev(h)), _ptr(h), od, n_img, k, float(k1), float(k2), float(b),
+                                        float(avgdl), _ptr(ws), _stream()))
+    _count(2)
+    return h

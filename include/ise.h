@@ -1,0 +1,148 @@
+/*
+ * ise.h -- C ABI of libise.so, the B200 (sm_100a) retrieval core that replaces the
+ * Faiss-CPU / NumPy arithmetic behind image-search-engine's hot path.
+ *
+ * The reference (ManuelZ/image-search-engine) has no FFI of its own: its hot path is
+ * Python calling the third-party `faiss` module.  Each entry point below names the
+ * reference call site (file:line under /root/reference/backend) whose arithmetic it
+ * replaces; INTEGRATION.md shows the ctypes binding a maintainer adds on the
+ * reference side.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; ise_last_error() returns
+ *     a thread-local message for the last failing call on this thread;
+ *   - all data pointers are DEVICE pointers owned by the caller unless the parameter is
+ *     documented as host memory; the library never allocates result memory, scratch is
+ *     sized by the matching *_workspace_bytes() call;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - row-major, float32 unless stated; ids are int64 like Faiss idx_t;
+ *   - no global mutable state besides the per-device ise_ctx.
+ */
+#ifndef ISE_H_
+#define ISE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISE_VERSION 100
+
+/* faiss MetricType values (faiss/MetricType.h): inner product = 0, L2 = 1 */
+#define ISE_METRIC_IP 0
+#define ISE_METRIC_L2 1
+
+/* element type of raw descriptor rows (descriptors.py:216-258: ORB/BRISK uint8, SIFT float32) */
+#define ISE_DTYPE_F32 0
+#define ISE_DTYPE_U8 1
+
+/* histogram binning: np.histogram(idx, bins=k) over [min,max] (bag_of_visual_words.py:103,
+ * SURVEY quirk Q1) or the intended bincount(idx, minlength=k) */
+#define ISE_HIST_NUMPY_COMPAT 0
+#define ISE_HIST_BINCOUNT 1
+
+/* output element type of the histogram matrix (reference: float64, bag_of_visual_words.py:100) */
+#define ISE_OUT_F32 0
+#define ISE_OUT_F64 1
+
+typedef struct ise_ctx ise_ctx;
+
+/* ---- context / errors ---------------------------------------------------------------- */
+int ise_version(void);
+const char* ise_last_error(void);
+/* device = CUDA ordinal; fails (no CPU fallback) when no sm_100 device is present */
+int ise_ctx_create(int device, ise_ctx** out);
+void ise_ctx_destroy(ise_ctx* ctx);
+int ise_ctx_sm_count(const ise_ctx* ctx);
+
+/* ---- host-side helpers (pure CPU, sequential RNG semantics of Faiss) ------------------ */
+/* faiss::rand_perm(perm, n, seed) restricted to its first m entries (Clustering.cpp
+ * subsample_training_set + centroid init; reached from kmeans_faiss.py:41).  out: HOST int64[m]. */
+int ise_rand_perm_prefix(int64_t n, int64_t seed, int64_t m, int64_t* out_host);
+/* faiss Clustering.cpp split_clusters(): given HOST hassign[k] (modified in place) computes the
+ * ordered list of (empty ci, donor cj) pairs with RandomGenerator(1234).  pairs_host: int32[2*k].
+ * Returns the number of splits in *nsplit. */
+int ise_split_plan(float* hassign_host, int64_t k, int64_t n, int32_t* pairs_host, int32_t* nsplit);
+
+/* ---- operand preparation --------------------------------------------------------------
+ * The distance contractions run on the tcgen05 tensor cores as FP16 "hi + lo" split
+ * products (hi*hi + hi*lo + lo*hi, FP32 accumulate) which carries ~22-24 mantissa bits:
+ * rows are scaled by a per-tensor power of two, hi = fp16(s*x), lo = fp16(s*x - hi).
+ * meta (device float[4]) = { scale, 1/scale, lo_nonzero (0/1), absmax }.
+ * ldp (elements) = row pitch of the planes, multiple of 8, >= d; pad columns are zeroed.
+ * norms (nullable) = exact FP32 sum of squares per row (fvec_norms_L2sqr).
+ * Replaces: the implicit float32 conversion `X.astype(np.float32)` + Faiss's internal
+ * operand packing for sgemm (kmeans_faiss.py:41,49; utils.py:327 index.add). */
+int ise_prepare_planes(ise_ctx* ctx, const void* x, int dtype, int64_t n, int d, int64_t ldx,
+                       void* hi, void* lo, int64_t ldp, float* norms, float* meta, void* stream);
+
+/* faiss.normalize_L2 (utils.py:303, engine.py:53, siamese/test_index.py:53): in place,
+ * x *= 1/sqrtf(sum x^2) for rows with non-zero norm. */
+int ise_normalize_l2(ise_ctx* ctx, float* x, int64_t n, int d, void* stream);
+
+/* ---- fused distance contraction + selection (the hot kernel) ---------------------------
+ * For every row r of A (m rows) selects the topk best columns of B (n rows) under
+ *   IP : score = <a_r, b_c>                  best = largest   (IndexFlatIP.search)
+ *   L2 : score = |a_r|^2 + |b_c|^2 - 2<a,b>  best = smallest, clamped at 0 (IndexFlatL2.search)
+ * without ever writing the m x n score matrix to HBM.  Ties: lower id wins.
+ * Output rows are sorted best-first; when topk > n the tail is id -1 / -+FLT_MAX like Faiss.
+ * a_lo / b_lo may be NULL when the corresponding meta says lo_nonzero == 0 (exact operand).
+ * a_norms / b_norms are required for L2 only.  out ids = column + id_base.
+ * Replaces index.search inside faiss.Kmeans.train (kmeans_faiss.py:41), FaissKMeans.transform
+ * (kmeans_faiss.py:49) and run_image_query (engine.py:55) / query_index (siamese/test_index.py:54). */
+size_t ise_gemm_select_workspace_bytes(ise_ctx* ctx, int64_t m, int64_t n, int d, int topk);
+int ise_gemm_select(ise_ctx* ctx,
+                    const void* a_hi, const void* a_lo, int64_t lda, const float* a_meta, const float* a_norms,
+                    const void* b_hi, const void* b_lo, int64_t ldb, const float* b_meta, const float* b_norms,
+                    int64_t m, int64_t n, int d, int metric, int topk, int64_t id_base,
+                    float* out_val, int64_t* out_idx,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Exact FP32 CUDA-core path for small query counts: Faiss computes n < 20 queries without the
+ * BLAS expansion (distances.cpp exhaustive_*_seq: direct dot / sum (x-y)^2), which is what the
+ * reference's single-image query hits (engine.py:55 with nq = 1).  Also used as the on-device
+ * cross-check of the tensor-core path in tests.  q, db: FP32 rows. */
+size_t ise_flat_search_exact_workspace_bytes(ise_ctx* ctx, int64_t nq, int64_t nb, int topk);
+int ise_flat_search_exact(ise_ctx* ctx, const float* q, int64_t nq, const float* db, int64_t nb, int d,
+                          int metric, int topk, int64_t id_base, float* out_val, int64_t* out_idx,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* Merge g sorted top-k lists per row ([g, m, topk] each) into one; canonical (score, id) order.
+ * Used for column-split partial results and for the cross-GPU merge of a sharded index. */
+int ise_topk_merge(ise_ctx* ctx, const float* val_parts, const int64_t* idx_parts, int g, int64_t m,
+                   int topk, int metric, float* out_val, int64_t* out_idx, void* stream);
+
+/* ---- k-means centroid update (faiss Clustering.cpp compute_centroids / split_clusters /
+ * post_process_centroids, reached from kmeans_faiss.py:41) ------------------------------- */
+/* sums[k,d] += x rows by assignment, counts[k] += 1 (float, like hassign), obj[0] += sum(dis).
+ * accum buffers must be zeroed by the caller (so several shards / ranks can add into them). */
+int ise_kmeans_accumulate(ise_ctx* ctx, const void* x, int dtype, int64_t n, int d, int64_t ldx,
+                          const int64_t* assign, const float* dis,
+                          float* sums, float* counts, double* obj, void* stream);
+/* centroids = sums / counts for non-empty clusters (empty rows stay zero); n_empty[0] = #empty */
+int ise_kmeans_mean(ise_ctx* ctx, const float* sums, const float* counts, int64_t k, int d,
+                    float* centroids, int32_t* n_empty, void* stream);
+/* apply the ordered split plan from ise_split_plan (pairs on DEVICE int32[2*nsplit]) */
+int ise_kmeans_apply_splits(ise_ctx* ctx, float* centroids, int64_t k, int d,
+                            const int32_t* pairs, int32_t nsplit, void* stream);
+
+/* ---- BoVW histogram + Okapi tf (bag_of_visual_words.py:98-106, utils.py:153-202) ------- */
+/* words[n] int64 visual-word ids, img_offsets[n_img+1] int64 (image i owns [off[i], off[i+1])).
+ * out[n_img, k] counts as f32/f64.  mode NUMPY_COMPAT reproduces np.histogram(idx, bins=k)
+ * bit-exactly (float64 edge arithmetic); BINCOUNT is bincount(idx, minlength=k).
+ * okapi != 0 fuses OkapiTransformer.transform: tf*k1/(tf*k1 + k2*(1-b+b*dl/avgdl)) with
+ * dl = row sum, avgdl = mean dl over this batch (zeros stay zero). */
+int ise_bovw_histogram(ise_ctx* ctx, const int64_t* words, const int64_t* img_offsets, int64_t n_img,
+                       int k, int mode, int out_dtype, void* out,
+                       int okapi, double k1, double k2, double b, void* stream);
+/* OkapiTransformer.transform on an existing dense [n_img,k] matrix, in place (f32 or f64).
+ * avgdl < 0 => mean row sum of this batch (utils.py:196).  dl_workspace: device double[n_img + 1]. */
+int ise_okapi_tf(ise_ctx* ctx, void* h, int out_dtype, int64_t n_img, int k,
+                 double k1, double k2, double b, double avgdl, double* dl_workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISE_H_ */
