@@ -1,0 +1,248 @@
+"""GPU parity tests of the libise kernels against the CPU oracle (through the C ABI via ops.py)."""
+import numpy as np
+import pytest
+import torch
+
+from tests._util import assert_topk_parity, orb_like, sift_like, unit_rows
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from image_search_engine_b200 import ops
+    return ops.require_cuda()
+
+
+def _oracle_knn(x, y, k, metric_ip):
+    from oracle import faiss_shim as fs
+    return fs.knn(x.astype(np.float32), y.astype(np.float32), k,
+                  fs.METRIC_INNER_PRODUCT if metric_ip else fs.METRIC_L2)
+
+
+def test_prepare_planes_f32(dev):
+    from image_search_engine_b200 import ops
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal((1000, 100)) * 3.7).astype(np.float32)
+    op = ops.prepare_operand(torch.from_numpy(x).to(dev))
+    assert op.lo is not None and op.ldp == 104
+    meta = op.meta.cpu().numpy()
+    scale = meta[0]
+    assert scale == 2.0 ** round(np.log2(scale)) and abs(meta[1] * scale - 1) == 0
+    assert 8192 <= np.abs(x).max() * scale < 16384
+    rec = (op.hi.float() + op.lo.float()).cpu().numpy()[:, :100] / scale
+    assert np.abs(rec - x).max() <= np.abs(x).max() * 2.0 ** -21
+    assert (op.hi.cpu().numpy()[:, 100:] == 0).all()
+    np.testing.assert_allclose(op.norms.cpu().numpy(), (x.astype(np.float64) ** 2).sum(1), rtol=2e-6)
+
+
+def test_prepare_planes_exact_inputs(dev):
+    from image_search_engine_b200 import ops
+    rng = np.random.default_rng(1)
+    u8 = orb_like(rng, 777, 32)
+    op = ops.prepare_operand(torch.from_numpy(u8).to(dev))
+    assert op.lo is None
+    assert np.array_equal(op.hi.float().cpu().numpy(), u8.astype(np.float32))
+    assert np.array_equal(op.norms.cpu().numpy(), (u8.astype(np.float64) ** 2).sum(1).astype(np.float32))
+    s = sift_like(rng, 500, 128)
+    op2 = ops.prepare_operand(torch.from_numpy(s).to(dev))
+    assert op2.lo is None  # integer-valued float32 is exact in one FP16 plane
+    scale = float(op2.meta[0])
+    assert np.array_equal(op2.hi.float().cpu().numpy() / scale, s)
+
+
+@pytest.mark.parametrize("m,n,d,kind", [
+    (300, 512, 32, "orb"), (1000, 4096, 128, "sift"), (129, 257, 100, "float"), (64, 40, 8, "float"),
+    (5000, 1000, 64, "float"), (257, 256, 2048, "unit"),
+])
+def test_assign_ip_top1(dev, m, n, d, kind):
+    from image_search_engine_b200 import ops
+    from image_search_engine_b200._lib import METRIC_IP
+    rng = np.random.default_rng(m + n + d)
+    if kind == "orb":
+        x = orb_like(rng, m, d)
+    elif kind == "sift":
+        x = sift_like(rng, m, d)
+    elif kind == "unit":
+        x = unit_rows(rng, m, d, relu=True)
+    else:
+        x = rng.standard_normal((m, d)).astype(np.float32)
+    c = unit_rows(rng, n, d)
+    a = ops.prepare_operand(torch.from_numpy(x).to(dev))
+    b = ops.prepare_operand(torch.from_numpy(c).to(dev))
+    val, idx = ops.gemm_select(a, b, METRIC_IP, 1)
+    D, I = _oracle_knn(x, c, 1, True)
+    xf = x.astype(np.float32)
+    nm = assert_topk_parity(idx.cpu().numpy(), I, xf, c, True, max_mismatch_frac=0.002)
+    np.testing.assert_allclose(val.cpu().numpy(), D, rtol=1e-4, atol=1e-4 * np.abs(D).max())
+    print(f"[assign {m}x{n}x{d} {kind}] near-tie mismatches: {nm}")
+
+
+@pytest.mark.parametrize("metric_ip", [True, False])
+@pytest.mark.parametrize("nq,nb,d,k", [(200, 3000, 64, 10), (128, 70000, 32, 20), (333, 1000, 512, 100),
+                                        (50, 7, 16, 10)])
+def test_flat_search_topk(dev, metric_ip, nq, nb, d, k):
+    from image_search_engine_b200 import ops
+    from image_search_engine_b200._lib import METRIC_IP, METRIC_L2
+    rng = np.random.default_rng(nq * 7 + nb + d + k)
+    db = unit_rows(rng, nb, d, relu=True)
+    q = db[rng.integers(0, nb, nq)] + 0.05 * rng.standard_normal((nq, d)).astype(np.float32)
+    q = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+    a = ops.prepare_operand(torch.from_numpy(q).to(dev))
+    b = ops.prepare_operand(torch.from_numpy(db).to(dev))
+    val, idx = ops.gemm_select(a, b, METRIC_IP if metric_ip else METRIC_L2, k)
+    D, I = _oracle_knn(q, db, k, metric_ip)
+    idx_h, val_h = idx.cpu().numpy(), val.cpu().numpy()
+    kk = min(k, nb)
+    assert (idx_h[:, kk:] == -1).all() and (I[:, kk:] == -1).all()
+    assert_topk_parity(idx_h[:, :kk], I[:, :kk], q, db, metric_ip, max_mismatch_frac=0.05)
+    np.testing.assert_allclose(val_h[:, :kk], D[:, :kk], rtol=1e-4, atol=2e-6)
+    # sortedness (best first) is size independent
+    srt = -val_h[:, :kk] if metric_ip else val_h[:, :kk]
+    assert (np.diff(srt, axis=1) >= 0).all()
+
+
+@pytest.mark.parametrize("metric_ip", [True, False])
+def test_exact_small_batch(dev, metric_ip):
+    from image_search_engine_b200 import ops
+    from image_search_engine_b200._lib import METRIC_IP, METRIC_L2
+    rng = np.random.default_rng(5)
+    db = rng.standard_normal((50000, 96)).astype(np.float32)
+    q = rng.standard_normal((7, 96)).astype(np.float32)
+    val, idx = ops.flat_search_exact(torch.from_numpy(q).to(dev), torch.from_numpy(db).to(dev),
+                                     METRIC_IP if metric_ip else METRIC_L2, 20)
+    D, I = _oracle_knn(q, db, 20, metric_ip)
+    assert_topk_parity(idx.cpu().numpy(), I, q, db, metric_ip, max_mismatch_frac=1.0)
+    np.testing.assert_allclose(val.cpu().numpy(), D, rtol=1e-4, atol=1e-4)
+
+
+def test_ties_lowest_id_wins(dev):
+    from image_search_engine_b200 import ops
+    from image_search_engine_b200._lib import METRIC_IP
+    x = np.eye(4, 16, dtype=np.float32)[[0, 1, 2, 3] * 40]          # 160 rows
+    c = np.zeros((600, 16), np.float32)
+    c[5, 0] = c[300, 0] = c[599, 0] = 1.0      # three identical best columns for e0
+    c[7, 1] = c[8, 1] = 2.0
+    a = ops.prepare_operand(torch.from_numpy(x).to(dev))
+    b = ops.prepare_operand(torch.from_numpy(c).to(dev))
+    _, idx = ops.gemm_select(a, b, METRIC_IP, 1)
+    idx = idx.cpu().numpy().ravel()
+    assert (idx[0::4] == 5).all() and (idx[1::4] == 7).all()
+    _, idx3 = ops.gemm_select(a, b, METRIC_IP, 3)
+    assert (idx3.cpu().numpy()[0] == [5, 300, 599]).all()
+    assert (idx[2::4] == 0).all()  # all-zero scores: first column
+
+
+def test_topk_merge_matches_unsharded(dev):
+    from image_search_engine_b200 import ops
+    from image_search_engine_b200._lib import METRIC_IP, METRIC_L2
+    rng = np.random.default_rng(11)
+    db = unit_rows(rng, 4000, 64)
+    q = unit_rows(rng, 150, 64)
+    a = ops.prepare_operand(torch.from_numpy(q).to(dev))
+    for metric in (METRIC_IP, METRIC_L2):
+        full = ops.gemm_select(a, ops.prepare_operand(torch.from_numpy(db).to(dev)), metric, 10)
+        parts_v, parts_i = [], []
+        for s in range(4):
+            b = ops.prepare_operand(torch.from_numpy(db[s * 1000:(s + 1) * 1000]).to(dev))
+            v, i = ops.gemm_select(a, b, metric, 10, id_base=s * 1000)
+            parts_v.append(v)
+            parts_i.append(i)
+        mv, mi = ops.topk_merge(torch.stack(parts_v), torch.stack(parts_i), metric)
+        assert_topk_parity(mi.cpu().numpy(), full[1].cpu().numpy(), q, db, metric == METRIC_IP,
+                           max_mismatch_frac=0.05)
+        np.testing.assert_allclose(mv.cpu().numpy(), full[0].cpu().numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_normalize_l2(dev):
+    from image_search_engine_b200 import ops
+    from oracle import faiss_shim as fs
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((1000, 100)).astype(np.float32)
+    x[10] = 0
+    ref = x.copy()
+    fs.normalize_L2(ref)
+    t = torch.from_numpy(x.copy()).to(dev)
+    ops.normalize_l2_(t)
+    np.testing.assert_allclose(t.cpu().numpy(), ref, rtol=1e-6, atol=1e-7)
+    assert (t[10] == 0).all()
+
+
+@pytest.mark.parametrize("k", [200, 512, 4096, 20000])
+@pytest.mark.parametrize("mode", ["numpy_compat", "bincount"])
+def test_histogram_bit_exact(dev, k, mode):
+    from image_search_engine_b200 import ops
+    from image_search_engine_b200._lib import HIST_BINCOUNT, HIST_NUMPY_COMPAT
+    rng = np.random.default_rng(k)
+    sizes = np.concatenate([[0, 1, 3], rng.integers(50, 900, 60)])
+    off = np.zeros(len(sizes) + 1, np.int64)
+    np.cumsum(sizes, out=off[1:])
+    words = rng.integers(0, k, off[-1]).astype(np.int64)
+    words[off[2]:off[3]] = 7                      # all-equal image -> range [v-.5, v+.5]
+    words[off[4]:off[4] + 2] = [0, k - 1]         # image hitting both ends -> identity binning
+    H = ops.bovw_histogram(torch.from_numpy(words).to(dev), torch.from_numpy(off).to(dev), k,
+                           mode=HIST_NUMPY_COMPAT if mode == "numpy_compat" else HIST_BINCOUNT).cpu().numpy()
+    assert H.dtype == np.float64
+    for i in range(len(sizes)):
+        w = words[off[i]:off[i + 1]]
+        ref = np.histogram(w, bins=k)[0] if mode == "numpy_compat" else np.bincount(w, minlength=k)
+        assert np.array_equal(H[i], ref), f"image {i} differs"
+    assert (H.sum(1) == sizes).all()
+
+
+def test_okapi_fused_and_dense(dev):
+    from image_search_engine_b200 import ops
+    from image_search_engine_b200._lib import HIST_BINCOUNT
+    rng = np.random.default_rng(9)
+    k, sizes = 300, rng.integers(1, 400, 80)
+    off = np.zeros(len(sizes) + 1, np.int64)
+    np.cumsum(sizes, out=off[1:])
+    words = rng.integers(0, k, off[-1]).astype(np.int64)
+    wd, od = torch.from_numpy(words).to(dev), torch.from_numpy(off).to(dev)
+    H = ops.bovw_histogram(wd, od, k, mode=HIST_BINCOUNT).cpu().numpy()
+    dl = H.sum(1, keepdims=True)
+    ref = H.copy()
+    ref *= 1
+    nz = ref != 0
+    den = ref + 1 * (1 - 0.75 + 0.75 * (dl / np.mean(dl)))
+    ref[nz] = (ref / den)[nz]
+    fused = ops.bovw_histogram(wd, od, k, mode=HIST_BINCOUNT, okapi=True).cpu().numpy()
+    assert np.array_equal(fused, ref)           # float64, same operation order -> bit exact
+    dense = ops.okapi_tf_(torch.from_numpy(H).to(dev)).cpu().numpy()
+    assert np.array_equal(dense, ref)
+    f32 = ops.bovw_histogram(wd, od, k, mode=HIST_BINCOUNT, okapi=True, out_dtype=torch.float32).cpu().numpy()
+    assert np.array_equal(f32, ref.astype(np.float32))
+
+
+def test_kmeans_update_and_split(dev):
+    from image_search_engine_b200 import ops
+    from oracle import faiss_shim as fs
+    rng = np.random.default_rng(21)
+    n, d, k = 20000, 64, 100
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    assign = rng.integers(0, k - 5, n).astype(np.int64)   # last 5 clusters empty
+    dis = rng.random(n).astype(np.float32)
+    cent_ref = np.zeros((k, d), np.float32)
+    h_ref = np.zeros(k, np.float32)
+    fs.compute_centroids(d, k, x, assign, h_ref, cent_ref)
+    counts_before = h_ref.copy()
+    ns_ref = fs.split_clusters(d, k, n, h_ref, cent_ref)
+    fs.normalize_L2(cent_ref)
+
+    xd = torch.from_numpy(x).to(dev)
+    accum = torch.zeros(k * d + k, device=dev)
+    sums, counts = accum[:k * d].view(k, d), accum[k * d:]
+    obj = torch.zeros(1, dtype=torch.float64, device=dev)
+    ops.kmeans_accumulate(xd, torch.from_numpy(assign).to(dev), torch.from_numpy(dis).to(dev), sums, counts, obj)
+    cent = torch.empty(k, d, device=dev)
+    n_empty = torch.zeros(1, dtype=torch.int32, device=dev)
+    ops.kmeans_mean(sums, counts, cent, n_empty)
+    assert int(n_empty.item()) == 5
+    assert np.array_equal(counts.cpu().numpy(), counts_before)
+    assert abs(float(obj.item()) - dis.astype(np.float64).sum()) < 1e-6 * n
+    pairs, h_new = ops.split_plan(counts.cpu().numpy(), n)
+    assert pairs.shape[0] == ns_ref == 5
+    assert np.array_equal(h_new, h_ref)
+    ops.kmeans_apply_splits(cent, torch.from_numpy(pairs).to(dev))
+    ops.normalize_l2_(cent)
+    np.testing.assert_allclose(cent.cpu().numpy(), cent_ref, rtol=1e-4, atol=1e-6)
