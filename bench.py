@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""Headline benchmark of the B200 retrieval core (contract: see the task statement / DESIGN.md section 6).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-knn]
+
+One "step" = one pass of the hot path over one batch of synthetic input at BASELINE.json configs[1]
+(C2): quantise 1,000,000 SIFT-like 128-D descriptors against a k=4096 codebook (fused tcgen05
+assign), per-image BoVW histogram over 10,000 images and Okapi tf weighting.  The second half of the
+metric (kNN QPS at 1M x 2048, top-10 = configs[2], C3) is measured in the same run and reported under
+"knn".  N > 1: one process per GPU (torchrun), every rank quantises its own C2-sized shard of images
+(no data-path collective, weak scaling) and holds its own 1M-row shard of the flat index (all_gather
+of per-rank top-k lists + on-device merge).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+C2 = dict(n_desc=1_000_000, d=128, k=4096, n_img=10_000, per_img=100)
+C3 = dict(nb=1_000_000, d=2048, nq=10_000, topk=10)
+METRIC = "Mdescriptors/s for k-means assign+histogram"
+
+
+def sift_like(rng, n, d):
+    g = rng.standard_normal((n, d), dtype=np.float32)
+    g *= g
+    g *= (512.0 / np.linalg.norm(g, axis=1, keepdims=True)).astype(np.float32)
+    np.rint(g, out=g)
+    np.minimum(g, 255, out=g)
+    return g
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        j = json.loads(p.read_text())
+        return dict(hbm=j["hbm_gbs"], tf_burst=j["bf16_tflops"], tf_sust=j.get("bf16_tflops_sustained"),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in Path(self.f.name).read_text().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons, power = [], [], set(), []
+        for r in rows:
+            try:
+                r = [c.strip() for c in r]
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                                  ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        load = [s for s, pw in zip(sm, power) if pw >= 0.5 * max(power)] or sm
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": float(max(power))}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm (oracle port of the reference loops; also the cpu_baseline leg of the GPU arm)
+# ----------------------------------------------------------------------------------------------
+def cpu_assign_histogram(n_img_sample, seed=2, reps=1):
+    """Times the reference's per-image quantise + np.histogram + Okapi loop on `n_img_sample` images."""
+    from oracle import cpu_baseline, faiss_shim
+    rng = np.random.default_rng(seed)
+    X = sift_like(rng, n_img_sample * C2["per_img"], C2["d"])
+    cent = X[rng.choice(X.shape[0], C2["k"], replace=X.shape[0] < C2["k"])].copy()
+    faiss_shim.normalize_L2(cent)
+    index = cpu_baseline.codebook_index(cent)
+    descs = [X[i * C2["per_img"]:(i + 1) * C2["per_img"]] for i in range(n_img_sample)]
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cpu_baseline.assign_histogram_step(index, descs, C2["k"])
+        best = min(best, time.perf_counter() - t0)
+    return X.shape[0] / best / 1e6, best
+
+
+def cpu_knn(nb_sample, nq_sample, seed=3):
+    from oracle import cpu_baseline
+    rng = np.random.default_rng(seed)
+    db = np.maximum(rng.standard_normal((nb_sample, C3["d"]), dtype=np.float32), 0)
+    db /= np.linalg.norm(db, axis=1, keepdims=True)
+    q = db[rng.integers(0, nb_sample, nq_sample)] + 0.05 * rng.standard_normal((nq_sample, C3["d"]), dtype=np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    t0 = time.perf_counter()
+    cpu_baseline.flat_search(db, q.astype(np.float32), C3["topk"], "ip")
+    dt = time.perf_counter() - t0
+    # flat search cost is linear in nb: QPS at the full 1M-row index = sample QPS * nb_sample / nb
+    return nq_sample / dt * (nb_sample / C3["nb"]), dt
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        n = os.cpu_count() or 1
+    return int(n)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = cpu_threads()
+    n_img = 1000  # bounded sample: 100,000 descriptors per step (1/10 of C2), same generator and codebook size
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, dt = cpu_assign_histogram(n_img)
+        if i >= args.warmup:
+            vals.append((v, dt))
+        if sum(d for _, d in vals) > 150:
+            break
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([d for _, d in vals]) * 1e3)
+    sample = (f"{n_img} of {C2['n_img']} images x {C2['per_img']} descriptors per step (1/10 of C2), "
+              f"per-image Faiss-shim search + np.histogram + Okapi, NumPy/OpenBLAS")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mdescriptors/s", "n_gpus": args.gpus,
+        "steps": len(vals), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2: 1M SIFT-like 128-D descriptors, k=4096 codebook, 10k images, histogram + Okapi tf",
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Mdescriptors/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Mdescriptors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    if not args.no_knn:
+        q, dt = cpu_knn(50_000, 500)
+        line["knn"] = {"metric": "kNN QPS at 1M x 2048 top-10", "value": q, "unit": "queries/s",
+                       "sample": "50k of 1M DB rows x 500 of 10k queries, scaled linearly in nb"}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from image_search_engine_b200 import BOVW, FaissKMeans, faiss_compat, ops
+    from image_search_engine_b200._lib import METRIC_IP
+    from image_search_engine_b200.bag_of_visual_words import PackedDescriptions
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    P = peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- C2 inputs (per rank: its own shard of 10k images) ----------------
+    rng = np.random.default_rng(2 + rank)
+    X_host = sift_like(rng, C2["n_desc"], C2["d"])
+    offsets = np.arange(0, C2["n_desc"] + 1, C2["per_img"], dtype=np.int64)
+    packed = PackedDescriptions(X_host, offsets).pin()
+    X_dev = packed.matrix.to(dev)
+    off_dev = torch.from_numpy(offsets).to(dev)
+
+    # codebook: 2 Lloyd iterations from the Faiss-style random init (untimed set-up)
+    km = FaissKMeans(C2["k"], n_init=1, max_iter=2)
+    km.fit(X_dev)
+    bovw = BOVW(None, n_clusters=C2["k"])
+    bovw.clusterer = km
+    cent_op = km.index._operand()
+
+    from image_search_engine_b200.utils import OkapiTransformer
+    okapi = OkapiTransformer()
+
+    def device_step(events=None):
+        a = ops.prepare_operand(X_dev)   # same call FaissKMeans.transform makes; lo plane skipped at run time
+        if events is not None:
+            events[0].record()
+        _, words = ops.gemm_select(a, cent_op, METRIC_IP, 1)
+        if events is not None:
+            events[1].record()
+        return ops.bovw_histogram(words.reshape(-1), off_dev, C2["k"], okapi=True, k1=okapi.k1, k2=okapi.k2,
+                                  b=okapi.b)
+
+    for _ in range(args.warmup):
+        device_step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    l0 = ops.launches()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for i in range(args.steps):
+        device_step(ev[i])
+    t_end.record()
+    barrier()
+    launches = ops.launches() - l0
+    ms_step = max_over_ranks(t_start.elapsed_time(t_end) / args.steps)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    value = world * C2["n_desc"] / (ms_step * 1e-3) / 1e6
+
+    # ---------------- e2e: host (pinned) descriptors -> host histogram matrix ----------------
+    out_pin = torch.empty((C2["n_img"], C2["k"]), dtype=torch.float64, pin_memory=True)
+    bovw.descriptions = None
+
+    def e2e_step_full():
+        Hd = bovw.histograms_device(packed, okapi=okapi)   # fused Okapi tf on the device
+        out_pin.copy_(Hd, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out_pin.numpy()
+
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_step_full()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step_full()
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    e2e_val = world * C2["n_desc"] / (e2e_ms * 1e-3) / 1e6
+    h2d = int(X_host.nbytes + offsets.nbytes)
+    d2h = int(out_pin.numel() * 8)
+
+    # ---------------- k-means training iteration time (extra) ----------------
+    barrier()
+    t0 = time.perf_counter()
+    km2 = FaissKMeans(C2["k"], n_init=1, max_iter=5)
+    km2.fit(X_dev)
+    torch.cuda.synchronize()
+    kmeans_iter_ms = (time.perf_counter() - t0) * 1e3 / 5
+
+    clocks = sampler.stop()
+    del km2
+
+    # ---------------- C3: flat IP search, 1M x 2048 per rank, 10k queries, top-10 ----------------
+    knn = None
+    if not args.no_knn:
+        g = torch.Generator(device=dev)
+        g.manual_seed(3 + rank)
+        db = torch.empty((C3["nb"], C3["d"]), dtype=torch.float32, device=dev)
+        for i in range(0, C3["nb"], 100_000):
+            blk = db[i:i + 100_000]
+            blk.normal_(generator=g)
+            blk.clamp_(min=0)
+        ops.normalize_l2_(db)
+        gq = torch.Generator(device=dev)
+        gq.manual_seed(1003)  # same queries on every rank
+        pick = torch.randint(0, C3["nb"], (C3["nq"],), generator=gq, device=dev)
+        q = db[pick] + 0.05 * torch.randn((C3["nq"], C3["d"]), generator=gq, device=dev)
+        if world > 1:
+            dist.broadcast(q, src=0)
+        ops.normalize_l2_(q)
+        index = faiss_compat.IndexFlatIP(C3["d"])
+        index._chunks, index._ntotal = [db], C3["nb"]   # adopt the device tensor without a copy
+        db_op = index._operand()
+        torch.cuda.synchronize()
+
+        def knn_step(qd, events=None):
+            a = ops.prepare_operand(qd)
+            if events is not None:
+                events[0].record()
+            D, I = ops.gemm_select(a, db_op, METRIC_IP, C3["topk"], id_base=rank * C3["nb"])
+            if events is not None:
+                events[1].record()
+            if world > 1:
+                Dg = torch.empty((world,) + D.shape, dtype=D.dtype, device=dev)
+                Ig = torch.empty((world,) + I.shape, dtype=I.dtype, device=dev)
+                dist.all_gather_into_tensor(Dg, D)
+                dist.all_gather_into_tensor(Ig, I)
+                D, I = ops.topk_merge(Dg, Ig, METRIC_IP)
+            return D, I
+
+        ksteps = max(2, min(args.steps, 5))
+        for _ in range(2):
+            knn_step(q)
+        barrier()
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(ksteps)]
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(ksteps):
+            D, I = knn_step(q, kev[i])
+        e.record()
+        barrier()
+        knn_ms = max_over_ranks(s.elapsed_time(e) / ksteps)
+        knn_kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+        # self-check (size independent): every query's best hit is the row it was derived from
+        hit = float((I[:, 0] == (pick + 0)).float().mean().item()) if world == 1 else None
+        # e2e: pinned host queries in, host (D, I) out
+        q_pin = q.cpu().pin_memory()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            qd = q_pin.to(dev, non_blocking=True)
+            D, I = knn_step(qd)
+            Dh, Ih = D.cpu(), I.cpu()
+        torch.cuda.synchronize()
+        knn_e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / ksteps)
+        flops = 2.0 * C3["nq"] * C3["nb"] * C3["d"]
+        knn = {
+            "metric": "kNN QPS at 1M x 2048 top-10", "value": C3["nq"] / (knn_ms * 1e-3), "unit": "queries/s",
+            "ms_per_step": knn_ms, "steps": ksteps, "nb_per_gpu": C3["nb"], "nb_total": C3["nb"] * world,
+            "e2e": {"value": C3["nq"] / (knn_e2e_ms * 1e-3), "unit": "queries/s",
+                    "h2d_bytes_per_step": int(q.numel() * 4), "d2h_bytes_per_step": int(C3["nq"] * C3["topk"] * 12)},
+            "roofline": {"bound": "tensor", "achieved": flops / (knn_kern_ms * 1e-3) / 1e12, "peak": P["tf_burst"],
+                         "unit": "TFLOP/s", "frac": flops / (knn_kern_ms * 1e-3) / 1e12 / P["tf_burst"],
+                         "traffic": None, "kernel": "gemm_select_kernel<2,2,IP,32>", "kernel_ms": knn_kern_ms,
+                         "peak_source": P["src"] + ", bf16 burst"},
+            "top1_self_hit": hit,
+        }
+        del db, index, db_op
+
+    # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v1, dt1 = cpu_assign_histogram(300)
+        n_img = int(min(C2["n_img"], max(300, 300 * 15.0 / max(dt1, 1e-3))))
+        v, dt = cpu_assign_histogram(n_img)
+        cpu = {"value": v, "unit": "Mdescriptors/s", "cores": cpu_threads(), "kind": "port",
+               "sample": f"{n_img} of {C2['n_img']} images x {C2['per_img']} descriptors ({dt:.1f} s): per-image "
+                         f"Faiss-shim IndexFlatIP.search + np.histogram + Okapi on NumPy/OpenBLAS"}
+        if knn is not None:
+            qv, qdt = cpu_knn(50_000, 500)
+            cpu["knn_qps"] = qv
+            cpu["knn_sample"] = f"50k of 1M DB rows x 500 of 10k queries ({qdt:.1f} s), scaled linearly in nb"
+
+    if rank == 0:
+        flops = 2.0 * C2["k"] * C2["d"] * C2["n_desc"]
+        ach = flops / (kern_ms * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mdescriptors/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16x2-split (fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": "C2: 1M SIFT-like 128-D descriptors per GPU, k=4096 codebook, 10k images, "
+                                   "fused assign + BoVW histogram (numpy-compat) + Okapi tf",
+                       "l2": "inputs larger than L2 (512 MB descriptors + 328 MB histogram per step)",
+                       "step": "prepare planes + gemm_select(top-1) + bovw_histogram(okapi)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": "Mdescriptors/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": P["tf_burst"], "unit": "TFLOP/s",
+                         "frac": ach / P["tf_burst"], "traffic": None, "kernel": "gemm_select_kernel<1,2,IP,1>",
+                         "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms / ms_step,
+                         "peak_source": P["src"] + ", bf16 burst"},
+            "cpu_baseline": cpu,
+            "kmeans_iter_ms": kmeans_iter_ms,
+            "knn": knn,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-knn", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -34,6 +34,8 @@ def describe_dataset(describer, X, prediction=False):
     array per image.  Feature extraction (OpenCV / CNN) is upstream of the retrieval core: the host
     application's ``descriptors.describe_dataset`` is used when importable; a describer may also be any
     callable ``paths -> list[np.ndarray]``; a list of arrays passes through unchanged."""
+    if isinstance(X, PackedDescriptions):
+        return X
     if isinstance(X, (list, tuple)) and len(X) and isinstance(X[0], (np.ndarray, torch.Tensor)):
         return list(X)
     if callable(describer):
@@ -46,8 +48,34 @@ def describe_dataset(describer, X, prediction=False):
     return host_describe(describer, X, prediction=prediction) if prediction else host_describe(describer, X)
 
 
-def pack_descriptions(descriptions):
+class PackedDescriptions:
+    """All images' descriptors as ONE [N, d] matrix (uint8 or float32) plus an int64 offsets vector
+    (image i owns rows [offsets[i], offsets[i+1])).  This is the ragged-ingestion format of the GPU
+    path: build it once (``pack_descriptions(list, pin=True)`` puts it in pinned host memory) and hand
+    it to ``BOVW.transform`` / ``run_clustering`` instead of the Python list."""
+
+    def __init__(self, matrix, offsets):
+        self.matrix = matrix
+        self.offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+
+    def __len__(self):
+        return self.offsets.shape[0] - 1
+
+    def pin(self):
+        if isinstance(self.matrix, np.ndarray):
+            self.matrix = torch.from_numpy(self.matrix)
+        if not self.matrix.is_cuda and not self.matrix.is_pinned():
+            self.matrix = self.matrix.pin_memory()
+        return self
+
+
+def pack_descriptions(descriptions, pin=False):
     """list[(n_i, d)] -> (matrix [N, d], offsets int64 [n_img + 1]); dtype uint8 or float32."""
+    if isinstance(descriptions, PackedDescriptions):
+        return descriptions.matrix, descriptions.offsets
+    if pin:
+        m, o = pack_descriptions(descriptions)
+        return PackedDescriptions(m, o).pin()
     if len(descriptions) == 0:
         raise ValueError("no images to quantise")
     counts = np.fromiter((len(x) for x in descriptions), dtype=np.int64, count=len(descriptions))
@@ -75,15 +103,16 @@ class BOVW(BaseEstimator):
         self.clusterer = run_clustering(self.descriptions, self.n_clusters)
         return self
 
-    def transform(self, X, y=None, output="numpy"):
-        """float64 (n_images, n_clusters) histogram matrix; ``output="device"`` keeps it in HBM."""
+    def transform(self, X, y=None, output="numpy", out=None):
+        """float64 (n_images, n_clusters) histogram matrix; ``output="device"`` keeps it in HBM,
+        ``out=`` is an optional pinned CPU tensor that receives the result."""
         descriptions = getattr(self, "descriptions", None)
         if descriptions is None:
             descriptions = describe_dataset(self.describer, X, prediction=True)
         H = self.histograms_device(descriptions)
         if output == "device":
             return H
-        return _to_host(H)
+        return _to_host(H, out)
 
     def histograms_device(self, descriptions, *, okapi: OkapiTransformer | None = None,
                           out_dtype=torch.float64) -> torch.Tensor:
@@ -107,20 +136,13 @@ class BOVW(BaseEstimator):
         return self.transform(X)
 
 
-_pinned: dict[tuple, torch.Tensor] = {}
-
-
-def _to_host(t: torch.Tensor) -> np.ndarray:
-    """Device -> fresh NumPy array through a cached pinned staging buffer."""
-    key = (tuple(t.shape), t.dtype)
-    buf = _pinned.get(key)
-    if buf is None:
-        _pinned.clear()
-        buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-        _pinned[key] = buf
-    buf.copy_(t, non_blocking=True)
-    torch.cuda.current_stream().synchronize()
-    return buf.numpy().copy()
+def _to_host(t: torch.Tensor, out: torch.Tensor | None = None) -> np.ndarray:
+    """Device -> NumPy.  ``out`` (a pinned CPU tensor of the same shape) makes the copy a single DMA."""
+    if out is not None:
+        out.copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out.numpy()
+    return t.cpu().numpy()
 
 
 def run_clustering(descriptions, n_clusters):

@@ -111,11 +111,17 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
 
     const int num_kb = (p.d + BLOCK_K - 1) / BLOCK_K;
     const int total_work = p.n_mtiles * p.n_splits;
+    // PA / PB are the plane SLOTS of a stage; whether a lo plane is really loaded and multiplied is a
+    // run-time property of the data (prepare.cu sets meta[LO_NONZERO]), so callers never have to
+    // synchronise with the host to find out that e.g. integer descriptors are exact in one plane.
+    const bool use_alo = (PA == 2) && (__ldg(p.a_meta + META_LO_NONZERO) != 0.f);
+    const bool use_blo = (PB == 2) && (__ldg(p.b_meta + META_LO_NONZERO) != 0.f);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t it = 0;
+            const uint32_t tx_bytes = A_TILE_BYTES * (1 + (int)use_alo) + B_TILE_BYTES * (1 + (int)use_blo);
             for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
                 const int split = w / p.n_mtiles, mt = w - split * p.n_mtiles;
                 const int nt0 = split * p.tiles_per_split;
@@ -126,13 +132,13 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                         const uint32_t ph = (it / STAGES) & 1;
                         ptx::mbar_wait(&aux->empty[s], ph ^ 1);
                         uint8_t* st = smem + s * STAGE_BYTES;
-                        ptx::mbar_arrive_expect_tx(&aux->full[s], STAGE_BYTES);
+                        ptx::mbar_arrive_expect_tx(&aux->full[s], tx_bytes);
                         ptx::tma_load_2d(st, &tm_a_hi, &aux->full[s], kb * BLOCK_K, mt * BLOCK_M);
-                        if (PA == 2)
+                        if (use_alo)
                             ptx::tma_load_2d(st + A_TILE_BYTES, &tm_a_lo, &aux->full[s], kb * BLOCK_K, mt * BLOCK_M);
                         ptx::tma_load_2d(st + PA * A_TILE_BYTES, &tm_b_hi, &aux->full[s], kb * BLOCK_K,
                                          nt * BLOCK_N);
-                        if (PB == 2)
+                        if (use_blo)
                             ptx::tma_load_2d(st + PA * A_TILE_BYTES + B_TILE_BYTES, &tm_b_lo, &aux->full[s],
                                              kb * BLOCK_K, nt * BLOCK_N);
                     }
@@ -171,8 +177,8 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                             // advancing 16 fp16 = 32 bytes inside the 128B swizzle span: +2 in the >>4 address
                             const uint64_t koff = (uint64_t)(ks * ((UMMA_K * 2) >> 4));
                             ptx::umma_f16_ss(tmem_d, da_hi + koff, db_hi + koff, idesc, (kb | ks) != 0);
-                            if (PB == 2) ptx::umma_f16_ss(tmem_d, da_hi + koff, db_lo + koff, idesc, 1);
-                            if (PA == 2) ptx::umma_f16_ss(tmem_d, da_lo + koff, db_hi + koff, idesc, 1);
+                            if (use_blo) ptx::umma_f16_ss(tmem_d, da_hi + koff, db_lo + koff, idesc, 1);
+                            if (use_alo) ptx::umma_f16_ss(tmem_d, da_lo + koff, db_hi + koff, idesc, 1);
                         }
                         ptx::umma_commit(&aux->empty[s]);  // frees the smem stage when these MMAs retire
                     }

@@ -340,7 +340,7 @@ class Kmeans:
             self.index.add(cent)
             return 0.0
 
-        a_op = ops.prepare_operand(xd)
+        a_op = ops.compact_operand(ops.prepare_operand(xd))
         dev = xd.device
         if init_centroids is not None:
             ic = np.ascontiguousarray(init_centroids, dtype=np.float32)
@@ -367,7 +367,7 @@ class Kmeans:
             self._post_process(cent)
             obj = 0.0
             for it in range(cp.niter):
-                b_op = ops.prepare_operand(cent, keep_lo=True)
+                b_op = ops.prepare_operand(cent)
                 dis, assign = ops.gemm_select(a_op, b_op, metric, 1)
                 accum.zero_()
                 objbuf.zero_()

@@ -93,9 +93,11 @@ class Operand:
 def prepare_operand(x: torch.Tensor, *, keep_lo: bool | None = None) -> Operand:
     """x: [n, d] float32 or uint8 CUDA tensor (row-major, last dim contiguous).
 
-    keep_lo=None reads the lo_nonzero flag back (one tiny D2H sync) and drops the lo plane when
-    the data is exactly representable in one FP16 plane (e.g. ORB / SIFT integer descriptors);
-    keep_lo=True/False skips the readback.
+    No host synchronisation: float32 inputs always get a lo plane and the device-side
+    ``meta[lo_nonzero]`` flag tells gemm_select at run time whether to load / multiply it (integer
+    valued descriptors are exact in the hi plane).  uint8 inputs never need one.  ``keep_lo=False``
+    skips the lo plane when the caller knows the data is exact; ``compact_operand`` drops it after
+    one flag readback (worth it for operands reused across many launches, e.g. k-means training).
     """
     if x.dim() != 2:
         raise IseError("prepare_operand expects a 2-D tensor")
@@ -119,10 +121,14 @@ def prepare_operand(x: torch.Tensor, *, keep_lo: bool | None = None) -> Operand:
         _lib.ctx(dev), _ptr(x), dt, n, d, x.stride(0) if n > 0 else d, _ptr(hi), _ptr(lo), ldp, _ptr(norms),
         _ptr(meta), _stream()))
     _count(2 if dt == DTYPE_F32 else 1)
-    if want_lo and keep_lo is None and n > 0:
-        if float(meta[2].item()) == 0.0:
-            lo = None
     return Operand(hi, lo, norms, meta, n, d, ldp)
+
+
+def compact_operand(op: Operand) -> Operand:
+    """Drops an all-zero lo plane (one 4-byte D2H readback): smaller smem stages, deeper pipeline."""
+    if op.lo is not None and op.n > 0 and float(op.meta[2].item()) == 0.0:
+        op.lo = None
+    return op
 
 
 def normalize_l2_(x: torch.Tensor) -> torch.Tensor:

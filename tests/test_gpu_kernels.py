@@ -40,12 +40,14 @@ def test_prepare_planes_exact_inputs(dev):
     from image_search_engine_b200 import ops
     rng = np.random.default_rng(1)
     u8 = orb_like(rng, 777, 32)
-    op = ops.prepare_operand(torch.from_numpy(u8).to(dev))
+    op = ops.compact_operand(ops.prepare_operand(torch.from_numpy(u8).to(dev)))
     assert op.lo is None
     assert np.array_equal(op.hi.float().cpu().numpy(), u8.astype(np.float32))
     assert np.array_equal(op.norms.cpu().numpy(), (u8.astype(np.float64) ** 2).sum(1).astype(np.float32))
     s = sift_like(rng, 500, 128)
     op2 = ops.prepare_operand(torch.from_numpy(s).to(dev))
+    assert op2.lo is not None and float(op2.meta[2]) == 0.0
+    op2 = ops.compact_operand(op2)
     assert op2.lo is None  # integer-valued float32 is exact in one FP16 plane
     scale = float(op2.meta[0])
     assert np.array_equal(op2.hi.float().cpu().numpy() / scale, s)
