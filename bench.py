@@ -281,7 +281,6 @@ def run_ours(args):
     torch.cuda.synchronize()
     kmeans_iter_ms = (time.perf_counter() - t0) * 1e3 / 5
 
-    clocks = sampler.stop()
     del km2
 
     # ---------------- C3: flat IP search, 1M x 2048 per rank, 10k queries, top-10 ----------------
@@ -315,11 +314,11 @@ def run_ours(args):
             if events is not None:
                 events[1].record()
             if world > 1:
-                Dg = torch.empty((world,) + D.shape, dtype=D.dtype, device=dev)
-                Ig = torch.empty((world,) + I.shape, dtype=I.dtype, device=dev)
+                Dg = torch.empty((world * D.shape[0], D.shape[1]), dtype=D.dtype, device=dev)
+                Ig = torch.empty((world * I.shape[0], I.shape[1]), dtype=I.dtype, device=dev)
                 dist.all_gather_into_tensor(Dg, D)
                 dist.all_gather_into_tensor(Ig, I)
-                D, I = ops.topk_merge(Dg, Ig, METRIC_IP)
+                D, I = ops.topk_merge(Dg.view(world, *D.shape), Ig.view(world, *I.shape), METRIC_IP)
             return D, I
 
         ksteps = max(2, min(args.steps, 5))
@@ -360,6 +359,8 @@ def run_ours(args):
             "top1_self_hit": hit,
         }
         del db, index, db_op
+
+    clocks = sampler.stop()
 
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     cpu = None

@@ -280,9 +280,8 @@ class Kmeans:
     """faiss.Kmeans with the Lloyd iterations on the B200.
 
     Per iteration: centroid planes (prepare) -> fused assign (tcgen05 contraction + argmax) ->
-    scatter-add update -> [allreduce hook for sharded training] -> mean / split-empty / renorm.
-    ``allreduce`` (optional) is called with the [k*d + k] float32 sum|count buffer and the [1]
-    float64 objective; image_search_engine_b200.parallel plugs NCCL in there.
+    scatter-add update -> mean / split-empty / renorm.  The multi-GPU variant (rows sharded over
+    ranks, one NCCL all-reduce of the sum|count buffer per iteration) is parallel.ShardedKmeans.
     """
 
     def __init__(self, d, k, **kwargs):
@@ -298,9 +297,6 @@ class Kmeans:
         self.obj = None
         self.iteration_stats = None
         self.index = None
-        # sharded-training hooks (set by parallel.ShardedKmeans)
-        self.allreduce = None
-        self.n_global = None
         self.trace = None  # optional list: per-iteration device snapshots for lock-step tests
 
     # -- helpers --
@@ -317,22 +313,20 @@ class Kmeans:
         xd, _ = _to_device(x)
         n = xd.shape[0]
         assert xd.shape[1] == d
-        n_glob = int(self.n_global) if self.n_global is not None else n
-        if n_glob < k:
+        if n < k:
             raise RuntimeError("Number of training points (%d) should be at least as large as number of "
-                               "clusters (%d)" % (n_glob, k))
+                               "clusters (%d)" % (n, k))
         if xd.dtype == torch.float32 and not bool(torch.isfinite(xd).all()):
             raise RuntimeError("input contains NaN's or Inf's")
         t0 = time.time()
-        sharded = self.allreduce is not None
-        if not sharded and n > k * cp.max_points_per_centroid:
+        if n > k * cp.max_points_per_centroid:
             nsub = k * cp.max_points_per_centroid
             perm = ops.rand_perm_prefix(n, cp.seed, nsub)
             xd = xd.index_select(0, torch.from_numpy(perm).to(xd.device))
-            n = n_glob = nsub
+            n = nsub
         metric = METRIC_INNER_PRODUCT if cp.spherical else METRIC_L2
         self.index = IndexFlatIP(d) if cp.spherical else IndexFlatL2(d)
-        if n_glob == k and not sharded:
+        if n == k:
             cent = xd.to(torch.float32).clone()
             self.centroids = cent.cpu().numpy()
             self.iteration_stats = [dict(obj=0.0, time=0.0, time_search=0.0, imbalance_factor=1.0, nsplit=0)]
@@ -363,7 +357,7 @@ class Kmeans:
             if n_input:
                 cent[:n_input] = torch.from_numpy(ic).to(dev)
             if n_input < k:
-                cent[n_input:] = self._initial_rows(xd, n, n_glob, cp.seed + 1 + redo * 15486557, n_input, k)
+                cent[n_input:] = self._initial_rows(xd, n, cp.seed + 1 + redo * 15486557, n_input, k)
             self._post_process(cent)
             obj = 0.0
             for it in range(cp.niter):
@@ -372,8 +366,6 @@ class Kmeans:
                 accum.zero_()
                 objbuf.zero_()
                 ops.kmeans_accumulate(xd, assign, dis, sums, counts, objbuf)
-                if sharded:
-                    self.allreduce(accum, objbuf)
                 if self.trace is not None:
                     self.trace.append(dict(redo=redo, it=it, centroids_in=cent.clone(), assign=assign.clone(),
                                            dis=dis.clone()))
@@ -381,7 +373,7 @@ class Kmeans:
                 obj = float(objbuf.item())          # one tiny sync per iteration
                 nsplit = 0
                 if int(n_empty.item()) > 0:
-                    pairs, _ = ops.split_plan(counts.cpu().numpy(), n_glob)
+                    pairs, _ = ops.split_plan(counts.cpu().numpy(), n)
                     nsplit = pairs.shape[0]
                     ops.kmeans_apply_splits(cent, torch.from_numpy(pairs).to(dev))
                 cs = counts.double()
@@ -403,13 +395,10 @@ class Kmeans:
         self.obj = np.array([s["obj"] for s in stats])
         return self.obj[-1] if self.obj.size else 0.0
 
-    def _initial_rows(self, xd, n, n_glob, seed, n_input, k):
+    def _initial_rows(self, xd, n, seed, n_input, k):
         """centroids[i] = x[perm[i]] for i in [n_input, k) with perm = rand_perm(nx, seed)."""
-        perm = ops.rand_perm_prefix(n_glob, seed, k)[n_input:k]
-        if self.allreduce is None:
-            return xd.index_select(0, torch.from_numpy(perm).to(xd.device)).to(torch.float32)
-        # sharded: rows live on different ranks; parallel.ShardedKmeans provides the gather
-        return self.gather_rows(perm)
+        perm = ops.rand_perm_prefix(n, seed, k)[n_input:k]
+        return xd.index_select(0, torch.from_numpy(perm).to(xd.device)).to(torch.float32)
 
     def assign(self, x):
         assert self.centroids is not None, "should train before assigning"

@@ -1,0 +1,245 @@
+"""Multi-GPU data parallelism for the two parts of the hot path that shard.
+
+One process per GPU, ``torch.distributed`` for the plumbing (NCCL over NVLink on the B200 box).
+
+* ShardedKmeans   descriptor rows are split contiguously over the ranks; every Lloyd iteration
+                  all-reduces ONE contiguous float32 buffer [k*d sums | k counts] plus the float64
+                  objective, then every rank runs the identical deterministic finalize (mean ->
+                  split-empty with mt19937(1234) -> renorm), so no broadcast is needed.
+                  33.8 MB per iteration at k = 65536, d = 128.
+* ShardedIndexFlat database rows are split contiguously (ids = local + id_base), queries are
+                  replicated, per-rank sorted top-k lists are all-gathered and merged on the device
+                  with the canonical (score, id) rule, so the result equals the unsharded search.
+
+The reference has no distributed code at all; the contract here is "same result as the single-GPU
+drop-in".  The collective-free part (quantise + histogram) shards by image with no exchange.
+
+``local_ops`` is the seam that lets the CPU test-suite drive this exact control flow over gloo with
+the oracle standing in for the kernels (tests/test_parallel_gloo.py); the product default is
+DeviceOps, which calls libise and has no fallback.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import ops
+from ._lib import METRIC_IP, METRIC_L2
+from .faiss_compat import ClusteringParameters, IndexFlat, IndexFlatIP, IndexFlatL2
+
+
+class DeviceOps:
+    """libise-backed local compute (the product path)."""
+
+    def device(self):
+        return ops.require_cuda()
+
+    def to_local(self, x):
+        dev = self.device()
+        t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+        if t.dtype not in (torch.float32, torch.uint8):
+            t = t.to(torch.float32)
+        return t.to(dev, non_blocking=True)
+
+    def prepare(self, x, reuse=False):
+        op = ops.prepare_operand(x)
+        return ops.compact_operand(op) if reuse else op
+
+    def assign(self, a_op, cent, metric):
+        return ops.gemm_select(a_op, ops.prepare_operand(cent), metric, 1)
+
+    def accumulate(self, x, assign, dis, sums, counts, obj):
+        ops.kmeans_accumulate(x, assign, dis, sums, counts, obj)
+
+    def finalize(self, sums, counts, cent, n_global, spherical):
+        """mean -> split empties (host plan, sequential Faiss RNG) -> renorm.  Returns nsplit."""
+        n_empty = torch.zeros((1,), dtype=torch.int32, device=cent.device)
+        ops.kmeans_mean(sums, counts, cent, n_empty)
+        nsplit = 0
+        if int(n_empty.item()) > 0:
+            pairs, _ = ops.split_plan(counts.cpu().numpy(), n_global)
+            nsplit = pairs.shape[0]
+            ops.kmeans_apply_splits(cent, torch.from_numpy(pairs).to(cent.device))
+        if spherical:
+            ops.normalize_l2_(cent)
+        return nsplit
+
+    def normalize(self, cent):
+        ops.normalize_l2_(cent)
+
+    def search(self, q_op, b_op, metric, k, id_base):
+        return ops.gemm_select(q_op, b_op, metric, k, id_base=id_base)
+
+    def merge(self, D_parts, I_parts, metric):
+        return ops.topk_merge(D_parts, I_parts, metric)
+
+
+def _world(group):
+    if not dist.is_available() or not dist.is_initialized():
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def shard_bounds(n: int, world: int) -> np.ndarray:
+    """Contiguous row partition: rank r owns [b[r], b[r+1])."""
+    base, rem = divmod(int(n), int(world))
+    sizes = np.full(world, base, dtype=np.int64)
+    sizes[:rem] += 1
+    b = np.zeros(world + 1, dtype=np.int64)
+    np.cumsum(sizes, out=b[1:])
+    return b
+
+
+class ShardedKmeans:
+    """faiss.Kmeans semantics (Clustering.cpp) over rows sharded across ranks."""
+
+    def __init__(self, d, k, group=None, local_ops=None, **kwargs):
+        self.d, self.k = int(d), int(k)
+        self.cp = ClusteringParameters()
+        for key, v in kwargs.items():
+            getattr(self.cp, key)
+            setattr(self.cp, key, v)
+        self.group = group
+        self.lops = local_ops or DeviceOps()
+        self.centroids = None
+        self.obj = None
+        self.iteration_stats = None
+        self.index = None
+
+    # -- collectives --
+    def _allreduce(self, t):
+        if _world(self.group)[1] > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def _gather_rows(self, x_local, start, global_ids):
+        """Rows of the global matrix by global id: each rank contributes the rows it owns (exactly one
+        rank owns each id), summed across ranks."""
+        ids = torch.as_tensor(global_ids, dtype=torch.int64, device=x_local.device)
+        n_local = x_local.shape[0]
+        mine = (ids >= start) & (ids < start + n_local)
+        rows = torch.zeros((ids.shape[0], self.d), dtype=torch.float32, device=x_local.device)
+        if bool(mine.any()):
+            rows[mine] = x_local.index_select(0, ids[mine] - start).to(torch.float32)
+        return self._allreduce(rows)
+
+    def train(self, x_local, init_centroids=None):
+        """x_local: this rank's contiguous slice of the descriptor matrix (rank order = row order)."""
+        cp, d, k = self.cp, self.d, self.k
+        rank, world = _world(self.group)
+        lops = self.lops
+        x = lops.to_local(x_local)
+        n_local = int(x.shape[0])
+        sizes = torch.zeros((world,), dtype=torch.float64, device=x.device)
+        sizes[rank] = n_local
+        self._allreduce(sizes)
+        sizes = sizes.cpu().numpy().astype(np.int64)
+        start = int(sizes[:rank].sum())
+        n_glob = int(sizes.sum())
+        if n_glob < k:
+            raise RuntimeError("Number of training points (%d) should be at least as large as number of "
+                               "clusters (%d)" % (n_glob, k))
+        # Faiss sub-samples to k*256 rows with rand_perm(n, seed): every rank derives the same global
+        # permutation and keeps the sampled rows it owns; sub_ids maps "row of the sub-sampled matrix"
+        # to global id so the centroid initialisation picks the same vectors as a single process.
+        sub_ids = None
+        if n_glob > k * cp.max_points_per_centroid:
+            nsub = k * cp.max_points_per_centroid
+            sub_ids = ops.rand_perm_prefix(n_glob, cp.seed, nsub)
+            mine = sub_ids[(sub_ids >= start) & (sub_ids < start + n_local)] - start
+            x_train = x.index_select(0, torch.from_numpy(mine).to(x.device))
+            n_train = nsub
+        else:
+            x_train, n_train = x, n_glob
+        metric = METRIC_IP if cp.spherical else METRIC_L2
+        a_op = lops.prepare(x_train, reuse=True)
+        if init_centroids is not None:
+            ic = np.ascontiguousarray(init_centroids, dtype=np.float32)[:k]
+        else:
+            ic = np.zeros((0, d), np.float32)
+        n_input = ic.shape[0]
+        dev = x.device
+        accum = torch.empty((k * d + k,), dtype=torch.float32, device=dev)
+        sums, counts = accum[:k * d].view(k, d), accum[k * d:]
+        obj = torch.zeros((1,), dtype=torch.float64, device=dev)
+        cent = torch.empty((k, d), dtype=torch.float32, device=dev)
+        lower_is_better = not cp.spherical
+        best_obj = float("inf") if lower_is_better else float("-inf")
+        best_cent, best_stats, stats = None, [], []
+        for redo in range(cp.nredo):
+            if n_input:
+                cent[:n_input] = torch.from_numpy(ic).to(dev)
+            if n_input < k:
+                perm = ops.rand_perm_prefix(n_train, cp.seed + 1 + redo * 15486557, k)[n_input:k]
+                gids = sub_ids[perm] if sub_ids is not None else perm
+                cent[n_input:] = self._gather_rows(x, start, gids)
+            if cp.spherical:
+                lops.normalize(cent)
+            o = 0.0
+            for it in range(cp.niter):
+                dis, assign = lops.assign(a_op, cent, metric)
+                accum.zero_()
+                obj.zero_()
+                lops.accumulate(x_train, assign, dis, sums, counts, obj)
+                self._allreduce(accum)     # [k*d sums | k counts] in one NCCL all-reduce
+                self._allreduce(obj)
+                nsplit = lops.finalize(sums, counts, cent, n_train, cp.spherical)
+                o = float(obj.item())
+                stats.append(dict(obj=o, nsplit=nsplit))
+            if cp.nredo > 1:
+                if (lower_is_better and o < best_obj) or (not lower_is_better and o > best_obj):
+                    best_cent, best_stats, best_obj = cent.clone(), list(stats), o
+        if cp.nredo > 1:
+            cent, stats = best_cent, best_stats
+        self.centroids = cent.cpu().numpy()
+        self.iteration_stats = stats
+        self.obj = np.array([s["obj"] for s in stats])
+        if isinstance(lops, DeviceOps):
+            self.index = IndexFlatIP(d) if cp.spherical else IndexFlatL2(d)
+            self.index.add(cent)
+        return self.obj[-1] if self.obj.size else 0.0
+
+
+class ShardedIndexFlat:
+    """Flat index whose rows are split contiguously across ranks; search results equal the unsharded ones."""
+
+    def __init__(self, d, metric=METRIC_IP, group=None, local_ops=None):
+        self.d, self.metric_type = int(d), int(metric)
+        self.group = group
+        self.lops = local_ops or DeviceOps()
+        self._local = None
+        self._b_op = None
+        self.id_base = 0
+        self.ntotal = 0
+
+    def add_local(self, x_local):
+        """x_local: this rank's slice; global ids follow rank order."""
+        rank, world = _world(self.group)
+        x = self.lops.to_local(x_local)
+        if x.dtype != torch.float32:
+            x = x.to(torch.float32)
+        sizes = torch.zeros((world,), dtype=torch.float64, device=x.device)
+        sizes[rank] = x.shape[0]
+        if world > 1:
+            dist.all_reduce(sizes, group=self.group)
+        sizes = sizes.cpu().numpy().astype(np.int64)
+        self.id_base = int(sizes[:rank].sum())
+        self.ntotal = int(sizes.sum())
+        self._local = x
+        self._b_op = self.lops.prepare(x, reuse=True)
+
+    def search(self, q, k):
+        """q replicated on every rank.  Returns (D [nq, k], I [nq, k]) identical on every rank."""
+        rank, world = _world(self.group)
+        qd = self.lops.to_local(q)
+        q_op = self.lops.prepare(qd)
+        D, I = self.lops.search(q_op, self._b_op, self.metric_type, int(k), self.id_base)
+        if world == 1:
+            return D, I
+        nq, kk = D.shape
+        Dg = torch.empty((world * nq, kk), dtype=D.dtype, device=D.device)   # rank-major concatenation
+        Ig = torch.empty((world * nq, kk), dtype=I.dtype, device=I.device)
+        dist.all_gather_into_tensor(Dg, D.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(Ig, I.contiguous(), group=self.group)
+        return self.lops.merge(Dg.view(world, nq, kk), Ig.view(world, nq, kk), self.metric_type)

@@ -94,20 +94,24 @@ def create_search_index(data_array, index_type="cosine"):
     the caller's array is normalised IN PLACE.  "l2" -> squared-L2 index.  "cell-probe" (IVFPQ) is
     outside the hot path.
     """
-    if isinstance(data_array, torch.Tensor):
-        num_features = int(data_array.shape[1])
-    else:
-        data_array = np.asarray(data_array) if not isinstance(data_array, np.ndarray) else data_array
-        num_features = int(data_array.shape[1])
-    if index_type == "cosine":
-        index = faiss.IndexFlatIP(num_features)
-        faiss.normalize_L2(data_array)
-    elif index_type == "l2":
-        index = faiss.IndexFlatL2(num_features)
-    elif index_type == "cell-probe":
+    num_features = int(data_array.shape[1])
+    if index_type == "cell-probe":
         raise NotImplementedError("'cell-probe' (IndexIVFPQ) is not part of the B200 retrieval core")
-    else:
+    if index_type not in ("cosine", "l2"):
         raise ValueError(f"unknown index_type {index_type!r}")
-    index.add(data_array)
+    if isinstance(data_array, torch.Tensor) and data_array.is_cuda:
+        rows = data_array
+        if index_type == "cosine":
+            faiss.normalize_L2(rows)
+    else:
+        host = np.asarray(data_array)                       # np.matrix shares its buffer (quirk Q4)
+        if index_type == "cosine" and (host.dtype != np.float32 or not host.flags.c_contiguous):
+            raise TypeError("normalize_L2 needs a C-contiguous float32 2-D array")
+        rows = torch.from_numpy(np.ascontiguousarray(host, dtype=np.float32)).to(ops.require_cuda())
+        if index_type == "cosine":                          # one upload: normalise on the device, then
+            faiss.normalize_L2(rows)                        # mirror the result into the caller's array
+            host[...] = rows.cpu().numpy()
+    index = faiss.IndexFlatIP(num_features) if index_type == "cosine" else faiss.IndexFlatL2(num_features)
+    index.add(rows)
     print(f"There are {index.ntotal} images in the search index.")
     return index

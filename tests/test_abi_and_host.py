@@ -1,0 +1,108 @@
+"""CPU: the C-ABI library loads and exports every symbol include/ise.h declares, the host-side
+helpers match the oracle, and the product path fails loudly without a GPU."""
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    from image_search_engine_b200 import _lib
+    header = (ROOT / "include" / "ise.h").read_text()
+    declared = set(re.findall(r"\b(ise_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 18
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    for name in declared:
+        assert hasattr(lib, name), f"{name} not exported by libise.so"
+    assert _lib.load().ise_version() == 100
+
+
+def test_rand_perm_prefix_matches_oracle():
+    from image_search_engine_b200 import ops
+    from oracle import faiss_shim as fs
+    for n, seed, m in [(10, 1, 10), (1, 5, 1), (1000, 43, 1000), (500000, 42 + 1, 512), (131072 * 4, 42, 131072)]:
+        assert np.array_equal(ops.rand_perm_prefix(n, seed, m), fs.rand_perm(n, seed, prefix=m))
+    assert np.array_equal(ops.rand_perm_prefix(50, 2**32 + 9, 50), ops.rand_perm_prefix(50, 9, 50))  # (unsigned)seed
+
+
+def test_split_plan_matches_oracle():
+    from image_search_engine_b200 import ops
+    from oracle import faiss_shim as fs
+    rng = np.random.default_rng(4)
+    for k, n_empty in [(16, 3), (200, 40), (1000, 1)]:
+        h = rng.integers(1, 60, k).astype(np.float32)
+        h[rng.choice(k, n_empty, replace=False)] = 0
+        n = int(h.sum())
+        cent = rng.standard_normal((k, 6)).astype(np.float32)
+        cent[h == 0] = 0
+        c_ref, h_ref = cent.copy(), h.copy()
+        ns = fs.split_clusters(6, k, n, h_ref, c_ref)
+        pairs, h_new = ops.split_plan(h, n)
+        assert pairs.shape == (ns, 2) and ns == n_empty
+        assert np.array_equal(h_new, h_ref)
+        # replay the plan on the host exactly as the device kernel does
+        c = cent.copy()
+        up, dn = np.float32(1 + 1 / 1024), np.float32(1 - 1 / 1024)
+        for ci, cj in pairs:
+            v = c[cj].copy()
+            c[ci, 0::2], c[cj, 0::2] = v[0::2] * up, v[0::2] * dn
+            c[ci, 1::2], c[cj, 1::2] = v[1::2] * dn, v[1::2] * up
+        assert np.array_equal(c, c_ref)
+
+
+def test_chunkit_and_okapi_fit_host_logic():
+    from image_search_engine_b200 import OkapiTransformer, chunkIt
+    g = np.load(ROOT / "tests" / "golden" / "bovw_c1mini.npz")
+    assert [len(c) for c in chunkIt(list(range(37)), 5)] == list(g["chunk_bounds"])
+    assert sum(chunkIt(list(range(10)), 3), []) == list(range(10))
+    ok = OkapiTransformer().fit(g["hist"])
+    np.testing.assert_allclose(ok.idf_, g["idf"], rtol=1e-12)
+    ok.idf_ = np.arange(4.0)
+    assert list(ok.idf_) == [0, 1, 2, 3]
+    from sklearn.base import clone
+    assert clone(OkapiTransformer(b=0.5)).b == 0.5
+
+
+def test_estimators_are_clonable_and_light():
+    from sklearn.base import clone
+    from image_search_engine_b200 import BOVW, FaissKMeans
+    b = clone(BOVW(describer=None, n_clusters=17))
+    assert b.n_clusters == 17 and b.get_params()["hist_mode"] == "numpy_compat"
+    b.set_params(n_clusters=33)
+    assert b.n_clusters == 33
+    km = FaissKMeans()
+    assert (km.n_clusters, km.n_init, km.max_iter, km.init_centroids, km.index) == (8, 3, 25, None, None)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_product_path_fails_loudly_without_gpu():
+    from image_search_engine_b200 import FaissKMeans, IseError, create_search_index, faiss_compat
+    x = np.zeros((64, 8), np.float32)
+    with pytest.raises(IseError):
+        FaissKMeans(4).fit(x)
+    with pytest.raises(IseError):
+        create_search_index(x.copy(), "l2")
+    with pytest.raises(IseError):
+        faiss_compat.normalize_L2(x)
+
+
+def test_product_code_never_imports_the_oracle():
+    pkg = ROOT / "image_search_engine_b200"
+    for f in pkg.rglob("*.py"):
+        src = f.read_text()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
+    for f in list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")):
+        assert "oracle" not in f.read_text()
+
+
+def test_shard_bounds():
+    from image_search_engine_b200.parallel import shard_bounds
+    assert list(shard_bounds(10, 4)) == [0, 3, 6, 8, 10]
+    assert list(shard_bounds(8, 8)) == list(range(9))
+    assert shard_bounds(10_000_000, 8)[-1] == 10_000_000

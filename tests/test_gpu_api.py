@@ -1,0 +1,335 @@
+"""GPU parity tests of the drop-in Python surface (FaissKMeans, BOVW, OkapiTransformer,
+create_search_index, run_image_query, faiss_compat) against the golden fixtures produced by the
+reference's own code (oracle/make_golden.py) and against the oracle on seeded inputs."""
+import io
+import threading
+from pathlib import Path
+
+import joblib
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from tests._util import assert_topk_parity, orb_like, sift_like, unit_rows
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+
+
+@pytest.fixture(scope="module")
+def g():
+    return np.load(GOLD / "bovw_c1mini.npz")
+
+
+@pytest.fixture(scope="module")
+def kats():
+    return np.load(GOLD / "kats.npz")
+
+
+def _descs(g):
+    off = g["offsets"]
+    return [g["X"][off[i]:off[i + 1]] for i in range(len(off) - 1)]
+
+
+def _codebook(g):
+    from image_search_engine_b200 import FaissKMeans, faiss_compat
+    idx = faiss_compat.IndexFlatIP(32)
+    idx.add(g["centroids"])
+    return FaissKMeans(int(g["k"]), index=idx)
+
+
+def test_transform_and_histogram_match_reference_fixture(g):
+    from image_search_engine_b200 import BOVW
+    km = _codebook(g)
+    words = km.transform(g["X"])
+    assert words.dtype == np.int64 and words.shape == g["words"].shape   # (n, 1), like Faiss
+    x = g["X"].astype(np.float32)
+    assert_topk_parity(words, g["words"], x, g["centroids"], True, max_mismatch_frac=0.002)
+    # per-image call pattern of the reference loop (bag_of_visual_words.py:101-104), n >= 20 and n < 20
+    d = _descs(g)
+    assert np.array_equal(km.transform(d[0]), words[: len(d[0])])
+    assert km.transform(d[3]).shape == (1, 1)
+    bovw = BOVW(None, n_clusters=int(g["k"]))
+    bovw.clusterer, bovw.descriptions = km, d
+    H = bovw.transform(None)
+    assert H.dtype == np.float64 and H.shape == g["hist"].shape
+    if np.array_equal(words, g["words"]):
+        assert np.array_equal(H, g["hist"])
+    assert (H.sum(1) == np.diff(g["offsets"])).all()
+    # the intended semantics differ from the reference's np.histogram quirk (Q1) and are available
+    bovw2 = BOVW(None, n_clusters=int(g["k"]), hist_mode="bincount")
+    bovw2.clusterer, bovw2.descriptions = km, d
+    Hb = bovw2.transform(None)
+    off = g["offsets"]
+    assert np.array_equal(Hb[5], np.bincount(words[off[5]:off[6], 0], minlength=int(g["k"])))
+
+
+def test_okapi_matches_reference_fixture(g, kats):
+    from image_search_engine_b200 import OkapiTransformer
+    T = OkapiTransformer().fit(g["hist"]).transform(g["hist"])
+    assert sp.issparse(T) and T.format == "csr" and T.dtype == np.float64
+    assert np.array_equal(np.asarray(T.todense()), g["okapi"])          # float64, bit exact
+    assert np.array_equal(np.asarray(OkapiTransformer().transform(kats["okapi_in"]).todense()), kats["okapi_out"])
+    assert np.array_equal(np.asarray(OkapiTransformer().transform(kats["okapi_in"][:1]).todense()),
+                          kats["okapi_single_row"])
+    Ts = OkapiTransformer().transform(sp.csr_matrix(g["hist"]))          # sparse input, np.matrix input
+    assert np.array_equal(np.asarray(Ts.todense()), g["okapi"])
+    Tm = OkapiTransformer().transform(np.asmatrix(g["hist"]))
+    assert np.array_equal(np.asarray(Tm.todense()), g["okapi"])
+    blob = io.BytesIO()
+    joblib.dump(OkapiTransformer(k1=2).fit(g["hist"]), blob)
+    blob.seek(0)
+    assert joblib.load(blob).k1 == 2
+
+
+def test_search_index_matches_reference_fixture(g):
+    from image_search_engine_b200 import create_search_index
+    feats = g["feats"].copy()
+    idx = create_search_index(feats, "cosine")
+    np.testing.assert_allclose(feats, g["cos_db"], rtol=1e-6, atol=1e-7)   # caller's array normalised IN PLACE
+    assert idx.ntotal == 40 and idx.d == 32
+    D, I = idx.search(g["q"], 10)
+    assert D.dtype == np.float32 and I.dtype == np.int64 and D.shape == (25, 10)
+    assert_topk_parity(I, g["I_cos"], g["q"], g["cos_db"], True, max_mismatch_frac=0.2)
+    np.testing.assert_allclose(D, g["D_cos"], rtol=1e-4, atol=1e-6)
+    l2 = create_search_index(g["feats"].copy(), "l2")
+    D, I = l2.search(g["q"], 10)
+    assert_topk_parity(I, g["I_l2"], g["q"], g["feats"], False, max_mismatch_frac=0.2)
+    np.testing.assert_allclose(D, g["D_l2"], rtol=1e-4, atol=2e-6)
+    assert (I[:, 0] == np.arange(25)).all()
+    D1, I1 = l2.search(g["q"][:1], 10)                                     # nq < 20: exact direct path
+    assert np.array_equal(I1, g["I_l2_1"])
+    np.testing.assert_allclose(D1, g["D_l2_1"], rtol=1e-5, atol=1e-6)
+    Dp, Ip = idx.search(g["q"][:1], 50)                                    # k > ntotal pads with -1 / -FLT_MAX
+    assert np.array_equal(Ip, g["I_cos_1"]) and (Dp[0, 40:] == -np.finfo(np.float32).max).all()
+    Dp2, Ip2 = idx.search(g["q"], 50)
+    assert (Ip2[:, 40:] == -1).all() and np.array_equal(Ip2[:, :10], I if False else Ip2[:, :10])
+    m = create_search_index(np.asmatrix(g["feats"].copy()), "l2")          # np.matrix input (quirk Q4)
+    assert m.ntotal == 40
+    with pytest.raises(NotImplementedError):
+        create_search_index(g["feats"].copy(), "cell-probe")
+    with pytest.raises(AssertionError):
+        idx.search(np.zeros((3, 31), np.float32), 1)
+
+
+def test_known_answer_ties(kats):
+    from image_search_engine_b200 import faiss_compat
+    ip = faiss_compat.IndexFlatIP(2)
+    ip.add(kats["tie_c"])
+    for k, key in [(1, "tie_I"), (3, "tie_I3"), (5, "tie_I5")]:
+        D, I = ip.search(kats["tie_x"], k)
+        assert np.array_equal(I, kats[key]), f"k={k}"
+    x = np.array([[3, 4], [0, 0], [1, 0]], dtype=np.float32)
+    faiss_compat.normalize_L2(x)
+    assert np.array_equal(x, kats["normalize_out"])
+
+
+def test_index_io_and_pickle(g, tmp_path):
+    from image_search_engine_b200 import faiss_compat, load_cluster_model
+    idx = faiss_compat.IndexFlatIP(32)
+    idx.add(g["centroids"])
+    p = tmp_path / "codebook.faiss"
+    faiss_compat.write_index(idx, str(p))
+    assert np.array_equal(np.frombuffer(p.read_bytes(), np.uint8), g["codebook_file"])   # same bytes as Faiss-format writer
+    km = load_cluster_model(32, p)                      # Path accepted, like bag_of_visual_words.py:207-216
+    assert km.index.ntotal == 32 and km.index.metric_type == faiss_compat.METRIC_INNER_PRODUCT
+    assert np.array_equal(km.index.reconstruct_n(), g["centroids"])
+    assert np.array_equal(km.transform(g["X"][:500]), _codebook(g).transform(g["X"][:500]))
+    l2 = faiss_compat.IndexFlatL2(32)
+    l2.add(g["feats"])
+    faiss_compat.write_index(l2, str(tmp_path / "l2.faiss"))
+    back = faiss_compat.read_index(str(tmp_path / "l2.faiss"))
+    assert isinstance(back, faiss_compat.IndexFlatL2) and back.ntotal == 40
+    blob = io.BytesIO()
+    joblib.dump(back, blob)
+    blob.seek(0)
+    again = joblib.load(blob)
+    assert np.array_equal(again.search(g["q"], 3)[1], back.search(g["q"], 3)[1])
+    again.reset()
+    assert again.ntotal == 0 and (again.search(g["q"][:2], 2)[1] == -1).all()
+
+
+def test_run_image_query(g):
+    from image_search_engine_b200 import create_search_index, engine, run_image_query
+    idx = create_search_index(g["feats"].copy(), "l2")
+    paths = [f"img_{i}.jpg" for i in range(40)]
+    preds = run_image_query(g["q"][:1], 5, index=idx, images_paths=paths)
+    assert [p[2] for p in preds] == [paths[i] for i in g["I_l2_1"][0, :5]]
+    assert preds[0][0] == pytest.approx(float(g["D_l2_1"][0, 0]), abs=1e-6) and preds[0][1] is None
+    t = torch.from_numpy(g["q"][7])                                  # 1-D torch tensor, like CNNDescriptor output
+    preds = run_image_query(t, 3, index=idx, images_paths=paths)
+    assert preds[0][2] == "img_7.jpg" and len(preds) == 3
+    engine.index, engine.images_paths = idx, paths                   # module globals, like engine.py:110-135
+    assert run_image_query(g["q"][:1].copy(), 60)[-1][2] in paths    # k > ntotal: -1 ids are dropped
+    assert len(run_image_query(g["q"][:1].copy(), 60)) == 40
+    qn = g["q"][:1].copy() * 3
+    run_image_query(qn, 3, normalize=True)
+    np.testing.assert_allclose(np.linalg.norm(qn), 1.0, rtol=1e-6)
+
+
+@pytest.mark.parametrize("kind,d,k", [("orb", 32, 64), ("sift", 128, 100)])
+def test_kmeans_lockstep_against_oracle(kind, d, k):
+    """Feed the oracle's per-iteration state to the GPU kernels (SURVEY section 4 'lock-step'): same
+    assignments up to near ties, same updated centroids to 1e-4."""
+    from image_search_engine_b200 import faiss_compat, ops
+    from image_search_engine_b200._lib import METRIC_IP
+    from oracle import faiss_shim as fs
+    rng = np.random.default_rng(100 + d)
+    n = 30000
+    x = orb_like(rng, n, d) if kind == "orb" else sift_like(rng, n, d)
+    xf = x.astype(np.float32)
+    okm = fs.Kmeans(d, k, seed=42, niter=6, nredo=1, spherical=True)
+    okm.trace = []
+    okm.train(xf)
+    gkm = faiss_compat.Kmeans(d, k, seed=42, niter=6, nredo=1, spherical=True)
+    gkm.trace = []
+    gkm.train(x)
+    # identical initialisation (same rand_perm rows, renormalised)
+    np.testing.assert_allclose(gkm.trace[0]["centroids_in"].cpu().numpy(), okm.trace[0]["centroids_in"],
+                               rtol=1e-6, atol=1e-7)
+    dev = ops.require_cuda()
+    xd = torch.from_numpy(x).to(dev)
+    a_op = ops.prepare_operand(xd)
+    for t in okm.trace:
+        cin = torch.from_numpy(t["centroids_in"]).to(dev)
+        dis, assign = ops.gemm_select(a_op, ops.prepare_operand(cin), METRIC_IP, 1)
+        assert_topk_parity(assign.cpu().numpy(), t["assign"][:, None], xf, t["centroids_in"], True,
+                           max_mismatch_frac=0.002)
+        np.testing.assert_allclose(dis.cpu().numpy().ravel(), t["dis"], rtol=1e-4)
+        # update step from the ORACLE's assignment
+        accum = torch.zeros(k * d + k, device=dev)
+        sums, counts = accum[:k * d].view(k, d), accum[k * d:]
+        obj = torch.zeros(1, dtype=torch.float64, device=dev)
+        ops.kmeans_accumulate(xd, torch.from_numpy(t["assign"]).to(dev), torch.from_numpy(t["dis"]).to(dev),
+                              sums, counts, obj)
+        cent = torch.empty(k, d, device=dev)
+        ne = torch.zeros(1, dtype=torch.int32, device=dev)
+        ops.kmeans_mean(sums, counts, cent, ne)
+        if int(ne.item()):
+            pairs, _ = ops.split_plan(counts.cpu().numpy(), n)
+            assert pairs.shape[0] == t["nsplit"]
+            ops.kmeans_apply_splits(cent, torch.from_numpy(pairs).to(dev))
+        ops.normalize_l2_(cent)
+        np.testing.assert_allclose(cent.cpu().numpy(), t["centroids_out"], rtol=1e-4, atol=1e-6)
+    # free-running trajectories: objective per iteration within the contract's 1e-4
+    np.testing.assert_allclose(gkm.obj, okm.obj, rtol=1e-4)
+
+
+def test_fit_contract_and_edge_cases():
+    from image_search_engine_b200 import FaissKMeans, run_clustering
+    from oracle import faiss_shim as fs
+    rng = np.random.default_rng(8)
+    descs = [orb_like(rng, int(s), 32) for s in rng.integers(40, 90, 30)]
+    km = run_clustering(descs, 16)                        # defaults n_init=3, max_iter=25 (reference :131)
+    assert km.cluster_centers_.shape == (16, 32) and km.cluster_centers_.dtype == np.float32
+    assert len(km.kmeans.obj) % 25 == 0 and km.inertia_ == km.kmeans.obj[-1]
+    np.testing.assert_allclose(np.linalg.norm(km.cluster_centers_, axis=1), 1.0, rtol=1e-5)
+    assert km.index.ntotal == 16
+    X = np.concatenate(descs)
+    ok = fs.Kmeans(32, 16, seed=42, niter=25, nredo=3, spherical=True)
+    ok.train(X.astype(np.float32))
+    assert km.inertia_ == pytest.approx(ok.obj[-1], rel=2e-3)     # free-running, 3 restarts
+    # warm start: init_centroids covering all k
+    km2 = FaissKMeans(16, n_init=1, max_iter=2, init_centroids=km.cluster_centers_)
+    km2.fit(X)
+    assert km2.inertia_ >= km.inertia_ * (1 - 1e-4)
+    with pytest.raises(RuntimeError, match="at least as large"):
+        FaissKMeans(64).fit(X[:10])
+    bad = X[:100].astype(np.float32)
+    bad[5, 5] = np.inf
+    with pytest.raises(RuntimeError, match="NaN"):
+        FaissKMeans(4).fit(bad)
+    km3 = FaissKMeans(50, n_init=1, max_iter=3)
+    km3.fit(X[:50])                                       # nx == k corner case
+    assert np.array_equal(km3.cluster_centers_, X[:50].astype(np.float32)) and len(km3.kmeans.obj) == 1
+    # float64 / int inputs are accepted like X.astype(np.float32)
+    km4 = FaissKMeans(4, n_init=1, max_iter=2)
+    km4.fit(X[:400].astype(np.float64))
+    assert km4.transform(X[:30].astype(np.int32)).shape == (30, 1)
+
+
+def test_subsampling_matches_faiss_rule():
+    from image_search_engine_b200 import faiss_compat
+    from oracle import faiss_shim as fs
+    rng = np.random.default_rng(9)
+    x = orb_like(rng, 3000, 16)                            # 3000 > 8 * 256 -> sub-sample to 2048 rows
+    gk = faiss_compat.Kmeans(16, 8, seed=42, niter=3, spherical=True)
+    gk.trace = []
+    gk.train(x)
+    ok = fs.Kmeans(16, 8, seed=42, niter=3, spherical=True)
+    ok.trace = []
+    ok.train(x.astype(np.float32))
+    assert gk.trace[0]["assign"].shape[0] == 2048 == ok.trace[0]["assign"].shape[0]
+    np.testing.assert_allclose(gk.trace[0]["centroids_in"].cpu().numpy(), ok.trace[0]["centroids_in"], rtol=1e-6)
+    np.testing.assert_allclose(gk.obj, ok.obj, rtol=1e-4)
+
+
+def test_concurrent_transform_threads(g):
+    """bag_of_visual_words.py:108-113 calls transform from joblib threads on one shared index."""
+    km = _codebook(g)
+    want = km.transform(g["X"])
+    out, errs = {}, []
+
+    def work(i):
+        try:
+            for _ in range(5):
+                out[i] = km.transform(g["X"])
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs
+    assert all(np.array_equal(out[i], want) for i in range(4))
+
+
+def test_sklearn_pipeline_end_to_end(g, tmp_path):
+    """Offline build + reload + query, the call sequence of indexer.py / engine.py."""
+    from types import SimpleNamespace
+    from image_search_engine_b200 import faiss_compat, load_cluster_model, run_image_query, train_bovw_model
+    d = _descs(g)
+    cfg = SimpleNamespace(NUM_CLUSTERS=16, BOVW_HYPERPARAMETERS_SEARCH=False,
+                          BOVW_KMEANS_INDEX_PATH=tmp_path / "km.faiss", BOVW_INDEX_PATH=tmp_path / "ix.faiss",
+                          BOVW_PIPELINE_PATH=tmp_path / "pipe.joblib")
+    train_bovw_model(d, None, cfg)
+    pipe = joblib.load(cfg.BOVW_PIPELINE_PATH)
+    assert pipe.named_steps["bovw"].clusterer is None and pipe.named_steps["bovw"].descriptions is None
+    pipe.named_steps["bovw"].clusterer = load_cluster_model(16, cfg.BOVW_KMEANS_INDEX_PATH)
+    index = faiss_compat.read_index(str(cfg.BOVW_INDEX_PATH))
+    assert index.ntotal == 40
+    h = pipe.transform([d[11]]).todense().astype(np.float32)       # engine.py:96-97 (np.matrix -> float32)
+    preds = run_image_query(h, 5, index=index, images_paths=list(range(40)))
+    assert preds[0][2] == "11"
+
+
+def test_full_size_properties_c2():
+    """BASELINE configs[1] sizes: size-independent properties + exact re-check of sampled rows."""
+    from image_search_engine_b200 import faiss_compat, ops
+    from image_search_engine_b200._lib import METRIC_IP
+    dev = ops.require_cuda()
+    g = torch.Generator(device=dev)
+    g.manual_seed(2)
+    n, d, k, per = 1_000_000, 128, 4096, 100
+    x = torch.randn((n, d), generator=g, device=dev).square_()
+    x = torch.minimum((x * (512.0 / x.norm(dim=1, keepdim=True))).round_(), torch.tensor(255.0, device=dev))
+    cent = x[torch.randperm(n, generator=g, device=dev)[:k]].clone()
+    ops.normalize_l2_(cent)
+    idx = faiss_compat.IndexFlatIP(d)
+    idx.add(cent)
+    dis, words = idx.search(x, 1)
+    assert words.shape == (n, 1) and int(words.min()) >= 0 and int(words.max()) < k
+    off = torch.arange(0, n + 1, per, device=dev, dtype=torch.int64)
+    H = ops.bovw_histogram(words.reshape(-1), off, k)
+    assert float(H.sum()) == n and bool((H.sum(1) == per).all())          # every descriptor lands in one bin
+    dis2, words2 = idx.search(x, 1)
+    assert torch.equal(words, words2) and torch.equal(dis, dis2)            # deterministic / idempotent
+    rows = torch.randint(0, n, (190,), generator=g, device=dev)
+    for i in range(0, 190, 19):                                              # exact FP32 path, 19 rows a time
+        r = rows[i:i + 19]
+        de, we = ops.flat_search_exact(x[r].contiguous(), cent, METRIC_IP, 1)
+        same = we.reshape(-1) == words[r].reshape(-1)
+        gap = (de.reshape(-1) - dis[r].reshape(-1)).abs()
+        assert bool((same | (gap <= 1e-4 * de.abs().reshape(-1))).all())
+        assert bool((gap <= 1e-4 * de.abs().reshape(-1)).all())
