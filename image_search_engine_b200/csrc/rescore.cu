@@ -1,0 +1,109 @@
+// Exact FP32 re-scoring + re-ranking of the candidates chosen by the tensor-core selection pass.
+//
+// The tcgen05 accumulator adds with truncation, so a K-long contraction carries a (mostly common-mode)
+// relative error of up to ~K/16 * 2^-23 -- harmless for choosing candidates, visible in returned
+// distances (e.g. a self-match at 2e-5 instead of 0).  This pass recomputes the k selected scores per
+// row with plain FP32 FMAs on the original rows, applies Faiss's own formulas (IndexFlat search,
+// distances.cpp: inner product, or |x|^2 + |y|^2 - 2<x,y> clamped at 0) and re-sorts the row by
+// (score, id).  HBM-bound and tiny: m*k rows of B gathered once.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxK = 128;
+
+template <typename TA, bool L2>
+__global__ void rescore_kernel(const TA* __restrict__ a, int64_t lda, const float* __restrict__ b, int64_t ldb,
+                               int64_t m, int64_t n, int d, int topk, int64_t id_base,
+                               const float* __restrict__ a_norms, const float* __restrict__ b_norms,
+                               float* __restrict__ val, int64_t* __restrict__ idx) {
+    extern __shared__ float s_a[];          // the row of A as float32
+    __shared__ float s_v[kMaxK];
+    __shared__ long long s_i[kMaxK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float worst = L2 ? 3.402823466e+38f : -3.402823466e+38f;
+    for (int64_t row = blockIdx.x; row < m; row += gridDim.x) {
+        const TA* arow = a + row * lda;
+        for (int c = threadIdx.x; c < d; c += kThreads) s_a[c] = (float)arow[c];
+        __syncthreads();
+        const float an = L2 ? a_norms[row] : 0.f;
+        for (int j = warp; j < topk; j += kWarps) {
+            const long long id = idx[row * topk + j];
+            float out = worst;
+            if (id >= 0) {
+                const int64_t col = id - id_base;
+                const float* brow = b + col * ldb;
+                float acc = 0.f;
+                if ((d & 3) == 0 && (ldb & 3) == 0) {
+                    const float4* b4 = reinterpret_cast<const float4*>(brow);
+                    const float4* a4 = reinterpret_cast<const float4*>(s_a);
+                    for (int c = lane; c < d / 4; c += 32) {
+                        const float4 y = __ldg(b4 + c);
+                        const float4 x = a4[c];
+                        acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc);
+                        acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+                    }
+                } else {
+                    for (int c = lane; c < d; c += 32) acc = fmaf(s_a[c], __ldg(brow + c), acc);
+                }
+                acc = warp_sum(acc);
+                if (L2) {
+                    float dis = an + b_norms[col] - 2.f * acc;   // x_norms[i] + y_norms[j] - 2 * ip
+                    out = dis < 0.f ? 0.f : dis;
+                } else {
+                    out = acc;
+                }
+            }
+            if (lane == 0) { s_v[j] = out; s_i[j] = id; }
+        }
+        __syncthreads();
+        // rank by counting: (score, id) is a strict total order over the real candidates
+        if (threadIdx.x < topk) {
+            const float v = s_v[threadIdx.x];
+            const long long id = s_i[threadIdx.x];
+            int rank = 0;
+            for (int t = 0; t < topk; ++t) {
+                if (t == (int)threadIdx.x) continue;
+                const bool t_first = (id < 0 && s_i[t] < 0) ? (t < (int)threadIdx.x)
+                                                            : cand_better<!L2>(s_v[t], s_i[t], v, id);
+                rank += t_first ? 1 : 0;
+            }
+            val[row * topk + rank] = v;
+            idx[row * topk + rank] = id;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+ISE_EXPORT int ise_rescore_topk(ise_ctx* ctx, const void* a, int a_dtype, int64_t lda, const float* b, int64_t ldb,
+                                int64_t m, int64_t n, int d, int metric, int topk, int64_t id_base,
+                                const float* a_norms, const float* b_norms, float* val, int64_t* idx,
+                                void* stream) {
+    ISE_CHECK_ARG(ctx != nullptr);
+    ISE_CHECK_ARG(metric == ISE_METRIC_IP || metric == ISE_METRIC_L2);
+    ISE_CHECK_ARG(a_dtype == ISE_DTYPE_F32 || a_dtype == ISE_DTYPE_U8);
+    ISE_CHECK_ARG(m >= 0 && n > 0 && d > 0 && topk >= 1 && topk <= kMaxK && lda >= d && ldb >= d);
+    ISE_CHECK_ARG((size_t)d * sizeof(float) <= 48 * 1024);
+    if (m == 0) return 0;
+    ISE_CHECK_ARG(a && b && val && idx);
+    if (metric == ISE_METRIC_L2) ISE_CHECK_ARG(a_norms && b_norms);
+    ISE_CHECK_ARG((reinterpret_cast<uintptr_t>(b) & 15) == 0);
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (int)std::min<int64_t>(m, (int64_t)ctx->sm_count * 16);
+    const size_t shm = (size_t)((d + 3) / 4 * 4) * sizeof(float);
+    const bool l2 = metric == ISE_METRIC_L2;
+    if (a_dtype == ISE_DTYPE_F32) {
+        if (l2) rescore_kernel<float, true><<<grid, kThreads, shm, st>>>((const float*)a, lda, b, ldb, m, n, d, topk, id_base, a_norms, b_norms, val, idx);
+        else rescore_kernel<float, false><<<grid, kThreads, shm, st>>>((const float*)a, lda, b, ldb, m, n, d, topk, id_base, a_norms, b_norms, val, idx);
+    } else {
+        if (l2) rescore_kernel<uint8_t, true><<<grid, kThreads, shm, st>>>((const uint8_t*)a, lda, b, ldb, m, n, d, topk, id_base, a_norms, b_norms, val, idx);
+        else rescore_kernel<uint8_t, false><<<grid, kThreads, shm, st>>>((const uint8_t*)a, lda, b, ldb, m, n, d, topk, id_base, a_norms, b_norms, val, idx);
+    }
+    ISE_LAUNCH_CHECK();
+    return 0;
+}

@@ -149,7 +149,9 @@ class IndexFlat:
             return D, I
         return D.cpu().numpy(), I.cpu().numpy()
 
-    def _search_device(self, q: torch.Tensor, k: int):
+    def _search_device(self, q: torch.Tensor, k: int, need_distances: bool = True):
+        """need_distances=False skips the exact FP32 re-score (callers that only use the ids, e.g.
+        quantisation); the returned scores are then the tensor-core accumulator values."""
         nq = q.shape[0]
         largest = self.metric_type == METRIC_INNER_PRODUCT
         pad = -_FLT_MAX if largest else _FLT_MAX
@@ -167,6 +169,8 @@ class IndexFlat:
             b = self._operand()
             a = ops.prepare_operand(q)
             D, I = ops.gemm_select(a, b, self.metric_type, kk)
+            if need_distances:
+                ops.rescore_topk_(q, self._database(), a, b, self.metric_type, D, I)
         if kk < k:
             Dp = torch.full((nq, k), pad, dtype=torch.float32, device=q.device)
             Ip = torch.full((nq, k), -1, dtype=torch.int64, device=q.device)

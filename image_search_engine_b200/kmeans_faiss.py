@@ -45,7 +45,9 @@ class FaissKMeans:
 
     def transform_device(self, X: torch.Tensor) -> torch.Tensor:
         """Batched variant for GPU-resident descriptors: int64 [n] CUDA tensor, no host round trip."""
-        _, words = self.index.search(X, 1)
+        if X.dim() != 2 or X.shape[1] != self.index.d:
+            raise AssertionError(f"expected (n, {self.index.d}) descriptors")
+        _, words = self.index._search_device(X, 1, need_distances=False)
         return words.reshape(-1)
 
 

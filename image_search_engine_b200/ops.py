@@ -169,6 +169,24 @@ def gemm_select(a: Operand, b: Operand, metric: int, topk: int, id_base: int = 0
     return val, idx
 
 
+def rescore_topk_(a_raw: torch.Tensor, b_raw: torch.Tensor, a_op: Operand, b_op: Operand, metric: int,
+                  val: torch.Tensor, idx: torch.Tensor, id_base: int = 0):
+    """Exact FP32 re-score + re-rank (in place) of candidates picked by gemm_select."""
+    if b_raw.dtype != torch.float32 or b_raw.stride(1) != 1:
+        raise IseError("rescore: column rows must be float32, row-major")
+    if a_raw.dtype not in (torch.float32, torch.uint8) or a_raw.stride(1) != 1:
+        raise IseError("rescore: rows must be float32 or uint8, row-major")
+    m, k = val.shape
+    if m == 0:
+        return val, idx
+    _lib.check(_lib.load().ise_rescore_topk(
+        _lib.ctx(_dev(val)), _ptr(a_raw), DTYPE_F32 if a_raw.dtype == torch.float32 else DTYPE_U8, a_raw.stride(0),
+        _ptr(b_raw), b_raw.stride(0), m, b_raw.shape[0], a_raw.shape[1], int(metric), k, int(id_base),
+        _ptr(a_op.norms), _ptr(b_op.norms), _ptr(val), _ptr(idx), _stream()))
+    _count()
+    return val, idx
+
+
 def flat_search_exact(q: torch.Tensor, db: torch.Tensor, metric: int, topk: int, id_base: int = 0):
     """Exact FP32 CUDA-core search (Faiss's n < 20 path)."""
     if q.dtype != torch.float32 or db.dtype != torch.float32 or not q.is_contiguous() or not db.is_contiguous():

@@ -109,6 +109,15 @@ int ise_flat_search_exact(ise_ctx* ctx, const float* q, int64_t nq, const float*
                           int metric, int topk, int64_t id_base, float* out_val, int64_t* out_idx,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* Exact FP32 re-score + re-rank of already selected candidates (CUDA cores).  The tensor-core
+ * accumulator truncates, which shows in returned distances (not in which candidates are picked); this
+ * recomputes val[m,topk] for the ids in idx[m,topk] from the original rows with Faiss's formulas
+ * (IP: <a,b>;  L2: max(0, |a|^2 + |b|^2 - 2<a,b>), distances.cpp) and re-sorts each row by (score, id).
+ * a: [m,d] f32 or u8 rows, b: [n,d] f32 rows, ids are global (= column + id_base), -1 = padding. */
+int ise_rescore_topk(ise_ctx* ctx, const void* a, int a_dtype, int64_t lda, const float* b, int64_t ldb,
+                     int64_t m, int64_t n, int d, int metric, int topk, int64_t id_base,
+                     const float* a_norms, const float* b_norms, float* val, int64_t* idx, void* stream);
+
 /* Merge g sorted top-k lists per row ([g, m, topk] each) into one; canonical (score, id) order.
  * Used for column-split partial results and for the cross-GPU merge of a sharded index. */
 int ise_topk_merge(ise_ctx* ctx, const float* val_parts, const int64_t* idx_parts, int g, int64_t m,

@@ -96,7 +96,9 @@ def test_search_index_matches_reference_fixture(g):
     l2 = create_search_index(g["feats"].copy(), "l2")
     D, I = l2.search(g["q"], 10)
     assert_topk_parity(I, g["I_l2"], g["q"], g["feats"], False, max_mismatch_frac=0.2)
-    np.testing.assert_allclose(D, g["D_l2"], rtol=1e-4, atol=2e-6)
+    # |x|^2 + |y|^2 - 2<x,y> cancels: FP32 noise is a few ulp of the norms, not of the distance
+    l2_atol = 8 * np.finfo(np.float32).eps * 2 * float((g["feats"].astype(np.float64) ** 2).sum(1).max())
+    np.testing.assert_allclose(D, g["D_l2"], rtol=1e-4, atol=l2_atol)
     assert (I[:, 0] == np.arange(25)).all()
     D1, I1 = l2.search(g["q"][:1], 10)                                     # nq < 20: exact direct path
     assert np.array_equal(I1, g["I_l2_1"])
@@ -176,7 +178,7 @@ def test_kmeans_lockstep_against_oracle(kind, d, k):
     from image_search_engine_b200._lib import METRIC_IP
     from oracle import faiss_shim as fs
     rng = np.random.default_rng(100 + d)
-    n = 30000
+    n = 15000   # <= 256 * k, so Faiss does not sub-sample and the trace covers every row
     x = orb_like(rng, n, d) if kind == "orb" else sift_like(rng, n, d)
     xf = x.astype(np.float32)
     okm = fs.Kmeans(d, k, seed=42, niter=6, nredo=1, spherical=True)
@@ -268,13 +270,14 @@ def test_subsampling_matches_faiss_rule():
 def test_concurrent_transform_threads(g):
     """bag_of_visual_words.py:108-113 calls transform from joblib threads on one shared index."""
     km = _codebook(g)
-    want = km.transform(g["X"])
+    X = g["X"]                      # NpzFile members are not thread-safe to read lazily
+    want = km.transform(X)
     out, errs = {}, []
 
     def work(i):
         try:
             for _ in range(5):
-                out[i] = km.transform(g["X"])
+                out[i] = km.transform(X)
         except Exception as e:  # pragma: no cover
             errs.append(e)
 
