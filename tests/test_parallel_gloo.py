@@ -49,7 +49,7 @@ class OracleOps:
     def normalize(self, cent):
         fs.normalize_L2(cent.numpy())
 
-    def search(self, q_op, b_op, metric, k, id_base):
+    def search(self, q, q_op, db, b_op, metric, k, id_base):
         D, I = fs.knn(q_op.numpy(), b_op.numpy(), k, metric)
         I = np.where(I >= 0, I + id_base, -1)
         return torch.from_numpy(D), torch.from_numpy(I)
