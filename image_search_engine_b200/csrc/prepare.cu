@@ -80,7 +80,11 @@ __global__ void prepare_planes_kernel(const T* __restrict__ x, int64_t n, int d,
             any_lo |= (__half2float(l0) != 0.f) | (__half2float(l1) != 0.f);
         }
         ss = warp_sum(ss);
-        if (norms && lane == 0) norms[r] = ss;
+        if (lane == 0) {
+            if (norms) norms[r] = ss;
+            // largest row norm^2 (non-negative floats order like ints): the coarse-pass error bound needs it
+            atomicMax(reinterpret_cast<int*>(meta + META_MAX_NORM_SQ), __float_as_int(ss));
+        }
     }
     if (__any_sync(0xffffffffu, any_lo) && lane == 0) meta[META_LO_NONZERO] = 1.f;
 }
@@ -135,7 +139,7 @@ ISE_EXPORT int ise_prepare_planes(ise_ctx* ctx, const void* x, int dtype, int64_
     ISE_CHECK_ARG(dtype == ISE_DTYPE_F32 || dtype == ISE_DTYPE_U8);
     DeviceGuard g(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
-    ISE_CUDA(cudaMemsetAsync(meta, 0, 4 * sizeof(float), st));
+    ISE_CUDA(cudaMemsetAsync(meta, 0, META_FLOATS * sizeof(float), st));
     if (n == 0) return 0;
     ISE_CHECK_ARG(x != nullptr);
     const int grid = grid_for_rows(ctx, n);

@@ -14,23 +14,51 @@ constexpr int kThreads = 128;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxK = 128;
 
+// kc candidates in (ids + coarse scores), topk exact results out.  With `flag_count` non-null the row is
+// verified against the coarse pass's error bound and appended to `flag_rows` when the candidate list
+// cannot be PROVEN to contain the true top-k (the caller re-runs those rows at full precision).
+//
+// Bound: the coarse pass multiplies the FP16 hi planes only.  With a = hi_a + lo_a, |lo_a| <= 2^-11 |a|
+// (round-to-nearest FP16; 0 when the plane is exact), the neglected terms are bounded by
+// (c_a + c_b + c_a c_b) * sum|a_i b_i| <= (c_a + c_b + 2^-22) |a| |b|  (Cauchy-Schwarz), and the truncating
+// FP32 accumulation adds at most (d/16 + 4) * 2^-23 * |a| |b|.  So every coarse inner product is within
+// eps = kappa * |a| * max_col|b| of the exact one; a column outside the candidate list has coarse score
+// <= T (the worst kept one), hence exact score <= T + eps: if the k-th exact candidate beats that, the
+// list provably holds the true top-k.  (L2: scores are |a|^2 + |b|^2 - 2<a,b>, so the slack is 2 eps.)
 template <typename TA, bool L2>
 __global__ void rescore_kernel(const TA* __restrict__ a, int64_t lda, const float* __restrict__ b, int64_t ldb,
-                               int64_t m, int64_t n, int d, int topk, int64_t id_base,
+                               int64_t m, int64_t n, int d, int kc, int topk, int64_t id_base,
                                const float* __restrict__ a_norms, const float* __restrict__ b_norms,
-                               float* __restrict__ val, int64_t* __restrict__ idx) {
+                               const float* __restrict__ cand_val, const int64_t* __restrict__ cand_idx,
+                               float* __restrict__ val, int64_t* __restrict__ idx,
+                               const float* __restrict__ a_meta, const float* __restrict__ b_meta,
+                               int32_t* __restrict__ flag_rows, int32_t* __restrict__ flag_count) {
     extern __shared__ float s_a[];          // the row of A as float32
     __shared__ float s_v[kMaxK];
     __shared__ long long s_i[kMaxK];
+    __shared__ float s_kth;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float worst = L2 ? 3.402823466e+38f : -3.402823466e+38f;
+    float kappa = 0.f, bn_max = 0.f, uf_a = 0.f, uf_b = 0.f;
+    if (flag_count) {
+        const float ca = a_meta[META_LO_NONZERO] != 0.f ? 4.8828125e-4f : 0.f;   // 2^-11
+        const float cb = b_meta[META_LO_NONZERO] != 0.f ? 4.8828125e-4f : 0.f;
+        kappa = 1.02f * (ca + cb) + 2.4e-7f + (float)(d / 16 + 4) * 1.1920929e-7f;
+        bn_max = b_meta[META_MAX_NORM_SQ];
+        // FP16 underflow: elements below 2^-14 after scaling round with absolute error <= 2^-25 (scaled
+        // units), i.e. 2^-25 / scale each; against the other operand that is <= 2^-25/scale * sqrt(d) * |.|
+        const float sq = sqrtf((float)d) * 5.9604645e-8f;                         // 2 * 2^-25 * sqrt(d)
+        uf_a = ca != 0.f ? sq * a_meta[META_INV_SCALE] : 0.f;                     // times |b|
+        uf_b = cb != 0.f ? sq * b_meta[META_INV_SCALE] : 0.f;                     // times |a|
+    }
     for (int64_t row = blockIdx.x; row < m; row += gridDim.x) {
         const TA* arow = a + row * lda;
         for (int c = threadIdx.x; c < d; c += kThreads) s_a[c] = (float)arow[c];
+        if (threadIdx.x == 0) s_kth = worst;
         __syncthreads();
-        const float an = L2 ? a_norms[row] : 0.f;
-        for (int j = warp; j < topk; j += kWarps) {
-            const long long id = idx[row * topk + j];
+        const float an = (L2 || flag_count) ? a_norms[row] : 0.f;
+        for (int j = warp; j < kc; j += kWarps) {
+            const long long id = cand_idx[row * kc + j];
             float out = worst;
             if (id >= 0) {
                 const int64_t col = id - id_base;
@@ -60,18 +88,32 @@ __global__ void rescore_kernel(const TA* __restrict__ a, int64_t lda, const floa
         }
         __syncthreads();
         // rank by counting: (score, id) is a strict total order over the real candidates
-        if (threadIdx.x < topk) {
+        if (threadIdx.x < kc) {
             const float v = s_v[threadIdx.x];
             const long long id = s_i[threadIdx.x];
             int rank = 0;
-            for (int t = 0; t < topk; ++t) {
+            for (int t = 0; t < kc; ++t) {
                 if (t == (int)threadIdx.x) continue;
                 const bool t_first = (id < 0 && s_i[t] < 0) ? (t < (int)threadIdx.x)
                                                             : cand_better<!L2>(s_v[t], s_i[t], v, id);
                 rank += t_first ? 1 : 0;
             }
-            val[row * topk + rank] = v;
-            idx[row * topk + rank] = id;
+            if (rank < topk) {
+                val[row * topk + rank] = v;
+                idx[row * topk + rank] = id;
+            }
+            if (rank == topk - 1 && id >= 0) s_kth = v;
+        }
+        __syncthreads();
+        if (flag_count && threadIdx.x == 0) {
+            const long long last_id = cand_idx[row * kc + kc - 1];
+            if (last_id >= 0) {                     // list is full: columns exist outside it
+                const float T = cand_val[row * kc + kc - 1];
+                const float na = sqrtf(an), nbm = sqrtf(bn_max);
+                const float eps = kappa * na * nbm + uf_a * nbm + uf_b * na;
+                const bool proven = L2 ? (s_kth < T - 2.f * eps) : (s_kth > T + eps);
+                if (!proven) flag_rows[atomicAdd(flag_count, 1)] = (int32_t)row;
+            }
         }
         __syncthreads();
     }
@@ -79,31 +121,55 @@ __global__ void rescore_kernel(const TA* __restrict__ a, int64_t lda, const floa
 
 }  // namespace
 
+static int launch_rescore(ise_ctx* ctx, const void* a, int a_dtype, int64_t lda, const float* b, int64_t ldb,
+                          int64_t m, int64_t n, int d, int metric, int kc, int topk, int64_t id_base,
+                          const float* a_norms, const float* b_norms, const float* cand_val, const int64_t* cand_idx,
+                          float* val, int64_t* idx, const float* a_meta, const float* b_meta, int32_t* flag_rows,
+                          int32_t* flag_count, void* stream) {
+    ISE_CHECK_ARG(ctx != nullptr);
+    ISE_CHECK_ARG(metric == ISE_METRIC_IP || metric == ISE_METRIC_L2);
+    ISE_CHECK_ARG(a_dtype == ISE_DTYPE_F32 || a_dtype == ISE_DTYPE_U8);
+    ISE_CHECK_ARG(m >= 0 && n > 0 && d > 0 && topk >= 1 && kc >= topk && kc <= kMaxK && lda >= d && ldb >= d);
+    ISE_CHECK_ARG((size_t)d * sizeof(float) <= 48 * 1024);
+    if (m == 0) return 0;
+    ISE_CHECK_ARG(a && b && val && idx && cand_idx);
+    if (metric == ISE_METRIC_L2) ISE_CHECK_ARG(a_norms && b_norms);
+    if (flag_count) ISE_CHECK_ARG(flag_rows && cand_val && a_meta && b_meta && a_norms);
+    ISE_CHECK_ARG((reinterpret_cast<uintptr_t>(b) & 15) == 0);
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (flag_count) ISE_CUDA(cudaMemsetAsync(flag_count, 0, sizeof(int32_t), st));
+    const int grid = (int)std::min<int64_t>(m, (int64_t)ctx->sm_count * 16);
+    const size_t shm = (size_t)((d + 3) / 4 * 4) * sizeof(float);
+    const bool l2 = metric == ISE_METRIC_L2;
+#define ISE_RESCORE_ARGS lda, b, ldb, m, n, d, kc, topk, id_base, a_norms, b_norms, cand_val, cand_idx, val, idx, \
+                         a_meta, b_meta, flag_rows, flag_count
+    if (a_dtype == ISE_DTYPE_F32) {
+        if (l2) rescore_kernel<float, true><<<grid, kThreads, shm, st>>>((const float*)a, ISE_RESCORE_ARGS);
+        else rescore_kernel<float, false><<<grid, kThreads, shm, st>>>((const float*)a, ISE_RESCORE_ARGS);
+    } else {
+        if (l2) rescore_kernel<uint8_t, true><<<grid, kThreads, shm, st>>>((const uint8_t*)a, ISE_RESCORE_ARGS);
+        else rescore_kernel<uint8_t, false><<<grid, kThreads, shm, st>>>((const uint8_t*)a, ISE_RESCORE_ARGS);
+    }
+#undef ISE_RESCORE_ARGS
+    ISE_LAUNCH_CHECK();
+    return 0;
+}
+
 ISE_EXPORT int ise_rescore_topk(ise_ctx* ctx, const void* a, int a_dtype, int64_t lda, const float* b, int64_t ldb,
                                 int64_t m, int64_t n, int d, int metric, int topk, int64_t id_base,
                                 const float* a_norms, const float* b_norms, float* val, int64_t* idx,
                                 void* stream) {
-    ISE_CHECK_ARG(ctx != nullptr);
-    ISE_CHECK_ARG(metric == ISE_METRIC_IP || metric == ISE_METRIC_L2);
-    ISE_CHECK_ARG(a_dtype == ISE_DTYPE_F32 || a_dtype == ISE_DTYPE_U8);
-    ISE_CHECK_ARG(m >= 0 && n > 0 && d > 0 && topk >= 1 && topk <= kMaxK && lda >= d && ldb >= d);
-    ISE_CHECK_ARG((size_t)d * sizeof(float) <= 48 * 1024);
-    if (m == 0) return 0;
-    ISE_CHECK_ARG(a && b && val && idx);
-    if (metric == ISE_METRIC_L2) ISE_CHECK_ARG(a_norms && b_norms);
-    ISE_CHECK_ARG((reinterpret_cast<uintptr_t>(b) & 15) == 0);
-    DeviceGuard guard(ctx->device);
-    cudaStream_t st = (cudaStream_t)stream;
-    const int grid = (int)std::min<int64_t>(m, (int64_t)ctx->sm_count * 16);
-    const size_t shm = (size_t)((d + 3) / 4 * 4) * sizeof(float);
-    const bool l2 = metric == ISE_METRIC_L2;
-    if (a_dtype == ISE_DTYPE_F32) {
-        if (l2) rescore_kernel<float, true><<<grid, kThreads, shm, st>>>((const float*)a, lda, b, ldb, m, n, d, topk, id_base, a_norms, b_norms, val, idx);
-        else rescore_kernel<float, false><<<grid, kThreads, shm, st>>>((const float*)a, lda, b, ldb, m, n, d, topk, id_base, a_norms, b_norms, val, idx);
-    } else {
-        if (l2) rescore_kernel<uint8_t, true><<<grid, kThreads, shm, st>>>((const uint8_t*)a, lda, b, ldb, m, n, d, topk, id_base, a_norms, b_norms, val, idx);
-        else rescore_kernel<uint8_t, false><<<grid, kThreads, shm, st>>>((const uint8_t*)a, lda, b, ldb, m, n, d, topk, id_base, a_norms, b_norms, val, idx);
-    }
-    ISE_LAUNCH_CHECK();
-    return 0;
+    return launch_rescore(ctx, a, a_dtype, lda, b, ldb, m, n, d, metric, topk, topk, id_base, a_norms, b_norms,
+                          nullptr, idx, val, idx, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+ISE_EXPORT int ise_rescore_select(ise_ctx* ctx, const void* a, int a_dtype, int64_t lda, const float* a_meta,
+                                  const float* a_norms, const float* b, int64_t ldb, const float* b_meta,
+                                  const float* b_norms, int64_t m, int64_t n, int d, int metric, int kc, int topk,
+                                  int64_t id_base, const float* cand_val, const int64_t* cand_idx, float* out_val,
+                                  int64_t* out_idx, int32_t* flag_rows, int32_t* flag_count, void* stream) {
+    ISE_CHECK_ARG(flag_rows && flag_count);
+    return launch_rescore(ctx, a, a_dtype, lda, b, ldb, m, n, d, metric, kc, topk, id_base, a_norms, b_norms, cand_val,
+                          cand_idx, out_val, out_idx, a_meta, b_meta, flag_rows, flag_count, stream);
 }

@@ -91,6 +91,9 @@ class IndexFlat:
         self._xb: torch.Tensor | None = None
         self._op: ops.Operand | None = None
         self._lock = threading.Lock()
+        # "verified": coarse tensor-core pass + exact FP32 re-score with a proven candidate list;
+        # "split": FP32-grade split products for every tile (see ops.search_topk)
+        self.precision = "verified"
 
     # ---- storage ----
     @property
@@ -168,9 +171,8 @@ class IndexFlat:
         else:
             b = self._operand()
             a = ops.prepare_operand(q)
-            D, I = ops.gemm_select(a, b, self.metric_type, kk)
-            if need_distances:
-                ops.rescore_topk_(q, self._database(), a, b, self.metric_type, D, I)
+            D, I = ops.search_topk(q, a, self._database(), b, self.metric_type, kk, precision=self.precision,
+                                   need_distances=need_distances)
         if kk < k:
             Dp = torch.full((nq, k), pad, dtype=torch.float32, device=q.device)
             Ip = torch.full((nq, k), -1, dtype=torch.int64, device=q.device)

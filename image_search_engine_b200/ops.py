@@ -84,7 +84,7 @@ class Operand:
     hi: torch.Tensor          # [n, ldp] float16
     lo: torch.Tensor | None   # [n, ldp] float16 (None when the source is exactly representable)
     norms: torch.Tensor       # [n] float32 sum of squares
-    meta: torch.Tensor        # [4] float32: scale, 1/scale, lo_nonzero, absmax
+    meta: torch.Tensor        # [8] float32: scale, 1/scale, lo_nonzero, absmax, max row norm^2, pad
     n: int
     d: int
     ldp: int
@@ -116,7 +116,7 @@ def prepare_operand(x: torch.Tensor, *, keep_lo: bool | None = None) -> Operand:
     want_lo = dt == DTYPE_F32 and keep_lo is not False
     lo = torch.empty((n, ldp), dtype=torch.float16, device=x.device) if want_lo else None
     norms = torch.empty((n,), dtype=torch.float32, device=x.device)
-    meta = torch.empty((4,), dtype=torch.float32, device=x.device)
+    meta = torch.empty((8,), dtype=torch.float32, device=x.device)
     _lib.check(_lib.load().ise_prepare_planes(
         _lib.ctx(dev), _ptr(x), dt, n, d, x.stride(0) if n > 0 else d, _ptr(hi), _ptr(lo), ldp, _ptr(norms),
         _ptr(meta), _stream()))
@@ -185,6 +185,69 @@ def rescore_topk_(a_raw: torch.Tensor, b_raw: torch.Tensor, a_op: Operand, b_op:
         _ptr(a_op.norms), _ptr(b_op.norms), _ptr(val), _ptr(idx), _stream()))
     _count()
     return val, idx
+
+
+def rescore_select(a_raw: torch.Tensor, b_raw: torch.Tensor, a_op: Operand, b_op: Operand, metric: int,
+                   cand_val: torch.Tensor, cand_idx: torch.Tensor, topk: int, id_base: int = 0):
+    """Exact FP32 re-score of kc coarse candidates -> exact top-k + the rows whose candidate list could
+    not be proven complete.  Returns (val [m,k], idx [m,k], flag_rows int32 [m], flag_count int32 [1])."""
+    m, kc = cand_idx.shape
+    dev = cand_idx.device
+    val = torch.empty((m, topk), dtype=torch.float32, device=dev)
+    idx = torch.empty((m, topk), dtype=torch.int64, device=dev)
+    flag_rows = torch.empty((max(m, 1),), dtype=torch.int32, device=dev)
+    flag_count = torch.zeros((1,), dtype=torch.int32, device=dev)
+    if m == 0:
+        return val, idx, flag_rows, flag_count
+    _lib.check(_lib.load().ise_rescore_select(
+        _lib.ctx(_dev(cand_idx)), _ptr(a_raw), DTYPE_F32 if a_raw.dtype == torch.float32 else DTYPE_U8,
+        a_raw.stride(0), _ptr(a_op.meta), _ptr(a_op.norms), _ptr(b_raw), b_raw.stride(0), _ptr(b_op.meta),
+        _ptr(b_op.norms), m, b_raw.shape[0], a_raw.shape[1], int(metric), kc, int(topk), int(id_base),
+        _ptr(cand_val.contiguous()), _ptr(cand_idx.contiguous()), _ptr(val), _ptr(idx), _ptr(flag_rows),
+        _ptr(flag_count), _stream()))
+    _count()
+    return val, idx, flag_rows, flag_count
+
+
+# statistics of the last search_topk call on this process (bench.py / tests read them)
+last_search_stats = {"mode": None, "fallback_rows": 0, "rows": 0}
+
+
+def search_topk(q_raw: torch.Tensor, a_op: Operand, db_raw: torch.Tensor, b_op: Operand, metric: int, k: int,
+                id_base: int = 0, precision: str = "verified", need_distances: bool = True):
+    """Flat top-k of every query row against the database operand (the tensor-core path, nq >= 20).
+
+    precision="verified" (default, k >= 2): ONE tcgen05 product per tile (FP16 hi planes) selects
+      kc = 32 / 128 candidates per query, ise_rescore_select re-scores them exactly in FP32 and proves
+      from a rigorous error bound that the list contains the true top-k; the (rare) rows it cannot prove
+      are re-run with the split products.  Results equal the split path's; ~3x fewer tensor-core flops.
+    precision="split": hi*hi + hi*lo + lo*hi products for every tile (FP32-grade scores throughout),
+      then exact re-score of the k winners.
+    """
+    nb = b_op.n
+    kc = 32 if k <= 16 else MAX_TOPK
+    if precision == "verified" and k >= 2 and nb > kc and need_distances:
+        cv, ci = gemm_select(Operand(a_op.hi, None, a_op.norms, a_op.meta, a_op.n, a_op.d, a_op.ldp),
+                             Operand(b_op.hi, None, b_op.norms, b_op.meta, b_op.n, b_op.d, b_op.ldp),
+                             metric, kc, id_base)
+        D, I, rows, cnt = rescore_select(q_raw, db_raw, a_op, b_op, metric, cv, ci, k, id_base)
+        nflag = int(cnt.item())                       # 4-byte readback: how many rows need the split path
+        last_search_stats.update(mode="verified", fallback_rows=nflag, rows=a_op.n)
+        if nflag:
+            sel = rows[:nflag].to(torch.int64)
+            sub = Operand(a_op.hi.index_select(0, sel), None if a_op.lo is None else a_op.lo.index_select(0, sel),
+                          a_op.norms.index_select(0, sel), a_op.meta, nflag, a_op.d, a_op.ldp)
+            q_sub = q_raw.index_select(0, sel)
+            D2, I2 = gemm_select(sub, b_op, metric, k, id_base)
+            rescore_topk_(q_sub, db_raw, sub, b_op, metric, D2, I2, id_base)
+            D.index_copy_(0, sel, D2)
+            I.index_copy_(0, sel, I2)
+        return D, I
+    D, I = gemm_select(a_op, b_op, metric, k, id_base)
+    if need_distances:
+        rescore_topk_(q_raw, db_raw, a_op, b_op, metric, D, I, id_base)
+    last_search_stats.update(mode="split", fallback_rows=0, rows=a_op.n)
+    return D, I
 
 
 def flat_search_exact(q: torch.Tensor, db: torch.Tensor, metric: int, topk: int, id_base: int = 0):

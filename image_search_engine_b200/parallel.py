@@ -70,8 +70,7 @@ class DeviceOps:
 
     def search(self, q, q_op, db, b_op, metric, k, id_base):
         """local top-k (tensor cores) + exact FP32 re-score, so the cross-rank merge compares exact scores"""
-        D, I = ops.gemm_select(q_op, b_op, metric, k, id_base=id_base)
-        return ops.rescore_topk_(q, db, q_op, b_op, metric, D, I, id_base=id_base)
+        return ops.search_topk(q, q_op, db, b_op, metric, k, id_base=id_base)
 
     def merge(self, D_parts, I_parts, metric):
         return ops.topk_merge(D_parts, I_parts, metric)

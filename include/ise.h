@@ -70,7 +70,7 @@ int ise_split_plan(float* hassign_host, int64_t k, int64_t n, int32_t* pairs_hos
  * The distance contractions run on the tcgen05 tensor cores as FP16 "hi + lo" split
  * products (hi*hi + hi*lo + lo*hi, FP32 accumulate) which carries ~22-24 mantissa bits:
  * rows are scaled by a per-tensor power of two, hi = fp16(s*x), lo = fp16(s*x - hi).
- * meta (device float[4]) = { scale, 1/scale, lo_nonzero (0/1), absmax }.
+ * meta (device float[8]) = { scale, 1/scale, lo_nonzero (0/1), absmax, max row norm^2, 0, 0, 0 }.
  * ldp (elements) = row pitch of the planes, multiple of 8, >= d; pad columns are zeroed.
  * norms (nullable) = exact FP32 sum of squares per row (fvec_norms_L2sqr).
  * Replaces: the implicit float32 conversion `X.astype(np.float32)` + Faiss's internal
@@ -117,6 +117,19 @@ int ise_flat_search_exact(ise_ctx* ctx, const float* q, int64_t nq, const float*
 int ise_rescore_topk(ise_ctx* ctx, const void* a, int a_dtype, int64_t lda, const float* b, int64_t ldb,
                      int64_t m, int64_t n, int d, int metric, int topk, int64_t id_base,
                      const float* a_norms, const float* b_norms, float* val, int64_t* idx, void* stream);
+
+/* Coarse-then-verify search: `cand_*` [m, kc] are the kc best columns per row found by a COARSE
+ * ise_gemm_select call (hi planes only: pass a_lo = b_lo = NULL, one tcgen05 product instead of three).
+ * This kernel re-scores all kc candidates exactly in FP32, writes the exact top-k [m, topk] and PROVES
+ * per row that no column outside the candidate list can belong to the top-k, using the rigorous bound
+ * |coarse - exact| <= kappa |a| max|b| (kappa from the FP16 rounding of the planes + accumulator
+ * truncation, see rescore.cu).  Rows that cannot be proven are appended to flag_rows[0 .. *flag_count)
+ * (device int32) and must be re-run by the caller with the full-precision split products. */
+int ise_rescore_select(ise_ctx* ctx, const void* a, int a_dtype, int64_t lda, const float* a_meta,
+                       const float* a_norms, const float* b, int64_t ldb, const float* b_meta,
+                       const float* b_norms, int64_t m, int64_t n, int d, int metric, int kc, int topk,
+                       int64_t id_base, const float* cand_val, const int64_t* cand_idx, float* out_val,
+                       int64_t* out_idx, int32_t* flag_rows, int32_t* flag_count, void* stream);
 
 /* Merge g sorted top-k lists per row ([g, m, topk] each) into one; canonical (score, id) order.
  * Used for column-split partial results and for the cross-GPU merge of a sharded index. */

@@ -248,3 +248,51 @@ def test_kmeans_update_and_split(dev):
     ops.kmeans_apply_splits(cent, torch.from_numpy(pairs).to(dev))
     ops.normalize_l2_(cent)
     np.testing.assert_allclose(cent.cpu().numpy(), cent_ref, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("metric_ip", [True, False])
+@pytest.mark.parametrize("nq,nb,d,k", [(300, 20000, 128, 10), (64, 5000, 2048, 10), (200, 9000, 64, 100)])
+def test_verified_coarse_search_equals_split(dev, metric_ip, nq, nb, d, k):
+    """Default index search = 1-product coarse pass + exact re-score + proof; must agree with the
+    3-product split path and with the oracle."""
+    from image_search_engine_b200 import faiss_compat, ops
+    rng = np.random.default_rng(nq + nb + d + k)
+    db = unit_rows(rng, nb, d, relu=True)
+    q = db[rng.integers(0, nb, nq)] + 0.05 * rng.standard_normal((nq, d)).astype(np.float32)
+    q = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+    idx = faiss_compat.IndexFlatIP(d) if metric_ip else faiss_compat.IndexFlatL2(d)
+    idx.add(db)
+    D, I = idx.search(q, k)
+    assert ops.last_search_stats["mode"] == "verified"
+    n_fallback = ops.last_search_stats["fallback_rows"]
+    idx.precision = "split"
+    D2, I2 = idx.search(q, k)
+    assert ops.last_search_stats["mode"] == "split"
+    assert_topk_parity(I, I2, q, db, metric_ip, max_mismatch_frac=0.05)
+    np.testing.assert_allclose(D, D2, rtol=1e-5, atol=2e-6)
+    Do, Io = _oracle_knn(q, db, k, metric_ip)
+    assert_topk_parity(I, Io, q, db, metric_ip, max_mismatch_frac=0.05)
+    np.testing.assert_allclose(D, Do, rtol=1e-4, atol=4e-6)
+    print(f"[verified {nq}x{nb}x{d} k={k} ip={metric_ip}] fallback rows: {n_fallback}")
+
+
+def test_verified_search_falls_back_on_unresolvable_rows(dev):
+    """Near-duplicate database rows are closer together than the coarse pass can resolve: those queries
+    must be flagged and re-run with the split products, and still match the oracle."""
+    from image_search_engine_b200 import faiss_compat, ops
+    rng = np.random.default_rng(77)
+    d, nb = 256, 6000
+    base = unit_rows(rng, 60, d)
+    db = np.repeat(base, 100, axis=0) + 2e-5 * rng.standard_normal((nb, d)).astype(np.float32)   # 100 near copies each
+    db = db.astype(np.float32)
+    q = np.concatenate([base[:40] + 1e-5 * rng.standard_normal((40, d)).astype(np.float32),
+                        unit_rows(rng, 60, d)]).astype(np.float32)
+    idx = faiss_compat.IndexFlatIP(d)
+    idx.add(db)
+    D, I = idx.search(q, 10)
+    assert ops.last_search_stats["fallback_rows"] >= 40, ops.last_search_stats
+    Do, Io = _oracle_knn(q, db, 10, True)
+    assert_topk_parity(I, Io, q, db, True, max_mismatch_frac=1.0)
+    np.testing.assert_allclose(D, Do, rtol=1e-4, atol=2e-6)
+    # each near-copy query finds only members of its own cluster
+    assert ((I[:40] // 100) == np.arange(40)[:, None]).all()
