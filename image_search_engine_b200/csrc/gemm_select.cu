@@ -54,6 +54,7 @@ struct Params {
     const float* b_meta;
     const float* a_norms;
     const float* b_norms;
+    const float* row_seed;  // optional [m]: a per-row score every kept candidate must beat (real units)
     float* out_val;    // [n_splits, m, topk]
     int64_t* out_idx;  // [n_splits, m, topk]
 };
@@ -69,7 +70,13 @@ struct Aux {  // lives after the stage ring in dynamic shared memory
 };
 static_assert(sizeof(Aux) <= AUX_BYTES, "aux area too small");
 
-// KSEL: 1 = running top-1 in registers, otherwise capacity of the thread-local list
+// selection state per epilogue thread: top-1 scalars, 32 register-resident slots, or a 128-entry sorted
+// thread-local list
+template <int KSEL> struct SelList { using type = TopKList<KSEL>; };
+template <> struct SelList<1> { using type = TopKList<1>; };
+template <> struct SelList<32> { using type = RegList32; };
+
+// KSEL: 1 = running top-1 in registers, otherwise capacity of the per-thread candidate set
 template <int PA, int PB, bool L2, int KSEL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
@@ -201,8 +208,17 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
 
             float best = -CUDART_INF_F;
             int best_id = -1;
-            TopKList<(KSEL > 1 ? KSEL : 1)> list;
-            if (KSEL > 1) list.init(p.topk);
+            typename SelList<KSEL>::type list;
+            if (KSEL > 1) {
+                // seed = score of a column already known to exist (from a pre-pass over a column sample):
+                // candidates that cannot beat it are never inserted, which removes almost all list traffic
+                float seed = -CUDART_INF_F;
+                if (p.row_seed != nullptr && row < p.m) {
+                    const float sr = __ldg(p.row_seed + row);
+                    seed = L2 ? (__ldg(p.a_norms + row) - sr) : sr * (p.a_meta[META_SCALE] * p.b_meta[META_SCALE]);
+                }
+                list.init(p.topk, seed);
+            }
 
             for (int nt = nt0; nt < nt1; ++nt, ++tile) {
                 const int as = tile & 1;
@@ -248,10 +264,23 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                             best_id = col0 + c + jj;
                         }
                     } else {
-                        if (mx > list.thr) {
+                        // rare path (a value beating the row's current threshold): extract the chunk's
+                        // maxima one by one -- a single copy of the insertion code, lowest column first
+                        // among equal values
+                        float cur = mx;
+#pragma unroll 1
+                        while (cur > list.thr) {
+                            int jj = 31;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (v[j] > list.thr) list.insert(v[j], col0 + c + j);
+                            for (int j = 30; j >= 0; --j) jj = (v[j] == cur) ? j : jj;
+                            list.insert(cur, col0 + c + jj);
+                            float nm = -CUDART_INF_F;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                v[j] = (j == jj) ? -CUDART_INF_F : v[j];
+                                nm = fmaxf(nm, v[j]);
+                            }
+                            cur = nm;
                         }
                     }
                 }
@@ -272,15 +301,20 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                         oi[0] = -1;
                     }
                 } else {
-#pragma unroll 1
-                    for (int j = 0; j < p.topk; ++j) {
-                        if (list.id[j] >= 0) {
-                            ov[j] = L2 ? fmaxf(an - list.v[j], 0.f) : list.v[j] * inv;
-                            oi[j] = p.id_base + list.id[j];
+                    auto emit = [&](int j, float v, int id) {
+                        if (id >= 0) {
+                            ov[j] = L2 ? fmaxf(an - v, 0.f) : v * inv;
+                            oi[j] = p.id_base + id;
                         } else {
                             ov[j] = L2 ? 3.402823466e+38f : -3.402823466e+38f;
                             oi[j] = -1;
                         }
+                    };
+                    if constexpr (KSEL == 32) {
+                        list.drain_sorted(emit);
+                    } else {
+#pragma unroll 1
+                        for (int j = 0; j < p.topk; ++j) emit(j, list.v[j], list.id[j]);
                     }
                 }
             }
@@ -457,8 +491,8 @@ ISE_EXPORT int ise_topk_merge(ise_ctx* ctx, const float* val_parts, const int64_
 ISE_EXPORT int ise_gemm_select(ise_ctx* ctx, const void* a_hi, const void* a_lo, int64_t lda, const float* a_meta,
                                const float* a_norms, const void* b_hi, const void* b_lo, int64_t ldb,
                                const float* b_meta, const float* b_norms, int64_t m, int64_t n, int d, int metric,
-                               int topk, int64_t id_base, float* out_val, int64_t* out_idx, void* workspace,
-                               size_t workspace_bytes, void* stream) {
+                               int topk, int64_t id_base, const float* row_seed, float* out_val, int64_t* out_idx,
+                               void* workspace, size_t workspace_bytes, void* stream) {
     ISE_CHECK_ARG(ctx != nullptr);
     ISE_CHECK_ARG(metric == ISE_METRIC_IP || metric == ISE_METRIC_L2);
     ISE_CHECK_ARG(m >= 0 && n >= 0 && d > 0 && topk >= 1 && topk <= 128);
@@ -468,6 +502,7 @@ ISE_EXPORT int ise_gemm_select(ise_ctx* ctx, const void* a_hi, const void* a_lo,
     ISE_CHECK_ARG(lda >= d && ldb >= d && lda % 8 == 0 && ldb % 8 == 0);
     ISE_CHECK_ARG((reinterpret_cast<uintptr_t>(a_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(b_hi) & 15) == 0);
     if (metric == ISE_METRIC_L2) ISE_CHECK_ARG(a_norms && b_norms);
+    if (row_seed) ISE_CHECK_ARG(topk > 1);
     ISE_CHECK_ARG(n > 0);  // an empty index is handled by the caller (Faiss pads with -1)
     DeviceGuard guard(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
@@ -479,6 +514,7 @@ ISE_EXPORT int ise_gemm_select(ise_ctx* ctx, const void* a_hi, const void* a_lo,
     p.tiles_per_split = pl.tiles_per_split; p.n_splits = pl.n_splits;
     p.topk = topk; p.id_base = id_base;
     p.a_meta = a_meta; p.b_meta = b_meta; p.a_norms = a_norms; p.b_norms = b_norms;
+    p.row_seed = row_seed;
     float* wv = nullptr;
     int64_t* wi = nullptr;
     if (pl.n_splits > 1) {

@@ -59,6 +59,7 @@ __global__ void prepare_planes_kernel(const T* __restrict__ x, int64_t n, int d,
         if (fixed_unit_scale) meta[META_ABSMAX] = 255.f;
     }
     bool any_lo = false;
+    float max_ss = 0.f;
     const int dp = (int)ldp;
     for (int64_t r = warp; r < n; r += nwarps) {
         const T* row = x + r * ldx;
@@ -80,12 +81,12 @@ __global__ void prepare_planes_kernel(const T* __restrict__ x, int64_t n, int d,
             any_lo |= (__half2float(l0) != 0.f) | (__half2float(l1) != 0.f);
         }
         ss = warp_sum(ss);
-        if (lane == 0) {
-            if (norms) norms[r] = ss;
-            // largest row norm^2 (non-negative floats order like ints): the coarse-pass error bound needs it
-            atomicMax(reinterpret_cast<int*>(meta + META_MAX_NORM_SQ), __float_as_int(ss));
-        }
+        if (norms && lane == 0) norms[r] = ss;
+        max_ss = fmaxf(max_ss, ss);
     }
+    // largest row norm^2 (non-negative floats order like ints; one atomic per warp): the coarse-pass
+    // error bound of ise_rescore_select needs it
+    if (lane == 0 && max_ss > 0.f) atomicMax(reinterpret_cast<int*>(meta + META_MAX_NORM_SQ), __float_as_int(max_ss));
     if (__any_sync(0xffffffffu, any_lo) && lane == 0) meta[META_LO_NONZERO] = 1.f;
 }
 

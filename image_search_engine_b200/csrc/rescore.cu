@@ -32,6 +32,7 @@ __global__ void rescore_kernel(const TA* __restrict__ a, int64_t lda, const floa
                                const float* __restrict__ cand_val, const int64_t* __restrict__ cand_idx,
                                float* __restrict__ val, int64_t* __restrict__ idx,
                                const float* __restrict__ a_meta, const float* __restrict__ b_meta,
+                               const float* __restrict__ row_seed,
                                int32_t* __restrict__ flag_rows, int32_t* __restrict__ flag_count) {
     extern __shared__ float s_a[];          // the row of A as float32
     __shared__ float s_v[kMaxK];
@@ -106,9 +107,18 @@ __global__ void rescore_kernel(const TA* __restrict__ a, int64_t lda, const floa
         }
         __syncthreads();
         if (flag_count && threadIdx.x == 0) {
-            const long long last_id = cand_idx[row * kc + kc - 1];
-            if (last_id >= 0) {                     // list is full: columns exist outside it
-                const float T = cand_val[row * kc + kc - 1];
+            // T bounds the coarse score of every column that is NOT in the list: the worst kept
+            // candidate when the list is full, and/or the seed every kept candidate had to beat
+            const bool full = cand_idx[row * kc + kc - 1] >= 0;
+            float T = worst;
+            bool bounded = false;
+            if (full) { T = cand_val[row * kc + kc - 1]; bounded = true; }
+            if (row_seed) {
+                const float sd = row_seed[row];
+                T = bounded ? (L2 ? fminf(T, sd) : fmaxf(T, sd)) : sd;
+                bounded = true;
+            }
+            if (bounded) {                          // otherwise every column is a candidate
                 const float na = sqrtf(an), nbm = sqrtf(bn_max);
                 const float eps = kappa * na * nbm + uf_a * nbm + uf_b * na;
                 const bool proven = L2 ? (s_kth < T - 2.f * eps) : (s_kth > T + eps);
@@ -124,8 +134,8 @@ __global__ void rescore_kernel(const TA* __restrict__ a, int64_t lda, const floa
 static int launch_rescore(ise_ctx* ctx, const void* a, int a_dtype, int64_t lda, const float* b, int64_t ldb,
                           int64_t m, int64_t n, int d, int metric, int kc, int topk, int64_t id_base,
                           const float* a_norms, const float* b_norms, const float* cand_val, const int64_t* cand_idx,
-                          float* val, int64_t* idx, const float* a_meta, const float* b_meta, int32_t* flag_rows,
-                          int32_t* flag_count, void* stream) {
+                          float* val, int64_t* idx, const float* a_meta, const float* b_meta, const float* row_seed,
+                          int32_t* flag_rows, int32_t* flag_count, void* stream) {
     ISE_CHECK_ARG(ctx != nullptr);
     ISE_CHECK_ARG(metric == ISE_METRIC_IP || metric == ISE_METRIC_L2);
     ISE_CHECK_ARG(a_dtype == ISE_DTYPE_F32 || a_dtype == ISE_DTYPE_U8);
@@ -143,7 +153,7 @@ static int launch_rescore(ise_ctx* ctx, const void* a, int a_dtype, int64_t lda,
     const size_t shm = (size_t)((d + 3) / 4 * 4) * sizeof(float);
     const bool l2 = metric == ISE_METRIC_L2;
 #define ISE_RESCORE_ARGS lda, b, ldb, m, n, d, kc, topk, id_base, a_norms, b_norms, cand_val, cand_idx, val, idx, \
-                         a_meta, b_meta, flag_rows, flag_count
+                         a_meta, b_meta, row_seed, flag_rows, flag_count
     if (a_dtype == ISE_DTYPE_F32) {
         if (l2) rescore_kernel<float, true><<<grid, kThreads, shm, st>>>((const float*)a, ISE_RESCORE_ARGS);
         else rescore_kernel<float, false><<<grid, kThreads, shm, st>>>((const float*)a, ISE_RESCORE_ARGS);
@@ -161,15 +171,16 @@ ISE_EXPORT int ise_rescore_topk(ise_ctx* ctx, const void* a, int a_dtype, int64_
                                 const float* a_norms, const float* b_norms, float* val, int64_t* idx,
                                 void* stream) {
     return launch_rescore(ctx, a, a_dtype, lda, b, ldb, m, n, d, metric, topk, topk, id_base, a_norms, b_norms,
-                          nullptr, idx, val, idx, nullptr, nullptr, nullptr, nullptr, stream);
+                          nullptr, idx, val, idx, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
 }
 
 ISE_EXPORT int ise_rescore_select(ise_ctx* ctx, const void* a, int a_dtype, int64_t lda, const float* a_meta,
                                   const float* a_norms, const float* b, int64_t ldb, const float* b_meta,
                                   const float* b_norms, int64_t m, int64_t n, int d, int metric, int kc, int topk,
-                                  int64_t id_base, const float* cand_val, const int64_t* cand_idx, float* out_val,
-                                  int64_t* out_idx, int32_t* flag_rows, int32_t* flag_count, void* stream) {
+                                  int64_t id_base, const float* row_seed, const float* cand_val,
+                                  const int64_t* cand_idx, float* out_val, int64_t* out_idx, int32_t* flag_rows,
+                                  int32_t* flag_count, void* stream) {
     ISE_CHECK_ARG(flag_rows && flag_count);
     return launch_rescore(ctx, a, a_dtype, lda, b, ldb, m, n, d, metric, kc, topk, id_base, a_norms, b_norms, cand_val,
-                          cand_idx, out_val, out_idx, a_meta, b_meta, flag_rows, flag_count, stream);
+                          cand_idx, out_val, out_idx, a_meta, b_meta, row_seed, flag_rows, flag_count, stream);
 }

@@ -136,7 +136,7 @@ class IndexFlat:
         xb = self._database()
         with self._lock:
             if self._op is None:
-                self._op = ops.prepare_operand(xb)
+                self._op = ops.attach_sample(ops.prepare_operand(xb))
             return self._op
 
     # ---- search ----

@@ -88,6 +88,7 @@ class Operand:
     n: int
     d: int
     ldp: int
+    sample: "Operand | None" = None   # strided row sample (hi plane only) used to seed selection thresholds
 
 
 def prepare_operand(x: torch.Tensor, *, keep_lo: bool | None = None) -> Operand:
@@ -124,6 +125,22 @@ def prepare_operand(x: torch.Tensor, *, keep_lo: bool | None = None) -> Operand:
     return Operand(hi, lo, norms, meta, n, d, ldp)
 
 
+SAMPLE_FRACTION = 64       # one row in 64 ...
+SAMPLE_MIN_ROWS = 1024     # ... but never fewer than this, and only for operands at least 64x larger
+SAMPLE_MAX_ROWS = 16384
+
+
+def attach_sample(op: Operand) -> Operand:
+    """Adds a strided sample of the rows to a (database) operand.  search_topk runs a cheap pre-pass
+    over it; each query's 2nd-best sample score seeds the selection threshold of the full pass."""
+    if op.n >= SAMPLE_FRACTION * SAMPLE_MIN_ROWS and op.sample is None:
+        ns = min(max(op.n // SAMPLE_FRACTION, SAMPLE_MIN_ROWS), SAMPLE_MAX_ROWS)
+        rows = torch.arange(ns, device=op.hi.device, dtype=torch.int64) * (op.n // ns)
+        op.sample = Operand(op.hi.index_select(0, rows), None, op.norms.index_select(0, rows), op.meta, ns, op.d,
+                            op.ldp)
+    return op
+
+
 def compact_operand(op: Operand) -> Operand:
     """Drops an all-zero lo plane (one 4-byte D2H readback): smaller smem stages, deeper pipeline."""
     if op.lo is not None and op.n > 0 and float(op.meta[2].item()) == 0.0:
@@ -142,8 +159,10 @@ def normalize_l2_(x: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------
 # fused contraction + selection
 # ------------------------------------------------------------------------------------------
-def gemm_select(a: Operand, b: Operand, metric: int, topk: int, id_base: int = 0):
-    """Top-k columns of b for every row of a.  Returns (val float32 [m, k], idx int64 [m, k])."""
+def gemm_select(a: Operand, b: Operand, metric: int, topk: int, id_base: int = 0,
+                row_seed: torch.Tensor | None = None):
+    """Top-k columns of b for every row of a.  Returns (val float32 [m, k], idx int64 [m, k]).
+    row_seed [m] (optional, topk > 1): only columns scoring strictly better than it are kept."""
     if a.d != b.d:
         raise IseError(f"dimension mismatch {a.d} vs {b.d}")
     if not 1 <= topk <= MAX_TOPK:
@@ -164,7 +183,8 @@ def gemm_select(a: Operand, b: Operand, metric: int, topk: int, id_base: int = 0
     _lib.check(lib.ise_gemm_select(
         ctx, _ptr(a.hi), _ptr(a_lo), a.ldp, _ptr(a.meta), _ptr(a.norms),
         _ptr(b.hi), _ptr(b_lo), b.ldp, _ptr(b.meta), _ptr(b.norms),
-        a.n, b.n, a.d, int(metric), int(topk), int(id_base), _ptr(val), _ptr(idx), _ptr(ws), ws_bytes, _stream()))
+        a.n, b.n, a.d, int(metric), int(topk), int(id_base), _ptr(row_seed), _ptr(val), _ptr(idx), _ptr(ws),
+        ws_bytes, _stream()))
     _count(2 if ws_bytes else 1)
     return val, idx
 
@@ -188,7 +208,8 @@ def rescore_topk_(a_raw: torch.Tensor, b_raw: torch.Tensor, a_op: Operand, b_op:
 
 
 def rescore_select(a_raw: torch.Tensor, b_raw: torch.Tensor, a_op: Operand, b_op: Operand, metric: int,
-                   cand_val: torch.Tensor, cand_idx: torch.Tensor, topk: int, id_base: int = 0):
+                   cand_val: torch.Tensor, cand_idx: torch.Tensor, topk: int, id_base: int = 0,
+                   row_seed: torch.Tensor | None = None):
     """Exact FP32 re-score of kc coarse candidates -> exact top-k + the rows whose candidate list could
     not be proven complete.  Returns (val [m,k], idx [m,k], flag_rows int32 [m], flag_count int32 [1])."""
     m, kc = cand_idx.shape
@@ -203,7 +224,7 @@ def rescore_select(a_raw: torch.Tensor, b_raw: torch.Tensor, a_op: Operand, b_op
         _lib.ctx(_dev(cand_idx)), _ptr(a_raw), DTYPE_F32 if a_raw.dtype == torch.float32 else DTYPE_U8,
         a_raw.stride(0), _ptr(a_op.meta), _ptr(a_op.norms), _ptr(b_raw), b_raw.stride(0), _ptr(b_op.meta),
         _ptr(b_op.norms), m, b_raw.shape[0], a_raw.shape[1], int(metric), kc, int(topk), int(id_base),
-        _ptr(cand_val.contiguous()), _ptr(cand_idx.contiguous()), _ptr(val), _ptr(idx), _ptr(flag_rows),
+        _ptr(row_seed), _ptr(cand_val.contiguous()), _ptr(cand_idx.contiguous()), _ptr(val), _ptr(idx), _ptr(flag_rows),
         _ptr(flag_count), _stream()))
     _count()
     return val, idx, flag_rows, flag_count
@@ -217,20 +238,26 @@ def search_topk(q_raw: torch.Tensor, a_op: Operand, db_raw: torch.Tensor, b_op: 
                 id_base: int = 0, precision: str = "verified", need_distances: bool = True):
     """Flat top-k of every query row against the database operand (the tensor-core path, nq >= 20).
 
-    precision="verified" (default, k >= 2): ONE tcgen05 product per tile (FP16 hi planes) selects
-      kc = 32 / 128 candidates per query, ise_rescore_select re-scores them exactly in FP32 and proves
-      from a rigorous error bound that the list contains the true top-k; the (rare) rows it cannot prove
-      are re-run with the split products.  Results equal the split path's; ~3x fewer tensor-core flops.
+    precision="verified" (default, 2 <= k <= 16): ONE tcgen05 product per tile (FP16 hi planes) selects
+      up to 32 candidates per query, ise_rescore_select re-scores them exactly in FP32 and proves from a
+      rigorous error bound that the list contains the true top-k; the (rare) rows it cannot prove are
+      re-run with the split products.  Results equal the split path's; ~3x fewer tensor-core flops.
     precision="split": hi*hi + hi*lo + lo*hi products for every tile (FP32-grade scores throughout),
       then exact re-score of the k winners.
     """
     nb = b_op.n
     kc = 32 if k <= 16 else MAX_TOPK
-    if precision == "verified" and k >= 2 and nb > kc and need_distances:
-        cv, ci = gemm_select(Operand(a_op.hi, None, a_op.norms, a_op.meta, a_op.n, a_op.d, a_op.ldp),
-                             Operand(b_op.hi, None, b_op.norms, b_op.meta, b_op.n, b_op.d, b_op.ldp),
-                             metric, kc, id_base)
-        D, I, rows, cnt = rescore_select(q_raw, db_raw, a_op, b_op, metric, cv, ci, k, id_base)
+    if precision == "verified" and 2 <= k <= 16 and nb > kc and need_distances:
+        a_hi = Operand(a_op.hi, None, a_op.norms, a_op.meta, a_op.n, a_op.d, a_op.ldp)
+        b_hi = Operand(b_op.hi, None, b_op.norms, b_op.meta, b_op.n, b_op.d, b_op.ldp)
+        seed = None
+        if b_op.sample is not None:
+            # pre-pass over 1/64 of the columns: the 2nd-best sample score of each query is a score some
+            # real column reaches, so nothing below it can be in the top-k unless fewer than k beat it
+            sv, _ = gemm_select(a_hi, b_op.sample, metric, 2)
+            seed = sv[:, 1].contiguous()
+        cv, ci = gemm_select(a_hi, b_hi, metric, kc, id_base, row_seed=seed)
+        D, I, rows, cnt = rescore_select(q_raw, db_raw, a_op, b_op, metric, cv, ci, k, id_base, row_seed=seed)
         nflag = int(cnt.item())                       # 4-byte readback: how many rows need the split path
         last_search_stats.update(mode="verified", fallback_rows=nflag, rows=a_op.n)
         if nflag:

@@ -229,6 +229,8 @@ class ShardedIndexFlat:
         self.ntotal = int(sizes.sum())
         self._local = x
         self._b_op = self.lops.prepare(x, reuse=True)
+        if isinstance(self.lops, DeviceOps):
+            ops.attach_sample(self._b_op)
 
     def search(self, q, k):
         """q replicated on every rank.  Returns (D [nq, k], I [nq, k]) identical on every rank."""

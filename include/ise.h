@@ -90,6 +90,9 @@ int ise_normalize_l2(ise_ctx* ctx, float* x, int64_t n, int d, void* stream);
  * Output rows are sorted best-first; when topk > n the tail is id -1 / -+FLT_MAX like Faiss.
  * a_lo / b_lo may be NULL when the corresponding meta says lo_nonzero == 0 (exact operand).
  * a_norms / b_norms are required for L2 only.  out ids = column + id_base.
+ * row_seed (nullable, topk > 1): per-row score of a column known to exist (IP score / L2 distance, e.g. the
+ * best hit in a column sample); only columns strictly better than it are kept, so lists may come back
+ * shorter than topk (padded with id -1).  It removes nearly all selection traffic from the epilogue.
  * Replaces index.search inside faiss.Kmeans.train (kmeans_faiss.py:41), FaissKMeans.transform
  * (kmeans_faiss.py:49) and run_image_query (engine.py:55) / query_index (siamese/test_index.py:54). */
 size_t ise_gemm_select_workspace_bytes(ise_ctx* ctx, int64_t m, int64_t n, int d, int topk);
@@ -97,7 +100,7 @@ int ise_gemm_select(ise_ctx* ctx,
                     const void* a_hi, const void* a_lo, int64_t lda, const float* a_meta, const float* a_norms,
                     const void* b_hi, const void* b_lo, int64_t ldb, const float* b_meta, const float* b_norms,
                     int64_t m, int64_t n, int d, int metric, int topk, int64_t id_base,
-                    float* out_val, int64_t* out_idx,
+                    const float* row_seed, float* out_val, int64_t* out_idx,
                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* Exact FP32 CUDA-core path for small query counts: Faiss computes n < 20 queries without the
@@ -124,12 +127,13 @@ int ise_rescore_topk(ise_ctx* ctx, const void* a, int a_dtype, int64_t lda, cons
  * per row that no column outside the candidate list can belong to the top-k, using the rigorous bound
  * |coarse - exact| <= kappa |a| max|b| (kappa from the FP16 rounding of the planes + accumulator
  * truncation, see rescore.cu).  Rows that cannot be proven are appended to flag_rows[0 .. *flag_count)
- * (device int32) and must be re-run by the caller with the full-precision split products. */
+ * (device int32) and must be re-run by the caller with the full-precision split products.
+ * row_seed (nullable): the seed the coarse call was given; it then also bounds the unseen columns. */
 int ise_rescore_select(ise_ctx* ctx, const void* a, int a_dtype, int64_t lda, const float* a_meta,
                        const float* a_norms, const float* b, int64_t ldb, const float* b_meta,
                        const float* b_norms, int64_t m, int64_t n, int d, int metric, int kc, int topk,
-                       int64_t id_base, const float* cand_val, const int64_t* cand_idx, float* out_val,
-                       int64_t* out_idx, int32_t* flag_rows, int32_t* flag_count, void* stream);
+                       int64_t id_base, const float* row_seed, const float* cand_val, const int64_t* cand_idx,
+                       float* out_val, int64_t* out_idx, int32_t* flag_rows, int32_t* flag_count, void* stream);
 
 /* Merge g sorted top-k lists per row ([g, m, topk] each) into one; canonical (score, id) order.
  * Used for column-split partial results and for the cross-GPU merge of a sharded index. */
