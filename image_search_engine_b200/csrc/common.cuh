@@ -89,4 +89,27 @@ __device__ __forceinline__ bool cand_better(float va, int64_t ia, float vb, int6
     return ia < ib;
 }
 
+// Rigorous bound on |coarse - exact| for an inner product computed from the FP16 hi planes only.
+// With a = hi_a + lo_a, |lo_a| <= 2^-11 |a| (round-to-nearest FP16; 0 when the plane is exact) the
+// neglected terms are <= (c_a + c_b + c_a c_b) sum|a_i b_i| <= (c_a + c_b + 2^-22) |a||b| (Cauchy-Schwarz);
+// the truncating FP32 accumulation adds <= (d/16 + 4) 2^-23 |a||b|; FP16 underflow (scaled elements below
+// 2^-14 round with absolute error <= 2^-25) adds <= 2^-25/scale * sqrt(d) * |other operand|.
+struct CoarseBound {
+    float kappa, uf_a, uf_b, nb_max;
+    __device__ __forceinline__ void init(const float* a_meta, const float* b_meta, int d) {
+        const float ca = a_meta[META_LO_NONZERO] != 0.f ? 4.8828125e-4f : 0.f;   // 2^-11
+        const float cb = b_meta[META_LO_NONZERO] != 0.f ? 4.8828125e-4f : 0.f;
+        kappa = 1.02f * (ca + cb) + 2.4e-7f + (float)(d / 16 + 4) * 1.1920929e-7f;
+        const float sq = sqrtf((float)d) * 5.9604645e-8f;                         // 2 * 2^-25 * sqrt(d)
+        uf_a = ca != 0.f ? sq * a_meta[META_INV_SCALE] : 0.f;                     // times |b|
+        uf_b = cb != 0.f ? sq * b_meta[META_INV_SCALE] : 0.f;                     // times |a|
+        nb_max = sqrtf(b_meta[META_MAX_NORM_SQ]);
+    }
+    // every coarse inner product of a row with squared norm `an` is within eps(an) of the exact one
+    __device__ __forceinline__ float eps(float an) const {
+        const float na = sqrtf(an);
+        return kappa * na * nb_max + uf_a * nb_max + uf_b * na;
+    }
+};
+
 #endif  // __CUDACC__

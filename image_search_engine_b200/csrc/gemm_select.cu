@@ -28,9 +28,11 @@ constexpr int BLOCK_K = 64;  // fp16 elements = one 128-byte swizzle span
 constexpr int UMMA_K = 16;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
 constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;  // 32 KiB
-constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
-constexpr int NUM_EPI_THREADS = 128;
+// top-1 (assign) epilogues are instruction bound at small d: two warps per TMEM lane quadrant, each
+// scanning half of the tile's columns; list epilogues (top-k) keep one warp per quadrant
+__host__ __device__ constexpr int epi_halves(int ksel) { return ksel == 1 ? 2 : 1; }
+__host__ __device__ constexpr int num_threads(int ksel) { return 128 + 128 * epi_halves(ksel); }
 constexpr int TMEM_COLS = 512;  // 2 accumulator stages x BLOCK_N fp32 columns
 constexpr int AUX_BYTES = 4096;
 constexpr int SMEM_LIMIT = 232448;  // 227 KiB opt-in per CTA on sm_100
@@ -55,6 +57,8 @@ struct Params {
     const float* a_norms;
     const float* b_norms;
     const float* row_seed;  // optional [m]: a per-row score every kept candidate must beat (real units)
+    int32_t* flag_rows;     // optional (top-1 only): rows whose winner is not provably unique under the
+    int32_t* flag_count;    //   coarse error bound are appended here for a full-precision re-run
     float* out_val;    // [n_splits, m, topk]
     int64_t* out_idx;  // [n_splits, m, topk]
 };
@@ -67,6 +71,9 @@ struct Aux {  // lives after the stage ring in dynamic shared memory
     uint32_t tmem_base;
     uint32_t pad_[3];
     float bnorm[2][BLOCK_N];
+    float xbest[BLOCK_M];   // half-1 -> half-0 hand-over of the top-1 state at the end of a work item
+    float xrun[BLOCK_M];
+    int xid[BLOCK_M];
 };
 static_assert(sizeof(Aux) <= AUX_BYTES, "aux area too small");
 
@@ -78,12 +85,15 @@ template <> struct SelList<32> { using type = RegList32; };
 
 // KSEL: 1 = running top-1 in registers, otherwise capacity of the per-thread candidate set
 template <int PA, int PB, bool L2, int KSEL>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(num_threads(KSEL), 1)
 gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const Params p) {
     constexpr int STAGES = num_stages(PA, PB);
     constexpr int STAGE_BYTES = stage_bytes(PA, PB);
+    constexpr int HALVES = epi_halves(KSEL);
+    constexpr int NUM_EPI_THREADS = 128 * HALVES;
+    constexpr int COLS_PER_HALF = BLOCK_N / HALVES;
     static_assert(STAGES >= 2 && STAGES <= 8, "pipeline depth");
 
     extern __shared__ uint8_t smem_raw[];
@@ -195,18 +205,25 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         }
     } else if (warp >= EPI_WARP0) {
         // ===================== epilogue: selection =====================
-        const int q = warp & 3;  // TMEM lane quadrant this warp may read
+        const int ew = warp - EPI_WARP0;
+        const int q = ew & 3;      // TMEM lane quadrant this warp may read (== warp % 4)
+        const int half = ew >> 2;  // which half of every tile's columns this warp scans
         const int et = threadIdx.x - EPI_WARP0 * 32;
         const float inv = p.a_meta[META_INV_SCALE] * p.b_meta[META_INV_SCALE];
         const float two_inv = 2.f * inv;
+        CoarseBound bound;
+        if (KSEL == 1 && p.flag_count != nullptr) bound.init(p.a_meta, p.b_meta, p.d);
         uint32_t tile = 0;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
             const int split = w / p.n_mtiles, mt = w - split * p.n_mtiles;
             const int nt0 = split * p.tiles_per_split;
             const int nt1 = min(nt0 + p.tiles_per_split, p.n_ntiles);
-            const int64_t row = (int64_t)mt * BLOCK_M + q * 32 + lane;
+            const int row_in_tile = q * 32 + lane;
+            const int64_t row = (int64_t)mt * BLOCK_M + row_in_tile;
 
-            float best = -CUDART_INF_F;
+            // top-1 state: best score / id, the best score among the OTHER columns of the chunk that
+            // holds the best (sib) and among all other chunks (m2): max(sib, m2) is the exact runner-up
+            float best = -CUDART_INF_F, sib = -CUDART_INF_F, m2 = -CUDART_INF_F;
             int best_id = -1;
             typename SelList<KSEL>::type list;
             if (KSEL > 1) {
@@ -233,8 +250,9 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 ptx::mbar_wait(&aux->tmem_full[as], aph);
                 ptx::tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N;
+                const int c_begin = half * COLS_PER_HALF;
 #pragma unroll 1
-                for (int c = 0; c < BLOCK_N; c += 32) {
+                for (int c = c_begin; c < c_begin + COLS_PER_HALF; c += 32) {
                     if (c >= ncols) break;
                     uint32_t r[32];
                     ptx::tmem_ld_32x32b_x32(taddr + c, r);
@@ -256,12 +274,19 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                     for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
                     if (KSEL == 1) {
                         if (mx > best) {  // strict: an equal score in a later column never replaces
+                            m2 = fmaxf(m2, best);   // the old best (and everything in its chunk) is now "other"
                             best = mx;
                             int jj = 31;
 #pragma unroll
                             for (int j = 30; j >= 0; --j)
                                 if (v[j] == mx) jj = j;  // lowest column among equals
                             best_id = col0 + c + jj;
+                            float s2 = -CUDART_INF_F;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) s2 = fmaxf(s2, (j == jj) ? -CUDART_INF_F : v[j]);
+                            sib = s2;
+                        } else {
+                            m2 = fmaxf(m2, mx);
                         }
                     } else {
                         // rare path (a value beating the row's current threshold): extract the chunk's
@@ -288,34 +313,61 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 ptx::mbar_arrive(&aux->tmem_empty[as]);
             }
 
-            if (row < p.m) {
-                const float an = L2 ? __ldg(p.a_norms + row) : 0.f;
-                float* ov = p.out_val + ((int64_t)split * p.m + row) * p.topk;
-                int64_t* oi = p.out_idx + ((int64_t)split * p.m + row) * p.topk;
-                if (KSEL == 1) {
+            if (KSEL == 1) {
+                // combine the two column halves of this row (half 1 hands its state to half 0)
+                float runner = fmaxf(sib, m2);
+                if (HALVES == 2) {
+                    if (half == 1) {
+                        aux->xbest[row_in_tile] = best;
+                        aux->xrun[row_in_tile] = runner;
+                        aux->xid[row_in_tile] = best_id;
+                    }
+                    asm volatile("bar.sync 2, %0;" ::"n"(NUM_EPI_THREADS) : "memory");
+                    if (half == 0) {
+                        const float ob = aux->xbest[row_in_tile], orun = aux->xrun[row_in_tile];
+                        const int oid = aux->xid[row_in_tile];
+                        const bool other_wins = (oid >= 0) && (best_id < 0 || ob > best || (ob == best && oid < best_id));
+                        runner = fmaxf(fmaxf(runner, orun), other_wins ? best : ob);
+                        if (other_wins) { best = ob; best_id = oid; }
+                    }
+                    asm volatile("bar.sync 2, %0;" ::"n"(NUM_EPI_THREADS) : "memory");
+                }
+                if (half == 0 && row < p.m) {
+                    const float an = (L2 || p.flag_count != nullptr) ? __ldg(p.a_norms + row) : 0.f;
+                    float* ov = p.out_val + ((int64_t)split * p.m + row) * p.topk;
+                    int64_t* oi = p.out_idx + ((int64_t)split * p.m + row) * p.topk;
                     if (best_id >= 0) {
                         ov[0] = L2 ? fmaxf(an - best, 0.f) : best * inv;
                         oi[0] = p.id_base + best_id;
+                        if (p.flag_count != nullptr) {
+                            // winner provably unique?  IP scores carry +-eps each, L2 scores (2<a,b> - |b|^2) +-2 eps
+                            const float gap = L2 ? (best - runner) : (best - runner) * inv;
+                            const float need = (L2 ? 4.f : 2.f) * bound.eps(an);
+                            if (!(gap > need)) p.flag_rows[atomicAdd(p.flag_count, 1)] = (int32_t)row;
+                        }
                     } else {
                         ov[0] = L2 ? 3.402823466e+38f : -3.402823466e+38f;
                         oi[0] = -1;
                     }
-                } else {
-                    auto emit = [&](int j, float v, int id) {
-                        if (id >= 0) {
-                            ov[j] = L2 ? fmaxf(an - v, 0.f) : v * inv;
-                            oi[j] = p.id_base + id;
-                        } else {
-                            ov[j] = L2 ? 3.402823466e+38f : -3.402823466e+38f;
-                            oi[j] = -1;
-                        }
-                    };
-                    if constexpr (KSEL == 32) {
-                        list.drain_sorted(emit);
+                }
+            } else if (row < p.m) {
+                const float an = L2 ? __ldg(p.a_norms + row) : 0.f;
+                float* ov = p.out_val + ((int64_t)split * p.m + row) * p.topk;
+                int64_t* oi = p.out_idx + ((int64_t)split * p.m + row) * p.topk;
+                auto emit = [&](int j, float v, int id) {
+                    if (id >= 0) {
+                        ov[j] = L2 ? fmaxf(an - v, 0.f) : v * inv;
+                        oi[j] = p.id_base + id;
                     } else {
-#pragma unroll 1
-                        for (int j = 0; j < p.topk; ++j) emit(j, list.v[j], list.id[j]);
+                        ov[j] = L2 ? 3.402823466e+38f : -3.402823466e+38f;
+                        oi[j] = -1;
                     }
+                };
+                if constexpr (KSEL == 32) {
+                    list.drain_sorted(emit);
+                } else {
+#pragma unroll 1
+                    for (int j = 0; j < p.topk; ++j) emit(j, list.v[j], list.id[j]);
                 }
             }
         }
@@ -442,7 +494,7 @@ static int launch(const ise_ctx* ctx, const CUtensorMap* maps, const Params& p, 
     ISE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int total = p.n_mtiles * p.n_splits;
     const int grid = std::min(total, ctx->sm_count);
-    kern<<<grid, NUM_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+    kern<<<grid, num_threads(KSEL), smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
     ISE_LAUNCH_CHECK();
     return 0;
 }
@@ -491,8 +543,9 @@ ISE_EXPORT int ise_topk_merge(ise_ctx* ctx, const float* val_parts, const int64_
 ISE_EXPORT int ise_gemm_select(ise_ctx* ctx, const void* a_hi, const void* a_lo, int64_t lda, const float* a_meta,
                                const float* a_norms, const void* b_hi, const void* b_lo, int64_t ldb,
                                const float* b_meta, const float* b_norms, int64_t m, int64_t n, int d, int metric,
-                               int topk, int64_t id_base, const float* row_seed, float* out_val, int64_t* out_idx,
-                               void* workspace, size_t workspace_bytes, void* stream) {
+                               int topk, int64_t id_base, const float* row_seed, int32_t* flag_rows,
+                               int32_t* flag_count, float* out_val, int64_t* out_idx, void* workspace,
+                               size_t workspace_bytes, void* stream) {
     ISE_CHECK_ARG(ctx != nullptr);
     ISE_CHECK_ARG(metric == ISE_METRIC_IP || metric == ISE_METRIC_L2);
     ISE_CHECK_ARG(m >= 0 && n >= 0 && d > 0 && topk >= 1 && topk <= 128);
@@ -515,6 +568,13 @@ ISE_EXPORT int ise_gemm_select(ise_ctx* ctx, const void* a_hi, const void* a_lo,
     p.topk = topk; p.id_base = id_base;
     p.a_meta = a_meta; p.b_meta = b_meta; p.a_norms = a_norms; p.b_norms = b_norms;
     p.row_seed = row_seed;
+    p.flag_rows = flag_rows;
+    p.flag_count = flag_count;
+    if (flag_count) {
+        ISE_CHECK_ARG(flag_rows && topk == 1 && a_norms);
+        if (pl.n_splits > 1) ISE_FAIL("top-1 verification needs an unsplit column range (workspace_bytes == 0)");
+        ISE_CUDA(cudaMemsetAsync(flag_count, 0, sizeof(int32_t), st));
+    }
     float* wv = nullptr;
     int64_t* wi = nullptr;
     if (pl.n_splits > 1) {

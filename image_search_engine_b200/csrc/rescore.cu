@@ -18,13 +18,10 @@ constexpr int kMaxK = 128;
 // verified against the coarse pass's error bound and appended to `flag_rows` when the candidate list
 // cannot be PROVEN to contain the true top-k (the caller re-runs those rows at full precision).
 //
-// Bound: the coarse pass multiplies the FP16 hi planes only.  With a = hi_a + lo_a, |lo_a| <= 2^-11 |a|
-// (round-to-nearest FP16; 0 when the plane is exact), the neglected terms are bounded by
-// (c_a + c_b + c_a c_b) * sum|a_i b_i| <= (c_a + c_b + 2^-22) |a| |b|  (Cauchy-Schwarz), and the truncating
-// FP32 accumulation adds at most (d/16 + 4) * 2^-23 * |a| |b|.  So every coarse inner product is within
-// eps = kappa * |a| * max_col|b| of the exact one; a column outside the candidate list has coarse score
-// <= T (the worst kept one), hence exact score <= T + eps: if the k-th exact candidate beats that, the
-// list provably holds the true top-k.  (L2: scores are |a|^2 + |b|^2 - 2<a,b>, so the slack is 2 eps.)
+// Bound (CoarseBound in common.cuh): every coarse inner product is within eps = kappa |a| max_col|b| of
+// the exact one; a column outside the candidate list has coarse score <= T (the worst kept one, or the
+// seed), hence exact score <= T + eps: if the k-th exact candidate beats that, the list provably holds
+// the true top-k.  (L2: scores are |a|^2 + |b|^2 - 2<a,b>, so the slack is 2 eps.)
 template <typename TA, bool L2>
 __global__ void rescore_kernel(const TA* __restrict__ a, int64_t lda, const float* __restrict__ b, int64_t ldb,
                                int64_t m, int64_t n, int d, int kc, int topk, int64_t id_base,
@@ -40,18 +37,8 @@ __global__ void rescore_kernel(const TA* __restrict__ a, int64_t lda, const floa
     __shared__ float s_kth;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float worst = L2 ? 3.402823466e+38f : -3.402823466e+38f;
-    float kappa = 0.f, bn_max = 0.f, uf_a = 0.f, uf_b = 0.f;
-    if (flag_count) {
-        const float ca = a_meta[META_LO_NONZERO] != 0.f ? 4.8828125e-4f : 0.f;   // 2^-11
-        const float cb = b_meta[META_LO_NONZERO] != 0.f ? 4.8828125e-4f : 0.f;
-        kappa = 1.02f * (ca + cb) + 2.4e-7f + (float)(d / 16 + 4) * 1.1920929e-7f;
-        bn_max = b_meta[META_MAX_NORM_SQ];
-        // FP16 underflow: elements below 2^-14 after scaling round with absolute error <= 2^-25 (scaled
-        // units), i.e. 2^-25 / scale each; against the other operand that is <= 2^-25/scale * sqrt(d) * |.|
-        const float sq = sqrtf((float)d) * 5.9604645e-8f;                         // 2 * 2^-25 * sqrt(d)
-        uf_a = ca != 0.f ? sq * a_meta[META_INV_SCALE] : 0.f;                     // times |b|
-        uf_b = cb != 0.f ? sq * b_meta[META_INV_SCALE] : 0.f;                     // times |a|
-    }
+    CoarseBound bound;
+    if (flag_count) bound.init(a_meta, b_meta, d);
     for (int64_t row = blockIdx.x; row < m; row += gridDim.x) {
         const TA* arow = a + row * lda;
         for (int c = threadIdx.x; c < d; c += kThreads) s_a[c] = (float)arow[c];
@@ -119,8 +106,7 @@ __global__ void rescore_kernel(const TA* __restrict__ a, int64_t lda, const floa
                 bounded = true;
             }
             if (bounded) {                          // otherwise every column is a candidate
-                const float na = sqrtf(an), nbm = sqrtf(bn_max);
-                const float eps = kappa * na * nbm + uf_a * nbm + uf_b * na;
+                const float eps = bound.eps(an);
                 const bool proven = L2 ? (s_kth < T - 2.f * eps) : (s_kth > T + eps);
                 if (!proven) flag_rows[atomicAdd(flag_count, 1)] = (int32_t)row;
             }

@@ -304,6 +304,7 @@ class Kmeans:
         self.iteration_stats = None
         self.index = None
         self.trace = None  # optional list: per-iteration device snapshots for lock-step tests
+        self.precision = "verified"  # see ops.search_topk
 
     # -- helpers --
     def _post_process(self, cent: torch.Tensor):
@@ -368,7 +369,7 @@ class Kmeans:
             obj = 0.0
             for it in range(cp.niter):
                 b_op = ops.prepare_operand(cent)
-                dis, assign = ops.gemm_select(a_op, b_op, metric, 1)
+                dis, assign = ops.search_topk(xd, a_op, cent, b_op, metric, 1, precision=self.precision)
                 accum.zero_()
                 objbuf.zero_()
                 ops.kmeans_accumulate(xd, assign, dis, sums, counts, objbuf)

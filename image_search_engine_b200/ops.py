@@ -160,7 +160,7 @@ def normalize_l2_(x: torch.Tensor) -> torch.Tensor:
 # fused contraction + selection
 # ------------------------------------------------------------------------------------------
 def gemm_select(a: Operand, b: Operand, metric: int, topk: int, id_base: int = 0,
-                row_seed: torch.Tensor | None = None):
+                row_seed: torch.Tensor | None = None, flags: tuple | None = None):
     """Top-k columns of b for every row of a.  Returns (val float32 [m, k], idx int64 [m, k]).
     row_seed [m] (optional, topk > 1): only columns scoring strictly better than it are kept."""
     if a.d != b.d:
@@ -183,7 +183,8 @@ def gemm_select(a: Operand, b: Operand, metric: int, topk: int, id_base: int = 0
     _lib.check(lib.ise_gemm_select(
         ctx, _ptr(a.hi), _ptr(a_lo), a.ldp, _ptr(a.meta), _ptr(a.norms),
         _ptr(b.hi), _ptr(b_lo), b.ldp, _ptr(b.meta), _ptr(b.norms),
-        a.n, b.n, a.d, int(metric), int(topk), int(id_base), _ptr(row_seed), _ptr(val), _ptr(idx), _ptr(ws),
+        a.n, b.n, a.d, int(metric), int(topk), int(id_base), _ptr(row_seed),
+        _ptr(flags[0] if flags else None), _ptr(flags[1] if flags else None), _ptr(val), _ptr(idx), _ptr(ws),
         ws_bytes, _stream()))
     _count(2 if ws_bytes else 1)
     return val, idx
@@ -238,18 +239,48 @@ def search_topk(q_raw: torch.Tensor, a_op: Operand, db_raw: torch.Tensor, b_op: 
                 id_base: int = 0, precision: str = "verified", need_distances: bool = True):
     """Flat top-k of every query row against the database operand (the tensor-core path, nq >= 20).
 
-    precision="verified" (default, 2 <= k <= 16): ONE tcgen05 product per tile (FP16 hi planes) selects
-      up to 32 candidates per query, ise_rescore_select re-scores them exactly in FP32 and proves from a
-      rigorous error bound that the list contains the true top-k; the (rare) rows it cannot prove are
-      re-run with the split products.  Results equal the split path's; ~3x fewer tensor-core flops.
+    precision="verified" (default): ONE tcgen05 product per tile (FP16 hi planes only).
+      k == 1 (quantisation / k-means assign): the kernel tracks the exact runner-up of every row and flags
+        the rows whose winner is not separated from it by more than the rigorous coarse error bound;
+      2 <= k <= 16: up to 32 candidates per query are kept, ise_rescore_select re-scores them exactly in
+        FP32 and proves from the same bound that the list contains the true top-k.
+      Flagged rows (rare) are re-run with the split products, so results equal the split path's at
+      roughly a third (k > 1) or half (k == 1, exact rows) of the tensor-core work.
     precision="split": hi*hi + hi*lo + lo*hi products for every tile (FP32-grade scores throughout),
       then exact re-score of the k winners.
     """
     nb = b_op.n
     kc = 32 if k <= 16 else MAX_TOPK
+    a_hi = Operand(a_op.hi, None, a_op.norms, a_op.meta, a_op.n, a_op.d, a_op.ldp)
+    b_hi = Operand(b_op.hi, None, b_op.norms, b_op.meta, b_op.n, b_op.d, b_op.ldp)
+
+    def rerun_rows(rows, cnt, D, I):
+        """Re-runs the flagged rows with the split products (planes gathered, not re-prepared)."""
+        nflag = int(cnt.item())                       # 4-byte readback: how many rows need the split path
+        if nflag:
+            sel = rows[:nflag].to(torch.int64)
+            sub = Operand(a_op.hi.index_select(0, sel), None if a_op.lo is None else a_op.lo.index_select(0, sel),
+                          a_op.norms.index_select(0, sel), a_op.meta, nflag, a_op.d, a_op.ldp)
+            D2, I2 = gemm_select(sub, b_op, metric, k, id_base)
+            if need_distances:
+                rescore_topk_(q_raw.index_select(0, sel), db_raw, sub, b_op, metric, D2, I2, id_base)
+            D.index_copy_(0, sel, D2)
+            I.index_copy_(0, sel, I2)
+        return nflag
+
+    if precision == "verified" and k == 1 and nb > 1 and a_op.n > 0:
+        lib, ctx = _lib.load(), _lib.ctx(_dev(a_op.hi))
+        if lib.ise_gemm_select_workspace_bytes(ctx, a_op.n, nb, a_op.d, 1) == 0:   # unsplit column range
+            rows = torch.empty((a_op.n,), dtype=torch.int32, device=a_op.hi.device)
+            cnt = torch.zeros((1,), dtype=torch.int32, device=a_op.hi.device)
+            # coarse top-1 + exact runner-up; rows whose winner is not provably unique are flagged
+            D, I = gemm_select(a_hi, b_hi, metric, 1, id_base, flags=(rows, cnt))
+            nflag = rerun_rows(rows, cnt, D, I)
+            if need_distances:
+                rescore_topk_(q_raw, db_raw, a_op, b_op, metric, D, I, id_base)
+            last_search_stats.update(mode="verified", fallback_rows=nflag, rows=a_op.n)
+            return D, I
     if precision == "verified" and 2 <= k <= 16 and nb > kc and need_distances:
-        a_hi = Operand(a_op.hi, None, a_op.norms, a_op.meta, a_op.n, a_op.d, a_op.ldp)
-        b_hi = Operand(b_op.hi, None, b_op.norms, b_op.meta, b_op.n, b_op.d, b_op.ldp)
         seed = None
         if b_op.sample is not None:
             # pre-pass over 1/64 of the columns: the 2nd-best sample score of each query is a score some
@@ -258,17 +289,8 @@ def search_topk(q_raw: torch.Tensor, a_op: Operand, db_raw: torch.Tensor, b_op: 
             seed = sv[:, 1].contiguous()
         cv, ci = gemm_select(a_hi, b_hi, metric, kc, id_base, row_seed=seed)
         D, I, rows, cnt = rescore_select(q_raw, db_raw, a_op, b_op, metric, cv, ci, k, id_base, row_seed=seed)
-        nflag = int(cnt.item())                       # 4-byte readback: how many rows need the split path
+        nflag = rerun_rows(rows, cnt, D, I)
         last_search_stats.update(mode="verified", fallback_rows=nflag, rows=a_op.n)
-        if nflag:
-            sel = rows[:nflag].to(torch.int64)
-            sub = Operand(a_op.hi.index_select(0, sel), None if a_op.lo is None else a_op.lo.index_select(0, sel),
-                          a_op.norms.index_select(0, sel), a_op.meta, nflag, a_op.d, a_op.ldp)
-            q_sub = q_raw.index_select(0, sel)
-            D2, I2 = gemm_select(sub, b_op, metric, k, id_base)
-            rescore_topk_(q_sub, db_raw, sub, b_op, metric, D2, I2, id_base)
-            D.index_copy_(0, sel, D2)
-            I.index_copy_(0, sel, I2)
         return D, I
     D, I = gemm_select(a_op, b_op, metric, k, id_base)
     if need_distances:

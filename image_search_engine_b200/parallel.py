@@ -46,8 +46,8 @@ class DeviceOps:
         op = ops.prepare_operand(x)
         return ops.compact_operand(op) if reuse else op
 
-    def assign(self, a_op, cent, metric):
-        return ops.gemm_select(a_op, ops.prepare_operand(cent), metric, 1)
+    def assign(self, x, a_op, cent, metric):
+        return ops.search_topk(x, a_op, cent, ops.prepare_operand(cent), metric, 1)
 
     def accumulate(self, x, assign, dis, sums, counts, obj):
         ops.kmeans_accumulate(x, assign, dis, sums, counts, obj)
@@ -179,7 +179,7 @@ class ShardedKmeans:
                 lops.normalize(cent)
             o = 0.0
             for it in range(cp.niter):
-                dis, assign = lops.assign(a_op, cent, metric)
+                dis, assign = lops.assign(x_train, a_op, cent, metric)
                 accum.zero_()
                 obj.zero_()
                 lops.accumulate(x_train, assign, dis, sums, counts, obj)

@@ -93,6 +93,11 @@ int ise_normalize_l2(ise_ctx* ctx, float* x, int64_t n, int d, void* stream);
  * row_seed (nullable, topk > 1): per-row score of a column known to exist (IP score / L2 distance, e.g. the
  * best hit in a column sample); only columns strictly better than it are kept, so lists may come back
  * shorter than topk (padded with id -1).  It removes nearly all selection traffic from the epilogue.
+ * flag_rows / flag_count (nullable, topk == 1, unsplit column range, a_norms required): coarse top-1
+ * verification.  Called with the hi planes only (a_lo = b_lo = NULL) the kernel also tracks the exact
+ * runner-up score of every row and appends to flag_rows[0 .. *flag_count) the rows whose winner is not
+ * separated from the runner-up by more than the rigorous coarse error bound (CoarseBound, common.cuh);
+ * the caller re-runs just those rows with the lo planes.  All other rows are provably correct.
  * Replaces index.search inside faiss.Kmeans.train (kmeans_faiss.py:41), FaissKMeans.transform
  * (kmeans_faiss.py:49) and run_image_query (engine.py:55) / query_index (siamese/test_index.py:54). */
 size_t ise_gemm_select_workspace_bytes(ise_ctx* ctx, int64_t m, int64_t n, int d, int topk);
@@ -100,7 +105,8 @@ int ise_gemm_select(ise_ctx* ctx,
                     const void* a_hi, const void* a_lo, int64_t lda, const float* a_meta, const float* a_norms,
                     const void* b_hi, const void* b_lo, int64_t ldb, const float* b_meta, const float* b_norms,
                     int64_t m, int64_t n, int d, int metric, int topk, int64_t id_base,
-                    const float* row_seed, float* out_val, int64_t* out_idx,
+                    const float* row_seed, int32_t* flag_rows, int32_t* flag_count,
+                    float* out_val, int64_t* out_idx,
                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* Exact FP32 CUDA-core path for small query counts: Faiss computes n < 20 queries without the

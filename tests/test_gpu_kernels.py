@@ -251,7 +251,8 @@ def test_kmeans_update_and_split(dev):
 
 
 @pytest.mark.parametrize("metric_ip", [True, False])
-@pytest.mark.parametrize("nq,nb,d,k", [(300, 20000, 128, 10), (64, 5000, 2048, 10), (200, 9000, 64, 100)])
+@pytest.mark.parametrize("nq,nb,d,k", [(300, 20000, 128, 10), (64, 5000, 2048, 10), (500, 70000, 96, 5),
+                                        (3000, 4096, 128, 1), (700, 300, 32, 1)])
 def test_verified_coarse_search_equals_split(dev, metric_ip, nq, nb, d, k):
     """Default index search = 1-product coarse pass + exact re-score + proof; must agree with the
     3-product split path and with the oracle."""
@@ -296,3 +297,29 @@ def test_verified_search_falls_back_on_unresolvable_rows(dev):
     np.testing.assert_allclose(D, Do, rtol=1e-4, atol=2e-6)
     # each near-copy query finds only members of its own cluster
     assert ((I[:40] // 100) == np.arange(40)[:, None]).all()
+
+
+def test_verified_assign_flags_ties_and_near_ties(dev):
+    """Coarse top-1: duplicated / nearly duplicated centroids cannot be separated by the FP16 pass; those
+    rows must be flagged and resolved by the split products (exact ties -> lowest id)."""
+    from image_search_engine_b200 import ops
+    from image_search_engine_b200._lib import METRIC_IP
+    rng = np.random.default_rng(5)
+    d, k, n = 64, 512, 4000
+    c = unit_rows(rng, k, d)
+    c[300] = c[7]                                    # exact duplicate: id 7 must win
+    c[301] = c[9] * np.float32(1 + 3e-5)             # near duplicate, slightly better
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    x[:50] = c[7] * 3 + 0.01 * rng.standard_normal((50, d)).astype(np.float32)
+    x[50:100] = c[9] * 2 + 0.01 * rng.standard_normal((50, d)).astype(np.float32)
+    xd, cd = torch.from_numpy(x).to(dev), torch.from_numpy(c).to(dev)
+    a, b = ops.prepare_operand(xd), ops.prepare_operand(cd)
+    D, I = ops.search_topk(xd, a, cd, b, METRIC_IP, 1)
+    st = dict(ops.last_search_stats)
+    assert st["mode"] == "verified" and 100 <= st["fallback_rows"] < n // 4, st
+    Do, Io = _oracle_knn(x, c, 1, True)
+    assert (I.cpu().numpy()[:50, 0] == 7).all() and (I.cpu().numpy()[50:100, 0] == 301).all()
+    assert_topk_parity(I.cpu().numpy(), Io, x, c, True, max_mismatch_frac=0.002)
+    np.testing.assert_allclose(D.cpu().numpy(), Do, rtol=1e-4, atol=1e-5)
+    D2, I2 = ops.search_topk(xd, a, cd, b, METRIC_IP, 1, precision="split")
+    assert torch.equal(I, I2)

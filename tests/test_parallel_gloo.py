@@ -26,7 +26,7 @@ class OracleOps:
     def prepare(self, x, reuse=False):
         return x
 
-    def assign(self, a_op, cent, metric):
+    def assign(self, x, a_op, cent, metric):
         D, I = fs.knn(a_op.numpy().astype(np.float32), cent.numpy(), 1, metric)
         return torch.from_numpy(D), torch.from_numpy(I)
 
