@@ -251,61 +251,72 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 ptx::tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N;
                 const int c_begin = half * COLS_PER_HALF;
+                const int c_end = min(c_begin + COLS_PER_HALF, ncols);
+                // software-pipelined TMEM reads in a ROLLED loop (one copy of the scan / insertion code):
+                // the load of chunk i+1 is issued as soon as chunk i has been moved out of `r`
+                uint32_t r[32];
+                if (c_begin < c_end) ptx::tmem_ld_32x32b_x32(taddr + c_begin, r);
 #pragma unroll 1
-                for (int c = c_begin; c < c_begin + COLS_PER_HALF; c += 32) {
-                    if (c >= ncols) break;
-                    uint32_t r[32];
-                    ptx::tmem_ld_32x32b_x32(taddr + c, r);
-                    ptx::tmem_ld_wait();
-                    float v[32];
+                for (int c = c_begin; c < c_end; c += 32) {
+                    {
+                        ptx::tmem_ld_wait();
+                        float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        v[j] = __uint_as_float(r[j]);
-                        // maximise 2<a,b> - |b|^2  ==  minimise |a|^2 + |b|^2 - 2<a,b>
-                        if (L2) v[j] = fmaf(v[j], two_inv, -aux->bnorm[as][c + j]);
-                    }
-                    if (c + 32 > ncols) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (c + j >= ncols) v[j] = -CUDART_INF_F;
-                    }
-                    float mx = v[0];
-#pragma unroll
-                    for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
-                    if (KSEL == 1) {
-                        if (mx > best) {  // strict: an equal score in a later column never replaces
-                            m2 = fmaxf(m2, best);   // the old best (and everything in its chunk) is now "other"
-                            best = mx;
-                            int jj = 31;
-#pragma unroll
-                            for (int j = 30; j >= 0; --j)
-                                if (v[j] == mx) jj = j;  // lowest column among equals
-                            best_id = col0 + c + jj;
-                            float s2 = -CUDART_INF_F;
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) s2 = fmaxf(s2, (j == jj) ? -CUDART_INF_F : v[j]);
-                            sib = s2;
-                        } else {
-                            m2 = fmaxf(m2, mx);
+                        for (int j = 0; j < 32; ++j) {
+                            v[j] = __uint_as_float(r[j]);
+                            // maximise 2<a,b> - |b|^2  ==  minimise |a|^2 + |b|^2 - 2<a,b>
+                            if (L2) v[j] = fmaf(v[j], two_inv, -aux->bnorm[as][c + j]);
                         }
-                    } else {
-                        // rare path (a value beating the row's current threshold): extract the chunk's
-                        // maxima one by one -- a single copy of the insertion code, lowest column first
-                        // among equal values
-                        float cur = mx;
-#pragma unroll 1
-                        while (cur > list.thr) {
-                            int jj = 31;
+                        if (c + 32 < c_end) ptx::tmem_ld_32x32b_x32(taddr + c + 32, r);
+                        if (c + 32 > ncols) {
 #pragma unroll
-                            for (int j = 30; j >= 0; --j) jj = (v[j] == cur) ? j : jj;
-                            list.insert(cur, col0 + c + jj);
-                            float nm = -CUDART_INF_F;
+                            for (int j = 0; j < 32; ++j)
+                                if (c + j >= ncols) v[j] = -CUDART_INF_F;
+                        }
+                        // balanced max tree (depth 5) instead of a 31-deep dependent chain
+                        float t16[16], t8[8], t4[4];
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                v[j] = (j == jj) ? -CUDART_INF_F : v[j];
-                                nm = fmaxf(nm, v[j]);
+                        for (int j = 0; j < 16; ++j) t16[j] = fmaxf(v[2 * j], v[2 * j + 1]);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) t8[j] = fmaxf(t16[2 * j], t16[2 * j + 1]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) t4[j] = fmaxf(t8[2 * j], t8[2 * j + 1]);
+                        const float mx = fmaxf(fmaxf(t4[0], t4[1]), fmaxf(t4[2], t4[3]));
+                        if (KSEL == 1) {
+                            if (mx > best) {  // strict: an equal score in a later column never replaces
+                                m2 = fmaxf(m2, best);   // the old best (and everything in its chunk) is now "other"
+                                best = mx;
+                                int jj = 31;
+#pragma unroll
+                                for (int j = 30; j >= 0; --j)
+                                    if (v[j] == mx) jj = j;  // lowest column among equals
+                                best_id = col0 + c + jj;
+                                float s2 = -CUDART_INF_F;
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) s2 = fmaxf(s2, (j == jj) ? -CUDART_INF_F : v[j]);
+                                sib = s2;
+                            } else {
+                                m2 = fmaxf(m2, mx);
                             }
-                            cur = nm;
+                        } else {
+                            // rare path (a value beating the row's current threshold): extract the chunk's
+                            // maxima one by one -- a single copy of the insertion code, lowest column first
+                            // among equal values
+                            float cur = mx;
+#pragma unroll 1
+                            while (cur > list.thr) {
+                                int jj = 31;
+#pragma unroll
+                                for (int j = 30; j >= 0; --j) jj = (v[j] == cur) ? j : jj;
+                                list.insert(cur, col0 + c + jj);
+                                float nm = -CUDART_INF_F;
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    v[j] = (j == jj) ? -CUDART_INF_F : v[j];
+                                    nm = fmaxf(nm, v[j]);
+                                }
+                                cur = nm;
+                            }
                         }
                     }
                 }
@@ -464,7 +475,7 @@ struct Plan {
     int n_mtiles, n_ntiles, tiles_per_split, n_splits;
 };
 
-static Plan make_plan(const ise_ctx* ctx, int64_t m, int64_t n) {
+static Plan make_plan(const ise_ctx* ctx, int64_t m, int64_t n, bool single_split = false) {
     Plan pl;
     pl.n_mtiles = (int)ceil_div64(m, BLOCK_M);
     pl.n_ntiles = (int)std::max<int64_t>(1, ceil_div64(n, BLOCK_N));
@@ -473,6 +484,7 @@ static Plan make_plan(const ise_ctx* ctx, int64_t m, int64_t n) {
     int64_t want = ceil_div64((int64_t)4 * ctx->sm_count, std::max(1, pl.n_mtiles));
     int64_t max_by_tiles = std::max<int64_t>(1, pl.n_ntiles / 8);
     int64_t s_hi = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(2 * want, max_by_tiles), 256));
+    if (single_split) s_hi = 1;  // top-1 verification keeps one runner-up per row, so columns are not split
     // pick the split count with the smallest makespan = waves x column tiles per item
     int64_t best_s = 1, best_cost = -1;
     for (int64_t s = 1; s <= s_hi; ++s) {
@@ -560,7 +572,7 @@ ISE_EXPORT int ise_gemm_select(ise_ctx* ctx, const void* a_hi, const void* a_lo,
     DeviceGuard guard(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
 
-    gs::Plan pl = gs::make_plan(ctx, m, n);
+    gs::Plan pl = gs::make_plan(ctx, m, n, flag_count != nullptr);
     gs::Params p;
     p.m = m; p.n = n; p.d = d;
     p.n_mtiles = pl.n_mtiles; p.n_ntiles = pl.n_ntiles;
@@ -572,7 +584,6 @@ ISE_EXPORT int ise_gemm_select(ise_ctx* ctx, const void* a_hi, const void* a_lo,
     p.flag_count = flag_count;
     if (flag_count) {
         ISE_CHECK_ARG(flag_rows && topk == 1 && a_norms);
-        if (pl.n_splits > 1) ISE_FAIL("top-1 verification needs an unsplit column range (workspace_bytes == 0)");
         ISE_CUDA(cudaMemsetAsync(flag_count, 0, sizeof(int32_t), st));
     }
     float* wv = nullptr;

@@ -115,6 +115,47 @@ __global__ void rescore_kernel(const TA* __restrict__ a, int64_t lda, const floa
     }
 }
 
+// topk == 1 fast path (k-means assign / quantisation distances): one warp per row, no sorting
+template <typename TA, bool L2>
+__global__ void rescore_top1_kernel(const TA* __restrict__ a, int64_t lda, const float* __restrict__ b, int64_t ldb,
+                                    int64_t m, int d, int64_t id_base, const float* __restrict__ a_norms,
+                                    const float* __restrict__ b_norms, float* __restrict__ val,
+                                    const int64_t* __restrict__ idx) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const bool vec = sizeof(TA) == 4 && (d & 3) == 0 && (lda & 3) == 0 && (ldb & 3) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(a) & 15) == 0);
+    for (int64_t row = warp; row < m; row += nwarps) {
+        const long long id = idx[row];
+        if (id < 0) continue;
+        const int64_t col = id - id_base;
+        const TA* arow = a + row * lda;
+        const float* brow = b + col * ldb;
+        float acc = 0.f;
+        if (vec) {
+            const float4* a4 = reinterpret_cast<const float4*>(arow);
+            const float4* b4 = reinterpret_cast<const float4*>(brow);
+            for (int c = lane; c < d / 4; c += 32) {
+                const float4 x = __ldg(a4 + c), y = __ldg(b4 + c);
+                acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc);
+                acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+            }
+        } else {
+            for (int c = lane; c < d; c += 32) acc = fmaf((float)arow[c], __ldg(brow + c), acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            if (L2) {
+                const float dis = a_norms[row] + b_norms[col] - 2.f * acc;
+                val[row] = dis < 0.f ? 0.f : dis;
+            } else {
+                val[row] = acc;
+            }
+        }
+    }
+}
+
 }  // namespace
 
 static int launch_rescore(ise_ctx* ctx, const void* a, int a_dtype, int64_t lda, const float* b, int64_t ldb,
@@ -135,9 +176,21 @@ static int launch_rescore(ise_ctx* ctx, const void* a, int a_dtype, int64_t lda,
     DeviceGuard guard(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (flag_count) ISE_CUDA(cudaMemsetAsync(flag_count, 0, sizeof(int32_t), st));
+    const bool l2 = metric == ISE_METRIC_L2;
+    if (kc == 1 && topk == 1 && !flag_count && cand_idx == idx) {
+        const int g1 = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(m, 8), (int64_t)ctx->sm_count * 8));
+        if (a_dtype == ISE_DTYPE_F32) {
+            if (l2) rescore_top1_kernel<float, true><<<g1, 256, 0, st>>>((const float*)a, lda, b, ldb, m, d, id_base, a_norms, b_norms, val, idx);
+            else rescore_top1_kernel<float, false><<<g1, 256, 0, st>>>((const float*)a, lda, b, ldb, m, d, id_base, a_norms, b_norms, val, idx);
+        } else {
+            if (l2) rescore_top1_kernel<uint8_t, true><<<g1, 256, 0, st>>>((const uint8_t*)a, lda, b, ldb, m, d, id_base, a_norms, b_norms, val, idx);
+            else rescore_top1_kernel<uint8_t, false><<<g1, 256, 0, st>>>((const uint8_t*)a, lda, b, ldb, m, d, id_base, a_norms, b_norms, val, idx);
+        }
+        ISE_LAUNCH_CHECK();
+        return 0;
+    }
     const int grid = (int)std::min<int64_t>(m, (int64_t)ctx->sm_count * 16);
     const size_t shm = (size_t)((d + 3) / 4 * 4) * sizeof(float);
-    const bool l2 = metric == ISE_METRIC_L2;
 #define ISE_RESCORE_ARGS lda, b, ldb, m, n, d, kc, topk, id_base, a_norms, b_norms, cand_val, cand_idx, val, idx, \
                          a_meta, b_meta, row_seed, flag_rows, flag_count
     if (a_dtype == ISE_DTYPE_F32) {

@@ -231,6 +231,11 @@ def rescore_select(a_raw: torch.Tensor, b_raw: torch.Tensor, a_op: Operand, b_op
     return val, idx, flag_rows, flag_count
 
 
+# Below this dimension a top-1 tile is bound by reading the 128 x 256 FP32 accumulator out of TMEM
+# (~2.4k cycles, measured) rather than by its MMAs (d/64 * 512 cycles per product), so dropping the lo
+# product buys nothing and the split products are used directly (profiles/r01_findings.md).
+COARSE_TOP1_MIN_D = 512
+
 # statistics of the last search_topk call on this process (bench.py / tests read them)
 last_search_stats = {"mode": None, "fallback_rows": 0, "rows": 0}
 
@@ -268,9 +273,10 @@ def search_topk(q_raw: torch.Tensor, a_op: Operand, db_raw: torch.Tensor, b_op: 
             I.index_copy_(0, sel, I2)
         return nflag
 
-    if precision == "verified" and k == 1 and nb > 1 and a_op.n > 0:
-        lib, ctx = _lib.load(), _lib.ctx(_dev(a_op.hi))
-        if lib.ise_gemm_select_workspace_bytes(ctx, a_op.n, nb, a_op.d, 1) == 0:   # unsplit column range
+    if precision == "verified" and k == 1 and nb > 1 and a_op.d >= COARSE_TOP1_MIN_D:
+        # the verifying kernel keeps one runner-up per row, i.e. does not split the column range over
+        # CTAs: only worth it when the rows alone give every SM a few 128-row tiles
+        if a_op.n >= 4 * 128 * _lib.load().ise_ctx_sm_count(_lib.ctx(_dev(a_op.hi))):
             rows = torch.empty((a_op.n,), dtype=torch.int32, device=a_op.hi.device)
             cnt = torch.zeros((1,), dtype=torch.int32, device=a_op.hi.device)
             # coarse top-1 + exact runner-up; rows whose winner is not provably unique are flagged

@@ -252,7 +252,7 @@ def test_kmeans_update_and_split(dev):
 
 @pytest.mark.parametrize("metric_ip", [True, False])
 @pytest.mark.parametrize("nq,nb,d,k", [(300, 20000, 128, 10), (64, 5000, 2048, 10), (500, 70000, 96, 5),
-                                        (3000, 4096, 128, 1), (700, 300, 32, 1)])
+                                        (80000, 1024, 512, 1)])
 def test_verified_coarse_search_equals_split(dev, metric_ip, nq, nb, d, k):
     """Default index search = 1-product coarse pass + exact re-score + proof; must agree with the
     3-product split path and with the oracle."""
@@ -264,7 +264,7 @@ def test_verified_coarse_search_equals_split(dev, metric_ip, nq, nb, d, k):
     idx = faiss_compat.IndexFlatIP(d) if metric_ip else faiss_compat.IndexFlatL2(d)
     idx.add(db)
     D, I = idx.search(q, k)
-    assert ops.last_search_stats["mode"] == "verified"
+    assert ops.last_search_stats["mode"] == "verified", ops.last_search_stats
     n_fallback = ops.last_search_stats["fallback_rows"]
     idx.precision = "split"
     D2, I2 = idx.search(q, k)
@@ -305,7 +305,7 @@ def test_verified_assign_flags_ties_and_near_ties(dev):
     from image_search_engine_b200 import ops
     from image_search_engine_b200._lib import METRIC_IP
     rng = np.random.default_rng(5)
-    d, k, n = 64, 512, 4000
+    d, k, n = 512, 512, 80000
     c = unit_rows(rng, k, d)
     c[300] = c[7]                                    # exact duplicate: id 7 must win
     c[301] = c[9] * np.float32(1 + 3e-5)             # near duplicate, slightly better
