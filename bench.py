@@ -266,10 +266,8 @@ def run_ours(args):
     bovw.descriptions = None
 
     def e2e_step_full():
-        Hd = bovw.histograms_device(packed, okapi=okapi)   # fused Okapi tf on the device
-        out_pin.copy_(Hd, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return out_pin.numpy()
+        # pinned host descriptors -> (H2D | prepare + assign + histogram/Okapi | D2H, chunk-pipelined) -> host matrix
+        return bovw.histograms_host(packed, out_pin, okapi=okapi)
 
     for _ in range(max(1, args.warmup // 2)):
         e2e_step_full()

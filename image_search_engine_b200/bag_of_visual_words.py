@@ -109,10 +109,63 @@ class BOVW(BaseEstimator):
         descriptions = getattr(self, "descriptions", None)
         if descriptions is None:
             descriptions = describe_dataset(self.describer, X, prediction=True)
+        if output != "device" and out is not None:
+            return self.histograms_host(descriptions, out)
         H = self.histograms_device(descriptions)
         if output == "device":
             return H
         return _to_host(H, out)
+
+    def histograms_host(self, descriptions, out: torch.Tensor, *, okapi: OkapiTransformer | None = None,
+                        n_chunks: int = 8) -> np.ndarray:
+        """Host descriptors in, host histogram matrix out, with the three legs overlapped: the images are
+        cut into ``n_chunks`` groups and chunk i+1's H2D copy, chunk i's kernels and chunk i-1's D2H copy
+        run concurrently on three streams (PCIe is full duplex).  ``out`` must be a pinned CPU tensor
+        [n_images, n_clusters] (float64 or float32); ``pack_descriptions(..., pin=True)`` pins the input."""
+        if self.hist_mode not in _HIST_MODES:
+            raise ValueError(f"hist_mode must be one of {sorted(_HIST_MODES)}")
+        dev = ops.require_cuda()
+        mat, offsets = pack_descriptions(descriptions)
+        if isinstance(mat, np.ndarray):
+            mat = torch.from_numpy(mat)
+        n_img = len(offsets) - 1
+        if tuple(out.shape) != (n_img, int(self.n_clusters)) or not out.is_pinned():
+            raise ValueError("out must be a pinned CPU tensor of shape (n_images, n_clusters)")
+        if mat.is_cuda or n_img < 2 * n_chunks:
+            H = self.histograms_device(descriptions, okapi=okapi, out_dtype=out.dtype)
+            return _to_host(H, out)
+        kw = dict(mode=_HIST_MODES[self.hist_mode], out_dtype=out.dtype)
+        if okapi is not None:
+            total = float(offsets[-1] - offsets[0])
+            kw.update(okapi=True, k1=okapi.k1, k2=okapi.k2, b=okapi.b, avgdl=total / n_img)   # batch-wide avgdl
+        # chunk boundaries in images, balanced by descriptor count
+        targets = offsets[0] + (offsets[-1] - offsets[0]) * np.arange(1, n_chunks) / n_chunks
+        cuts = np.unique(np.concatenate([[0], np.searchsorted(offsets, targets), [n_img]])).astype(np.int64)
+        main = torch.cuda.current_stream()
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        s_in.wait_stream(main)
+        keep = []
+        for i0, i1 in zip(cuts[:-1], cuts[1:]):
+            r0, r1 = int(offsets[i0]), int(offsets[i1])
+            with torch.cuda.stream(s_in):
+                xd = mat[r0:r1].to(dev, non_blocking=True)
+                off = torch.from_numpy(offsets[i0:i1 + 1] - r0).to(dev, non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(s_in)
+            main.wait_event(ev_in)
+            xd.record_stream(main)
+            off.record_stream(main)
+            words = self.clusterer.transform_device(xd)
+            H = ops.bovw_histogram(words, off, int(self.n_clusters), **kw)
+            ev_c = torch.cuda.Event()
+            ev_c.record(main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_c)
+                H.record_stream(s_out)
+                out[int(i0):int(i1)].copy_(H, non_blocking=True)
+            keep.append((xd, off, H))
+        s_out.synchronize()
+        return out.numpy()
 
     def histograms_device(self, descriptions, *, okapi: OkapiTransformer | None = None,
                           out_dtype=torch.float64) -> torch.Tensor:

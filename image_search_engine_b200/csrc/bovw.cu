@@ -48,10 +48,13 @@ __device__ __forceinline__ double okapi_weight(double tf, double k1, double k2, 
 
 template <typename OutT, bool SMEM>
 __global__ void histogram_kernel(const int64_t* __restrict__ words, const int64_t* __restrict__ off, int64_t n_img,
-                                 int k, int mode, OutT* __restrict__ out, int okapi, double k1, double k2, double b) {
+                                 int k, int mode, OutT* __restrict__ out, int okapi, double k1, double k2, double b,
+                                 double avgdl_in) {
     extern __shared__ int s_cnt[];
     __shared__ long long s_mn, s_mx;
-    const double avgdl = (double)(off[n_img] - off[0]) / (double)n_img;  // np.mean(dl) over the batch
+    // np.mean(dl) over the batch being transformed (utils.py:196); a caller that feeds the batch in
+    // several launches passes the whole batch's mean explicitly
+    const double avgdl = avgdl_in >= 0.0 ? avgdl_in : (double)(off[n_img] - off[0]) / (double)n_img;
     for (int64_t img = blockIdx.x; img < n_img; img += gridDim.x) {
         const int64_t lo = off[img], hi = off[img + 1];
         const int64_t cnt = hi - lo;
@@ -147,7 +150,7 @@ __global__ void okapi_dense_kernel(T* __restrict__ h, int64_t n_img, int k, doub
 
 ISE_EXPORT int ise_bovw_histogram(ise_ctx* ctx, const int64_t* words, const int64_t* img_offsets, int64_t n_img,
                                   int k, int mode, int out_dtype, void* out, int okapi, double k1, double k2,
-                                  double b, void* stream) {
+                                  double b, double avgdl, void* stream) {
     ISE_CHECK_ARG(ctx && n_img >= 0 && k >= 1);
     ISE_CHECK_ARG(mode == ISE_HIST_NUMPY_COMPAT || mode == ISE_HIST_BINCOUNT);
     ISE_CHECK_ARG(out_dtype == ISE_OUT_F32 || out_dtype == ISE_OUT_F64);
@@ -162,14 +165,14 @@ ISE_EXPORT int ise_bovw_histogram(ise_ctx* ctx, const int64_t* words, const int6
     const size_t shm = smem ? (size_t)k * sizeof(int) : 0;
     if (out_dtype == ISE_OUT_F64) {
         if (smem) histogram_kernel<double, true><<<grid, kThreads, shm, st>>>(words, img_offsets, n_img, k, mode,
-                                                                              (double*)out, okapi, k1, k2, b);
+                                                                              (double*)out, okapi, k1, k2, b, avgdl);
         else histogram_kernel<double, false><<<grid, kThreads, 0, st>>>(words, img_offsets, n_img, k, mode,
-                                                                        (double*)out, okapi, k1, k2, b);
+                                                                        (double*)out, okapi, k1, k2, b, avgdl);
     } else {
         if (smem) histogram_kernel<float, true><<<grid, kThreads, shm, st>>>(words, img_offsets, n_img, k, mode,
-                                                                             (float*)out, okapi, k1, k2, b);
+                                                                             (float*)out, okapi, k1, k2, b, avgdl);
         else histogram_kernel<float, false><<<grid, kThreads, 0, st>>>(words, img_offsets, n_img, k, mode,
-                                                                       (float*)out, okapi, k1, k2, b);
+                                                                       (float*)out, okapi, k1, k2, b, avgdl);
     }
     ISE_LAUNCH_CHECK();
     return 0;

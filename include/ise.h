@@ -165,10 +165,11 @@ int ise_kmeans_apply_splits(ise_ctx* ctx, float* centroids, int64_t k, int d,
  * out[n_img, k] counts as f32/f64.  mode NUMPY_COMPAT reproduces np.histogram(idx, bins=k)
  * bit-exactly (float64 edge arithmetic); BINCOUNT is bincount(idx, minlength=k).
  * okapi != 0 fuses OkapiTransformer.transform: tf*k1/(tf*k1 + k2*(1-b+b*dl/avgdl)) with
- * dl = row sum, avgdl = mean dl over this batch (zeros stay zero). */
+ * dl = row sum, avgdl = mean dl over this batch when the argument is < 0, else the given value (a batch
+ * fed in several launches passes the whole batch's mean); zeros stay zero. */
 int ise_bovw_histogram(ise_ctx* ctx, const int64_t* words, const int64_t* img_offsets, int64_t n_img,
                        int k, int mode, int out_dtype, void* out,
-                       int okapi, double k1, double k2, double b, void* stream);
+                       int okapi, double k1, double k2, double b, double avgdl, void* stream);
 /* OkapiTransformer.transform on an existing dense [n_img,k] matrix, in place (f32 or f64).
  * avgdl < 0 => mean row sum of this batch (utils.py:196).  dl_workspace: device double[n_img + 1]. */
 int ise_okapi_tf(ise_ctx* ctx, void* h, int out_dtype, int64_t n_img, int k,

@@ -336,3 +336,25 @@ def test_full_size_properties_c2():
         gap = (de.reshape(-1) - dis[r].reshape(-1)).abs()
         assert bool((same | (gap <= 1e-4 * de.abs().reshape(-1))).all())
         assert bool((gap <= 1e-4 * de.abs().reshape(-1)).all())
+
+
+def test_pipelined_host_transform_equals_device_path(g):
+    """BOVW.transform(out=pinned) overlaps H2D / kernels / D2H over image chunks; same matrix as one shot,
+    including the batch-wide avgdl of the fused Okapi weighting."""
+    from image_search_engine_b200 import BOVW, OkapiTransformer
+    from image_search_engine_b200.bag_of_visual_words import pack_descriptions
+    rng = np.random.default_rng(3)
+    descs = [orb_like(rng, int(s), 32) for s in rng.integers(5, 200, 300)]
+    km = _codebook(g)
+    bovw = BOVW(None, n_clusters=int(g["k"]))
+    bovw.clusterer = km
+    packed = pack_descriptions(descs, pin=True)
+    ref = bovw.histograms_device(packed).cpu().numpy()
+    out = torch.empty(ref.shape, dtype=torch.float64, pin_memory=True)
+    got = bovw.transform(packed, out=out)
+    assert np.array_equal(got, ref)
+    ok = OkapiTransformer()
+    ref_tf = bovw.histograms_device(packed, okapi=ok).cpu().numpy()
+    got_tf = bovw.histograms_host(packed, out, okapi=ok, n_chunks=7)
+    assert np.array_equal(got_tf, ref_tf)
+    assert np.array_equal(ref_tf, np.asarray(ok.transform(ref).todense()))
