@@ -51,49 +51,74 @@ def peaks():
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons DURING the timed regions, read through NVML from a thread of
+    this process (pynvml).  Spawning `nvidia-smi -lms` instead was measured to slow host-side CUDA calls
+    enough to distort millisecond-scale steps (profiles/r01_findings.md); pause() stops sampling for the
+    host/PCIe-bound e2e legs."""
 
-    def __init__(self, gpu_index):
-        self.gpu = gpu_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+    def __init__(self, gpu_index, period_s=0.02):
+        import threading
+        self.mode = os.environ.get("ISE_BENCH_SAMPLER", "on")   # debugging aid: on | idle | off
+        self.period = period_s
+        self.rows = []
+        self.active = threading.Event()
+        self.quit = threading.Event()
+        self.h = None
+        self.err = None
+        try:
+            if self.mode == "off":
+                raise RuntimeError("sampler disabled by ISE_BENCH_SAMPLER=off")
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = gpu_index
+            if vis:
+                ent = vis.split(",")[gpu_index].strip()
+                phys = int(ent) if ent.isdigit() else None
+            self.h = (pynvml.nvmlDeviceGetHandleByIndex(phys) if phys is not None
+                      else pynvml.nvmlDeviceGetHandleByUUID(ent))
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+        except Exception as e:  # pragma: no cover - depends on the box
+            self.err = repr(e)
+
+    def _run(self):
+        nv = self.nv
+        while not self.quit.is_set():
+            if self.active.is_set():
+                try:
+                    sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                    pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    self.rows.append((float(sm), float(pw), int(rs)))
+                except Exception as e:  # pragma: no cover
+                    self.err = repr(e)
+            time.sleep(self.period)
 
     def start(self):
-        try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
-        except Exception:
-            self.p = None
+        if self.mode == "on":
+            self.active.set()
+
+    def pause(self):
+        self.active.clear()
 
     def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        rows = [r.split(",") for r in Path(self.f.name).read_text().strip().splitlines() if r.strip()]
-        os.unlink(self.f.name)
-        sm, mx, reasons, power = [], [], set(), []
-        for r in rows:
-            try:
-                r = [c.strip() for c in r]
-                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
-                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
-                                  ("sw_power_cap", 8)):
-                    if r[col].lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                continue
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        load = [s for s, pw in zip(sm, power) if pw >= 0.5 * max(power)] or sm
-        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": float(max(power))}
+        self.pause()
+        self.quit.set()
+        if self.h is None or not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: %s" % self.err]}
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        reasons = sorted(n for n, bit in names.items() if any(r[2] & bit for r in self.rows))
+        pmax = max(r[1] for r in self.rows)
+        load = [r[0] for r in self.rows if r[1] >= 0.5 * pmax] or [r[0] for r in self.rows]
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": self.sm_max, "reasons": reasons,
+                "samples": len(self.rows), "power_w_max": pmax, "source": "NVML, 20 ms period, device-timed regions"}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -262,6 +287,7 @@ def run_ours(args):
     value = world * C2["n_desc"] / (ms_step * 1e-3) / 1e6
 
     # ---------------- e2e: host (pinned) descriptors -> host histogram matrix ----------------
+    sampler.pause()   # clocks are sampled during the device-timed regions only (see ClockSampler.pause)
     out_pin = torch.empty((C2["n_img"], C2["k"]), dtype=torch.float64, pin_memory=True)
     bovw.descriptions = None
 
@@ -269,7 +295,7 @@ def run_ours(args):
         # pinned host descriptors -> (H2D | prepare + assign + histogram/Okapi | D2H, chunk-pipelined) -> host matrix
         return bovw.histograms_host(packed, out_pin, okapi=okapi)
 
-    for _ in range(max(1, args.warmup // 2)):
+    for _ in range(args.warmup):
         e2e_step_full()
     barrier()
     t0 = time.perf_counter()
@@ -325,6 +351,7 @@ def run_ours(args):
         for _ in range(2):
             knn_step(q)
         barrier()
+        sampler.start()
         kernel_events.clear()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
@@ -336,6 +363,7 @@ def run_ours(args):
         # sample pre-pass + coarse main launch + split re-run of unproven rows, all tcgen05 gemm_select launches
         knn_kern_ms = float(np.sum([a.elapsed_time(b) for a, b in kernel_events]) / ksteps)
         knn_stats = dict(ops.last_search_stats)
+        sampler.pause()
         # self-check (size independent): every query's best hit is the row it was derived from (rank 0's shard)
         hit = float((I[:, 0] == pick).float().mean().item())
         # e2e: pinned host queries in, host (D, I) out

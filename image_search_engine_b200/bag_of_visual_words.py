@@ -98,6 +98,11 @@ class BOVW(BaseEstimator):
         self.n_clusters = n_clusters
         self.hist_mode = hist_mode
 
+    def __getstate__(self):
+        state = super().__getstate__()
+        state.pop("_pipe_cache", None)      # CUDA streams / events / staging buffers are not persisted
+        return state
+
     def fit(self, X, y=None):
         self.descriptions = describe_dataset(self.describer, X)
         self.clusterer = run_clustering(self.descriptions, self.n_clusters)
@@ -141,29 +146,45 @@ class BOVW(BaseEstimator):
         # chunk boundaries in images, balanced by descriptor count
         targets = offsets[0] + (offsets[-1] - offsets[0]) * np.arange(1, n_chunks) / n_chunks
         cuts = np.unique(np.concatenate([[0], np.searchsorted(offsets, targets), [n_img]])).astype(np.int64)
-        main = torch.cuda.current_stream()
-        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        max_rows = int(max(offsets[i1] - offsets[i0] for i0, i1 in zip(cuts[:-1], cuts[1:])))
+        max_imgs = int(np.diff(cuts).max())
+        # Device staging buffers, streams and events are created once and reused: allocating per call
+        # through the caching allocator across three streams forces cudaMalloc/cudaFree churn that
+        # costs more than the copies themselves (profiles/r01_findings.md).
+        NB = 3
+        key = (max_rows, int(mat.shape[1]), mat.dtype, max_imgs, int(self.n_clusters), out.dtype, str(dev))
+        pc = self.__dict__.get("_pipe_cache")
+        if pc is None or pc["key"] != key:
+            pc = dict(key=key, s_in=torch.cuda.Stream(), s_out=torch.cuda.Stream(),
+                      xd=[torch.empty((max_rows, mat.shape[1]), dtype=mat.dtype, device=dev) for _ in range(NB)],
+                      H=[torch.empty((max_imgs, int(self.n_clusters)), dtype=out.dtype, device=dev) for _ in range(NB)],
+                      ev_in=[torch.cuda.Event() for _ in range(NB)], ev_c=[torch.cuda.Event() for _ in range(NB)],
+                      ev_out=[torch.cuda.Event() for _ in range(NB)])
+            self.__dict__["_pipe_cache"] = pc
+        main, s_in, s_out = torch.cuda.current_stream(), pc["s_in"], pc["s_out"]
+        off_dev = torch.from_numpy(offsets).to(dev)
         s_in.wait_stream(main)
-        keep = []
-        for i0, i1 in zip(cuts[:-1], cuts[1:]):
+        s_out.wait_stream(main)
+        for ci, (i0, i1) in enumerate(zip(cuts[:-1], cuts[1:])):
+            b = ci % NB
             r0, r1 = int(offsets[i0]), int(offsets[i1])
+            ni, nr = int(i1 - i0), r1 - r0
+            xd, H = pc["xd"][b][:nr], pc["H"][b][:ni]
             with torch.cuda.stream(s_in):
-                xd = mat[r0:r1].to(dev, non_blocking=True)
-                off = torch.from_numpy(offsets[i0:i1 + 1] - r0).to(dev, non_blocking=True)
-                ev_in = torch.cuda.Event()
-                ev_in.record(s_in)
-            main.wait_event(ev_in)
-            xd.record_stream(main)
-            off.record_stream(main)
+                if ci >= NB:
+                    s_in.wait_event(pc["ev_c"][b])        # kernels of chunk ci-NB are done with this buffer
+                xd.copy_(mat[r0:r1], non_blocking=True)
+                pc["ev_in"][b].record(s_in)
+            main.wait_event(pc["ev_in"][b])
+            if ci >= NB:
+                main.wait_event(pc["ev_out"][b])          # D2H of chunk ci-NB has drained this H buffer
             words = self.clusterer.transform_device(xd)
-            H = ops.bovw_histogram(words, off, int(self.n_clusters), **kw)
-            ev_c = torch.cuda.Event()
-            ev_c.record(main)
+            ops.bovw_histogram(words, off_dev[i0:i1 + 1] - r0, int(self.n_clusters), out=H, **kw)
+            pc["ev_c"][b].record(main)
             with torch.cuda.stream(s_out):
-                s_out.wait_event(ev_c)
-                H.record_stream(s_out)
+                s_out.wait_event(pc["ev_c"][b])
                 out[int(i0):int(i1)].copy_(H, non_blocking=True)
-            keep.append((xd, off, H))
+                pc["ev_out"][b].record(s_out)
         s_out.synchronize()
         return out.numpy()
 

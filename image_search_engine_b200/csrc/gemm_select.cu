@@ -29,9 +29,10 @@ constexpr int UMMA_K = 16;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
 constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;  // 32 KiB
 constexpr int EPI_WARP0 = 4;
-// top-1 (assign) epilogues are instruction bound at small d: two warps per TMEM lane quadrant, each
-// scanning half of the tile's columns; list epilogues (top-k) keep one warp per quadrant
-__host__ __device__ constexpr int epi_halves(int ksel) { return ksel == 1 ? 2 : 1; }
+// One epilogue warp per TMEM lane quadrant.  (Two warps per quadrant, each scanning half of a tile's
+// columns, was measured SLOWER for the d = 128 assign: 1.57-1.67 ms vs 1.43 ms at C2 -- the tile is bound
+// by the TMEM -> register read of the 128 x 256 accumulator, not by issue slots; the code path is kept.)
+__host__ __device__ constexpr int epi_halves(int ksel) { return 1; }
 __host__ __device__ constexpr int num_threads(int ksel) { return 128 + 128 * epi_halves(ksel); }
 constexpr int TMEM_COLS = 512;  // 2 accumulator stages x BLOCK_N fp32 columns
 constexpr int AUX_BYTES = 4096;
@@ -83,8 +84,9 @@ template <int KSEL> struct SelList { using type = TopKList<KSEL>; };
 template <> struct SelList<1> { using type = TopKList<1>; };
 template <> struct SelList<32> { using type = RegList32; };
 
-// KSEL: 1 = running top-1 in registers, otherwise capacity of the per-thread candidate set
-template <int PA, int PB, bool L2, int KSEL>
+// KSEL: 1 = running top-1 in registers, otherwise capacity of the per-thread candidate set.
+// VERIFY (top-1 only): also track the exact runner-up and flag rows whose winner is not provably unique.
+template <int PA, int PB, bool L2, int KSEL, bool VERIFY>
 __global__ void __launch_bounds__(num_threads(KSEL), 1)
 gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -212,7 +214,7 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         const float inv = p.a_meta[META_INV_SCALE] * p.b_meta[META_INV_SCALE];
         const float two_inv = 2.f * inv;
         CoarseBound bound;
-        if (KSEL == 1 && p.flag_count != nullptr) bound.init(p.a_meta, p.b_meta, p.d);
+        if (KSEL == 1 && VERIFY) bound.init(p.a_meta, p.b_meta, p.d);
         uint32_t tile = 0;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
             const int split = w / p.n_mtiles, mt = w - split * p.n_mtiles;
@@ -284,18 +286,20 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                         const float mx = fmaxf(fmaxf(t4[0], t4[1]), fmaxf(t4[2], t4[3]));
                         if (KSEL == 1) {
                             if (mx > best) {  // strict: an equal score in a later column never replaces
-                                m2 = fmaxf(m2, best);   // the old best (and everything in its chunk) is now "other"
+                                if (VERIFY) m2 = fmaxf(m2, best);   // the old best's whole chunk is now "other"
                                 best = mx;
                                 int jj = 31;
 #pragma unroll
                                 for (int j = 30; j >= 0; --j)
                                     if (v[j] == mx) jj = j;  // lowest column among equals
                                 best_id = col0 + c + jj;
-                                float s2 = -CUDART_INF_F;
+                                if (VERIFY) {
+                                    float s2 = -CUDART_INF_F;
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) s2 = fmaxf(s2, (j == jj) ? -CUDART_INF_F : v[j]);
-                                sib = s2;
-                            } else {
+                                    for (int j = 0; j < 32; ++j) s2 = fmaxf(s2, (j == jj) ? -CUDART_INF_F : v[j]);
+                                    sib = s2;
+                                }
+                            } else if (VERIFY) {
                                 m2 = fmaxf(m2, mx);
                             }
                         } else {
@@ -344,13 +348,13 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                     asm volatile("bar.sync 2, %0;" ::"n"(NUM_EPI_THREADS) : "memory");
                 }
                 if (half == 0 && row < p.m) {
-                    const float an = (L2 || p.flag_count != nullptr) ? __ldg(p.a_norms + row) : 0.f;
+                    const float an = (L2 || VERIFY) ? __ldg(p.a_norms + row) : 0.f;
                     float* ov = p.out_val + ((int64_t)split * p.m + row) * p.topk;
                     int64_t* oi = p.out_idx + ((int64_t)split * p.m + row) * p.topk;
                     if (best_id >= 0) {
                         ov[0] = L2 ? fmaxf(an - best, 0.f) : best * inv;
                         oi[0] = p.id_base + best_id;
-                        if (p.flag_count != nullptr) {
+                        if (VERIFY) {
                             // winner provably unique?  IP scores carry +-eps each, L2 scores (2<a,b> - |b|^2) +-2 eps
                             const float gap = L2 ? (best - runner) : (best - runner) * inv;
                             const float need = (L2 ? 4.f : 2.f) * bound.eps(an);
@@ -499,9 +503,9 @@ static Plan make_plan(const ise_ctx* ctx, int64_t m, int64_t n, bool single_spli
     return pl;
 }
 
-template <int PA, int PB, bool L2, int KSEL>
+template <int PA, int PB, bool L2, int KSEL, bool VERIFY = false>
 static int launch(const ise_ctx* ctx, const CUtensorMap* maps, const Params& p, cudaStream_t st) {
-    auto kern = gemm_select_kernel<PA, PB, L2, KSEL>;
+    auto kern = gemm_select_kernel<PA, PB, L2, KSEL, VERIFY>;
     const int smem = num_stages(PA, PB) * stage_bytes(PA, PB) + AUX_BYTES + 1024;
     ISE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int total = p.n_mtiles * p.n_splits;
@@ -513,7 +517,13 @@ static int launch(const ise_ctx* ctx, const CUtensorMap* maps, const Params& p, 
 
 template <int PA, int PB, bool L2>
 static int dispatch_k(const ise_ctx* ctx, const CUtensorMap* maps, const Params& p, cudaStream_t st) {
-    if (p.topk == 1) return launch<PA, PB, L2, 1>(ctx, maps, p, st);
+    if (p.topk == 1) {
+        if (p.flag_count != nullptr) {
+            if constexpr (PA == 1 && PB == 1) return launch<PA, PB, L2, 1, true>(ctx, maps, p, st);
+            ISE_FAIL("top-1 verification is a coarse-pass feature: call with a_lo = b_lo = NULL");
+        }
+        return launch<PA, PB, L2, 1>(ctx, maps, p, st);
+    }
     if (p.topk <= 32) return launch<PA, PB, L2, 32>(ctx, maps, p, st);
     return launch<PA, PB, L2, 128>(ctx, maps, p, st);
 }

@@ -378,7 +378,7 @@ def kmeans_apply_splits(centroids: torch.Tensor, pairs: torch.Tensor):
 # ------------------------------------------------------------------------------------------
 def bovw_histogram(words: torch.Tensor, img_offsets: torch.Tensor, k: int, *, mode: int = HIST_NUMPY_COMPAT,
                    out_dtype: torch.dtype = torch.float64, okapi: bool = False, k1: float = 1.0, k2: float = 1.0,
-                   b: float = 0.75, avgdl: float = -1.0) -> torch.Tensor:
+                   b: float = 0.75, avgdl: float = -1.0, out: torch.Tensor | None = None) -> torch.Tensor:
     if words.dtype != torch.int64 or img_offsets.dtype != torch.int64:
         raise IseError("bovw_histogram: words and img_offsets must be int64")
     words = words.reshape(-1).contiguous()
@@ -386,7 +386,10 @@ def bovw_histogram(words: torch.Tensor, img_offsets: torch.Tensor, k: int, *, mo
     od = OUT_F64 if out_dtype == torch.float64 else OUT_F32
     if out_dtype not in (torch.float32, torch.float64):
         raise IseError("bovw_histogram: float32 or float64 output")
-    out = torch.empty((n_img, k), dtype=out_dtype, device=words.device)
+    if out is None:
+        out = torch.empty((n_img, k), dtype=out_dtype, device=words.device)
+    elif tuple(out.shape) != (n_img, k) or out.dtype != out_dtype or not out.is_contiguous():
+        raise IseError("bovw_histogram: out must be a contiguous [n_img, k] tensor of out_dtype")
     _lib.check(_lib.load().ise_bovw_histogram(
         _lib.ctx(_dev(img_offsets)), _ptr(words), _ptr(img_offsets), n_img, int(k), int(mode), od, _ptr(out),
         1 if okapi else 0, float(k1), float(k2), float(b), float(avgdl), _stream()))
