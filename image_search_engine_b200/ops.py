@@ -235,6 +235,7 @@ def rescore_select(a_raw: torch.Tensor, b_raw: torch.Tensor, a_op: Operand, b_op
 # (~2.4k cycles, measured) rather than by its MMAs (d/64 * 512 cycles per product), so dropping the lo
 # product buys nothing and the split products are used directly (profiles/r01_findings.md).
 COARSE_TOP1_MIN_D = 512
+VERIFIED_MAX_K = 100   # coarse candidates: 32 per query for k <= 16, 128 for k <= 100
 
 # statistics of the last search_topk call on this process (bench.py / tests read them)
 last_search_stats = {"mode": None, "fallback_rows": 0, "rows": 0}
@@ -247,8 +248,8 @@ def search_topk(q_raw: torch.Tensor, a_op: Operand, db_raw: torch.Tensor, b_op: 
     precision="verified" (default): ONE tcgen05 product per tile (FP16 hi planes only).
       k == 1 (quantisation / k-means assign): the kernel tracks the exact runner-up of every row and flags
         the rows whose winner is not separated from it by more than the rigorous coarse error bound;
-      2 <= k <= 16: up to 32 candidates per query are kept, ise_rescore_select re-scores them exactly in
-        FP32 and proves from the same bound that the list contains the true top-k.
+      2 <= k <= 100: up to 32 (k <= 16) or 128 candidates per query are kept, ise_rescore_select re-scores
+        them exactly in FP32 and proves from the same bound that the list contains the true top-k.
       Flagged rows (rare) are re-run with the split products, so results equal the split path's at
       roughly a third (k > 1) or half (k == 1, exact rows) of the tensor-core work.
     precision="split": hi*hi + hi*lo + lo*hi products for every tile (FP32-grade scores throughout),
@@ -286,13 +287,15 @@ def search_topk(q_raw: torch.Tensor, a_op: Operand, db_raw: torch.Tensor, b_op: 
                 rescore_topk_(q_raw, db_raw, a_op, b_op, metric, D, I, id_base)
             last_search_stats.update(mode="verified", fallback_rows=nflag, rows=a_op.n)
             return D, I
-    if precision == "verified" and 2 <= k <= 16 and nb > kc and need_distances:
+    if precision == "verified" and 2 <= k <= VERIFIED_MAX_K and nb > kc and need_distances:
         seed = None
         if b_op.sample is not None:
-            # pre-pass over 1/64 of the columns: the 2nd-best sample score of each query is a score some
-            # real column reaches, so nothing below it can be in the top-k unless fewer than k beat it
-            sv, _ = gemm_select(a_hi, b_op.sample, metric, 2)
-            seed = sv[:, 1].contiguous()
+            # pre-pass over 1/64 of the columns: the r-th best sample score of each query is a score real
+            # columns reach, and about 64*r columns of the full set beat it (r grows with k so that at
+            # least ~2k do); nothing at or below it needs to be tracked by the main pass
+            r = max(2, -(-2 * k // SAMPLE_FRACTION) + 1)
+            sv, _ = gemm_select(a_hi, b_op.sample, metric, r)
+            seed = sv[:, r - 1].contiguous()
         cv, ci = gemm_select(a_hi, b_hi, metric, kc, id_base, row_seed=seed)
         D, I, rows, cnt = rescore_select(q_raw, db_raw, a_op, b_op, metric, cv, ci, k, id_base, row_seed=seed)
         nflag = rerun_rows(rows, cnt, D, I)
