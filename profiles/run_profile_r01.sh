@@ -8,9 +8,13 @@ CMD="python bench.py --steps 2 --warmup 3 --no-cpu"
 $CMD > gpurun_out/plain_a.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01_launches.csv $CMD > gpurun_out/ncu_a.log 2>&1
 echo "launch-list rc=$?"
-# 15 assign launches precede the kNN ones (fit 2 + warm 3 + timed 2 + e2e 1+2 + fit 5): capture the last
-# assign kernel and the first kNN kernel with the full section set
-$CMD > gpurun_out/plain_b.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:gemm_select -s 14 -c 2 -f -o gpurun_out/r01_gemm_select $CMD > gpurun_out/ncu_b.log 2>&1
-echo "full-capture rc=$?"
+# full section set for the two hot shapes, from minimal drivers (one plain run each, then ncu):
+#   profiles/ncu_assign.py : split top-1, 1M x 4096 x 128 (C2)
+#   profiles/ncu_knn.py    : coarse seeded top-32, 10k x 1M x 2048 (C3)
+python profiles/ncu_assign.py > gpurun_out/plain_b.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:gemm_select -s 2 -c 1 -f -o gpurun_out/r01_assign_final python profiles/ncu_assign.py > gpurun_out/ncu_b.log 2>&1
+echo "assign capture rc=$?"
+python profiles/ncu_knn.py > gpurun_out/plain_c.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:gemm_select -s 3 -c 1 -f -o gpurun_out/r01_knn_final python profiles/ncu_knn.py > gpurun_out/ncu_c.log 2>&1
+echo "knn capture rc=$?"
 ls -la gpurun_out
