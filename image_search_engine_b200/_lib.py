@@ -45,7 +45,12 @@ PROTOTYPES = {
                                 _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "ise_rescore_select": (_int, [_c_void_p, _c_void_p, _int, _i64, _c_void_p, _c_void_p, _c_void_p, _i64, _c_void_p,
                                   _c_void_p, _i64, _i64, _int, _int, _int, _int, _i64, _c_void_p, _c_void_p, _c_void_p,
-                                  _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+                                  _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "ise_gemm_collect": (_int, [_c_void_p,
+                                _c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p,
+                                _c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p,
+                                _i64, _i64, _int, _int, _i64, _c_void_p, _int,
+                                _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "ise_topk_merge": (_int, [_c_void_p, _c_void_p, _c_void_p, _int, _i64, _int, _int, _c_void_p, _c_void_p,
                               _c_void_p]),
     "ise_kmeans_accumulate": (_int, [_c_void_p, _c_void_p, _int, _i64, _int, _i64, _c_void_p, _c_void_p,

@@ -58,6 +58,7 @@ struct Params {
     const float* a_norms;
     const float* b_norms;
     const float* row_seed;  // optional [m]: a per-row score every kept candidate must beat (real units)
+    int32_t* row_count;     // collect mode (KSEL == 0): per-row append counters, out_* are [m, topk] buffers
     int32_t* flag_rows;     // optional (top-1 only): rows whose winner is not provably unique under the
     int32_t* flag_count;    //   coarse error bound are appended here for a full-precision re-run
     float* out_val;    // [n_splits, m, topk]
@@ -82,9 +83,12 @@ static_assert(sizeof(Aux) <= AUX_BYTES, "aux area too small");
 // thread-local list
 template <int KSEL> struct SelList { using type = TopKList<KSEL>; };
 template <> struct SelList<1> { using type = TopKList<1>; };
+template <> struct SelList<0> { using type = TopKList<1>; };   // collect mode keeps no list
 template <> struct SelList<32> { using type = RegList32; };
 
-// KSEL: 1 = running top-1 in registers, otherwise capacity of the per-thread candidate set.
+// KSEL: 1 = running top-1 in registers; 0 = COLLECT: append every column beating the row's seed to a
+// per-row global buffer (large k: nothing is ordered or evicted on the device, the exact re-score sorts);
+// otherwise capacity of the per-thread candidate set.
 // VERIFY (top-1 only): also track the exact runner-up and flag rows whose winner is not provably unique.
 template <int PA, int PB, bool L2, int KSEL, bool VERIFY>
 __global__ void __launch_bounds__(num_threads(KSEL), 1)
@@ -228,6 +232,13 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             float best = -CUDART_INF_F, sib = -CUDART_INF_F, m2 = -CUDART_INF_F;
             int best_id = -1;
             typename SelList<KSEL>::type list;
+            float collect_thr = CUDART_INF_F;   // collect mode: rows beyond m never append
+            if (KSEL == 0) {
+                if (row < p.m) {
+                    const float sr = __ldg(p.row_seed + row);
+                    collect_thr = L2 ? (__ldg(p.a_norms + row) - sr) : sr * (p.a_meta[META_SCALE] * p.b_meta[META_SCALE]);
+                }
+            }
             if (KSEL > 1) {
                 // seed = score of a column already known to exist (from a pre-pass over a column sample):
                 // candidates that cannot beat it are never inserted, which removes almost all list traffic
@@ -284,7 +295,28 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
 #pragma unroll
                         for (int j = 0; j < 4; ++j) t4[j] = fmaxf(t8[2 * j], t8[2 * j + 1]);
                         const float mx = fmaxf(fmaxf(t4[0], t4[1]), fmaxf(t4[2], t4[3]));
-                        if (KSEL == 1) {
+                        if (KSEL == 0) {
+                            float cur = mx;
+#pragma unroll 1
+                            while (cur > collect_thr) {
+                                int jj = 31;
+#pragma unroll
+                                for (int j = 30; j >= 0; --j) jj = (v[j] == cur) ? j : jj;
+                                const int pos = atomicAdd(p.row_count + row, 1);
+                                if (pos < p.topk) {
+                                    const float an_c = L2 ? __ldg(p.a_norms + row) : 0.f;
+                                    p.out_val[row * p.topk + pos] = L2 ? fmaxf(an_c - cur, 0.f) : cur * inv;
+                                    p.out_idx[row * p.topk + pos] = p.id_base + col0 + c + jj;
+                                }
+                                float nm = -CUDART_INF_F;
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    v[j] = (j == jj) ? -CUDART_INF_F : v[j];
+                                    nm = fmaxf(nm, v[j]);
+                                }
+                                cur = nm;
+                            }
+                        } else if (KSEL == 1) {
                             if (mx > best) {  // strict: an equal score in a later column never replaces
                                 if (VERIFY) m2 = fmaxf(m2, best);   // the old best's whole chunk is now "other"
                                 best = mx;
@@ -365,7 +397,7 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                         oi[0] = -1;
                     }
                 }
-            } else if (row < p.m) {
+            } else if (KSEL > 1 && row < p.m) {
                 const float an = L2 ? __ldg(p.a_norms + row) : 0.f;
                 float* ov = p.out_val + ((int64_t)split * p.m + row) * p.topk;
                 int64_t* oi = p.out_idx + ((int64_t)split * p.m + row) * p.topk;
@@ -562,6 +594,53 @@ ISE_EXPORT int ise_topk_merge(ise_ctx* ctx, const float* val_parts, const int64_
     return 0;
 }
 
+// shared argument validation + tensor maps
+static int setup_maps(ise_ctx* ctx, const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi,
+                      const void* b_lo, int64_t ldb, int64_t m, int64_t n, int d, CUtensorMap* maps) {
+    ISE_CHECK_ARG(lda >= d && ldb >= d && lda % 8 == 0 && ldb % 8 == 0);
+    ISE_CHECK_ARG((reinterpret_cast<uintptr_t>(a_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(b_hi) & 15) == 0);
+    if (gs::make_plane_map(ctx, &maps[0], a_hi, m, d, lda, gs::BLOCK_M)) return 1;
+    if (gs::make_plane_map(ctx, &maps[1], a_lo ? a_lo : a_hi, m, d, lda, gs::BLOCK_M)) return 1;
+    if (gs::make_plane_map(ctx, &maps[2], b_hi, n, d, ldb, gs::BLOCK_N)) return 1;
+    if (gs::make_plane_map(ctx, &maps[3], b_lo ? b_lo : b_hi, n, d, ldb, gs::BLOCK_N)) return 1;
+    return 0;
+}
+
+ISE_EXPORT int ise_gemm_collect(ise_ctx* ctx, const void* a_hi, const void* a_lo, int64_t lda, const float* a_meta,
+                                const float* a_norms, const void* b_hi, const void* b_lo, int64_t ldb,
+                                const float* b_meta, const float* b_norms, int64_t m, int64_t n, int d, int metric,
+                                int64_t id_base, const float* row_seed, int cap, float* cand_val, int64_t* cand_idx,
+                                int32_t* row_count, void* stream) {
+    ISE_CHECK_ARG(ctx != nullptr);
+    ISE_CHECK_ARG(metric == ISE_METRIC_IP || metric == ISE_METRIC_L2);
+    ISE_CHECK_ARG(m >= 0 && n > 0 && d > 0 && cap >= 1 && n < (int64_t)1 << 31 && m < (int64_t)1 << 31);
+    if (m == 0) return 0;
+    ISE_CHECK_ARG(a_hi && b_hi && a_meta && b_meta && row_seed && cand_val && cand_idx && row_count);
+    if (metric == ISE_METRIC_L2) ISE_CHECK_ARG(a_norms && b_norms);
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    gs::Plan pl = gs::make_plan(ctx, m, n);
+    gs::Params p;
+    p.m = m; p.n = n; p.d = d;
+    p.n_mtiles = pl.n_mtiles; p.n_ntiles = pl.n_ntiles;
+    p.tiles_per_split = pl.tiles_per_split; p.n_splits = pl.n_splits;
+    p.topk = cap; p.id_base = id_base;
+    p.a_meta = a_meta; p.b_meta = b_meta; p.a_norms = a_norms; p.b_norms = b_norms;
+    p.row_seed = row_seed; p.row_count = row_count; p.flag_rows = nullptr; p.flag_count = nullptr;
+    p.out_val = cand_val; p.out_idx = cand_idx;
+    // empty slots read as id -1 / count 0
+    ISE_CUDA(cudaMemsetAsync(cand_idx, 0xFF, (size_t)m * cap * sizeof(int64_t), st));
+    ISE_CUDA(cudaMemsetAsync(row_count, 0, (size_t)m * sizeof(int32_t), st));
+    CUtensorMap maps[4];
+    if (setup_maps(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, m, n, d, maps)) return 1;
+    const int pa = a_lo ? 2 : 1, pb = b_lo ? 2 : 1;
+    const bool l2 = metric == ISE_METRIC_L2;
+    if (pa == 1 && pb == 1) return l2 ? gs::launch<1, 1, true, 0>(ctx, maps, p, st) : gs::launch<1, 1, false, 0>(ctx, maps, p, st);
+    if (pa == 1 && pb == 2) return l2 ? gs::launch<1, 2, true, 0>(ctx, maps, p, st) : gs::launch<1, 2, false, 0>(ctx, maps, p, st);
+    if (pa == 2 && pb == 2) return l2 ? gs::launch<2, 2, true, 0>(ctx, maps, p, st) : gs::launch<2, 2, false, 0>(ctx, maps, p, st);
+    ISE_FAIL("a_lo without b_lo is not supported: pass a zero b_lo plane");
+}
+
 ISE_EXPORT int ise_gemm_select(ise_ctx* ctx, const void* a_hi, const void* a_lo, int64_t lda, const float* a_meta,
                                const float* a_norms, const void* b_hi, const void* b_lo, int64_t ldb,
                                const float* b_meta, const float* b_norms, int64_t m, int64_t n, int d, int metric,
@@ -590,6 +669,7 @@ ISE_EXPORT int ise_gemm_select(ise_ctx* ctx, const void* a_hi, const void* a_lo,
     p.topk = topk; p.id_base = id_base;
     p.a_meta = a_meta; p.b_meta = b_meta; p.a_norms = a_norms; p.b_norms = b_norms;
     p.row_seed = row_seed;
+    p.row_count = nullptr;
     p.flag_rows = flag_rows;
     p.flag_count = flag_count;
     if (flag_count) {

@@ -12,7 +12,7 @@ namespace {
 
 constexpr int kThreads = 128;
 constexpr int kWarps = kThreads / 32;
-constexpr int kMaxK = 128;
+constexpr int kMaxK = 1024;   // candidates per row (collect mode hands in up to 1024 unsorted ones)
 
 // kc candidates in (ids + coarse scores), topk exact results out.  With `flag_count` non-null the row is
 // verified against the coarse pass's error bound and appended to `flag_rows` when the candidate list
@@ -29,7 +29,7 @@ __global__ void rescore_kernel(const TA* __restrict__ a, int64_t lda, const floa
                                const float* __restrict__ cand_val, const int64_t* __restrict__ cand_idx,
                                float* __restrict__ val, int64_t* __restrict__ idx,
                                const float* __restrict__ a_meta, const float* __restrict__ b_meta,
-                               const float* __restrict__ row_seed,
+                               const float* __restrict__ row_seed, const int32_t* __restrict__ row_count,
                                int32_t* __restrict__ flag_rows, int32_t* __restrict__ flag_count) {
     extern __shared__ float s_a[];          // the row of A as float32
     __shared__ float s_v[kMaxK];
@@ -76,13 +76,13 @@ __global__ void rescore_kernel(const TA* __restrict__ a, int64_t lda, const floa
         }
         __syncthreads();
         // rank by counting: (score, id) is a strict total order over the real candidates
-        if (threadIdx.x < kc) {
-            const float v = s_v[threadIdx.x];
-            const long long id = s_i[threadIdx.x];
+        for (int me = threadIdx.x; me < kc; me += kThreads) {
+            const float v = s_v[me];
+            const long long id = s_i[me];
             int rank = 0;
             for (int t = 0; t < kc; ++t) {
-                if (t == (int)threadIdx.x) continue;
-                const bool t_first = (id < 0 && s_i[t] < 0) ? (t < (int)threadIdx.x)
+                if (t == me) continue;
+                const bool t_first = (id < 0 && s_i[t] < 0) ? (t < me)
                                                             : cand_better<!L2>(s_v[t], s_i[t], v, id);
                 rank += t_first ? 1 : 0;
             }
@@ -96,7 +96,10 @@ __global__ void rescore_kernel(const TA* __restrict__ a, int64_t lda, const floa
         if (flag_count && threadIdx.x == 0) {
             // T bounds the coarse score of every column that is NOT in the list: the worst kept
             // candidate when the list is full, and/or the seed every kept candidate had to beat
-            const bool full = cand_idx[row * kc + kc - 1] >= 0;
+            // collect mode (row_count given): the buffer holds EVERY column beating the seed unless it
+            // overflowed; list mode: the list is sorted by coarse score and full when its last slot is used
+            const bool overflow = row_count != nullptr && row_count[row] > kc;
+            const bool full = row_count == nullptr && cand_idx[row * kc + kc - 1] >= 0;
             float T = worst;
             bool bounded = false;
             if (full) { T = cand_val[row * kc + kc - 1]; bounded = true; }
@@ -107,7 +110,7 @@ __global__ void rescore_kernel(const TA* __restrict__ a, int64_t lda, const floa
             }
             if (bounded) {                          // otherwise every column is a candidate
                 const float eps = bound.eps(an);
-                const bool proven = L2 ? (s_kth < T - 2.f * eps) : (s_kth > T + eps);
+                const bool proven = !overflow && (L2 ? (s_kth < T - 2.f * eps) : (s_kth > T + eps));
                 if (!proven) flag_rows[atomicAdd(flag_count, 1)] = (int32_t)row;
             }
         }
@@ -162,7 +165,7 @@ static int launch_rescore(ise_ctx* ctx, const void* a, int a_dtype, int64_t lda,
                           int64_t m, int64_t n, int d, int metric, int kc, int topk, int64_t id_base,
                           const float* a_norms, const float* b_norms, const float* cand_val, const int64_t* cand_idx,
                           float* val, int64_t* idx, const float* a_meta, const float* b_meta, const float* row_seed,
-                          int32_t* flag_rows, int32_t* flag_count, void* stream) {
+                          const int32_t* row_count, int32_t* flag_rows, int32_t* flag_count, void* stream) {
     ISE_CHECK_ARG(ctx != nullptr);
     ISE_CHECK_ARG(metric == ISE_METRIC_IP || metric == ISE_METRIC_L2);
     ISE_CHECK_ARG(a_dtype == ISE_DTYPE_F32 || a_dtype == ISE_DTYPE_U8);
@@ -172,6 +175,7 @@ static int launch_rescore(ise_ctx* ctx, const void* a, int a_dtype, int64_t lda,
     ISE_CHECK_ARG(a && b && val && idx && cand_idx);
     if (metric == ISE_METRIC_L2) ISE_CHECK_ARG(a_norms && b_norms);
     if (flag_count) ISE_CHECK_ARG(flag_rows && cand_val && a_meta && b_meta && a_norms);
+    if (row_count) ISE_CHECK_ARG(row_seed != nullptr);
     ISE_CHECK_ARG((reinterpret_cast<uintptr_t>(b) & 15) == 0);
     DeviceGuard guard(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
@@ -192,7 +196,7 @@ static int launch_rescore(ise_ctx* ctx, const void* a, int a_dtype, int64_t lda,
     const int grid = (int)std::min<int64_t>(m, (int64_t)ctx->sm_count * 16);
     const size_t shm = (size_t)((d + 3) / 4 * 4) * sizeof(float);
 #define ISE_RESCORE_ARGS lda, b, ldb, m, n, d, kc, topk, id_base, a_norms, b_norms, cand_val, cand_idx, val, idx, \
-                         a_meta, b_meta, row_seed, flag_rows, flag_count
+                         a_meta, b_meta, row_seed, row_count, flag_rows, flag_count
     if (a_dtype == ISE_DTYPE_F32) {
         if (l2) rescore_kernel<float, true><<<grid, kThreads, shm, st>>>((const float*)a, ISE_RESCORE_ARGS);
         else rescore_kernel<float, false><<<grid, kThreads, shm, st>>>((const float*)a, ISE_RESCORE_ARGS);
@@ -210,16 +214,17 @@ ISE_EXPORT int ise_rescore_topk(ise_ctx* ctx, const void* a, int a_dtype, int64_
                                 const float* a_norms, const float* b_norms, float* val, int64_t* idx,
                                 void* stream) {
     return launch_rescore(ctx, a, a_dtype, lda, b, ldb, m, n, d, metric, topk, topk, id_base, a_norms, b_norms,
-                          nullptr, idx, val, idx, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
+                          nullptr, idx, val, idx, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
 }
 
 ISE_EXPORT int ise_rescore_select(ise_ctx* ctx, const void* a, int a_dtype, int64_t lda, const float* a_meta,
                                   const float* a_norms, const float* b, int64_t ldb, const float* b_meta,
                                   const float* b_norms, int64_t m, int64_t n, int d, int metric, int kc, int topk,
-                                  int64_t id_base, const float* row_seed, const float* cand_val,
-                                  const int64_t* cand_idx, float* out_val, int64_t* out_idx, int32_t* flag_rows,
-                                  int32_t* flag_count, void* stream) {
+                                  int64_t id_base, const float* row_seed, const int32_t* row_count,
+                                  const float* cand_val, const int64_t* cand_idx, float* out_val, int64_t* out_idx,
+                                  int32_t* flag_rows, int32_t* flag_count, void* stream) {
     ISE_CHECK_ARG(flag_rows && flag_count);
     return launch_rescore(ctx, a, a_dtype, lda, b, ldb, m, n, d, metric, kc, topk, id_base, a_norms, b_norms, cand_val,
-                          cand_idx, out_val, out_idx, a_meta, b_meta, row_seed, flag_rows, flag_count, stream);
+                          cand_idx, out_val, out_idx, a_meta, b_meta, row_seed, row_count, flag_rows, flag_count,
+                          stream);
 }

@@ -88,7 +88,8 @@ class Operand:
     n: int
     d: int
     ldp: int
-    sample: "Operand | None" = None   # strided row sample (hi plane only) used to seed selection thresholds
+    sample: "Operand | None" = None        # strided 1/64 row sample (hi plane only): seeds for k <= 16
+    sample_dense: "Operand | None" = None  # strided 1/16 row sample: seeds for the collect mode (k > 16)
 
 
 def prepare_operand(x: torch.Tensor, *, keep_lo: bool | None = None) -> Operand:
@@ -128,16 +129,21 @@ def prepare_operand(x: torch.Tensor, *, keep_lo: bool | None = None) -> Operand:
 SAMPLE_FRACTION = 64       # one row in 64 ...
 SAMPLE_MIN_ROWS = 1024     # ... but never fewer than this, and only for operands at least 64x larger
 SAMPLE_MAX_ROWS = 16384
+DENSE_SAMPLE_FRACTION = 16   # collect mode (k > 16) needs a tighter handle on how many columns beat the seed
+DENSE_SAMPLE_MIN_ROWS = 4096
 
 
 def attach_sample(op: Operand) -> Operand:
     """Adds a strided sample of the rows to a (database) operand.  search_topk runs a cheap pre-pass
     over it; each query's 2nd-best sample score seeds the selection threshold of the full pass."""
-    if op.n >= SAMPLE_FRACTION * SAMPLE_MIN_ROWS and op.sample is None:
-        ns = min(max(op.n // SAMPLE_FRACTION, SAMPLE_MIN_ROWS), SAMPLE_MAX_ROWS)
+    def strided(ns):
         rows = torch.arange(ns, device=op.hi.device, dtype=torch.int64) * (op.n // ns)
-        op.sample = Operand(op.hi.index_select(0, rows), None, op.norms.index_select(0, rows), op.meta, ns, op.d,
-                            op.ldp)
+        return Operand(op.hi.index_select(0, rows), None, op.norms.index_select(0, rows), op.meta, ns, op.d, op.ldp)
+
+    if op.n >= SAMPLE_FRACTION * SAMPLE_MIN_ROWS and op.sample is None:
+        op.sample = strided(min(max(op.n // SAMPLE_FRACTION, SAMPLE_MIN_ROWS), SAMPLE_MAX_ROWS))
+    if op.n >= DENSE_SAMPLE_FRACTION * DENSE_SAMPLE_MIN_ROWS and op.sample_dense is None:
+        op.sample_dense = strided(op.n // DENSE_SAMPLE_FRACTION)
     return op
 
 
@@ -208,9 +214,27 @@ def rescore_topk_(a_raw: torch.Tensor, b_raw: torch.Tensor, a_op: Operand, b_op:
     return val, idx
 
 
+def gemm_collect(a: Operand, b: Operand, metric: int, row_seed: torch.Tensor, cap: int, id_base: int = 0):
+    """Collect mode: every column of b whose score beats row_seed[row] is appended (unsorted) to the row's
+    buffer.  Returns (cand_val [m, cap], cand_idx [m, cap] (-1 = empty), row_count int32 [m])."""
+    dev = a.hi.device
+    cv = torch.empty((a.n, cap), dtype=torch.float32, device=dev)
+    ci = torch.empty((a.n, cap), dtype=torch.int64, device=dev)
+    cnt = torch.empty((max(a.n, 1),), dtype=torch.int32, device=dev)
+    a_lo, b_lo = a.lo, b.lo
+    if a_lo is not None and b_lo is None:
+        b_lo = torch.zeros_like(b.hi)
+    _lib.check(_lib.load().ise_gemm_collect(
+        _lib.ctx(_dev(a.hi)), _ptr(a.hi), _ptr(a_lo), a.ldp, _ptr(a.meta), _ptr(a.norms),
+        _ptr(b.hi), _ptr(b_lo), b.ldp, _ptr(b.meta), _ptr(b.norms), a.n, b.n, a.d, int(metric), int(id_base),
+        _ptr(row_seed), int(cap), _ptr(cv), _ptr(ci), _ptr(cnt), _stream()))
+    _count()
+    return cv, ci, cnt
+
+
 def rescore_select(a_raw: torch.Tensor, b_raw: torch.Tensor, a_op: Operand, b_op: Operand, metric: int,
                    cand_val: torch.Tensor, cand_idx: torch.Tensor, topk: int, id_base: int = 0,
-                   row_seed: torch.Tensor | None = None):
+                   row_seed: torch.Tensor | None = None, row_count: torch.Tensor | None = None):
     """Exact FP32 re-score of kc coarse candidates -> exact top-k + the rows whose candidate list could
     not be proven complete.  Returns (val [m,k], idx [m,k], flag_rows int32 [m], flag_count int32 [1])."""
     m, kc = cand_idx.shape
@@ -225,7 +249,7 @@ def rescore_select(a_raw: torch.Tensor, b_raw: torch.Tensor, a_op: Operand, b_op
         _lib.ctx(_dev(cand_idx)), _ptr(a_raw), DTYPE_F32 if a_raw.dtype == torch.float32 else DTYPE_U8,
         a_raw.stride(0), _ptr(a_op.meta), _ptr(a_op.norms), _ptr(b_raw), b_raw.stride(0), _ptr(b_op.meta),
         _ptr(b_op.norms), m, b_raw.shape[0], a_raw.shape[1], int(metric), kc, int(topk), int(id_base),
-        _ptr(row_seed), _ptr(cand_val.contiguous()), _ptr(cand_idx.contiguous()), _ptr(val), _ptr(idx), _ptr(flag_rows),
+        _ptr(row_seed), _ptr(row_count), _ptr(cand_val.contiguous()), _ptr(cand_idx.contiguous()), _ptr(val), _ptr(idx), _ptr(flag_rows),
         _ptr(flag_count), _stream()))
     _count()
     return val, idx, flag_rows, flag_count
@@ -287,6 +311,20 @@ def search_topk(q_raw: torch.Tensor, a_op: Operand, db_raw: torch.Tensor, b_op: 
                 rescore_topk_(q_raw, db_raw, a_op, b_op, metric, D, I, id_base)
             last_search_stats.update(mode="verified", fallback_rows=nflag, rows=a_op.n)
             return D, I
+    if (precision == "verified" and 16 < k <= VERIFIED_MAX_K and need_distances and b_op.sample_dense is not None
+            and nb >= 64 * k):
+        # large k: seed = r-th best of a 1/16 column sample (about 16 r +- 16 sqrt(r) columns beat it, with
+        # r chosen for ~3.75 k), COLLECT every column beating the seed, then sort / prove on the exact scores
+        r = min(32, -(-15 * k // (4 * DENSE_SAMPLE_FRACTION)))
+        cap = 256 if k <= 32 else 1024
+        sv, _ = gemm_select(a_hi, b_op.sample_dense, metric, r)
+        seed = sv[:, r - 1].contiguous()
+        cv, ci, rc = gemm_collect(a_hi, b_hi, metric, seed, cap, id_base)
+        D, I, rows, cnt = rescore_select(q_raw, db_raw, a_op, b_op, metric, cv, ci, k, id_base, row_seed=seed,
+                                         row_count=rc)
+        nflag = rerun_rows(rows, cnt, D, I)
+        last_search_stats.update(mode="verified-collect", fallback_rows=nflag, rows=a_op.n)
+        return D, I
     if precision == "verified" and 2 <= k <= VERIFIED_MAX_K and nb > kc and need_distances:
         seed = None
         if b_op.sample is not None:

@@ -109,6 +109,17 @@ int ise_gemm_select(ise_ctx* ctx,
                     float* out_val, int64_t* out_idx,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* COLLECT variant of the fused contraction for large k: instead of keeping a bounded list per row, every
+ * column whose (coarse) score beats row_seed[row] is appended to the row's buffer cand_*[row, 0..cap)
+ * (unsorted; row_count[row] = number of qualifying columns, which may exceed cap = overflow; unused slots
+ * hold id -1).  ise_rescore_select(row_count=...) then sorts and proves the top-k.  Same operand rules as
+ * ise_gemm_select. */
+int ise_gemm_collect(ise_ctx* ctx,
+                     const void* a_hi, const void* a_lo, int64_t lda, const float* a_meta, const float* a_norms,
+                     const void* b_hi, const void* b_lo, int64_t ldb, const float* b_meta, const float* b_norms,
+                     int64_t m, int64_t n, int d, int metric, int64_t id_base, const float* row_seed, int cap,
+                     float* cand_val, int64_t* cand_idx, int32_t* row_count, void* stream);
+
 /* Exact FP32 CUDA-core path for small query counts: Faiss computes n < 20 queries without the
  * BLAS expansion (distances.cpp exhaustive_*_seq: direct dot / sum (x-y)^2), which is what the
  * reference's single-image query hits (engine.py:55 with nq = 1).  Also used as the on-device
@@ -134,11 +145,13 @@ int ise_rescore_topk(ise_ctx* ctx, const void* a, int a_dtype, int64_t lda, cons
  * |coarse - exact| <= kappa |a| max|b| (kappa from the FP16 rounding of the planes + accumulator
  * truncation, see rescore.cu).  Rows that cannot be proven are appended to flag_rows[0 .. *flag_count)
  * (device int32) and must be re-run by the caller with the full-precision split products.
- * row_seed (nullable): the seed the coarse call was given; it then also bounds the unseen columns. */
+ * row_seed (nullable): the seed the coarse call was given; it then also bounds the unseen columns.
+ * row_count (nullable): candidates come from ise_gemm_collect (unsorted, kc = cap <= 1024). */
 int ise_rescore_select(ise_ctx* ctx, const void* a, int a_dtype, int64_t lda, const float* a_meta,
                        const float* a_norms, const float* b, int64_t ldb, const float* b_meta,
                        const float* b_norms, int64_t m, int64_t n, int d, int metric, int kc, int topk,
-                       int64_t id_base, const float* row_seed, const float* cand_val, const int64_t* cand_idx,
+                       int64_t id_base, const float* row_seed, const int32_t* row_count,
+                       const float* cand_val, const int64_t* cand_idx,
                        float* out_val, int64_t* out_idx, int32_t* flag_rows, int32_t* flag_count, void* stream);
 
 /* Merge g sorted top-k lists per row ([g, m, topk] each) into one; canonical (score, id) order.

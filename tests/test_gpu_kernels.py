@@ -252,7 +252,8 @@ def test_kmeans_update_and_split(dev):
 
 @pytest.mark.parametrize("metric_ip", [True, False])
 @pytest.mark.parametrize("nq,nb,d,k", [(300, 20000, 128, 10), (64, 5000, 2048, 10), (500, 70000, 96, 5),
-                                        (80000, 1024, 512, 1), (200, 30000, 64, 100), (150, 70000, 128, 40)])
+                                        (80000, 1024, 512, 1), (200, 30000, 64, 100), (150, 70000, 128, 40),
+                                        (300, 200000, 64, 100)])
 def test_verified_coarse_search_equals_split(dev, metric_ip, nq, nb, d, k):
     """Default index search = 1-product coarse pass + exact re-score + proof; must agree with the
     3-product split path and with the oracle."""
@@ -264,7 +265,7 @@ def test_verified_coarse_search_equals_split(dev, metric_ip, nq, nb, d, k):
     idx = faiss_compat.IndexFlatIP(d) if metric_ip else faiss_compat.IndexFlatL2(d)
     idx.add(db)
     D, I = idx.search(q, k)
-    assert ops.last_search_stats["mode"] == "verified", ops.last_search_stats
+    assert ops.last_search_stats["mode"].startswith("verified"), ops.last_search_stats
     n_fallback = ops.last_search_stats["fallback_rows"]
     idx.precision = "split"
     D2, I2 = idx.search(q, k)
