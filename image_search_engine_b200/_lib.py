@@ -12,7 +12,7 @@ import threading
 from pathlib import Path
 
 _PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = _PKG_DIR / "libise.so"
+LIB_PATH = Path(os.environ.get("ISE_LIB_PATH", _PKG_DIR / "libise.so"))   # override: kernel A/B testing only
 
 _c_void_p = C.c_void_p
 _i64 = C.c_int64
@@ -54,7 +54,7 @@ PROTOTYPES = {
     "ise_topk_merge": (_int, [_c_void_p, _c_void_p, _c_void_p, _int, _i64, _int, _int, _c_void_p, _c_void_p,
                               _c_void_p]),
     "ise_kmeans_accumulate": (_int, [_c_void_p, _c_void_p, _int, _i64, _int, _i64, _c_void_p, _c_void_p,
-                                     _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+                                     _c_void_p, _int, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "ise_kmeans_mean": (_int, [_c_void_p, _c_void_p, _c_void_p, _i64, _int, _c_void_p, _c_void_p, _c_void_p]),
     "ise_kmeans_apply_splits": (_int, [_c_void_p, _c_void_p, _i64, _int, _c_void_p, C.c_int32, _c_void_p]),
     "ise_bovw_histogram": (_int, [_c_void_p, _c_void_p, _c_void_p, _i64, _int, _int, _int, _c_void_p, _int,

@@ -20,6 +20,15 @@
 #include "sm100_ptx.cuh"
 #include "topk_list.cuh"
 
+// epilogue variants (A/B-tested on the B200, see profiles/r01_findings.md)
+#ifndef ISE_EPI_PREFETCH
+#define ISE_EPI_PREFETCH 0   // 1 = issue the next chunk's tcgen05.ld before scanning the current one
+                             // (measured SLOWER: C2 assign 1.53 vs 1.41 ms split, 1.32 vs 1.01 ms coarse)
+#endif
+#ifndef ISE_EPI_TREE
+#define ISE_EPI_TREE 1       // balanced max tree instead of a 31-deep FMNMX chain
+#endif
+
 namespace gs {
 
 constexpr int BLOCK_M = 128;
@@ -265,13 +274,17 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N;
                 const int c_begin = half * COLS_PER_HALF;
                 const int c_end = min(c_begin + COLS_PER_HALF, ncols);
-                // software-pipelined TMEM reads in a ROLLED loop (one copy of the scan / insertion code):
-                // the load of chunk i+1 is issued as soon as chunk i has been moved out of `r`
+                // ROLLED loop over 32-column chunks: one copy of the scan / insertion code (I-cache)
                 uint32_t r[32];
+#if ISE_EPI_PREFETCH
                 if (c_begin < c_end) ptx::tmem_ld_32x32b_x32(taddr + c_begin, r);
+#endif
 #pragma unroll 1
                 for (int c = c_begin; c < c_end; c += 32) {
                     {
+#if !ISE_EPI_PREFETCH
+                        ptx::tmem_ld_32x32b_x32(taddr + c, r);
+#endif
                         ptx::tmem_ld_wait();
                         float v[32];
 #pragma unroll
@@ -280,13 +293,16 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                             // maximise 2<a,b> - |b|^2  ==  minimise |a|^2 + |b|^2 - 2<a,b>
                             if (L2) v[j] = fmaf(v[j], two_inv, -aux->bnorm[as][c + j]);
                         }
+#if ISE_EPI_PREFETCH
                         if (c + 32 < c_end) ptx::tmem_ld_32x32b_x32(taddr + c + 32, r);
+#endif
                         if (c + 32 > ncols) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
                                 if (c + j >= ncols) v[j] = -CUDART_INF_F;
                         }
                         // balanced max tree (depth 5) instead of a 31-deep dependent chain
+#if ISE_EPI_TREE
                         float t16[16], t8[8], t4[4];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) t16[j] = fmaxf(v[2 * j], v[2 * j + 1]);
@@ -295,6 +311,11 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
 #pragma unroll
                         for (int j = 0; j < 4; ++j) t4[j] = fmaxf(t8[2 * j], t8[2 * j + 1]);
                         const float mx = fmaxf(fmaxf(t4[0], t4[1]), fmaxf(t4[2], t4[3]));
+#else
+                        float mx = v[0];
+#pragma unroll
+                        for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
+#endif
                         if (KSEL == 0) {
                             float cur = mx;
 #pragma unroll 1

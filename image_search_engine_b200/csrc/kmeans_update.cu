@@ -17,9 +17,13 @@ __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
                  : "memory");
 }
 
+// cent != nullptr: the objective term of each row is recomputed here in exact FP32 from the row that is
+// already in registers and its centroid (L2-resident): <x, c> (spherical / IP) or sum (x - c)^2 (L2),
+// instead of trusting a distance that came out of the tensor-core accumulator.
 template <typename T>
 __global__ void accumulate_kernel(const T* __restrict__ x, int64_t n, int d, int64_t ldx,
                                   const int64_t* __restrict__ assign, const float* __restrict__ dis,
+                                  const float* __restrict__ cent, int metric,
                                   float* __restrict__ sums, float* __restrict__ counts, double* __restrict__ obj) {
     __shared__ double s_obj[kWarps];
     const int lane = threadIdx.x & 31;
@@ -34,15 +38,41 @@ __global__ void accumulate_kernel(const T* __restrict__ x, int64_t n, int d, int
         if (a < 0) continue;
         float* dst = sums + a * (int64_t)d;
         const T* row = x + r * ldx;
+        const float* crow = cent ? cent + a * (int64_t)d : nullptr;
+        float acc = 0.f;
         if (vec4) {
             const float4* row4 = reinterpret_cast<const float4*>(row);
-            for (int c = lane; c < d / 4; c += 32) red_add_v4(dst + 4 * c, __ldg(row4 + c));
+            for (int c = lane; c < d / 4; c += 32) {
+                const float4 v = __ldg(row4 + c);
+                red_add_v4(dst + 4 * c, v);
+                if (crow) {
+                    const float4 y = __ldg(reinterpret_cast<const float4*>(crow) + c);
+                    if (metric == ISE_METRIC_IP) {
+                        acc = fmaf(v.x, y.x, acc); acc = fmaf(v.y, y.y, acc);
+                        acc = fmaf(v.z, y.z, acc); acc = fmaf(v.w, y.w, acc);
+                    } else {
+                        const float e0 = v.x - y.x, e1 = v.y - y.y, e2 = v.z - y.z, e3 = v.w - y.w;
+                        acc = fmaf(e0, e0, acc); acc = fmaf(e1, e1, acc);
+                        acc = fmaf(e2, e2, acc); acc = fmaf(e3, e3, acc);
+                    }
+                }
+            }
         } else {
-            for (int c = lane; c < d; c += 32) atomicAdd(dst + c, (float)row[c]);
+            for (int c = lane; c < d; c += 32) {
+                const float v = (float)row[c];
+                atomicAdd(dst + c, v);
+                if (crow) {
+                    const float y = __ldg(crow + c);
+                    if (metric == ISE_METRIC_IP) acc = fmaf(v, y, acc);
+                    else { const float e = v - y; acc = fmaf(e, e, acc); }
+                }
+            }
         }
+        if (crow) acc = warp_sum(acc);
         if (lane == 0) {
             atomicAdd(counts + a, 1.0f);
-            if (dis) my_obj += (double)__ldg(dis + r);
+            if (crow) my_obj += (double)acc;
+            else if (dis) my_obj += (double)__ldg(dis + r);
         }
     }
     if (lane == 0) s_obj[wib] = my_obj;
@@ -93,20 +123,22 @@ __global__ void apply_splits_kernel(float* __restrict__ centroids, int d, const 
 }  // namespace
 
 ISE_EXPORT int ise_kmeans_accumulate(ise_ctx* ctx, const void* x, int dtype, int64_t n, int d, int64_t ldx,
-                                     const int64_t* assign, const float* dis, float* sums, float* counts,
-                                     double* obj, void* stream) {
+                                     const int64_t* assign, const float* dis, const float* centroids, int metric,
+                                     float* sums, float* counts, double* obj, void* stream) {
     ISE_CHECK_ARG(ctx && n >= 0 && d > 0 && ldx >= d);
     ISE_CHECK_ARG(dtype == ISE_DTYPE_F32 || dtype == ISE_DTYPE_U8);
     if (n == 0) return 0;
     ISE_CHECK_ARG(x && assign && sums && counts);
+    ISE_CHECK_ARG(metric == ISE_METRIC_IP || metric == ISE_METRIC_L2);
+    if (centroids) ISE_CHECK_ARG((reinterpret_cast<uintptr_t>(centroids) & 15) == 0);
     DeviceGuard guard(ctx->device);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(n, kWarps), (int64_t)ctx->sm_count * 8));
     if (dtype == ISE_DTYPE_F32)
         accumulate_kernel<float><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const float*)x, n, d, ldx, assign, dis,
-                                                                             sums, counts, obj);
+                                                                             centroids, metric, sums, counts, obj);
     else
         accumulate_kernel<uint8_t><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const uint8_t*)x, n, d, ldx, assign,
-                                                                               dis, sums, counts, obj);
+                                                                               dis, centroids, metric, sums, counts, obj);
     ISE_LAUNCH_CHECK();
     return 0;
 }

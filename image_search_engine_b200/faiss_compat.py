@@ -369,10 +369,12 @@ class Kmeans:
             obj = 0.0
             for it in range(cp.niter):
                 b_op = ops.prepare_operand(cent)
-                dis, assign = ops.search_topk(xd, a_op, cent, b_op, metric, 1, precision=self.precision)
+                # ids from the tensor cores; the objective terms are recomputed exactly inside the update
+                dis, assign = ops.search_topk(xd, a_op, cent, b_op, metric, 1, precision=self.precision,
+                                              need_distances=False)
                 accum.zero_()
                 objbuf.zero_()
-                ops.kmeans_accumulate(xd, assign, dis, sums, counts, objbuf)
+                ops.kmeans_accumulate(xd, assign, None, sums, counts, objbuf, centroids=cent, metric=metric)
                 if self.trace is not None:
                     self.trace.append(dict(redo=redo, it=it, centroids_in=cent.clone(), assign=assign.clone(),
                                            dis=dis.clone()))

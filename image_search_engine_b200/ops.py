@@ -7,6 +7,7 @@ of the hot path is a libise kernel.  All functions take CUDA tensors and launch 
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
 from dataclasses import dataclass
 
@@ -258,7 +259,7 @@ def rescore_select(a_raw: torch.Tensor, b_raw: torch.Tensor, a_op: Operand, b_op
 # Below this dimension a top-1 tile is bound by reading the 128 x 256 FP32 accumulator out of TMEM
 # (~2.4k cycles, measured) rather than by its MMAs (d/64 * 512 cycles per product), so dropping the lo
 # product buys nothing and the split products are used directly (profiles/r01_findings.md).
-COARSE_TOP1_MIN_D = 512
+COARSE_TOP1_MIN_D = int(os.environ.get("ISE_COARSE_TOP1_MIN_D", "512"))
 VERIFIED_MAX_K = 100   # coarse candidates: 32 per query for k <= 16, 128 for k <= 100
 
 # statistics of the last search_topk call on this process (bench.py / tests read them)
@@ -385,7 +386,9 @@ def topk_merge(val_parts: torch.Tensor, idx_parts: torch.Tensor, metric: int):
 # k-means update
 # ------------------------------------------------------------------------------------------
 def kmeans_accumulate(x: torch.Tensor, assign: torch.Tensor, dis: torch.Tensor | None, sums: torch.Tensor,
-                      counts: torch.Tensor, obj: torch.Tensor | None):
+                      counts: torch.Tensor, obj: torch.Tensor | None, centroids: torch.Tensor | None = None,
+                      metric: int = METRIC_IP):
+    """centroids given: the objective is recomputed in exact FP32 inside the kernel (dis is ignored)."""
     dt = DTYPE_F32 if x.dtype == torch.float32 else DTYPE_U8
     if x.dtype not in (torch.float32, torch.uint8):
         raise IseError("kmeans_accumulate: float32 or uint8 rows")
@@ -394,8 +397,8 @@ def kmeans_accumulate(x: torch.Tensor, assign: torch.Tensor, dis: torch.Tensor |
     if dis is not None:
         dis = dis.reshape(-1)
     _lib.check(_lib.load().ise_kmeans_accumulate(
-        _lib.ctx(_dev(x)), _ptr(x), dt, n, d, x.stride(0) if n > 0 else d, _ptr(assign), _ptr(dis), _ptr(sums),
-        _ptr(counts), _ptr(obj), _stream()))
+        _lib.ctx(_dev(x)), _ptr(x), dt, n, d, x.stride(0) if n > 0 else d, _ptr(assign), _ptr(dis),
+        _ptr(centroids), int(metric), _ptr(sums), _ptr(counts), _ptr(obj), _stream()))
     _count()
 
 

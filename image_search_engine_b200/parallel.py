@@ -47,10 +47,11 @@ class DeviceOps:
         return ops.compact_operand(op) if reuse else op
 
     def assign(self, x, a_op, cent, metric):
-        return ops.search_topk(x, a_op, cent, ops.prepare_operand(cent), metric, 1)
+        return ops.search_topk(x, a_op, cent, ops.prepare_operand(cent), metric, 1, need_distances=False)
 
-    def accumulate(self, x, assign, dis, sums, counts, obj):
-        ops.kmeans_accumulate(x, assign, dis, sums, counts, obj)
+    def accumulate(self, x, assign, dis, sums, counts, obj, cent=None, metric=METRIC_IP):
+        ops.kmeans_accumulate(x, assign, None if cent is not None else dis, sums, counts, obj, centroids=cent,
+                              metric=metric)
 
     def finalize(self, sums, counts, cent, n_global, spherical):
         """mean -> split empties (host plan, sequential Faiss RNG) -> renorm.  Returns nsplit."""
@@ -182,7 +183,7 @@ class ShardedKmeans:
                 dis, assign = lops.assign(x_train, a_op, cent, metric)
                 accum.zero_()
                 obj.zero_()
-                lops.accumulate(x_train, assign, dis, sums, counts, obj)
+                lops.accumulate(x_train, assign, dis, sums, counts, obj, cent, metric)
                 self._allreduce(accum)     # [k*d sums | k counts] in one NCCL all-reduce
                 self._allreduce(obj)
                 nsplit = lops.finalize(sums, counts, cent, n_train, cp.spherical)
