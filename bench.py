@@ -30,6 +30,8 @@ sys.path.insert(0, str(ROOT))
 C2 = dict(n_desc=1_000_000, d=128, k=4096, n_img=10_000, per_img=100)
 C3 = dict(nb=1_000_000, d=2048, nq=10_000, topk=10)
 METRIC = "Mdescriptors/s for k-means assign+histogram"
+WORKLOAD = ("C2: 1M SIFT-like 128-D float32 descriptors per GPU, k=4096 codebook, 10k images: quantise (assign) + "
+            "BoVW histogram (numpy-compat) + Okapi tf")
 
 
 def sift_like(rng, n, d):
@@ -185,16 +187,15 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mdescriptors/s", "n_gpus": args.gpus,
         "steps": len(vals), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: 1M SIFT-like 128-D descriptors, k=4096 codebook, 10k images, histogram + Okapi tf",
-                   "sample": sample},
+        "config": {"workload": WORKLOAD, "sample": sample},
         "cpu_baseline": {"value": value, "unit": "Mdescriptors/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Mdescriptors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     if not args.no_knn:
-        q, dt = cpu_knn(50_000, 500)
+        q, dt = cpu_knn(200_000, 1000)
         line["knn"] = {"metric": "kNN QPS at 1M x 2048 top-10", "value": q, "unit": "queries/s",
-                       "sample": "50k of 1M DB rows x 500 of 10k queries, scaled linearly in nb"}
+                       "sample": "200k of 1M DB rows x 1000 of 10k queries (%.1f s), scaled linearly in nb" % dt}
     emit(line)
 
 
@@ -404,9 +405,9 @@ def run_ours(args):
                "sample": f"{n_img} of {C2['n_img']} images x {C2['per_img']} descriptors ({dt:.1f} s): per-image "
                          f"Faiss-shim IndexFlatIP.search + np.histogram + Okapi on NumPy/OpenBLAS"}
         if knn is not None:
-            qv, qdt = cpu_knn(50_000, 500)
+            qv, qdt = cpu_knn(200_000, 1000)
             cpu["knn_qps"] = qv
-            cpu["knn_sample"] = f"50k of 1M DB rows x 500 of 10k queries ({qdt:.1f} s), scaled linearly in nb"
+            cpu["knn_sample"] = f"200k of 1M DB rows x 1000 of 10k queries ({qdt:.1f} s), scaled linearly in nb"
 
     if rank == 0:
         flops = 2.0 * C2["k"] * C2["d"] * C2["n_desc"]
@@ -415,8 +416,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "Mdescriptors/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16x2-split (fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": "C2: 1M SIFT-like 128-D descriptors per GPU, k=4096 codebook, 10k images, "
-                                   "fused assign + BoVW histogram (numpy-compat) + Okapi tf",
+            "config": {"workload": WORKLOAD,
                        "l2": "inputs larger than L2 (512 MB descriptors + 328 MB histogram per step)",
                        "step": "prepare planes + gemm_select(top-1) + bovw_histogram(okapi)"},
             "clocks": clocks,

@@ -8,6 +8,7 @@ Okapi tf, and flat kNN search, behind the reference's own Python call surface:
     train_bovw_model                              (backend/bag_of_visual_words.py)
     OkapiTransformer, create_search_index, chunkIt (backend/utils.py)
     run_image_query                               (backend/engine.py)
+    query_index                                   (backend/siamese/test_index.py)
     faiss_compat                                  (the subset of the `faiss` module those files call)
 
 All arithmetic runs in hand-written sm_100a kernels exported by libise.so (include/ise.h).
@@ -17,9 +18,9 @@ extension and a B200, and raises otherwise -- there is no CPU fallback.
 from . import faiss_compat
 from ._lib import IseError
 from .bag_of_visual_words import BOVW, load_cluster_model, run_clustering, train_bovw_model
-from .engine import run_image_query
+from .engine import query_index, run_image_query
 from .kmeans_faiss import FaissKMeans
 from .utils import OkapiTransformer, chunkIt, create_search_index
 
 __all__ = ["faiss_compat", "IseError", "BOVW", "load_cluster_model", "run_clustering", "train_bovw_model",
-           "run_image_query", "FaissKMeans", "OkapiTransformer", "chunkIt", "create_search_index"]
+           "run_image_query", "query_index", "FaissKMeans", "OkapiTransformer", "chunkIt", "create_search_index"]

@@ -48,3 +48,27 @@ def run_image_query(image_features, n_images, normalize=False, *, index=None, im
         path = paths[i] if paths is not None else i
         predictions.append((dist, thumb(path) if thumb else None, str(path)))
     return predictions
+
+
+def query_index(embedding, index, index_type, n_results):
+    """Drop-in for backend/siamese/test_index.py:query_index (:49-71).
+
+    "faiss": L2-normalise the query in place and search the (inner-product) index (:52-56).
+    "dict" : the reference's fallback over a pickled [n, d] array -- query divided by its norm, Euclidean
+             distance to every row, ascending (:58-69); here the array is searched on the device through an
+             L2 index and the square roots are taken on the k winners.
+    Returns (indices, distances) like the reference.
+    """
+    if index_type == "faiss":
+        faiss.normalize_L2(embedding)
+        distances, indices = index.search(embedding, n_results)
+        return indices.ravel().tolist(), distances.ravel().tolist()
+    if index_type == "dict":
+        q = np.asarray(embedding, dtype=np.float64)
+        q = (q / np.linalg.norm(q)).astype(np.float32).reshape(1, -1)
+        flat = faiss.IndexFlatL2(q.shape[1])
+        flat.add(np.ascontiguousarray(np.asarray(index), dtype=np.float32))
+        d2, ids = flat.search(q, n_results)
+        keep = ids.ravel() >= 0
+        return ids.ravel()[keep], np.sqrt(d2.ravel()[keep])
+    raise ValueError(f"unknown index_type {index_type!r}")

@@ -358,3 +358,22 @@ def test_pipelined_host_transform_equals_device_path(g):
     got_tf = bovw.histograms_host(packed, out, okapi=ok, n_chunks=7)
     assert np.array_equal(got_tf, ref_tf)
     assert np.array_equal(ref_tf, np.asarray(ok.transform(ref).todense()))
+
+
+def test_query_index_siamese_helper():
+    """backend/siamese/test_index.py:query_index -- "faiss" (normalise + IP search) and "dict" (brute force)."""
+    from image_search_engine_b200 import faiss_compat, query_index
+    rng = np.random.default_rng(12)
+    emb = unit_rows(rng, 500, 128)
+    idx = faiss_compat.IndexFlatIP(128)
+    idx.add(emb)
+    q = (emb[42] * 7.5).reshape(1, -1).copy()
+    ids, dist = query_index(q, idx, "faiss", 5)
+    assert ids[0] == 42 and dist[0] == pytest.approx(1.0, abs=1e-5)
+    np.testing.assert_allclose(np.linalg.norm(q), 1.0, rtol=1e-6)          # normalised in place
+    ids2, dist2 = query_index(emb[42] * 3, emb.astype(np.float64), "dict", 5)
+    ref = np.linalg.norm(emb.astype(np.float64) - emb[42].astype(np.float64) / np.linalg.norm(emb[42]), axis=1)
+    order = ref.argsort()[:5]
+    assert list(ids2) == list(order)
+    np.testing.assert_allclose(dist2[1:], ref[order][1:], rtol=1e-4)
+    assert dist2[0] < 1e-3
