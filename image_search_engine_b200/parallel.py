@@ -20,6 +20,8 @@ DeviceOps, which calls libise and has no fallback.
 """
 from __future__ import annotations
 
+import time
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -169,6 +171,7 @@ class ShardedKmeans:
         lower_is_better = not cp.spherical
         best_obj = float("inf") if lower_is_better else float("-inf")
         best_cent, best_stats, stats = None, [], []
+        t_start = time.time()
         for redo in range(cp.nredo):
             if n_input:
                 cent[:n_input] = torch.from_numpy(ic).to(dev)
@@ -188,7 +191,7 @@ class ShardedKmeans:
                 self._allreduce(obj)
                 nsplit = lops.finalize(sums, counts, cent, n_train, cp.spherical)
                 o = float(obj.item())
-                stats.append(dict(obj=o, nsplit=nsplit))
+                stats.append(dict(obj=o, nsplit=nsplit, time=time.time() - t_start))
             if cp.nredo > 1:
                 if (lower_is_better and o < best_obj) or (not lower_is_better and o > best_obj):
                     best_cent, best_stats, best_obj = cent.clone(), list(stats), o

@@ -31,11 +31,15 @@ g = torch.Generator(device=dev); g.manual_seed(40 + rank)
 x = centres[torch.randint(0, centres.shape[0], (n_local,), generator=g, device=dev)]
 x = (x + 8.0 * torch.randn((n_local, d), generator=g, device=dev)).round_().clamp_(0, 255)
 km = ShardedKmeans(d, k, seed=42, niter=args.iters, spherical=True)
+warm = torch.ones(1 << 20, device=dev)
+for _ in range(3):
+    dist.all_reduce(warm)          # NCCL communicator set-up is not part of the k-means time
 dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
 km.train(x)
 torch.cuda.synchronize(); dist.barrier(); t1 = time.perf_counter()
 out["c4"] = {"n": n_local * world, "d": d, "k": k, "iters": args.iters, "s_total": t1 - t0,
-             "s_per_iter_incl_setup": (t1 - t0) / args.iters, "obj": [float(o) for o in km.obj],
+             "s_per_iter_incl_setup": (t1 - t0) / args.iters,
+             "iter_end_times_s": [s_["time"] for s_ in km.iteration_stats], "obj": [float(o) for o in km.obj],
              "nsplit": [s["nsplit"] for s in km.iteration_stats],
              "allreduce_bytes_per_iter": 4 * (k * d + k) + 8}
 del x, km
