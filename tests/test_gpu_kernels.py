@@ -324,3 +324,26 @@ def test_verified_assign_flags_ties_and_near_ties(dev):
     np.testing.assert_allclose(D.cpu().numpy(), Do, rtol=1e-4, atol=1e-5)
     D2, I2 = ops.search_topk(xd, a, cd, b, METRIC_IP, 1, precision="split")
     assert torch.equal(I, I2)
+
+
+@pytest.mark.parametrize("metric_ip", [True, False])
+@pytest.mark.parametrize("d,kind,k", [(32, "orb", 512), (128, "sift", 1000), (100, "float", 300), (256, "float", 257),
+                                       (64, "float", 4096)])
+def test_stationary_assign_kernel(dev, metric_ip, d, kind, k):
+    """>= 2 row tiles per SM and d <= 256 selects the A-stationary top-1 kernel (resident A planes, per-plane
+    B ring); same parity bar as the streaming kernel, including ragged tails in rows, columns and d."""
+    from image_search_engine_b200 import ops
+    from image_search_engine_b200._lib import METRIC_IP, METRIC_L2
+    rng = np.random.default_rng(d * 7 + k)
+    m = 128 * 148 * 2 + 77
+    x = orb_like(rng, m, d) if kind == "orb" else sift_like(rng, m, d) if kind == "sift" else \
+        rng.standard_normal((m, d)).astype(np.float32)
+    c = unit_rows(rng, k, d) if metric_ip else (rng.standard_normal((k, d)) * 2).astype(np.float32)
+    xd = torch.from_numpy(x).to(dev)
+    a = ops.prepare_operand(xd)
+    b = ops.prepare_operand(torch.from_numpy(c).to(dev))
+    val, idx = ops.gemm_select(a, b, METRIC_IP if metric_ip else METRIC_L2, 1)
+    D, I = _oracle_knn(x, c, 1, metric_ip)
+    xf = x.astype(np.float32)
+    assert_topk_parity(idx.cpu().numpy(), I, xf, c, metric_ip, max_mismatch_frac=0.002)
+    np.testing.assert_allclose(val.cpu().numpy(), D, rtol=2e-4, atol=2e-4 * np.abs(D).max())
