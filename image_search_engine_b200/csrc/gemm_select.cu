@@ -450,221 +450,6 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------
-// A-stationary top-1 kernel for small d (k-means assign / quantisation: d <= 256, many row tiles).
-//
-// In gemm_select_kernel every k-block stage carries an A tile that is identical for all column tiles of
-// a row tile, and a stage is a whole k-block (80-96 KB), so only two stages fit and the MMA issuer
-// regularly waits for TMA (ncu: tensor pipe 70-79 % at C2).  Here the row tile's A planes are loaded ONCE
-// per 128 rows into a double-buffered resident area and the ring holds single B planes (32 KB each,
-// 3-5 stages): fewer bytes per MMA and a deeper, finer-grained pipeline.  Same epilogue (running top-1).
-// ------------------------------------------------------------------------------------------
-struct AuxStat {
-    uint64_t a_full[2];
-    uint64_t a_empty[2];
-    uint64_t b_full[8];
-    uint64_t b_empty[8];
-    uint64_t tmem_full[2];
-    uint64_t tmem_empty[2];
-    uint32_t tmem_base;
-    uint32_t pad_[3];
-    float bnorm[2][BLOCK_N];
-};
-static_assert(sizeof(AuxStat) <= AUX_BYTES, "aux area too small");
-
-template <int PA, int PB, bool L2>
-__global__ void __launch_bounds__(256, 1)
-assign_stationary_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
-                         const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
-                         const Params p, const int nkb, const int smem_avail) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    // The layout is decided at RUN time: whether the lo planes exist in the data is only known on the
-    // device (meta[LO_NONZERO]); an exact A operand (integer descriptors) frees its lo slots for B stages.
-    const bool use_alo = (PA == 2) && (__ldg(p.a_meta + META_LO_NONZERO) != 0.f);
-    const bool use_blo = (PB == 2) && (__ldg(p.b_meta + META_LO_NONZERO) != 0.f);
-    const int a_buf_bytes = (1 + (int)use_alo) * nkb * A_TILE_BYTES;   // one row tile: planes x k-blocks
-    const int b_stages = min(8, (smem_avail - 2 * a_buf_bytes) / B_TILE_BYTES);
-    uint8_t* smem_b = smem + 2 * a_buf_bytes;
-    AuxStat* aux = reinterpret_cast<AuxStat*>(smem + smem_avail);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp == 0 && lane == 0) {
-        ptx::prefetch_tensormap(&tm_a_hi);
-        ptx::prefetch_tensormap(&tm_b_hi);
-        if (PA == 2) ptx::prefetch_tensormap(&tm_a_lo);
-        if (PB == 2) ptx::prefetch_tensormap(&tm_b_lo);
-    }
-    if (warp == 1 && lane == 0) {
-        for (int i = 0; i < 2; ++i) {
-            ptx::mbar_init(&aux->a_full[i], 1);
-            ptx::mbar_init(&aux->a_empty[i], 1);
-            ptx::mbar_init(&aux->tmem_full[i], 1);
-            ptx::mbar_init(&aux->tmem_empty[i], 128);
-        }
-        for (int i = 0; i < b_stages; ++i) {
-            ptx::mbar_init(&aux->b_full[i], 1);
-            ptx::mbar_init(&aux->b_empty[i], 1);
-        }
-        ptx::fence_barrier_init();
-    }
-    if (warp == 2) ptx::tmem_alloc(&aux->tmem_base, TMEM_COLS);
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::tc_fence_after();
-    const uint32_t tmem_base = aux->tmem_base;
-
-    if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            uint32_t itb = 0, mcount = 0;
-            for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x, ++mcount) {
-                const int ab = mcount & 1;
-                ptx::mbar_wait(&aux->a_empty[ab], ((mcount >> 1) & 1) ^ 1);
-                uint8_t* sa = smem + ab * a_buf_bytes;
-                ptx::mbar_arrive_expect_tx(&aux->a_full[ab], (uint32_t)(nkb * A_TILE_BYTES * (1 + (int)use_alo)));
-                for (int kb = 0; kb < nkb; ++kb) {
-                    ptx::tma_load_2d(sa + kb * A_TILE_BYTES, &tm_a_hi, &aux->a_full[ab], kb * BLOCK_K, mt * BLOCK_M);
-                    if (use_alo)
-                        ptx::tma_load_2d(sa + (nkb + kb) * A_TILE_BYTES, &tm_a_lo, &aux->a_full[ab], kb * BLOCK_K,
-                                         mt * BLOCK_M);
-                }
-                for (int nt = 0; nt < p.n_ntiles; ++nt) {
-                    for (int kb = 0; kb < nkb; ++kb) {
-                        for (int pl = 0; pl < 1 + (int)use_blo; ++pl, ++itb) {
-                            const int s = itb % b_stages;
-                            ptx::mbar_wait(&aux->b_empty[s], ((itb / b_stages) & 1) ^ 1);
-                            ptx::mbar_arrive_expect_tx(&aux->b_full[s], B_TILE_BYTES);
-                            ptx::tma_load_2d(smem_b + s * B_TILE_BYTES, pl == 0 ? &tm_b_hi : &tm_b_lo, &aux->b_full[s],
-                                             kb * BLOCK_K, nt * BLOCK_N);
-                        }
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_f16_f32(BLOCK_M, BLOCK_N);
-            const uint32_t smem_base = ptx::smem_u32(smem);
-            const uint32_t smem_b_base = ptx::smem_u32(smem_b);
-            uint32_t itb = 0, tile = 0, mcount = 0;
-            for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x, ++mcount) {
-                const int ab = mcount & 1;
-                ptx::mbar_wait(&aux->a_full[ab], (mcount >> 1) & 1);
-                ptx::tc_fence_after();
-                const uint32_t sa = smem_base + ab * a_buf_bytes;
-                for (int nt = 0; nt < p.n_ntiles; ++nt, ++tile) {
-                    const int as = tile & 1;
-                    ptx::mbar_wait(&aux->tmem_empty[as], ((tile >> 1) & 1) ^ 1);
-                    ptx::tc_fence_after();
-                    const uint32_t tmem_d = tmem_base + as * BLOCK_N;
-                    uint32_t acc = 0;
-                    for (int kb = 0; kb < nkb; ++kb) {
-                        const int rem = p.d - kb * BLOCK_K;
-                        const int ksteps = rem >= BLOCK_K ? BLOCK_K / UMMA_K : (rem + UMMA_K - 1) / UMMA_K;
-                        const uint64_t da_hi = ptx::make_smem_desc_sw128(sa + kb * A_TILE_BYTES);
-                        const uint64_t da_lo = ptx::make_smem_desc_sw128(sa + (nkb + kb) * A_TILE_BYTES);
-                        for (int pl = 0; pl < 1 + (int)use_blo; ++pl, ++itb) {
-                            const int s = itb % b_stages;
-                            ptx::mbar_wait(&aux->b_full[s], (itb / b_stages) & 1);
-                            ptx::tc_fence_after();
-                            const uint64_t db = ptx::make_smem_desc_sw128(smem_b_base + s * B_TILE_BYTES);
-                            for (int ks = 0; ks < ksteps; ++ks) {
-                                const uint64_t koff = (uint64_t)(ks * ((UMMA_K * 2) >> 4));
-                                ptx::umma_f16_ss(tmem_d, da_hi + koff, db + koff, idesc, acc);   // hi*hi / hi*lo
-                                acc = 1;
-                                if (pl == 0 && use_alo) ptx::umma_f16_ss(tmem_d, da_lo + koff, db + koff, idesc, 1);
-                            }
-                            ptx::umma_commit(&aux->b_empty[s]);
-                        }
-                    }
-                    ptx::umma_commit(&aux->tmem_full[as]);
-                }
-                ptx::umma_commit(&aux->a_empty[ab]);   // every MMA reading this A buffer has retired
-            }
-        }
-    } else if (warp >= EPI_WARP0) {
-        // ===================== epilogue: running top-1 per row =====================
-        const int q = warp & 3;
-        const int et = threadIdx.x - EPI_WARP0 * 32;
-        const float inv = p.a_meta[META_INV_SCALE] * p.b_meta[META_INV_SCALE];
-        const float two_inv = 2.f * inv;
-        uint32_t tile = 0;
-        for (int mt = blockIdx.x; mt < p.n_mtiles; mt += gridDim.x) {
-            const int64_t row = (int64_t)mt * BLOCK_M + q * 32 + lane;
-            float best = -CUDART_INF_F;
-            int best_id = -1;
-            for (int nt = 0; nt < p.n_ntiles; ++nt, ++tile) {
-                const int as = tile & 1;
-                const int col0 = nt * BLOCK_N;
-                const int ncols = (int)min((int64_t)BLOCK_N, p.n - col0);
-                if (L2) {
-                    for (int c = et; c < BLOCK_N; c += 128)
-                        aux->bnorm[as][c] = (c < ncols) ? __ldg(p.b_norms + col0 + c) : 0.f;
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                }
-                ptx::mbar_wait(&aux->tmem_full[as], (tile >> 1) & 1);
-                ptx::tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N;
-#pragma unroll 1
-                for (int c = 0; c < ncols; c += 32) {
-                    uint32_t r[32];
-                    ptx::tmem_ld_32x32b_x32(taddr + c, r);
-                    ptx::tmem_ld_wait();
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        v[j] = __uint_as_float(r[j]);
-                        if (L2) v[j] = fmaf(v[j], two_inv, -aux->bnorm[as][c + j]);
-                    }
-                    if (c + 32 > ncols) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (c + j >= ncols) v[j] = -CUDART_INF_F;
-                    }
-                    float t16[16], t8[8], t4[4];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) t16[j] = fmaxf(v[2 * j], v[2 * j + 1]);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) t8[j] = fmaxf(t16[2 * j], t16[2 * j + 1]);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) t4[j] = fmaxf(t8[2 * j], t8[2 * j + 1]);
-                    const float mx = fmaxf(fmaxf(t4[0], t4[1]), fmaxf(t4[2], t4[3]));
-                    if (mx > best) {  // strict: an equal score in a later column never replaces
-                        best = mx;
-                        int jj = 31;
-#pragma unroll
-                        for (int j = 30; j >= 0; --j)
-                            if (v[j] == mx) jj = j;
-                        best_id = col0 + c + jj;
-                    }
-                }
-                ptx::tc_fence_before();
-                ptx::mbar_arrive(&aux->tmem_empty[as]);
-            }
-            if (row < p.m) {
-                const float an = L2 ? __ldg(p.a_norms + row) : 0.f;
-                if (best_id >= 0) {
-                    p.out_val[row] = L2 ? fmaxf(an - best, 0.f) : best * inv;
-                    p.out_idx[row] = p.id_base + best_id;
-                } else {
-                    p.out_val[row] = L2 ? 3.402823466e+38f : -3.402823466e+38f;
-                    p.out_idx[row] = -1;
-                }
-            }
-        }
-    }
-
-    ptx::tc_fence_before();
-    __syncthreads();
-    if (warp == 2) {
-        ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, TMEM_COLS);
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // merge of g sorted lists per row: one warp per row, each lane owns lists lane, lane+32, ...
 // ------------------------------------------------------------------------------------------
 constexpr int MERGE_MAX_LISTS_PER_LANE = 8;
@@ -796,40 +581,9 @@ static int dispatch_k(const ise_ctx* ctx, const CUtensorMap* maps, const Params&
     return launch<PA, PB, L2, 128>(ctx, maps, p, st);
 }
 
-// A-stationary top-1: eligible when the resident A planes (2 buffers) leave room for >= 3 B stages and the
-// row tiles alone keep every SM busy (no column splits).
-static bool stationary_ok(const ise_ctx* ctx, const Params& p, int pa, int* nkb_out, int* avail_out) {
-#ifdef ISE_NO_STATIONARY
-    return false;
-#endif
-    const int nkb = (p.d + BLOCK_K - 1) / BLOCK_K;
-    const int avail = (SMEM_LIMIT - AUX_BYTES - 1024) / 1024 * 1024;     // stage area, 1 KiB aligned
-    const int worst_stages = (avail - 2 * pa * nkb * A_TILE_BYTES) / B_TILE_BYTES;  // if the lo planes are live
-    *nkb_out = nkb;
-    *avail_out = avail;
-    return p.topk == 1 && p.flag_count == nullptr && p.n_splits == 1 && worst_stages >= 2 &&
-           p.n_mtiles >= 2 * ctx->sm_count;
-}
-
-template <int PA, int PB, bool L2>
-static int launch_stationary(const ise_ctx* ctx, const CUtensorMap* maps, const Params& p, int nkb, int avail,
-                             cudaStream_t st) {
-    auto kern = assign_stationary_kernel<PA, PB, L2>;
-    const int smem = avail + AUX_BYTES + 1024;
-    ISE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int grid = std::min(p.n_mtiles, ctx->sm_count);
-    kern<<<grid, 256, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p, nkb, avail);
-    ISE_LAUNCH_CHECK();
-    return 0;
-}
-
 template <int PA, int PB>
 static int dispatch_metric(const ise_ctx* ctx, const CUtensorMap* maps, const Params& p, int metric,
                            cudaStream_t st) {
-    int nkb = 0, avail = 0;
-    if (stationary_ok(ctx, p, PA, &nkb, &avail))
-        return metric == ISE_METRIC_L2 ? launch_stationary<PA, PB, true>(ctx, maps, p, nkb, avail, st)
-                                       : launch_stationary<PA, PB, false>(ctx, maps, p, nkb, avail, st);
     return metric == ISE_METRIC_L2 ? dispatch_k<PA, PB, true>(ctx, maps, p, st)
                                    : dispatch_k<PA, PB, false>(ctx, maps, p, st);
 }

@@ -329,9 +329,9 @@ def test_verified_assign_flags_ties_and_near_ties(dev):
 @pytest.mark.parametrize("metric_ip", [True, False])
 @pytest.mark.parametrize("d,kind,k", [(32, "orb", 512), (128, "sift", 1000), (100, "float", 300), (256, "float", 257),
                                        (64, "float", 4096)])
-def test_stationary_assign_kernel(dev, metric_ip, d, kind, k):
-    """>= 2 row tiles per SM and d <= 256 selects the A-stationary top-1 kernel (resident A planes, per-plane
-    B ring); same parity bar as the streaming kernel, including ragged tails in rows, columns and d."""
+def test_assign_many_row_tiles(dev, metric_ip, d, kind, k):
+    """Top-1 over >= 2 row tiles per SM (the persistent loop wraps several times, no column splits), with
+    ragged tails in rows, columns and d, both metrics, uint8 / integer / general float rows."""
     from image_search_engine_b200 import ops
     from image_search_engine_b200._lib import METRIC_IP, METRIC_L2
     rng = np.random.default_rng(d * 7 + k)
