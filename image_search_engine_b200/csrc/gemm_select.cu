@@ -47,9 +47,12 @@ constexpr int TMEM_COLS = 512;  // 2 accumulator stages x BLOCK_N fp32 columns
 constexpr int AUX_BYTES = 4096;
 constexpr int SMEM_LIMIT = 232448;  // 227 KiB opt-in per CTA on sm_100
 
-__host__ __device__ constexpr int stage_bytes(int pa, int pb) { return pa * A_TILE_BYTES + pb * B_TILE_BYTES; }
-__host__ __device__ constexpr int num_stages(int pa, int pb) {
-    int s = (SMEM_LIMIT - AUX_BYTES - 1024) / stage_bytes(pa, pb);
+// cg = CTAs per MMA (cta_group): with 2, each CTA of the pair stages only half of every B tile
+__host__ __device__ constexpr int stage_bytes(int pa, int pb, int cg = 1) {
+    return pa * A_TILE_BYTES + pb * (B_TILE_BYTES / cg);
+}
+__host__ __device__ constexpr int num_stages(int pa, int pb, int cg = 1) {
+    int s = (SMEM_LIMIT - AUX_BYTES - 1024) / stage_bytes(pa, pb, cg);
     return s > 6 ? 6 : s;
 }
 
@@ -99,13 +102,21 @@ template <> struct SelList<32> { using type = RegList32; };
 // per-row global buffer (large k: nothing is ordered or evicted on the device, the exact re-score sorts);
 // otherwise capacity of the per-thread candidate set.
 // VERIFY (top-1 only): also track the exact runner-up and flag rows whose winner is not provably unique.
-template <int PA, int PB, bool L2, int KSEL, bool VERIFY>
+// CG = 2: CTA PAIRS (cluster of 2 on one TPC, tcgen05 cta_group::2).  The pair owns two adjacent row tiles
+//   (M = 256 per MMA); each CTA stages its own A rows and only HALF of every B tile (128 of the 256
+//   columns), so the L2 -> smem bytes per MMA cycle drop by ~40 % and stages get smaller (deeper ring).
+//   Only the leader CTA issues MMAs; TMA completions of both CTAs signal the leader's `full` barrier;
+//   tcgen05.commit multicasts `empty` / `tmem_full` to both CTAs; both epilogues arrive on the leader's
+//   `tmem_empty`.  Each CTA's epilogue reads its own 128 TMEM lanes exactly as in the single-CTA case.
+template <int PA, int PB, bool L2, int KSEL, bool VERIFY, int CG>
 __global__ void __launch_bounds__(num_threads(KSEL), 1)
 gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const Params p) {
-    constexpr int STAGES = num_stages(PA, PB);
-    constexpr int STAGE_BYTES = stage_bytes(PA, PB);
+    constexpr int STAGES = num_stages(PA, PB, CG);
+    constexpr int STAGE_BYTES = stage_bytes(PA, PB, CG);
+    constexpr int B_LOAD_BYTES = B_TILE_BYTES / CG;   // this CTA's share of a B tile (one plane)
+    constexpr int B_LOAD_ROWS = BLOCK_N / CG;
     constexpr int HALVES = epi_halves(KSEL);
     constexpr int NUM_EPI_THREADS = 128 * HALVES;
     constexpr int COLS_PER_HALF = BLOCK_N / HALVES;
@@ -124,25 +135,34 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         if (PA == 2) ptx::prefetch_tensormap(&tm_a_lo);
         if (PB == 2) ptx::prefetch_tensormap(&tm_b_lo);
     }
+    const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
-            ptx::mbar_init(&aux->full[i], 1);
-            ptx::mbar_init(&aux->empty[i], 1);
+            ptx::mbar_init(&aux->full[i], CG);      // one arrival per CTA of the pair (+ their TMA bytes)
+            ptx::mbar_init(&aux->empty[i], 1);       // tcgen05.commit (multicast to both CTAs when CG == 2)
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&aux->tmem_full[i], 1);
-            ptx::mbar_init(&aux->tmem_empty[i], NUM_EPI_THREADS);
+            ptx::mbar_init(&aux->tmem_empty[i], NUM_EPI_THREADS * CG);   // both CTAs' epilogues (leader's copy)
         }
         ptx::fence_barrier_init();
     }
-    if (warp == 2) ptx::tmem_alloc(&aux->tmem_base, TMEM_COLS);
+    if (CG == 2) ptx::cluster_sync_all();            // peer barriers exist before anything signals them
+    if (warp == 2) {
+        if (CG == 2) ptx::tmem_alloc_2sm(&aux->tmem_base, TMEM_COLS);
+        else ptx::tmem_alloc(&aux->tmem_base, TMEM_COLS);
+    }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = aux->tmem_base;
 
     const int num_kb = (p.d + BLOCK_K - 1) / BLOCK_K;
-    const int total_work = p.n_mtiles * p.n_splits;
+    // work items are (column split, group of CG adjacent row tiles); a pair walks them together
+    const int n_mgroups = (p.n_mtiles + CG - 1) / CG;
+    const int total_work = n_mgroups * p.n_splits;
+    const int w_begin = blockIdx.x / CG, w_step = gridDim.x / CG;
     // PA / PB are the plane SLOTS of a stage; whether a lo plane is really loaded and multiplied is a
     // run-time property of the data (prepare.cu sets meta[LO_NONZERO]), so callers never have to
     // synchronise with the host to find out that e.g. integer descriptors are exact in one plane.
@@ -153,9 +173,9 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t it = 0;
-            const uint32_t tx_bytes = A_TILE_BYTES * (1 + (int)use_alo) + B_TILE_BYTES * (1 + (int)use_blo);
-            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-                const int split = w / p.n_mtiles, mt = w - split * p.n_mtiles;
+            const uint32_t tx_bytes = A_TILE_BYTES * (1 + (int)use_alo) + B_LOAD_BYTES * (1 + (int)use_blo);
+            for (int w = w_begin; w < total_work; w += w_step) {
+                const int split = w / n_mgroups, mt = (w - split * n_mgroups) * CG + (int)cta_rank;
                 const int nt0 = split * p.tiles_per_split;
                 const int nt1 = min(nt0 + p.tiles_per_split, p.n_ntiles);
                 for (int nt = nt0; nt < nt1; ++nt) {
@@ -164,27 +184,41 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                         const uint32_t ph = (it / STAGES) & 1;
                         ptx::mbar_wait(&aux->empty[s], ph ^ 1);
                         uint8_t* st = smem + s * STAGE_BYTES;
-                        ptx::mbar_arrive_expect_tx(&aux->full[s], tx_bytes);
-                        ptx::tma_load_2d(st, &tm_a_hi, &aux->full[s], kb * BLOCK_K, mt * BLOCK_M);
-                        if (use_alo)
-                            ptx::tma_load_2d(st + A_TILE_BYTES, &tm_a_lo, &aux->full[s], kb * BLOCK_K, mt * BLOCK_M);
-                        ptx::tma_load_2d(st + PA * A_TILE_BYTES, &tm_b_hi, &aux->full[s], kb * BLOCK_K,
-                                         nt * BLOCK_N);
-                        if (use_blo)
-                            ptx::tma_load_2d(st + PA * A_TILE_BYTES + B_TILE_BYTES, &tm_b_lo, &aux->full[s],
-                                             kb * BLOCK_K, nt * BLOCK_N);
+                        const int bcol = nt * BLOCK_N + (int)cta_rank * B_LOAD_ROWS;   // this CTA's half of the tile
+                        if (CG == 1) {
+                            ptx::mbar_arrive_expect_tx(&aux->full[s], tx_bytes);
+                            ptx::tma_load_2d(st, &tm_a_hi, &aux->full[s], kb * BLOCK_K, mt * BLOCK_M);
+                            if (use_alo)
+                                ptx::tma_load_2d(st + A_TILE_BYTES, &tm_a_lo, &aux->full[s], kb * BLOCK_K, mt * BLOCK_M);
+                            ptx::tma_load_2d(st + PA * A_TILE_BYTES, &tm_b_hi, &aux->full[s], kb * BLOCK_K, bcol);
+                            if (use_blo)
+                                ptx::tma_load_2d(st + PA * A_TILE_BYTES + B_LOAD_BYTES, &tm_b_lo, &aux->full[s],
+                                                 kb * BLOCK_K, bcol);
+                        } else {
+                            // both CTAs' bytes are counted on the LEADER's barrier
+                            if (leader) ptx::mbar_arrive_expect_tx(&aux->full[s], 2 * tx_bytes);
+                            else ptx::mbar_arrive_remote(&aux->full[s], 0);
+                            ptx::tma_load_2d_2sm(st, &tm_a_hi, &aux->full[s], kb * BLOCK_K, mt * BLOCK_M);
+                            if (use_alo)
+                                ptx::tma_load_2d_2sm(st + A_TILE_BYTES, &tm_a_lo, &aux->full[s], kb * BLOCK_K,
+                                                     mt * BLOCK_M);
+                            ptx::tma_load_2d_2sm(st + PA * A_TILE_BYTES, &tm_b_hi, &aux->full[s], kb * BLOCK_K, bcol);
+                            if (use_blo)
+                                ptx::tma_load_2d_2sm(st + PA * A_TILE_BYTES + B_LOAD_BYTES, &tm_b_lo, &aux->full[s],
+                                                     kb * BLOCK_K, bcol);
+                        }
                     }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_f16_f32(BLOCK_M, BLOCK_N);
+        if (lane == 0 && leader) {   // CG == 2: only the leader CTA of a pair issues MMAs
+            constexpr uint32_t idesc = ptx::make_idesc_f16_f32(BLOCK_M * CG, BLOCK_N);
             const uint32_t smem_base = ptx::smem_u32(smem);
             uint32_t it = 0, tile = 0;
-            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-                const int split = w / p.n_mtiles;
+            for (int w = w_begin; w < total_work; w += w_step) {
+                const int split = w / n_mgroups;
                 const int nt0 = split * p.tiles_per_split;
                 const int nt1 = min(nt0 + p.tiles_per_split, p.n_ntiles);
                 for (int nt = nt0; nt < nt1; ++nt, ++tile) {
@@ -202,19 +236,29 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                         const uint64_t da_hi = ptx::make_smem_desc_sw128(st);
                         const uint64_t da_lo = ptx::make_smem_desc_sw128(st + A_TILE_BYTES);
                         const uint64_t db_hi = ptx::make_smem_desc_sw128(st + PA * A_TILE_BYTES);
-                        const uint64_t db_lo = ptx::make_smem_desc_sw128(st + PA * A_TILE_BYTES + B_TILE_BYTES);
+                        const uint64_t db_lo = ptx::make_smem_desc_sw128(st + PA * A_TILE_BYTES + B_LOAD_BYTES);
                         const int rem = p.d - kb * BLOCK_K;
                         const int ksteps = rem >= BLOCK_K ? BLOCK_K / UMMA_K : (rem + UMMA_K - 1) / UMMA_K;
                         for (int ks = 0; ks < ksteps; ++ks) {
                             // advancing 16 fp16 = 32 bytes inside the 128B swizzle span: +2 in the >>4 address
                             const uint64_t koff = (uint64_t)(ks * ((UMMA_K * 2) >> 4));
-                            ptx::umma_f16_ss(tmem_d, da_hi + koff, db_hi + koff, idesc, (kb | ks) != 0);
-                            if (use_blo) ptx::umma_f16_ss(tmem_d, da_hi + koff, db_lo + koff, idesc, 1);
-                            if (use_alo) ptx::umma_f16_ss(tmem_d, da_lo + koff, db_hi + koff, idesc, 1);
+                            if (CG == 1) {
+                                ptx::umma_f16_ss(tmem_d, da_hi + koff, db_hi + koff, idesc, (kb | ks) != 0);
+                                if (use_blo) ptx::umma_f16_ss(tmem_d, da_hi + koff, db_lo + koff, idesc, 1);
+                                if (use_alo) ptx::umma_f16_ss(tmem_d, da_lo + koff, db_hi + koff, idesc, 1);
+                            } else {
+                                ptx::umma_f16_ss_2sm(tmem_d, da_hi + koff, db_hi + koff, idesc, (kb | ks) != 0);
+                                if (use_blo) ptx::umma_f16_ss_2sm(tmem_d, da_hi + koff, db_lo + koff, idesc, 1);
+                                if (use_alo) ptx::umma_f16_ss_2sm(tmem_d, da_lo + koff, db_hi + koff, idesc, 1);
+                            }
                         }
-                        ptx::umma_commit(&aux->empty[s]);  // frees the smem stage when these MMAs retire
+                        // frees the smem stage (in both CTAs) when these MMAs retire
+                        if (CG == 1) ptx::umma_commit(&aux->empty[s]);
+                        else ptx::umma_commit_2sm(&aux->empty[s]);
                     }
-                    ptx::umma_commit(&aux->tmem_full[as]);  // accumulator complete -> epilogue
+                    // accumulator complete -> epilogue (of both CTAs)
+                    if (CG == 1) ptx::umma_commit(&aux->tmem_full[as]);
+                    else ptx::umma_commit_2sm(&aux->tmem_full[as]);
                 }
             }
         }
@@ -229,8 +273,8 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         CoarseBound bound;
         if (KSEL == 1 && VERIFY) bound.init(p.a_meta, p.b_meta, p.d);
         uint32_t tile = 0;
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-            const int split = w / p.n_mtiles, mt = w - split * p.n_mtiles;
+        for (int w = w_begin; w < total_work; w += w_step) {
+            const int split = w / n_mgroups, mt = (w - split * n_mgroups) * CG + (int)cta_rank;
             const int nt0 = split * p.tiles_per_split;
             const int nt1 = min(nt0 + p.tiles_per_split, p.n_ntiles);
             const int row_in_tile = q * 32 + lane;
@@ -378,7 +422,10 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                     }
                 }
                 ptx::tc_fence_before();
-                ptx::mbar_arrive(&aux->tmem_empty[as]);
+                // the MMA issuer (leader CTA) may overwrite this accumulator once every epilogue thread of
+                // the pair has drained it
+                if (CG == 1 || leader) ptx::mbar_arrive(&aux->tmem_empty[as]);
+                else ptx::mbar_arrive_remote(&aux->tmem_empty[as], 0);
             }
 
             if (KSEL == 1) {
@@ -442,10 +489,12 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     }
 
     ptx::tc_fence_before();
-    __syncthreads();
+    if (CG == 2) ptx::cluster_sync_all();   // neither CTA of a pair may retire while the other can still signal it
+    else __syncthreads();
     if (warp == 2) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+        if (CG == 2) ptx::tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+        else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -532,13 +581,24 @@ struct Plan {
     int n_mtiles, n_ntiles, tiles_per_split, n_splits;
 };
 
+// CTA pairs (cta_group::2) whenever there are at least two pairs' worth of row tiles
+static int pick_cg(int64_t m) {
+#ifdef ISE_FORCE_CG1
+    return 1;
+#endif
+    return ceil_div64(m, BLOCK_M) >= 4 ? 2 : 1;
+}
+
 static Plan make_plan(const ise_ctx* ctx, int64_t m, int64_t n, bool single_split = false) {
     Plan pl;
     pl.n_mtiles = (int)ceil_div64(m, BLOCK_M);
     pl.n_ntiles = (int)std::max<int64_t>(1, ceil_div64(n, BLOCK_N));
+    const int cg = pick_cg(m);
+    const int groups = (pl.n_mtiles + cg - 1) / cg;      // work is scheduled per CTA pair
+    const int slots = std::max(1, ctx->sm_count / cg);
     // enough work items for ~4 waves of the persistent grid, but never less than 8 column tiles per
     // item (a fresh item restarts its selection threshold) and at most 256 partial lists per row
-    int64_t want = ceil_div64((int64_t)4 * ctx->sm_count, std::max(1, pl.n_mtiles));
+    int64_t want = ceil_div64((int64_t)4 * slots, std::max(1, groups));
     int64_t max_by_tiles = std::max<int64_t>(1, pl.n_ntiles / 8);
     int64_t s_hi = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(2 * want, max_by_tiles), 256));
     if (single_split) s_hi = 1;  // top-1 verification keeps one runner-up per row, so columns are not split
@@ -547,7 +607,7 @@ static Plan make_plan(const ise_ctx* ctx, int64_t m, int64_t n, bool single_spli
     for (int64_t s = 1; s <= s_hi; ++s) {
         const int64_t tps = ceil_div64(pl.n_ntiles, s);
         const int64_t ns = ceil_div64(pl.n_ntiles, tps);
-        const int64_t waves = ceil_div64((int64_t)pl.n_mtiles * ns, ctx->sm_count);
+        const int64_t waves = ceil_div64((int64_t)groups * ns, slots);
         const int64_t cost = waves * tps;
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_s = ns; }
     }
@@ -556,16 +616,34 @@ static Plan make_plan(const ise_ctx* ctx, int64_t m, int64_t n, bool single_spli
     return pl;
 }
 
+template <int PA, int PB, bool L2, int KSEL, bool VERIFY, int CG>
+static int launch_cg(const ise_ctx* ctx, const CUtensorMap* maps, const Params& p, cudaStream_t st) {
+    auto kern = gemm_select_kernel<PA, PB, L2, KSEL, VERIFY, CG>;
+    const int smem = num_stages(PA, PB, CG) * stage_bytes(PA, PB, CG) + AUX_BYTES + 1024;
+    ISE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int groups = (p.n_mtiles + CG - 1) / CG;
+    const int total = groups * p.n_splits;
+    const int grid = CG * std::min(total, std::max(1, ctx->sm_count / CG));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)num_threads(KSEL));
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;   // CG == 2: the two CTAs of a pair form a cluster
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ISE_CUDA(cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], p));
+    return 0;
+}
+
 template <int PA, int PB, bool L2, int KSEL, bool VERIFY = false>
 static int launch(const ise_ctx* ctx, const CUtensorMap* maps, const Params& p, cudaStream_t st) {
-    auto kern = gemm_select_kernel<PA, PB, L2, KSEL, VERIFY>;
-    const int smem = num_stages(PA, PB) * stage_bytes(PA, PB) + AUX_BYTES + 1024;
-    ISE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int total = p.n_mtiles * p.n_splits;
-    const int grid = std::min(total, ctx->sm_count);
-    kern<<<grid, num_threads(KSEL), smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
-    ISE_LAUNCH_CHECK();
-    return 0;
+    return pick_cg(p.m) == 2 ? launch_cg<PA, PB, L2, KSEL, VERIFY, 2>(ctx, maps, p, st)
+                             : launch_cg<PA, PB, L2, KSEL, VERIFY, 1>(ctx, maps, p, st);
 }
 
 template <int PA, int PB, bool L2>
@@ -618,12 +696,13 @@ ISE_EXPORT int ise_topk_merge(ise_ctx* ctx, const float* val_parts, const int64_
 // shared argument validation + tensor maps
 static int setup_maps(ise_ctx* ctx, const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi,
                       const void* b_lo, int64_t ldb, int64_t m, int64_t n, int d, CUtensorMap* maps) {
+    const int b_box = gs::BLOCK_N / gs::pick_cg(m);   // a CTA of a pair stages half of every B tile
     ISE_CHECK_ARG(lda >= d && ldb >= d && lda % 8 == 0 && ldb % 8 == 0);
     ISE_CHECK_ARG((reinterpret_cast<uintptr_t>(a_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(b_hi) & 15) == 0);
     if (gs::make_plane_map(ctx, &maps[0], a_hi, m, d, lda, gs::BLOCK_M)) return 1;
     if (gs::make_plane_map(ctx, &maps[1], a_lo ? a_lo : a_hi, m, d, lda, gs::BLOCK_M)) return 1;
-    if (gs::make_plane_map(ctx, &maps[2], b_hi, n, d, ldb, gs::BLOCK_N)) return 1;
-    if (gs::make_plane_map(ctx, &maps[3], b_lo ? b_lo : b_hi, n, d, ldb, gs::BLOCK_N)) return 1;
+    if (gs::make_plane_map(ctx, &maps[2], b_hi, n, d, ldb, b_box)) return 1;
+    if (gs::make_plane_map(ctx, &maps[3], b_lo ? b_lo : b_hi, n, d, ldb, b_box)) return 1;
     return 0;
 }
 
@@ -712,10 +791,7 @@ ISE_EXPORT int ise_gemm_select(ise_ctx* ctx, const void* a_hi, const void* a_lo,
 
     const int pa = a_lo ? 2 : 1, pb = b_lo ? 2 : 1;
     CUtensorMap maps[4];
-    if (gs::make_plane_map(ctx, &maps[0], a_hi, m, d, lda, gs::BLOCK_M)) return 1;
-    if (gs::make_plane_map(ctx, &maps[1], a_lo ? a_lo : a_hi, m, d, lda, gs::BLOCK_M)) return 1;
-    if (gs::make_plane_map(ctx, &maps[2], b_hi, n, d, ldb, gs::BLOCK_N)) return 1;
-    if (gs::make_plane_map(ctx, &maps[3], b_lo ? b_lo : b_hi, n, d, ldb, gs::BLOCK_N)) return 1;
+    if (setup_maps(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, m, n, d, maps)) return 1;
 
     int rc;
     if (pa == 1 && pb == 1) rc = gs::dispatch_metric<1, 1>(ctx, maps, p, metric, st);

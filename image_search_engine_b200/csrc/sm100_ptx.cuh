@@ -104,6 +104,69 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster on one TPC share every B tile --------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 remAddr32;\n\t"
+        "mapa.shared::cluster.u32 remAddr32, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [remAddr32];\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(cta)
+        : "memory");
+}
+// TMA load issued by either CTA of a pair; the transaction bytes are signalled on the LEADER's barrier
+// (same offset, CTA-rank bit of the shared::cluster address cleared)
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
+                                                int32_t c1) {
+    const uint32_t leader_bar = smem_u32(bar) & 0xFEFFFFFFu;
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+        "%4}], [%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// M = 256 MMA over the pair: issued by ONE thread of the leader CTA; A rows 0-127 / 128-255 and the two
+// halves of B come from the same smem offsets of the two CTAs, D rows land in each CTA's own TMEM
+__device__ __forceinline__ void umma_f16_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// commit -> arrive on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+}
+
 // ---- UMMA descriptors --------------------------------------------------------------------
 // Shared-memory matrix descriptor for a K-major tile whose rows are exactly one 128-byte
 // swizzle span (64 fp16), stored by TMA with CU_TENSOR_MAP_SWIZZLE_128B:
