@@ -581,19 +581,26 @@ struct Plan {
     int n_mtiles, n_ntiles, tiles_per_split, n_splits;
 };
 
-// CTA pairs (cta_group::2) whenever there are at least two pairs' worth of row tiles
-static int pick_cg(int64_t m) {
+// CTA pairs (cta_group::2) for the SPLIT products when there are at least two pairs' worth of row tiles.
+// Measured on the B200 (profiles/r01_findings.md section 7): with the lo planes in play a stage is 48-64 KB per
+// CTA and carries 8-12 MMAs, and pairs win 4-6 % (C2 assign 1.36 vs 1.41 ms, C3 split top-1 92 vs 98 ms);
+// for the coarse pass (hi planes only, 4 MMAs per 32 KB stage) the cross-CTA signalling round trip is
+// exposed and pairs lose 3-20 %, so the coarse pass stays single-CTA.
+static int pick_cg(int64_t m, bool split_products) {
 #ifdef ISE_FORCE_CG1
     return 1;
 #endif
-    return ceil_div64(m, BLOCK_M) >= 4 ? 2 : 1;
+#ifdef ISE_FORCE_CG2
+    split_products = true;
+#endif
+    return (split_products && ceil_div64(m, BLOCK_M) >= 4) ? 2 : 1;
 }
 
-static Plan make_plan(const ise_ctx* ctx, int64_t m, int64_t n, bool single_split = false) {
+static Plan make_plan(const ise_ctx* ctx, int64_t m, int64_t n, bool single_split = false, bool split_products = false) {
     Plan pl;
     pl.n_mtiles = (int)ceil_div64(m, BLOCK_M);
     pl.n_ntiles = (int)std::max<int64_t>(1, ceil_div64(n, BLOCK_N));
-    const int cg = pick_cg(m);
+    const int cg = pick_cg(m, split_products);
     const int groups = (pl.n_mtiles + cg - 1) / cg;      // work is scheduled per CTA pair
     const int slots = std::max(1, ctx->sm_count / cg);
     // enough work items for ~4 waves of the persistent grid, but never less than 8 column tiles per
@@ -642,8 +649,8 @@ static int launch_cg(const ise_ctx* ctx, const CUtensorMap* maps, const Params& 
 
 template <int PA, int PB, bool L2, int KSEL, bool VERIFY = false>
 static int launch(const ise_ctx* ctx, const CUtensorMap* maps, const Params& p, cudaStream_t st) {
-    return pick_cg(p.m) == 2 ? launch_cg<PA, PB, L2, KSEL, VERIFY, 2>(ctx, maps, p, st)
-                             : launch_cg<PA, PB, L2, KSEL, VERIFY, 1>(ctx, maps, p, st);
+    return pick_cg(p.m, PB == 2) == 2 ? launch_cg<PA, PB, L2, KSEL, VERIFY, 2>(ctx, maps, p, st)
+                                      : launch_cg<PA, PB, L2, KSEL, VERIFY, 1>(ctx, maps, p, st);
 }
 
 template <int PA, int PB, bool L2>
@@ -670,9 +677,10 @@ static int dispatch_metric(const ise_ctx* ctx, const CUtensorMap* maps, const Pa
 
 ISE_EXPORT size_t ise_gemm_select_workspace_bytes(ise_ctx* ctx, int64_t m, int64_t n, int d, int topk) {
     if (!ctx || m <= 0 || topk <= 0) return 0;
-    gs::Plan pl = gs::make_plan(ctx, m, n);
-    if (pl.n_splits <= 1) return 0;
-    return (size_t)pl.n_splits * (size_t)m * (size_t)topk * (sizeof(float) + sizeof(int64_t)) + 256;
+    // the split count depends on whether the call will run CTA pairs (lo planes present): size for the larger
+    const int ns = std::max(gs::make_plan(ctx, m, n, false, false).n_splits, gs::make_plan(ctx, m, n, false, true).n_splits);
+    if (ns <= 1) return 0;
+    return (size_t)ns * (size_t)m * (size_t)topk * (sizeof(float) + sizeof(int64_t)) + 256;
 }
 
 ISE_EXPORT int ise_topk_merge(ise_ctx* ctx, const float* val_parts, const int64_t* idx_parts, int g, int64_t m,
@@ -696,7 +704,7 @@ ISE_EXPORT int ise_topk_merge(ise_ctx* ctx, const float* val_parts, const int64_
 // shared argument validation + tensor maps
 static int setup_maps(ise_ctx* ctx, const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi,
                       const void* b_lo, int64_t ldb, int64_t m, int64_t n, int d, CUtensorMap* maps) {
-    const int b_box = gs::BLOCK_N / gs::pick_cg(m);   // a CTA of a pair stages half of every B tile
+    const int b_box = gs::BLOCK_N / gs::pick_cg(m, b_lo != nullptr);   // a CTA of a pair stages half of every B tile
     ISE_CHECK_ARG(lda >= d && ldb >= d && lda % 8 == 0 && ldb % 8 == 0);
     ISE_CHECK_ARG((reinterpret_cast<uintptr_t>(a_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(b_hi) & 15) == 0);
     if (gs::make_plane_map(ctx, &maps[0], a_hi, m, d, lda, gs::BLOCK_M)) return 1;
@@ -719,7 +727,7 @@ ISE_EXPORT int ise_gemm_collect(ise_ctx* ctx, const void* a_hi, const void* a_lo
     if (metric == ISE_METRIC_L2) ISE_CHECK_ARG(a_norms && b_norms);
     DeviceGuard guard(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
-    gs::Plan pl = gs::make_plan(ctx, m, n);
+    gs::Plan pl = gs::make_plan(ctx, m, n, false, b_lo != nullptr);
     gs::Params p;
     p.m = m; p.n = n; p.d = d;
     p.n_mtiles = pl.n_mtiles; p.n_ntiles = pl.n_ntiles;
@@ -761,7 +769,7 @@ ISE_EXPORT int ise_gemm_select(ise_ctx* ctx, const void* a_hi, const void* a_lo,
     DeviceGuard guard(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
 
-    gs::Plan pl = gs::make_plan(ctx, m, n, flag_count != nullptr);
+    gs::Plan pl = gs::make_plan(ctx, m, n, flag_count != nullptr, b_lo != nullptr);
     gs::Params p;
     p.m = m; p.n = n; p.d = d;
     p.n_mtiles = pl.n_mtiles; p.n_ntiles = pl.n_ntiles;
@@ -779,7 +787,7 @@ ISE_EXPORT int ise_gemm_select(ise_ctx* ctx, const void* a_hi, const void* a_lo,
     float* wv = nullptr;
     int64_t* wi = nullptr;
     if (pl.n_splits > 1) {
-        const size_t need = ise_gemm_select_workspace_bytes(ctx, m, n, d, topk);
+        const size_t need = (size_t)pl.n_splits * (size_t)m * (size_t)topk * (sizeof(float) + sizeof(int64_t)) + 256;
         if (!workspace || workspace_bytes < need) ISE_FAIL("workspace too small: need " + std::to_string(need));
         const size_t cnt = (size_t)pl.n_splits * (size_t)m * (size_t)topk;
         wi = reinterpret_cast<int64_t*>(workspace);  // int64 first keeps both arrays aligned
