@@ -54,7 +54,7 @@ PROTOTYPES = {
     "ise_topk_merge": (_int, [_c_void_p, _c_void_p, _c_void_p, _int, _i64, _int, _int, _c_void_p, _c_void_p,
                               _c_void_p]),
     "ise_kmeans_accumulate": (_int, [_c_void_p, _c_void_p, _int, _i64, _int, _i64, _c_void_p, _c_void_p,
-                                     _c_void_p, _int, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+                                     _c_void_p, _i64, _int, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "ise_kmeans_mean": (_int, [_c_void_p, _c_void_p, _c_void_p, _i64, _int, _c_void_p, _c_void_p, _c_void_p]),
     "ise_kmeans_apply_splits": (_int, [_c_void_p, _c_void_p, _i64, _int, _c_void_p, C.c_int32, _c_void_p]),
     "ise_bovw_histogram": (_int, [_c_void_p, _c_void_p, _c_void_p, _i64, _int, _int, _int, _c_void_p, _int,

@@ -1,5 +1,5 @@
-// BoVW histogram (+ fused Okapi/BM25 tf weighting): one CTA per image, shared-memory-privatised
-// counts, 128-bit id loads, vectorised row stores.  HBM-bound: 8 B per descriptor id read plus one
+// BoVW histogram (+ fused Okapi/BM25 tf weighting): CTAs walk images, shared-memory-privatised counts,
+// ids read once into registers (next image prefetched), 128-bit row stores with the counters cleared in the same sweep.  HBM-bound: 8 B per descriptor id read plus one
 // write of the [n_img, k] matrix.
 // Replaces create_visual_word_histogram (bag_of_visual_words.py:98-106: np.histogram per image into a
 // float64 matrix) and OkapiTransformer.transform (utils.py:153-202).
@@ -46,58 +46,121 @@ __device__ __forceinline__ double okapi_weight(double tf, double k1, double k2, 
     return __ddiv_rn(t, den);
 }
 
+// 4 (float) or 2 x 2 (double) values per 128-bit store
+__device__ __forceinline__ void store4(float* p, double a, double b, double c, double d) {
+    *reinterpret_cast<float4*>(p) = make_float4((float)a, (float)b, (float)c, (float)d);
+}
+__device__ __forceinline__ void store4(double* p, double a, double b, double c, double d) {
+    reinterpret_cast<double2*>(p)[0] = make_double2(a, b);
+    reinterpret_cast<double2*>(p)[1] = make_double2(c, d);
+}
+
+// One CTA walks images (grid-stride).  Per image: the ids are read ONCE into registers (up to WPT per thread;
+// longer images re-read the tail from L2), min/max for the numpy-compat edges (32-bit redux), shared-memory atomic
+// counts, then the row is written with 128-bit stores while the counters are cleared in the same sweep (no
+// separate zeroing phase); the NEXT image's ids are already in flight during the write-out.  The Okapi weight
+// depends only on (tf, dl): the weights of tf = 1..kTfTable are computed once per image by 32 threads and the
+// write-out looks them up -- with the FP64 divisions inlined in the write-out the first version was
+// instruction-bound (6.1 k warp instructions per image, 0.44 of HBM peak; profiles/r01_findings.md section 9).
+// Ids must fit in int32 (k < 2^31 is checked by the entry point; other values cannot come out of the assign).
+constexpr int kTfTable = 32;
+
 template <typename OutT, bool SMEM>
-__global__ void histogram_kernel(const int64_t* __restrict__ words, const int64_t* __restrict__ off, int64_t n_img,
-                                 int k, int mode, OutT* __restrict__ out, int okapi, double k1, double k2, double b,
-                                 double avgdl_in) {
+__global__ void __launch_bounds__(kThreads, 4)
+histogram_kernel(const int64_t* __restrict__ words, const int64_t* __restrict__ off, int64_t n_img, int k, int mode,
+                 OutT* __restrict__ out, int okapi, double k1, double k2, double b, double avgdl_in) {
+    constexpr int WPT = 4;                       // ids held in registers per thread (covers 1024 per image)
     extern __shared__ int s_cnt[];
-    __shared__ long long s_mn, s_mx;
+    __shared__ int s_mn, s_mx;
+    __shared__ double s_w[kTfTable + 1];
     // np.mean(dl) over the batch being transformed (utils.py:196); a caller that feeds the batch in
     // several launches passes the whole batch's mean explicitly
     const double avgdl = avgdl_in >= 0.0 ? avgdl_in : (double)(off[n_img] - off[0]) / (double)n_img;
+    if (SMEM) {
+        for (int j = threadIdx.x; j < k; j += kThreads) s_cnt[j] = 0;
+    }
+    if (threadIdx.x == 0) { s_mn = INT_MAX; s_mx = INT_MIN; }
+    int w[WPT];
+    int64_t lo = 0, hi = 0;
+    auto fetch = [&](int64_t img) {
+        lo = off[img]; hi = off[img + 1];
+#pragma unroll
+        for (int i = 0; i < WPT; ++i) {
+            const int64_t j = lo + threadIdx.x + i * kThreads;
+            w[i] = j < hi ? (int)__ldg(words + j) : 0;
+        }
+    };
+    if (blockIdx.x < n_img) fetch(blockIdx.x);
+    __syncthreads();
+    const bool vec_ok = (k % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     for (int64_t img = blockIdx.x; img < n_img; img += gridDim.x) {
-        const int64_t lo = off[img], hi = off[img + 1];
         const int64_t cnt = hi - lo;
         OutT* orow = out + img * (int64_t)k;
-        if (SMEM) {
-            for (int j = threadIdx.x; j < k; j += kThreads) s_cnt[j] = 0;
-        }
-        if (threadIdx.x == 0) { s_mn = LLONG_MAX; s_mx = LLONG_MIN; }
-        __syncthreads();
+        const double ratio = __ddiv_rn((double)cnt, avgdl);  // rep / avgdl
+        if (okapi && threadIdx.x >= kThreads - kTfTable)     // the last warp: usually holds no ids
+            s_w[threadIdx.x - (kThreads - kTfTable) + 1] =
+                okapi_weight((double)(threadIdx.x - (kThreads - kTfTable) + 1), k1, k2, b, ratio);
         NumpyBins nb;
         if (mode == ISE_HIST_NUMPY_COMPAT && cnt > 0) {
-            long long mn = LLONG_MAX, mx = LLONG_MIN;
-            for (int64_t j = lo + threadIdx.x; j < hi; j += kThreads) {
-                const long long w = words[j];
-                mn = min(mn, w); mx = max(mx, w);
-            }
+            int mn = INT_MAX, mx = INT_MIN;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-                mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            for (int i = 0; i < WPT; ++i)
+                if (lo + threadIdx.x + i * kThreads < hi) { mn = min(mn, w[i]); mx = max(mx, w[i]); }
+            for (int64_t j = lo + threadIdx.x + WPT * kThreads; j < hi; j += kThreads) {
+                const int v = (int)words[j];
+                mn = min(mn, v); mx = max(mx, v);
             }
-            if ((threadIdx.x & 31) == 0) { atomicMin(&s_mn, mn); atomicMax(&s_mx, mx); }
+            mn = __reduce_min_sync(0xffffffffu, mn);
+            mx = __reduce_max_sync(0xffffffffu, mx);
+            if ((threadIdx.x & 31) == 0 && mn <= mx) { atomicMin(&s_mn, mn); atomicMax(&s_mx, mx); }
             __syncthreads();
             nb.setup(s_mn, s_mx, k);
         }
-        for (int64_t j = lo + threadIdx.x; j < hi; j += kThreads) {
-            const int64_t w = words[j];
+        auto count = [&](int v) {
             int bin;
-            if (mode == ISE_HIST_NUMPY_COMPAT) bin = nb.bin(w);
-            else bin = (w >= 0 && w < k) ? (int)w : -1;
+            if (mode == ISE_HIST_NUMPY_COMPAT) bin = nb.bin(v);
+            else bin = (v >= 0 && v < k) ? v : -1;
             if (bin >= 0 && bin < k) {
                 if (SMEM) atomicAdd(&s_cnt[bin], 1);
                 else atomicAdd(orow + bin, (OutT)1);  // row was zeroed by the caller's memset
             }
-        }
+        };
+#pragma unroll
+        for (int i = 0; i < WPT; ++i)
+            if (lo + threadIdx.x + i * kThreads < hi) count(w[i]);
+        for (int64_t j = lo + threadIdx.x + WPT * kThreads; j < hi; j += kThreads) count((int)words[j]);
+        // ids of the next image: in flight while this row is written
+        if (img + gridDim.x < n_img) fetch(img + gridDim.x);
         __syncthreads();
-        const double ratio = __ddiv_rn((double)cnt, avgdl);  // rep / avgdl
+        if (threadIdx.x == 0) { s_mn = INT_MAX; s_mx = INT_MIN; }   // read by everyone before the barrier above
+        auto weight = [&](int c) -> double {
+            if (!okapi) return (double)c;
+            return c <= kTfTable ? s_w[c] : okapi_weight((double)c, k1, k2, b, ratio);
+        };
         if (SMEM) {
-            for (int j = threadIdx.x; j < k; j += kThreads) {
-                const int c = s_cnt[j];
-                double v = (double)c;
-                if (okapi && c != 0) v = okapi_weight(v, k1, k2, b, ratio);
-                orow[j] = (OutT)v;
+            if (vec_ok) {
+                for (int j = threadIdx.x * 4; j < k; j += kThreads * 4) {
+                    const int4 c = *reinterpret_cast<const int4*>(s_cnt + j);
+                    double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+                    if ((c.x | c.y | c.z | c.w) != 0) {
+                        *reinterpret_cast<int4*>(s_cnt + j) = make_int4(0, 0, 0, 0);
+                        if (c.x) v0 = weight(c.x);
+                        if (c.y) v1 = weight(c.y);
+                        if (c.z) v2 = weight(c.z);
+                        if (c.w) v3 = weight(c.w);
+                    }
+                    store4(orow + j, v0, v1, v2, v3);
+                }
+            } else {
+                for (int j = threadIdx.x; j < k; j += kThreads) {
+                    const int c = s_cnt[j];
+                    double v = 0.0;
+                    if (c != 0) {
+                        s_cnt[j] = 0;
+                        v = weight(c);
+                    }
+                    orow[j] = (OutT)v;
+                }
             }
         } else if (okapi) {
             for (int j = threadIdx.x; j < k; j += kThreads) {
@@ -117,7 +180,13 @@ __global__ void row_sum_kernel(const T* __restrict__ h, int64_t n_img, int k, do
     for (int64_t img = blockIdx.x; img < n_img; img += gridDim.x) {
         const T* row = h + img * (int64_t)k;
         double acc = 0.0;
-        for (int j = threadIdx.x; j < k; j += kThreads) acc += (double)row[j];
+        // summed in the same per-thread column order whatever the unrolling: four loads in flight
+        int j = threadIdx.x;
+        for (; j + 3 * kThreads < k; j += 4 * kThreads) {
+            const T a0 = row[j], a1 = row[j + kThreads], a2 = row[j + 2 * kThreads], a3 = row[j + 3 * kThreads];
+            acc += (double)a0; acc += (double)a1; acc += (double)a2; acc += (double)a3;
+        }
+        for (; j < k; j += kThreads) acc += (double)row[j];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
@@ -139,7 +208,16 @@ __global__ void okapi_dense_kernel(T* __restrict__ h, int64_t n_img, int k, doub
     for (int64_t img = blockIdx.x; img < n_img; img += gridDim.x) {
         T* row = h + img * (int64_t)k;
         const double ratio = __ddiv_rn(dl[img], avgdl);
-        for (int j = threadIdx.x; j < k; j += kThreads) {
+        int j = threadIdx.x;
+        for (; j + 3 * kThreads < k; j += 4 * kThreads) {
+            T a[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) a[u] = row[j + u * kThreads];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if ((double)a[u] != 0.0) row[j + u * kThreads] = (T)okapi_weight((double)a[u], k1, k2, b, ratio);
+        }
+        for (; j < k; j += kThreads) {
             const double c = (double)row[j];
             if (c != 0.0) row[j] = (T)okapi_weight(c, k1, k2, b, ratio);
         }
@@ -151,7 +229,7 @@ __global__ void okapi_dense_kernel(T* __restrict__ h, int64_t n_img, int k, doub
 ISE_EXPORT int ise_bovw_histogram(ise_ctx* ctx, const int64_t* words, const int64_t* img_offsets, int64_t n_img,
                                   int k, int mode, int out_dtype, void* out, int okapi, double k1, double k2,
                                   double b, double avgdl, void* stream) {
-    ISE_CHECK_ARG(ctx && n_img >= 0 && k >= 1);
+    ISE_CHECK_ARG(ctx && n_img >= 0 && k >= 1);   // ids are handled as int32 (k is an int)
     ISE_CHECK_ARG(mode == ISE_HIST_NUMPY_COMPAT || mode == ISE_HIST_BINCOUNT);
     ISE_CHECK_ARG(out_dtype == ISE_OUT_F32 || out_dtype == ISE_OUT_F64);
     if (n_img == 0) return 0;

@@ -7,21 +7,30 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kWarpsPerBlock = kThreads / 32;
 
+__device__ __forceinline__ float absmax4(float4 v) {
+    return fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+}
+
 __global__ void absmax_f32_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ldx, float* meta) {
     const int lane = threadIdx.x & 31;
-    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
     float m = 0.f;
-    const bool vec = (d % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-    for (int64_t r = warp; r < n; r += nwarps) {
-        const float* row = x + r * ldx;
-        if (vec) {
-            const float4* row4 = reinterpret_cast<const float4*>(row);
-            for (int c = lane; c < d / 4; c += 32) {
-                float4 v = __ldg(row4 + c);
-                m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
-            }
-        } else {
+    if (ldx == d && ((n * d) % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0)) {
+        // contiguous matrix: a flat stream of float4, four independent loads in flight per thread
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        const int64_t total = n * d / 4;
+        const int64_t stride = (int64_t)gridDim.x * kThreads;
+        int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+        for (; i + 3 * stride < total; i += 4 * stride) {
+            const float4 a = __ldg(x4 + i), b = __ldg(x4 + i + stride), c = __ldg(x4 + i + 2 * stride),
+                         e = __ldg(x4 + i + 3 * stride);
+            m = fmaxf(m, fmaxf(fmaxf(absmax4(a), absmax4(b)), fmaxf(absmax4(c), absmax4(e))));
+        }
+        for (; i < total; i += stride) m = fmaxf(m, absmax4(__ldg(x4 + i)));
+    } else {
+        const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+        const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+        for (int64_t r = warp; r < n; r += nwarps) {
+            const float* row = x + r * ldx;
             for (int c = lane; c < d; c += 32) m = fmaxf(m, fabsf(__ldg(row + c)));
         }
     }
@@ -90,27 +99,167 @@ __global__ void prepare_planes_kernel(const T* __restrict__ x, int64_t n, int d,
     if (__any_sync(0xffffffffu, any_lo) && lane == 0) meta[META_LO_NONZERO] = 1.f;
 }
 
+// split one scaled value into its FP16 hi / lo parts
+__device__ __forceinline__ void split_f16(float s, __half& h, __half& l) {
+    h = __float2half_rn(s);
+    l = __float2half_rn(s - __half2float(h));
+}
+
+// Fast path, float32 rows with d % 4 == 0 (16-byte aligned rows and planes): a lane converts four consecutive
+// columns per step (one 128-bit load, one 64-bit store per plane) and every warp keeps ROWS rows in flight --
+// one row per warp iteration leaves ~32 KB of loads in flight per SM, which is what held the first version at
+// 0.6 of HBM peak (profiles/r01_findings.md section 9).
+template <int ROWS>
+__global__ void prepare_planes_f32x4_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ldx,
+                                            __half* __restrict__ hi, __half* __restrict__ lo, int64_t ldp,
+                                            float* __restrict__ norms, float* meta) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+    const float scale = scale_from_absmax(meta[META_ABSMAX]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        meta[META_SCALE] = scale;
+        meta[META_INV_SCALE] = 1.f / scale;
+    }
+    bool any_lo = false;
+    float max_ss = 0.f;
+    const int d4 = d >> 2, dp4 = (int)(ldp >> 2);
+    for (int64_t r0 = warp * ROWS; r0 < n; r0 += nwarps * ROWS) {
+        float ss[ROWS];
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) ss[i] = 0.f;
+        for (int c = lane; c < dp4; c += 32) {
+            float4 v[ROWS];
+#pragma unroll
+            for (int i = 0; i < ROWS; ++i) {
+                const int64_t r = r0 + i;
+                v[i] = (r < n && c < d4) ? __ldg(reinterpret_cast<const float4*>(x + r * ldx) + c)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < ROWS; ++i) {
+                const int64_t r = r0 + i;
+                if (r >= n) continue;
+                ss[i] = fmaf(v[i].x, v[i].x, ss[i]); ss[i] = fmaf(v[i].y, v[i].y, ss[i]);
+                ss[i] = fmaf(v[i].z, v[i].z, ss[i]); ss[i] = fmaf(v[i].w, v[i].w, ss[i]);
+                __half h0, h1, h2, h3, l0, l1, l2, l3;
+                split_f16(v[i].x * scale, h0, l0); split_f16(v[i].y * scale, h1, l1);
+                split_f16(v[i].z * scale, h2, l2); split_f16(v[i].w * scale, h3, l3);
+                const __half2 ha = __halves2half2(h0, h1), hb = __halves2half2(h2, h3);
+                const __half2 la = __halves2half2(l0, l1), lb = __halves2half2(l2, l3);
+                uint2 hv, lv;
+                hv.x = *reinterpret_cast<const uint32_t*>(&ha); hv.y = *reinterpret_cast<const uint32_t*>(&hb);
+                lv.x = *reinterpret_cast<const uint32_t*>(&la); lv.y = *reinterpret_cast<const uint32_t*>(&lb);
+                reinterpret_cast<uint2*>(hi + r * ldp)[c] = hv;
+                if (lo) reinterpret_cast<uint2*>(lo + r * ldp)[c] = lv;
+                any_lo |= ((lv.x | lv.y) & 0x7FFF7FFFu) != 0u;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) {
+            const float t = warp_sum(ss[i]);
+            if (r0 + i < n) {
+                if (norms && lane == 0) norms[r0 + i] = t;
+                max_ss = fmaxf(max_ss, t);
+            }
+        }
+    }
+    if (lane == 0 && max_ss > 0.f) atomicMax(reinterpret_cast<int*>(meta + META_MAX_NORM_SQ), __float_as_int(max_ss));
+    if (__any_sync(0xffffffffu, any_lo) && lane == 0) meta[META_LO_NONZERO] = 1.f;
+}
+
+// Fast path, uint8 rows (ORB / BRISK bytes) with d % 16 == 0 and d / 16 a power of two <= 32, contiguous rows and
+// planes: the matrix is a flat stream of 16-byte groups; a lane converts one group (16 columns: one 128-bit
+// load, two 128-bit stores), and the LPR = d / 16 lanes that share a row reduce its norm with shuffles.
+__global__ void prepare_planes_u8x16_kernel(const uint8_t* __restrict__ x, int64_t n, int d, __half* __restrict__ hi,
+                                            float* __restrict__ norms, float* meta) {
+    const int lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        meta[META_SCALE] = 1.f;
+        meta[META_INV_SCALE] = 1.f;
+        meta[META_ABSMAX] = 255.f;
+    }
+    const int lpr = d >> 4;                               // lanes per row
+    const int64_t groups = n * lpr;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    const int64_t g_end = (groups + 31) / 32 * 32;        // whole warps stay converged for the shuffles
+    float max_ss = 0.f;
+    auto convert = [&](int64_t g, const uint4& v) {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t out[8];
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float b0 = (float)(w[i] & 0xFFu), b1 = (float)((w[i] >> 8) & 0xFFu);
+            const float b2 = (float)((w[i] >> 16) & 0xFFu), b3 = (float)(w[i] >> 24);
+            ss = fmaf(b0, b0, ss); ss = fmaf(b1, b1, ss); ss = fmaf(b2, b2, ss); ss = fmaf(b3, b3, ss);
+            const __half2 p = __floats2half2_rn(b0, b1), q = __floats2half2_rn(b2, b3);
+            out[2 * i] = *reinterpret_cast<const uint32_t*>(&p);
+            out[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&q);
+        }
+        if (g < groups) {
+            uint4* dst = reinterpret_cast<uint4*>(hi) + 2 * g;
+            dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+            dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+        }
+        for (int o = lpr >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if (g < groups && (lane & (lpr - 1)) == 0) {
+            if (norms) norms[g / lpr] = ss;
+            max_ss = fmaxf(max_ss, ss);
+        }
+    };
+    // four independent 128-bit loads in flight per thread
+    for (int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x; g < g_end; g += 4 * stride) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t gu = g + u * stride;
+            v[u] = gu < groups ? __ldg(reinterpret_cast<const uint4*>(x) + gu) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (g + u * stride < g_end) convert(g + u * stride, v[u]);
+    }
+    max_ss = warp_max(max_ss);
+    if (lane == 0 && max_ss > 0.f) atomicMax(reinterpret_cast<int*>(meta + META_MAX_NORM_SQ), __float_as_int(max_ss));
+}
+
+// faiss fvec_renorm_L2: x *= 1 / sqrtf(sum x^2), zero rows untouched.  ROWS rows in flight per warp (one row per
+// warp iteration keeps too few loads in flight to fill HBM); the second sweep re-reads the rows from L1/L2.
+template <int ROWS>
 __global__ void normalize_l2_kernel(float* __restrict__ x, int64_t n, int d) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
     const bool vec = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-    for (int64_t r = warp; r < n; r += nwarps) {
-        float* row = x + r * (int64_t)d;
-        float ss = 0.f;
+    for (int64_t r0 = warp * ROWS; r0 < n; r0 += nwarps * ROWS) {
+        float ss[ROWS];
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) ss[i] = 0.f;
         if (vec) {
-            float4* row4 = reinterpret_cast<float4*>(row);
             for (int c = lane; c < d / 4; c += 32) {
-                float4 v = row4[c];
-                ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss);
-                ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+                float4 v[ROWS];
+#pragma unroll
+                for (int i = 0; i < ROWS; ++i)
+                    v[i] = r0 + i < n ? reinterpret_cast<const float4*>(x + (r0 + i) * (int64_t)d)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < ROWS; ++i) {
+                    ss[i] = fmaf(v[i].x, v[i].x, ss[i]); ss[i] = fmaf(v[i].y, v[i].y, ss[i]);
+                    ss[i] = fmaf(v[i].z, v[i].z, ss[i]); ss[i] = fmaf(v[i].w, v[i].w, ss[i]);
+                }
             }
         } else {
-            for (int c = lane; c < d; c += 32) { float v = row[c]; ss = fmaf(v, v, ss); }
+#pragma unroll
+            for (int i = 0; i < ROWS; ++i)
+                if (r0 + i < n)
+                    for (int c = lane; c < d; c += 32) { const float v = x[(r0 + i) * (int64_t)d + c]; ss[i] = fmaf(v, v, ss[i]); }
         }
-        ss = warp_sum(ss);
-        if (ss > 0.f) {
-            const float inv = 1.0f / sqrtf(ss);  // fvec_renorm_L2: inv_nr = 1.0 / sqrtf(nr)
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) {
+            const float t = warp_sum(ss[i]);
+            if (r0 + i >= n || !(t > 0.f)) continue;
+            const float inv = 1.0f / sqrtf(t);  // fvec_renorm_L2: inv_nr = 1.0 / sqrtf(nr)
+            float* row = x + (r0 + i) * (int64_t)d;
             if (vec) {
                 float4* row4 = reinterpret_cast<float4*>(row);
                 for (int c = lane; c < d / 4; c += 32) {
@@ -144,14 +293,29 @@ ISE_EXPORT int ise_prepare_planes(ise_ctx* ctx, const void* x, int dtype, int64_
     if (n == 0) return 0;
     ISE_CHECK_ARG(x != nullptr);
     const int grid = grid_for_rows(ctx, n);
+    const bool al16 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15) == 0;
     if (dtype == ISE_DTYPE_F32) {
         absmax_f32_kernel<<<grid, kThreads, 0, st>>>((const float*)x, n, d, ldx, meta);
         ISE_LAUNCH_CHECK();
-        prepare_planes_kernel<float><<<grid, kThreads, 0, st>>>((const float*)x, n, d, ldx, (__half*)hi,
-                                                                (__half*)lo, ldp, norms, meta, false);
+        if (d % 4 == 0 && ldx % 4 == 0 && al16) {
+            constexpr int ROWS = 4;
+            const int g4 = grid_for_rows(ctx, ceil_div64(n, ROWS));
+            prepare_planes_f32x4_kernel<ROWS><<<g4, kThreads, 0, st>>>((const float*)x, n, d, ldx, (__half*)hi, (__half*)lo,
+                                                                       ldp, norms, meta);
+        } else {
+            prepare_planes_kernel<float><<<grid, kThreads, 0, st>>>((const float*)x, n, d, ldx, (__half*)hi,
+                                                                    (__half*)lo, ldp, norms, meta, false);
+        }
     } else {
-        prepare_planes_kernel<uint8_t><<<grid, kThreads, 0, st>>>((const uint8_t*)x, n, d, ldx, (__half*)hi,
-                                                                  (__half*)lo, ldp, norms, meta, true);
+        const int lpr = d / 16;
+        if (d % 16 == 0 && lpr <= 32 && (lpr & (lpr - 1)) == 0 && ldx == d && ldp == d && al16 && lo == nullptr) {
+            const int64_t groups = n * lpr;
+            const int gu = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(groups, kThreads), (int64_t)ctx->sm_count * 8));
+            prepare_planes_u8x16_kernel<<<gu, kThreads, 0, st>>>((const uint8_t*)x, n, d, (__half*)hi, norms, meta);
+        } else {
+            prepare_planes_kernel<uint8_t><<<grid, kThreads, 0, st>>>((const uint8_t*)x, n, d, ldx, (__half*)hi,
+                                                                      (__half*)lo, ldp, norms, meta, true);
+        }
     }
     ISE_LAUNCH_CHECK();
     return 0;
@@ -162,7 +326,7 @@ ISE_EXPORT int ise_normalize_l2(ise_ctx* ctx, float* x, int64_t n, int d, void* 
     if (n == 0) return 0;
     ISE_CHECK_ARG(x != nullptr);
     DeviceGuard g(ctx->device);
-    normalize_l2_kernel<<<grid_for_rows(ctx, n), kThreads, 0, (cudaStream_t)stream>>>(x, n, d);
+    normalize_l2_kernel<4><<<grid_for_rows(ctx, ceil_div64(n, 4)), kThreads, 0, (cudaStream_t)stream>>>(x, n, d);
     ISE_LAUNCH_CHECK();
     return 0;
 }

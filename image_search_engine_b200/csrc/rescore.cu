@@ -118,8 +118,9 @@ __global__ void rescore_kernel(const TA* __restrict__ a, int64_t lda, const floa
     }
 }
 
-// topk == 1 fast path (k-means assign / quantisation distances): one warp per row, no sorting
-template <typename TA, bool L2>
+// topk == 1 fast path (k-means assign / quantisation distances): one warp per row, no sorting; ROWS rows (and their
+// gathered winners) in flight per warp so the loads cover HBM latency
+template <typename TA, bool L2, int ROWS>
 __global__ void rescore_top1_kernel(const TA* __restrict__ a, int64_t lda, const float* __restrict__ b, int64_t ldb,
                                     int64_t m, int d, int64_t id_base, const float* __restrict__ a_norms,
                                     const float* __restrict__ b_norms, float* __restrict__ val,
@@ -129,31 +130,49 @@ __global__ void rescore_top1_kernel(const TA* __restrict__ a, int64_t lda, const
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     const bool vec = sizeof(TA) == 4 && (d & 3) == 0 && (lda & 3) == 0 && (ldb & 3) == 0 &&
                      ((reinterpret_cast<uintptr_t>(a) & 15) == 0);
-    for (int64_t row = warp; row < m; row += nwarps) {
-        const long long id = idx[row];
-        if (id < 0) continue;
-        const int64_t col = id - id_base;
-        const TA* arow = a + row * lda;
-        const float* brow = b + col * ldb;
-        float acc = 0.f;
+    for (int64_t r0 = warp * ROWS; r0 < m; r0 += nwarps * ROWS) {
+        int64_t col[ROWS];
+        float acc[ROWS];
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) {
+            const long long id = r0 + i < m ? idx[r0 + i] : -1;
+            col[i] = id < 0 ? -1 : id - id_base;
+            acc[i] = 0.f;
+        }
         if (vec) {
-            const float4* a4 = reinterpret_cast<const float4*>(arow);
-            const float4* b4 = reinterpret_cast<const float4*>(brow);
             for (int c = lane; c < d / 4; c += 32) {
-                const float4 x = __ldg(a4 + c), y = __ldg(b4 + c);
-                acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc);
-                acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+                float4 x[ROWS], y[ROWS];
+#pragma unroll
+                for (int i = 0; i < ROWS; ++i) {
+                    if (col[i] < 0) continue;
+                    x[i] = __ldg(reinterpret_cast<const float4*>(a + (r0 + i) * lda) + c);
+                    y[i] = __ldg(reinterpret_cast<const float4*>(b + col[i] * ldb) + c);
+                }
+#pragma unroll
+                for (int i = 0; i < ROWS; ++i) {
+                    if (col[i] < 0) continue;
+                    acc[i] = fmaf(x[i].x, y[i].x, acc[i]); acc[i] = fmaf(x[i].y, y[i].y, acc[i]);
+                    acc[i] = fmaf(x[i].z, y[i].z, acc[i]); acc[i] = fmaf(x[i].w, y[i].w, acc[i]);
+                }
             }
         } else {
-            for (int c = lane; c < d; c += 32) acc = fmaf((float)arow[c], __ldg(brow + c), acc);
+#pragma unroll
+            for (int i = 0; i < ROWS; ++i)
+                if (col[i] >= 0)
+                    for (int c = lane; c < d; c += 32)
+                        acc[i] = fmaf((float)a[(r0 + i) * lda + c], __ldg(b + col[i] * ldb + c), acc[i]);
         }
-        acc = warp_sum(acc);
-        if (lane == 0) {
-            if (L2) {
-                const float dis = a_norms[row] + b_norms[col] - 2.f * acc;
-                val[row] = dis < 0.f ? 0.f : dis;
-            } else {
-                val[row] = acc;
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) {
+            if (col[i] < 0) continue;      // warp-uniform
+            const float t = warp_sum(acc[i]);
+            if (lane == 0) {
+                if (L2) {
+                    const float dis = a_norms[r0 + i] + b_norms[col[i]] - 2.f * t;
+                    val[r0 + i] = dis < 0.f ? 0.f : dis;
+                } else {
+                    val[r0 + i] = t;
+                }
             }
         }
     }
@@ -182,13 +201,13 @@ static int launch_rescore(ise_ctx* ctx, const void* a, int a_dtype, int64_t lda,
     if (flag_count) ISE_CUDA(cudaMemsetAsync(flag_count, 0, sizeof(int32_t), st));
     const bool l2 = metric == ISE_METRIC_L2;
     if (kc == 1 && topk == 1 && !flag_count && cand_idx == idx) {
-        const int g1 = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(m, 8), (int64_t)ctx->sm_count * 8));
+        const int g1 = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(m, 8 * 4), (int64_t)ctx->sm_count * 8));
         if (a_dtype == ISE_DTYPE_F32) {
-            if (l2) rescore_top1_kernel<float, true><<<g1, 256, 0, st>>>((const float*)a, lda, b, ldb, m, d, id_base, a_norms, b_norms, val, idx);
-            else rescore_top1_kernel<float, false><<<g1, 256, 0, st>>>((const float*)a, lda, b, ldb, m, d, id_base, a_norms, b_norms, val, idx);
+            if (l2) rescore_top1_kernel<float, true, 4><<<g1, 256, 0, st>>>((const float*)a, lda, b, ldb, m, d, id_base, a_norms, b_norms, val, idx);
+            else rescore_top1_kernel<float, false, 4><<<g1, 256, 0, st>>>((const float*)a, lda, b, ldb, m, d, id_base, a_norms, b_norms, val, idx);
         } else {
-            if (l2) rescore_top1_kernel<uint8_t, true><<<g1, 256, 0, st>>>((const uint8_t*)a, lda, b, ldb, m, d, id_base, a_norms, b_norms, val, idx);
-            else rescore_top1_kernel<uint8_t, false><<<g1, 256, 0, st>>>((const uint8_t*)a, lda, b, ldb, m, d, id_base, a_norms, b_norms, val, idx);
+            if (l2) rescore_top1_kernel<uint8_t, true, 4><<<g1, 256, 0, st>>>((const uint8_t*)a, lda, b, ldb, m, d, id_base, a_norms, b_norms, val, idx);
+            else rescore_top1_kernel<uint8_t, false, 4><<<g1, 256, 0, st>>>((const uint8_t*)a, lda, b, ldb, m, d, id_base, a_norms, b_norms, val, idx);
         }
         ISE_LAUNCH_CHECK();
         return 0;

@@ -398,7 +398,7 @@ def kmeans_accumulate(x: torch.Tensor, assign: torch.Tensor, dis: torch.Tensor |
         dis = dis.reshape(-1)
     _lib.check(_lib.load().ise_kmeans_accumulate(
         _lib.ctx(_dev(x)), _ptr(x), dt, n, d, x.stride(0) if n > 0 else d, _ptr(assign), _ptr(dis),
-        _ptr(centroids), int(metric), _ptr(sums), _ptr(counts), _ptr(obj), _stream()))
+        _ptr(centroids), int(sums.shape[0]), int(metric), _ptr(sums), _ptr(counts), _ptr(obj), _stream()))
     _count()
 
 

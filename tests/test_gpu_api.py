@@ -414,3 +414,50 @@ def test_uint8_and_float_descriptors_agree(g):
     km = _codebook(g)
     assert np.array_equal(km.transform(g["X"]), km.transform(g["X"].astype(np.float32)))
     assert np.array_equal(km.transform(g["X"]), km.transform(g["X"].astype(np.float64)))
+
+
+def test_c1_full_size_pipeline_against_oracle():
+    """BASELINE configs[0] (C1) at full size, lock-step with the oracle: 1000 images of ~500 ORB-like uint8
+    descriptors, k = 512.  The codebook comes from the ORACLE (so both sides quantise against the same
+    centroids); words, numpy-compat histograms, Okapi, cosine and L2 top-10 must match."""
+    from image_search_engine_b200 import BOVW, FaissKMeans, OkapiTransformer, create_search_index, faiss_compat
+    from oracle import cpu_baseline, faiss_shim as fs
+    rng = np.random.default_rng(1)
+    sizes = np.clip(np.rint(rng.normal(500, 100, 1000)), 50, 1024).astype(int)
+    descs = [orb_like(rng, int(s), 32) for s in sizes]
+    X = np.concatenate(descs)
+    okm = fs.Kmeans(32, 512, seed=42, niter=3, nredo=1, spherical=True)
+    okm.train(X.astype(np.float32))                       # sub-samples to 131072 rows like Faiss
+    gkm = faiss_compat.Kmeans(32, 512, seed=42, niter=3, nredo=1, spherical=True)
+    gkm.train(X)
+    np.testing.assert_allclose(gkm.obj, okm.obj, rtol=1e-4)
+    cent = okm.centroids
+    gidx = faiss_compat.IndexFlatIP(32)
+    gidx.add(cent)
+    clusterer = FaissKMeans(512, index=gidx)
+    words = clusterer.transform(X)
+    _, ow = okm.index.search(X.astype(np.float32), 1)
+    n_diff = assert_topk_parity(words, ow, X.astype(np.float32), cent, True, max_mismatch_frac=0.001)
+    bovw = BOVW(None, n_clusters=512)
+    bovw.clusterer, bovw.descriptions = clusterer, descs
+    H = bovw.transform(None)
+    Ho = cpu_baseline.visual_word_histograms(cpu_baseline.codebook_index(cent), descs, 512)
+    assert (H.sum(1) == sizes).all()
+    rows_equal = (H == Ho).all(axis=1)
+    assert rows_equal.sum() >= 1000 - n_diff               # rows can differ only where a word differs
+    T = OkapiTransformer().fit(Ho).transform(Ho)
+    assert np.array_equal(np.asarray(T.todense()), np.asarray(cpu_baseline.okapi_transform(Ho).todense()))
+    feats = np.asarray(T.todense()).astype(np.float32)
+    for kind, metric in (("cosine", fs.METRIC_INNER_PRODUCT), ("l2", fs.METRIC_L2)):
+        db = feats.copy()
+        index = create_search_index(db, kind)                # cosine normalises db in place
+        D, I = index.search(feats, 10)
+        Do, Io = fs.knn(feats, db, 10, metric)
+        assert_topk_parity(I, Io, feats, db, metric == fs.METRIC_INNER_PRODUCT, max_mismatch_frac=0.05)
+        # Faiss's n >= 20 path evaluates L2 as |x|^2 + |y|^2 - 2<x,y> in FP32, so its own value carries an absolute
+        # error of ~eps*(|x|^2 + |y|^2) (a self-match comes back as 6e-5..5e-4 instead of 0); the product re-scores
+        # with the direct sum.  Tolerance: 1e-4 relative + 1e-5 of the expansion's term scale.
+        scale = float((db.astype(np.float64) ** 2).sum(1).max() + (feats.astype(np.float64) ** 2).sum(1).max())
+        np.testing.assert_allclose(D, Do, rtol=1e-4, atol=1e-5 * scale)
+        if kind == "l2":
+            assert (I[:, 0] == np.arange(1000)).all()
