@@ -100,7 +100,8 @@ class BOVW(BaseEstimator):
 
     def __getstate__(self):
         state = super().__getstate__()
-        state.pop("_pipe_cache", None)      # CUDA streams / events / staging buffers are not persisted
+        for key in ("_pipe_cache", "_csr_cache", "_csr_bufs"):   # CUDA streams / events / staging buffers are not persisted
+            state.pop(key, None)
         return state
 
     def fit(self, X, y=None):
@@ -187,6 +188,103 @@ class BOVW(BaseEstimator):
                 pc["ev_out"][b].record(s_out)
         s_out.synchronize()
         return out.numpy()
+
+    # ---- CSR path: what `Pipeline([bovw, tfidf]).transform(...)` returns in the reference is a scipy CSR
+    # matrix (utils.py:153-202); building it on the device never materialises the dense matrix ----
+    def _csr_kwargs(self, okapi):
+        if self.hist_mode not in _HIST_MODES:
+            raise ValueError(f"hist_mode must be one of {sorted(_HIST_MODES)}")
+        kw = dict(mode=_HIST_MODES[self.hist_mode])
+        if okapi is not None:
+            kw.update(okapi=True, k1=okapi.k1, k2=okapi.k2, b=okapi.b)
+        return kw
+
+    def csr_device(self, descriptions, *, okapi: OkapiTransformer | None = None, out_dtype=torch.float64):
+        """(indptr int32, indices int32, data) CUDA tensors of the histogram (+ Okapi tf) matrix; the used length
+        of indices / data is indptr[-1]."""
+        dev = ops.require_cuda()
+        mat, offsets = pack_descriptions(descriptions)
+        xd = mat.to(dev, non_blocking=True) if isinstance(mat, torch.Tensor) else \
+            torch.from_numpy(mat).to(dev, non_blocking=True)
+        off = torch.from_numpy(offsets).to(dev, non_blocking=True)
+        words = self.clusterer.transform_device(xd)
+        return ops.bovw_histogram_csr(words, off, int(self.n_clusters), out_dtype=out_dtype, **self._csr_kwargs(okapi))
+
+    def transform_csr(self, X=None, *, okapi: OkapiTransformer | None = None, n_chunks: int = 8, copy: bool = True):
+        """Host descriptors in, scipy CSR float64 (n_images, n_clusters) out == OkapiTransformer().transform(
+        BOVW.transform(X)) of the reference (``okapi=None``: the plain histogram as CSR).  The host -> device copy
+        of the descriptors is cut into ``n_chunks`` pieces overlapped with the quantisation of the previous
+        piece; the ids stay in HBM, the CSR arrays are built there for the whole batch and come back in one
+        small copy (~12 B per non-zero instead of 8 B per matrix cell).  ``copy=False`` returns a matrix that
+        aliases this object's pinned result buffers (valid until the next call)."""
+        import scipy.sparse as sp
+        # like transform(): cached descriptions win over X (bag_of_visual_words.py:89-92), except that an explicit
+        # PackedDescriptions batch is always taken as given
+        descriptions = X if isinstance(X, PackedDescriptions) else getattr(self, "descriptions", None)
+        if descriptions is None:
+            descriptions = describe_dataset(self.describer, X, prediction=True)
+        dev = ops.require_cuda()
+        k = int(self.n_clusters)
+        mat, offsets = pack_descriptions(descriptions)
+        if isinstance(mat, np.ndarray):
+            mat = torch.from_numpy(mat)
+        n_img, n_rows = len(offsets) - 1, int(mat.shape[0])
+        kw = self._csr_kwargs(okapi)
+        off_dev = torch.from_numpy(offsets).to(dev, non_blocking=True)
+        if mat.is_cuda or n_img < 2 * n_chunks or not mat.is_pinned():
+            words = self.clusterer.transform_device(mat.to(dev, non_blocking=True))
+        else:
+            # chunked H2D (copy stream) overlapped with the assign of the previous chunk (current stream)
+            NB = 3
+            cuts = np.unique(np.linspace(0, n_rows, n_chunks + 1).astype(np.int64))
+            max_rows = int(np.diff(cuts).max())
+            key = ("csr", max_rows, int(mat.shape[1]), mat.dtype, str(dev))
+            pc = self.__dict__.get("_csr_cache")
+            if pc is None or pc["key"] != key:
+                pc = dict(key=key, s_in=torch.cuda.Stream(),
+                          xd=[torch.empty((max_rows, mat.shape[1]), dtype=mat.dtype, device=dev) for _ in range(NB)],
+                          ev_in=[torch.cuda.Event() for _ in range(NB)], ev_c=[torch.cuda.Event() for _ in range(NB)])
+                self.__dict__["_csr_cache"] = pc
+            main, s_in = torch.cuda.current_stream(), pc["s_in"]
+            s_in.wait_stream(main)
+            words = torch.empty((n_rows,), dtype=torch.int64, device=dev)
+            for ci, (r0, r1) in enumerate(zip(cuts[:-1], cuts[1:])):
+                b = ci % NB
+                xd = pc["xd"][b][: int(r1 - r0)]
+                with torch.cuda.stream(s_in):
+                    if ci >= NB:
+                        s_in.wait_event(pc["ev_c"][b])
+                    xd.copy_(mat[int(r0):int(r1)], non_blocking=True)
+                    pc["ev_in"][b].record(s_in)
+                main.wait_event(pc["ev_in"][b])
+                words[int(r0):int(r1)] = self.clusterer.transform_device(xd)
+                pc["ev_c"][b].record(main)
+        # persistent device + pinned result buffers (indptr | indices | data), grown on demand
+        rb = self.__dict__.get("_csr_bufs")
+        if rb is None or rb["cap"] < max(n_rows, 1) or rb["n_img"] < n_img or rb["dev"] != str(dev):
+            cap = max(n_rows, 1)
+            rb = dict(cap=cap, n_img=n_img, dev=str(dev),
+                      d=(torch.empty((n_img + 1,), dtype=torch.int32, device=dev),
+                         torch.empty((cap,), dtype=torch.int32, device=dev),
+                         torch.empty((cap,), dtype=torch.float64, device=dev)),
+                      h=(torch.empty((n_img + 1,), dtype=torch.int32, pin_memory=True),
+                         torch.empty((cap,), dtype=torch.int32, pin_memory=True),
+                         torch.empty((cap,), dtype=torch.float64, pin_memory=True)))
+            self.__dict__["_csr_bufs"] = rb
+        d_ptr, d_idx, d_dat = rb["d"]
+        h_ptr, h_idx, h_dat = rb["h"]
+        ops.bovw_histogram_csr(words, off_dev, k, out=(d_ptr[: n_img + 1], d_idx, d_dat), **kw)
+        h_ptr[: n_img + 1].copy_(d_ptr[: n_img + 1], non_blocking=True)
+        # the non-zero count is only known on the device: ship the upper bound (one entry per descriptor)
+        h_idx[:n_rows].copy_(d_idx[:n_rows], non_blocking=True)
+        h_dat[:n_rows].copy_(d_dat[:n_rows], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        indptr = h_ptr[: n_img + 1].numpy()
+        nnz = int(indptr[-1])
+        indices, data = h_idx[:nnz].numpy(), h_dat[:nnz].numpy()
+        if copy:
+            indptr, indices, data = indptr.copy(), indices.copy(), data.copy()
+        return sp.csr_matrix((data, indices, indptr), shape=(n_img, k), copy=False)
 
     def histograms_device(self, descriptions, *, okapi: OkapiTransformer | None = None,
                           out_dtype=torch.float64) -> torch.Tensor:

@@ -172,6 +172,137 @@ histogram_kernel(const int64_t* __restrict__ words, const int64_t* __restrict__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// CSR output: the histogram matrix is ~97 % zeros at BoVW sizes (100-1000 words per image against thousands of
+// bins), and OkapiTransformer.transform returns a scipy CSR matrix anyway (utils.py:153-202), so the
+// pipeline-level call never has to materialise (or ship over PCIe) the dense [n_img, k] float64 matrix.
+//   pass 0  distinct bins per image (atomicAdd's old value == 0 marks a bin's first hit)  -> row_nnz[n_img]
+//   scan    exclusive prefix sum                                                          -> indptr[n_img + 1]
+//   pass 1  recount, then an ordered compaction of the k counters (thread t owns a contiguous run of bins,
+//           block-wide exclusive scan of the per-thread non-zero counts)                  -> indices, data
+// Column indices come out sorted, like scipy's dense -> CSR conversion.
+// ------------------------------------------------------------------------------------------
+template <typename OutT, int PASS>
+__global__ void __launch_bounds__(kThreads, 4)
+histogram_csr_kernel(const int64_t* __restrict__ words, const int64_t* __restrict__ off, int64_t n_img, int k, int mode,
+                     int32_t* __restrict__ row_nnz, const int32_t* __restrict__ indptr, int32_t* __restrict__ indices,
+                     OutT* __restrict__ data, int okapi, double k1, double k2, double b, double avgdl_in) {
+    extern __shared__ int s_cnt[];
+    __shared__ int s_mn, s_mx, s_total;
+    __shared__ int s_warp[kThreads / 32];
+    __shared__ double s_w[kTfTable + 1];
+    const double avgdl = avgdl_in >= 0.0 ? avgdl_in : (double)(off[n_img] - off[0]) / (double)n_img;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    for (int j = threadIdx.x; j < k; j += kThreads) s_cnt[j] = 0;
+    if (threadIdx.x == 0) { s_mn = INT_MAX; s_mx = INT_MIN; s_total = 0; }
+    __syncthreads();
+    const int cpt = ((k + kThreads - 1) / kThreads + 3) / 4 * 4;     // bins per thread in the compaction (multiple of 4)
+    for (int64_t img = blockIdx.x; img < n_img; img += gridDim.x) {
+        const int64_t lo = off[img], hi = off[img + 1];
+        const int64_t cnt = hi - lo;
+        NumpyBins nb;
+        if (mode == ISE_HIST_NUMPY_COMPAT && cnt > 0) {
+            int mn = INT_MAX, mx = INT_MIN;
+            for (int64_t j = lo + threadIdx.x; j < hi; j += kThreads) {
+                const int v = (int)__ldg(words + j);
+                mn = min(mn, v); mx = max(mx, v);
+            }
+            mn = __reduce_min_sync(0xffffffffu, mn);
+            mx = __reduce_max_sync(0xffffffffu, mx);
+            if (lane == 0 && mn <= mx) { atomicMin(&s_mn, mn); atomicMax(&s_mx, mx); }
+            __syncthreads();
+            nb.setup(s_mn, s_mx, k);
+        }
+        int fresh = 0;
+        for (int64_t j = lo + threadIdx.x; j < hi; j += kThreads) {
+            const int v = (int)__ldg(words + j);
+            int bin;
+            if (mode == ISE_HIST_NUMPY_COMPAT) bin = nb.bin(v);
+            else bin = (v >= 0 && v < k) ? v : -1;
+            if (bin >= 0 && bin < k) fresh += atomicAdd(&s_cnt[bin], 1) == 0 ? 1 : 0;
+        }
+        if (PASS == 0) {
+            fresh = __reduce_add_sync(0xffffffffu, fresh);
+            if (lane == 0 && fresh) atomicAdd(&s_total, fresh);
+            __syncthreads();
+            if (threadIdx.x == 0) { row_nnz[img] = s_total; s_total = 0; s_mn = INT_MAX; s_mx = INT_MIN; }
+            // clear only the bins this image touched
+            for (int64_t j = lo + threadIdx.x; j < hi; j += kThreads) {
+                const int v = (int)__ldg(words + j);
+                int bin;
+                if (mode == ISE_HIST_NUMPY_COMPAT) bin = nb.bin(v);
+                else bin = (v >= 0 && v < k) ? v : -1;
+                if (bin >= 0 && bin < k) s_cnt[bin] = 0;
+            }
+            __syncthreads();
+        } else {
+            const double ratio = __ddiv_rn((double)cnt, avgdl);
+            if (okapi && threadIdx.x >= kThreads - kTfTable)
+                s_w[threadIdx.x - (kThreads - kTfTable) + 1] =
+                    okapi_weight((double)(threadIdx.x - (kThreads - kTfTable) + 1), k1, k2, b, ratio);
+            __syncthreads();
+            if (threadIdx.x == 0) { s_mn = INT_MAX; s_mx = INT_MIN; }
+            // ordered compaction: thread t owns bins [t * cpt, t * cpt + cpt)
+            const int c_lo = threadIdx.x * cpt, c_hi = min(k, c_lo + cpt);
+            int mine = 0;
+            for (int c = c_lo; c < c_hi; ++c) mine += s_cnt[c] != 0 ? 1 : 0;
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) s_warp[wib] = incl;
+            __syncthreads();
+            int base = 0;
+#pragma unroll
+            for (int i = 0; i < kThreads / 32; ++i) base += i < wib ? s_warp[i] : 0;
+            int pos = indptr[img] + base + incl - mine;
+            for (int c = c_lo; c < c_hi; ++c) {
+                const int v = s_cnt[c];
+                if (v != 0) {
+                    s_cnt[c] = 0;
+                    indices[pos] = c;
+                    double w = (double)v;
+                    if (okapi) w = v <= kTfTable ? s_w[v] : okapi_weight((double)v, k1, k2, b, ratio);
+                    data[pos] = (OutT)w;
+                    ++pos;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// exclusive prefix sum of n int32 values -> out[n + 1] (single CTA; n is the number of images)
+__global__ void exclusive_scan_i32_kernel(const int32_t* __restrict__ in, int64_t n, int32_t* __restrict__ out) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n; base += blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        const int v = i < n ? in[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[wib] = incl;
+        __syncthreads();
+        int wbase = 0;
+        for (int w = 0; w < wib; ++w) wbase += s_warp[w];
+        const int carry = s_carry;
+        if (i < n) out[i] = carry + wbase + incl - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = carry + wbase + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = s_carry;
+}
+
 // dense in-place Okapi: pass 1 row sums (document lengths), pass 2 weights
 template <typename T>
 __global__ void row_sum_kernel(const T* __restrict__ h, int64_t n_img, int k, double* __restrict__ dl,
@@ -277,6 +408,38 @@ ISE_EXPORT int ise_okapi_tf(ise_ctx* ctx, void* h, int out_dtype, int64_t n_img,
         ISE_LAUNCH_CHECK();
         okapi_dense_kernel<float><<<grid, kThreads, 0, st>>>((float*)h, n_img, k, k1, k2, b, avgdl, dl, total);
     }
+    ISE_LAUNCH_CHECK();
+    return 0;
+}
+
+ISE_EXPORT int ise_bovw_histogram_csr(ise_ctx* ctx, const int64_t* words, const int64_t* img_offsets, int64_t n_img,
+                                      int k, int mode, int out_dtype, int32_t* row_nnz, int32_t* indptr,
+                                      int32_t* indices, void* data, int okapi, double k1, double k2, double b,
+                                      double avgdl, void* stream) {
+    ISE_CHECK_ARG(ctx && n_img >= 0 && k >= 1 && k <= kMaxSmemBins);
+    ISE_CHECK_ARG(mode == ISE_HIST_NUMPY_COMPAT || mode == ISE_HIST_BINCOUNT);
+    ISE_CHECK_ARG(out_dtype == ISE_OUT_F32 || out_dtype == ISE_OUT_F64);
+    ISE_CHECK_ARG(indptr != nullptr);
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_img == 0) {
+        ISE_CUDA(cudaMemsetAsync(indptr, 0, sizeof(int32_t), st));
+        return 0;
+    }
+    ISE_CHECK_ARG(words && img_offsets && row_nnz && indices && data);
+    const int grid = (int)std::min<int64_t>(n_img, (int64_t)ctx->sm_count * 8);
+    const size_t shm = (size_t)k * sizeof(int);
+    histogram_csr_kernel<double, 0><<<grid, kThreads, shm, st>>>(words, img_offsets, n_img, k, mode, row_nnz, nullptr,
+                                                                 nullptr, nullptr, 0, k1, k2, b, avgdl);
+    ISE_LAUNCH_CHECK();
+    exclusive_scan_i32_kernel<<<1, 1024, 0, st>>>(row_nnz, n_img, indptr);
+    ISE_LAUNCH_CHECK();
+    if (out_dtype == ISE_OUT_F64)
+        histogram_csr_kernel<double, 1><<<grid, kThreads, shm, st>>>(words, img_offsets, n_img, k, mode, row_nnz, indptr,
+                                                                     indices, (double*)data, okapi, k1, k2, b, avgdl);
+    else
+        histogram_csr_kernel<float, 1><<<grid, kThreads, shm, st>>>(words, img_offsets, n_img, k, mode, row_nnz, indptr,
+                                                                    indices, (float*)data, okapi, k1, k2, b, avgdl);
     ISE_LAUNCH_CHECK();
     return 0;
 }

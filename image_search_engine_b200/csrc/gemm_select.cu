@@ -41,8 +41,16 @@ constexpr int EPI_WARP0 = 4;
 // One epilogue warp per TMEM lane quadrant.  (Two warps per quadrant, each scanning half of a tile's
 // columns, was measured SLOWER for the d = 128 assign: 1.57-1.67 ms vs 1.43 ms at C2 -- the tile is bound
 // by the TMEM -> register read of the 128 x 256 accumulator, not by issue slots; the code path is kept.)
-__host__ __device__ constexpr int epi_halves(int ksel) { return 1; }
-__host__ __device__ constexpr int num_threads(int ksel) { return 128 + 128 * epi_halves(ksel); }
+#ifndef ISE_EPI_HALVES_COARSE_TOP1
+#define ISE_EPI_HALVES_COARSE_TOP1 1
+#endif
+// The COARSE top-1 pass (one product per tile, d <= 128: 1 024 MMA cycles per tile) is bound by the epilogue's
+// instruction stream, not by its TMEM reads (profiles/r01_findings.md section 8), so it gets two warps per
+// quadrant; everything else is MMA-bound and keeps one.
+__host__ __device__ constexpr int epi_halves(int ksel, int pa, int pb) {
+    return (ksel == 1 && pa == 1 && pb == 1) ? ISE_EPI_HALVES_COARSE_TOP1 : 1;
+}
+__host__ __device__ constexpr int num_threads(int ksel, int pa, int pb) { return 128 + 128 * epi_halves(ksel, pa, pb); }
 constexpr int TMEM_COLS = 512;  // 2 accumulator stages x BLOCK_N fp32 columns
 constexpr int AUX_BYTES = 4096;
 constexpr int SMEM_LIMIT = 232448;  // 227 KiB opt-in per CTA on sm_100
@@ -109,7 +117,7 @@ template <> struct SelList<32> { using type = RegList32; };
 //   tcgen05.commit multicasts `empty` / `tmem_full` to both CTAs; both epilogues arrive on the leader's
 //   `tmem_empty`.  Each CTA's epilogue reads its own 128 TMEM lanes exactly as in the single-CTA case.
 template <int PA, int PB, bool L2, int KSEL, bool VERIFY, int CG>
-__global__ void __launch_bounds__(num_threads(KSEL), 1)
+__global__ void __launch_bounds__(num_threads(KSEL, PA, PB), 1)
 gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const Params p) {
@@ -117,7 +125,7 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     constexpr int STAGE_BYTES = stage_bytes(PA, PB, CG);
     constexpr int B_LOAD_BYTES = B_TILE_BYTES / CG;   // this CTA's share of a B tile (one plane)
     constexpr int B_LOAD_ROWS = BLOCK_N / CG;
-    constexpr int HALVES = epi_halves(KSEL);
+    constexpr int HALVES = epi_halves(KSEL, PA, PB);
     constexpr int NUM_EPI_THREADS = 128 * HALVES;
     constexpr int COLS_PER_HALF = BLOCK_N / HALVES;
     static_assert(STAGES >= 2 && STAGES <= 8, "pipeline depth");
@@ -633,7 +641,7 @@ static int launch_cg(const ise_ctx* ctx, const CUtensorMap* maps, const Params& 
     const int grid = CG * std::min(total, std::max(1, ctx->sm_count / CG));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3((unsigned)num_threads(KSEL));
+    cfg.blockDim = dim3((unsigned)num_threads(KSEL, PA, PB));
     cfg.dynamicSmemBytes = (size_t)smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];

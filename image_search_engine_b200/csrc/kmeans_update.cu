@@ -209,14 +209,12 @@ accumulate_priv_kernel(const T* __restrict__ x, int64_t n, int d, int64_t ldx, c
                     }
                 }
             }
+            // objective terms stay per lane (reduced once at the end); counts by lane 0
 #pragma unroll
             for (int u = 0; u < kPrivUnroll; ++u) {
                 if (cl[u] < 0) continue;
-                if (cent) acc[u] = warp_sum(acc[u]);
-                if (lane == 0) {
-                    s_cnt[cl[u]] += 1.0f;
-                    my_obj += (double)acc[u];
-                }
+                my_obj += (double)acc[u];
+                if (lane == 0) s_cnt[cl[u]] += 1.0f;
             }
         }
         __syncwarp();

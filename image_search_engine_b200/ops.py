@@ -441,6 +441,35 @@ def bovw_histogram(words: torch.Tensor, img_offsets: torch.Tensor, k: int, *, mo
     return out
 
 
+def bovw_histogram_csr(words: torch.Tensor, img_offsets: torch.Tensor, k: int, *, mode: int = HIST_NUMPY_COMPAT,
+                       out_dtype: torch.dtype = torch.float64, okapi: bool = False, k1: float = 1.0, k2: float = 1.0,
+                       b: float = 0.75, avgdl: float = -1.0, out: tuple | None = None):
+    """Histogram (+ fused Okapi) as CSR: returns (indptr int32 [n_img+1], indices int32 [cap], data [cap]) on the
+    device; the used length is indptr[-1] <= cap = number of words.  ``out`` = preallocated (indptr, indices, data)."""
+    if words.dtype != torch.int64 or img_offsets.dtype != torch.int64:
+        raise IseError("bovw_histogram_csr: words and img_offsets must be int64")
+    if out_dtype not in (torch.float32, torch.float64):
+        raise IseError("bovw_histogram_csr: float32 or float64 data")
+    words = words.reshape(-1).contiguous()
+    n_img = img_offsets.numel() - 1
+    cap = max(int(words.numel()), 1)
+    dev = words.device
+    if out is None:
+        out = (torch.empty((n_img + 1,), dtype=torch.int32, device=dev), torch.empty((cap,), dtype=torch.int32, device=dev),
+               torch.empty((cap,), dtype=out_dtype, device=dev))
+    indptr, indices, data = out
+    if indptr.numel() < n_img + 1 or indices.numel() < words.numel() or data.numel() < words.numel() or \
+            indptr.dtype != torch.int32 or indices.dtype != torch.int32 or data.dtype != out_dtype:
+        raise IseError("bovw_histogram_csr: out buffers too small or of the wrong dtype")
+    row_nnz = torch.empty((max(n_img, 1),), dtype=torch.int32, device=dev)
+    _lib.check(_lib.load().ise_bovw_histogram_csr(
+        _lib.ctx(_dev(img_offsets)), _ptr(words), _ptr(img_offsets), n_img, int(k), int(mode),
+        OUT_F64 if out_dtype == torch.float64 else OUT_F32, _ptr(row_nnz), _ptr(indptr), _ptr(indices), _ptr(data),
+        1 if okapi else 0, float(k1), float(k2), float(b), float(avgdl), _stream()))
+    _count(3)
+    return indptr, indices, data
+
+
 def okapi_tf_(h: torch.Tensor, k1: float = 1.0, k2: float = 1.0, b: float = 0.75, avgdl: float = -1.0):
     if h.dtype not in (torch.float32, torch.float64) or h.dim() != 2 or not h.is_contiguous():
         raise IseError("okapi_tf_: contiguous float32/float64 matrix")

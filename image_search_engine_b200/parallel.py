@@ -31,6 +31,37 @@ from ._lib import METRIC_IP, METRIC_L2
 from .faiss_compat import ClusteringParameters, IndexFlat, IndexFlatIP, IndexFlatL2
 
 
+def bind_to_gpu_numa(device_index: int) -> list[int] | None:
+    """Pins this process to the CPUs NVML reports as local to ``device_index`` (physical index, after
+    CUDA_VISIBLE_DEVICES).  One process per GPU means eight processes pin host staging buffers and drive
+    eight PCIe links at once; with first-touch allocation the pinned buffers then live on the GPU's own NUMA
+    node instead of wherever torchrun happened to start the rank.  Returns the CPU list, or None when NVML
+    has no answer (single-socket VMs): never an error."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = device_index
+        if vis:
+            ent = vis.split(",")[device_index].strip()
+            if not ent.isdigit():
+                return None
+            phys = int(ent)
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus or len(cpus) == len(allowed):
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 class DeviceOps:
     """libise-backed local compute (the product path)."""
 

@@ -187,6 +187,16 @@ int ise_kmeans_apply_splits(ise_ctx* ctx, float* centroids, int64_t k, int d,
 int ise_bovw_histogram(ise_ctx* ctx, const int64_t* words, const int64_t* img_offsets, int64_t n_img,
                        int k, int mode, int out_dtype, void* out,
                        int okapi, double k1, double k2, double b, double avgdl, void* stream);
+/* Same histogram (+ fused Okapi), as a CSR matrix with sorted column indices -- what
+ * OkapiTransformer.transform returns (scipy CSR, utils.py:153-202) and what
+ * `pipeline.transform(...)` hands to its caller (engine.py:96, bag_of_visual_words.py:181-183): the dense
+ * [n_img,k] matrix (97 % zeros) is never materialised.  row_nnz: workspace int32[n_img]; indptr:
+ * int32[n_img+1]; indices / data: capacity >= number of words (an upper bound on the non-zeros; the used
+ * length is indptr[n_img]).  k <= 12288 (shared-memory counters). */
+int ise_bovw_histogram_csr(ise_ctx* ctx, const int64_t* words, const int64_t* img_offsets, int64_t n_img,
+                           int k, int mode, int out_dtype, int32_t* row_nnz, int32_t* indptr,
+                           int32_t* indices, void* data,
+                           int okapi, double k1, double k2, double b, double avgdl, void* stream);
 /* OkapiTransformer.transform on an existing dense [n_img,k] matrix, in place (f32 or f64).
  * avgdl < 0 => mean row sum of this batch (utils.py:196).  dl_workspace: device double[n_img + 1]. */
 int ise_okapi_tf(ise_ctx* ctx, void* h, int out_dtype, int64_t n_img, int k,

@@ -34,3 +34,6 @@ print("H2D only              : %.2f ms" % t(lambda: packed.matrix.to(dev, non_bl
 H = bovw.histograms_device(PackedDescriptions(xd, offsets), okapi=ok)
 print("D2H only              : %.2f ms" % t(lambda: out.copy_(H, non_blocking=True)))
 print("device only           : %.2f ms" % t(lambda: bovw.histograms_device(PackedDescriptions(xd, offsets), okapi=ok)))
+for nc in (4, 8, 16):
+    print("transform_csr n_chunks=%2d : %.2f ms" % (nc, t(lambda: bovw.transform_csr(packed, okapi=ok, n_chunks=nc, copy=False))))
+print("csr device only       : %.2f ms" % t(lambda: bovw.csr_device(PackedDescriptions(xd, offsets), okapi=ok)))

@@ -461,3 +461,54 @@ def test_c1_full_size_pipeline_against_oracle():
         np.testing.assert_allclose(D, Do, rtol=1e-4, atol=1e-5 * scale)
         if kind == "l2":
             assert (I[:, 0] == np.arange(1000)).all()
+
+
+@pytest.mark.parametrize("mode", ["numpy_compat", "bincount"])
+@pytest.mark.parametrize("k,use_okapi", [(512, True), (4096, True), (200, False), (1001, True)])
+def test_histogram_csr_equals_dense(mode, k, use_okapi):
+    """Device-built CSR (sorted indices) == scipy's CSR of the dense kernel's matrix, bit for bit: ragged images,
+    an empty image, a one-word image, an image longer than the kernel's register window, k % 4 != 0."""
+    import scipy.sparse as sp
+    from image_search_engine_b200 import ops
+    from image_search_engine_b200._lib import HIST_BINCOUNT, HIST_NUMPY_COMPAT
+    dev = ops.require_cuda()
+    rng = np.random.default_rng(k)
+    sizes = np.concatenate([[0, 1, 2500, 3], rng.integers(20, 700, 60), [0]])
+    off = np.zeros(len(sizes) + 1, np.int64)
+    np.cumsum(sizes, out=off[1:])
+    words = rng.integers(0, k, int(off[-1]))
+    words[off[2]:off[3]][:40] = 7                       # heavy repeats: tf beyond the Okapi lookup table
+    m = HIST_NUMPY_COMPAT if mode == "numpy_compat" else HIST_BINCOUNT
+    wd, od = torch.from_numpy(words).to(dev), torch.from_numpy(off).to(dev)
+    kw = dict(okapi=True, k1=1.2, k2=0.9, b=0.6) if use_okapi else {}
+    H = ops.bovw_histogram(wd, od, k, mode=m, **kw).cpu().numpy()
+    indptr, indices, data = ops.bovw_histogram_csr(wd, od, k, mode=m, **kw)
+    indptr = indptr.cpu().numpy()
+    nnz = int(indptr[-1])
+    got = sp.csr_matrix((data.cpu().numpy()[:nnz], indices.cpu().numpy()[:nnz], indptr), shape=H.shape)
+    want = sp.csr_matrix(H)
+    assert np.array_equal(got.indptr, want.indptr)
+    assert np.array_equal(got.indices, want.indices)
+    assert np.array_equal(got.data, want.data)
+    assert indptr[1] == 0 and indptr[2] == 1 and indptr[-1] == indptr[-2]     # empty / one-word / trailing empty image
+
+
+def test_transform_csr_matches_reference_pipeline(g):
+    """BOVW.transform_csr(okapi=...) == OkapiTransformer().transform(BOVW.transform(X)) (the reference's
+    Pipeline output, a scipy CSR float64 matrix), through both the direct and the chunk-pipelined pinned path."""
+    from image_search_engine_b200 import BOVW, OkapiTransformer
+    from image_search_engine_b200.bag_of_visual_words import pack_descriptions
+    km = _codebook(g)
+    bovw = BOVW(None, n_clusters=km.n_clusters)
+    bovw.clusterer = km
+    descs = _descs(g)
+    ok = OkapiTransformer()
+    bovw.descriptions = descs
+    dense = bovw.transform(None)
+    want = ok.fit(dense).transform(dense)
+    for X in (None, pack_descriptions(descs, pin=True)):        # cached list (direct) / pinned batch (chunk-pipelined)
+        got = bovw.transform_csr(X, okapi=ok, n_chunks=2)
+        assert got.shape == want.shape and got.dtype == np.float64
+        assert np.array_equal(got.indptr, want.indptr)
+        assert np.array_equal(got.indices, want.indices)
+        assert np.array_equal(got.data, want.data)
