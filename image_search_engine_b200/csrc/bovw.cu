@@ -9,7 +9,7 @@
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 128;   // 8 CTAs per SM: the per-image critical path (barriers, FP64 edges) wants many images in flight
 constexpr int kMaxSmemBins = 12 * 1024;  // 48 KiB of int32 counters
 
 // np.histogram(a, bins=k) for integer input, restated with the same float64 operations
@@ -65,8 +65,14 @@ __device__ __forceinline__ void store4(double* p, double a, double b, double c, 
 // Ids must fit in int32 (k < 2^31 is checked by the entry point; other values cannot come out of the assign).
 constexpr int kTfTable = 32;
 
+// out-of-line on purpose: inlined, the compiler if-converts `tf <= table ? table[tf] : weight(tf)` and runs the FP64
+// division for EVERY non-zero (ncu: 45 % of the kernel's instructions were that speculated DFMA chain)
+__device__ __noinline__ double okapi_weight_rare(double tf, double k1, double k2, double b, double ratio) {
+    return okapi_weight(tf, k1, k2, b, ratio);
+}
+
 template <typename OutT, bool SMEM>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, 8)
 histogram_kernel(const int64_t* __restrict__ words, const int64_t* __restrict__ off, int64_t n_img, int k, int mode,
                  OutT* __restrict__ out, int okapi, double k1, double k2, double b, double avgdl_in) {
     constexpr int WPT = 4;                       // ids held in registers per thread (covers 1024 per image)
@@ -135,7 +141,8 @@ histogram_kernel(const int64_t* __restrict__ words, const int64_t* __restrict__ 
         if (threadIdx.x == 0) { s_mn = INT_MAX; s_mx = INT_MIN; }   // read by everyone before the barrier above
         auto weight = [&](int c) -> double {
             if (!okapi) return (double)c;
-            return c <= kTfTable ? s_w[c] : okapi_weight((double)c, k1, k2, b, ratio);
+            if (c <= kTfTable) return s_w[c];
+            return okapi_weight_rare((double)c, k1, k2, b, ratio);
         };
         if (SMEM) {
             if (vec_ok) {
@@ -183,7 +190,7 @@ histogram_kernel(const int64_t* __restrict__ words, const int64_t* __restrict__ 
 // Column indices come out sorted, like scipy's dense -> CSR conversion.
 // ------------------------------------------------------------------------------------------
 template <typename OutT, int PASS>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, 8)
 histogram_csr_kernel(const int64_t* __restrict__ words, const int64_t* __restrict__ off, int64_t n_img, int k, int mode,
                      int32_t* __restrict__ row_nnz, const int32_t* __restrict__ indptr, int32_t* __restrict__ indices,
                      OutT* __restrict__ data, int okapi, double k1, double k2, double b, double avgdl_in) {
@@ -264,7 +271,7 @@ histogram_csr_kernel(const int64_t* __restrict__ words, const int64_t* __restric
                     s_cnt[c] = 0;
                     indices[pos] = c;
                     double w = (double)v;
-                    if (okapi) w = v <= kTfTable ? s_w[v] : okapi_weight((double)v, k1, k2, b, ratio);
+                    if (okapi) w = v <= kTfTable ? s_w[v] : okapi_weight_rare((double)v, k1, k2, b, ratio);
                     data[pos] = (OutT)w;
                     ++pos;
                 }
@@ -368,7 +375,7 @@ ISE_EXPORT int ise_bovw_histogram(ise_ctx* ctx, const int64_t* words, const int6
     DeviceGuard guard(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
     const bool smem = k <= kMaxSmemBins;
-    const int grid = (int)std::min<int64_t>(n_img, (int64_t)ctx->sm_count * 8);
+    const int grid = (int)std::min<int64_t>(n_img, (int64_t)ctx->sm_count * 16);
     const size_t elt = out_dtype == ISE_OUT_F64 ? 8 : 4;
     if (!smem) ISE_CUDA(cudaMemsetAsync(out, 0, (size_t)n_img * k * elt, st));
     const size_t shm = smem ? (size_t)k * sizeof(int) : 0;
@@ -398,7 +405,7 @@ ISE_EXPORT int ise_okapi_tf(ise_ctx* ctx, void* h, int out_dtype, int64_t n_img,
     double* dl = dl_workspace;
     double* total = dl_workspace + n_img;
     ISE_CUDA(cudaMemsetAsync(total, 0, sizeof(double), st));
-    const int grid = (int)std::min<int64_t>(n_img, (int64_t)ctx->sm_count * 8);
+    const int grid = (int)std::min<int64_t>(n_img, (int64_t)ctx->sm_count * 16);
     if (out_dtype == ISE_OUT_F64) {
         row_sum_kernel<double><<<grid, kThreads, 0, st>>>((const double*)h, n_img, k, dl, total);
         ISE_LAUNCH_CHECK();
@@ -427,7 +434,7 @@ ISE_EXPORT int ise_bovw_histogram_csr(ise_ctx* ctx, const int64_t* words, const 
         return 0;
     }
     ISE_CHECK_ARG(words && img_offsets && row_nnz && indices && data);
-    const int grid = (int)std::min<int64_t>(n_img, (int64_t)ctx->sm_count * 8);
+    const int grid = (int)std::min<int64_t>(n_img, (int64_t)ctx->sm_count * 16);
     const size_t shm = (size_t)k * sizeof(int);
     histogram_csr_kernel<double, 0><<<grid, kThreads, shm, st>>>(words, img_offsets, n_img, k, mode, row_nnz, nullptr,
                                                                  nullptr, nullptr, 0, k1, k2, b, avgdl);
