@@ -334,14 +334,30 @@ def load_cluster_model(n_clusters, index=None):
 
 
 def train_bovw_model(images_paths, describer, config):
-    """Offline index build (bag_of_visual_words.py:137-204).  ``config`` supplies NUM_CLUSTERS and the
-    three artefact paths; the optional GridSearchCV branch (:149-181) is outside the hot path."""
+    """Offline index build (bag_of_visual_words.py:137-204).  ``config`` supplies NUM_CLUSTERS, the three artefact
+    paths and, with BOVW_HYPERPARAMETERS_SEARCH, the cluster-count grid (:149-181)."""
     print(f"Received {len(images_paths)} images to process")
-    if getattr(config, "BOVW_HYPERPARAMETERS_SEARCH", False):
-        raise NotImplementedError("cluster-count grid search is outside the B200 retrieval core")
     pipeline = Pipeline([("bovw", BOVW(describer, n_clusters=config.NUM_CLUSTERS)), ("tfidf", OkapiTransformer())])
-    bovw, tfidf = pipeline.named_steps["bovw"], pipeline.named_steps["tfidf"]
-    bovw.fit(images_paths)
+    if getattr(config, "BOVW_HYPERPARAMETERS_SEARCH", False):
+        # cluster-count grid search (:149-181): every candidate is a full fit on the GPU; the scorer labels all
+        # cached descriptors with one assign launch.  n_jobs stays 1: the candidates share one device.
+        from sklearn.model_selection import GridSearchCV
+        from . import utils as _utils
+        _utils.CLUSTER_EVAL_SAMPLE_SIZE = getattr(config, "CLUSTER_EVAL_SAMPLE_SIZE", _utils.CLUSTER_EVAL_SAMPLE_SIZE)
+        _utils.CLUSTER_EVAL_N_SAMPLES = getattr(config, "CLUSTER_EVAL_N_SAMPLES", _utils.CLUSTER_EVAL_N_SAMPLES)
+        clusters_to_test = np.unique(np.linspace(config.MIN_NUM_CLUSTERS, config.MAX_NUM_CLUSTERS,
+                                                 config.NUM_CLUSTERS_TO_TEST).round().astype(int))
+        search = GridSearchCV(estimator=pipeline, param_grid={"bovw__n_clusters": clusters_to_test}, n_jobs=1,
+                              verbose=1, scoring=_utils.calc_sampled_cluster_score)
+        search.fit(images_paths)
+        print("Search finished.")
+        print(f"Best score: {search.best_score_:.3f}")
+        print(f"Best parameters: {search.best_params_}")
+        pipeline = search.best_estimator_
+        bovw, tfidf = pipeline.named_steps["bovw"], pipeline.named_steps["tfidf"]
+    else:
+        bovw, tfidf = pipeline.named_steps["bovw"], pipeline.named_steps["tfidf"]
+        bovw.fit(images_paths)
     # GPU-resident build: histogram + Okapi fused, float32 rows, normalise + add without leaving HBM
     H = bovw.histograms_device(bovw.descriptions, okapi=tfidf, out_dtype=torch.float32)
     tfidf.fit(H)

@@ -50,6 +50,99 @@ def run_image_query(image_features, n_images, normalize=False, *, index=None, im
     return predictions
 
 
+class QueryBatcher:
+    """Micro-batching front end for the online query path (engine.py:68-107 serves one upload per request and
+    calls ``index.search`` with nq = 1): requests arriving from concurrent server threads within ``max_wait_ms``
+    are stacked into ONE ``index.search`` call, so the database is streamed once for the whole batch instead of
+    once per request.  ``submit`` returns a ``concurrent.futures.Future`` resolving to the same
+    ``[(dist, thumbnail, path), ...]`` list ``run_image_query`` returns; ``query`` is the blocking form.
+
+    Faiss (and this index) evaluates L2 distances with a different formula below nq = 20 (direct sum of squared
+    differences) than above (|x|^2 + |y|^2 - 2<x,y>), so near-tied neighbours could swap with the
+    batch size.  The batcher therefore pads every batch to at least 20 rows: all requests take the tensor-core
+    path, whose per-row result (exactly re-scored, canonically ordered) does not depend on the other rows --
+    a request's answer is independent of who else was in its batch (tests/test_gpu_api.py)."""
+
+    def __init__(self, index, images_paths=None, get_image=None, *, max_batch=256, max_wait_ms=2.0):
+        import queue
+        import threading
+        self.index, self.images_paths, self.get_image = index, images_paths, get_image
+        self.max_batch, self.max_wait = int(max_batch), float(max_wait_ms) / 1e3
+        self._q = queue.Queue()
+        self._stop = threading.Event()
+        self.batches = []                      # sizes of the batches served (observability / tests)
+        self._device = torch.cuda.current_device() if torch.cuda.is_available() else None
+        self._t = threading.Thread(target=self._serve, name="ise-query-batcher", daemon=True)
+        self._t.start()
+
+    def submit(self, image_features, n_images, normalize=False):
+        from concurrent.futures import Future
+        if isinstance(image_features, torch.Tensor):
+            image_features = image_features.detach().cpu().numpy()
+        q = np.ascontiguousarray(np.asarray(image_features, dtype=np.float32).reshape(1, -1))
+        if normalize:
+            faiss.normalize_L2(q)
+        fut = Future()
+        self._q.put((q, int(n_images), fut))
+        return fut
+
+    def query(self, image_features, n_images, normalize=False):
+        return self.submit(image_features, n_images, normalize).result()
+
+    def close(self):
+        self._stop.set()
+        self._q.put(None)
+        self._t.join()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _serve(self):
+        import queue
+        import time
+        if self._device is not None:
+            torch.cuda.set_device(self._device)     # the current device is per thread
+        while not self._stop.is_set():
+            item = self._q.get()
+            if item is None:
+                break
+            batch = [item]
+            deadline = time.monotonic() + self.max_wait
+            while len(batch) < self.max_batch:
+                left = deadline - time.monotonic()
+                if left <= 0:
+                    break
+                try:
+                    nxt = self._q.get(timeout=left)
+                except queue.Empty:
+                    break
+                if nxt is None:
+                    self._stop.set()
+                    break
+                batch.append(nxt)
+            try:
+                k = max(n for _, n, _ in batch)
+                rows = [q for q, _, _ in batch]
+                rows += [rows[-1]] * max(0, faiss.distance_compute_blas_threshold - len(rows))   # one code path
+                D, I = self.index.search(np.concatenate(rows, axis=0), k)
+                self.batches.append(len(batch))
+                for row, (_, n, fut) in enumerate(batch):
+                    preds = []
+                    for dist, i in zip(D[row, :n].tolist(), I[row, :n].tolist()):
+                        if i < 0:
+                            continue
+                        path = self.images_paths[i] if self.images_paths is not None else i
+                        preds.append((dist, self.get_image(path) if self.get_image else None, str(path)))
+                    fut.set_result(preds)
+            except Exception as exc:      # a failed search fails its requests, not the server thread
+                for _, _, fut in batch:
+                    if not fut.done():
+                        fut.set_exception(exc)
+
+
 def query_index(embedding, index, index_type, n_results):
     """Drop-in for backend/siamese/test_index.py:query_index (:49-71).
 

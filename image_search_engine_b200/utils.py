@@ -115,3 +115,32 @@ def create_search_index(data_array, index_type="cosine"):
     index.add(rows)
     print(f"There are {index.ntotal} images in the search index.")
     return index
+
+
+# ------------------------------------------------------------------------------------------
+# cluster-quality scorer for the optional cluster-count grid search (utils.py:235-290)
+# ------------------------------------------------------------------------------------------
+rs = np.random.RandomState(42)          # module-level stream, like the reference (utils.py:26)
+CLUSTER_EVAL_SAMPLE_SIZE = 2000         # config.py:97-100
+CLUSTER_EVAL_N_SAMPLES = 10
+
+
+def calc_sampled_cluster_score(estimator, X, y=None):
+    """Drop-in for utils.calc_sampled_cluster_score: minus the mean Davies-Bouldin score of
+    ``CLUSTER_EVAL_N_SAMPLES`` random samples of ``CLUSTER_EVAL_SAMPLE_SIZE`` descriptors, labelled by the fitted
+    codebook.  The part that scales with the data set -- assigning EVERY cached descriptor to its visual word
+    (utils.py:274-275) -- is one fused assign launch; the 2000-row Davies-Bouldin evaluations stay scikit-learn's.
+    Like the reference it scores ``estimator.named_steps["bovw"].descriptions`` and ignores X."""
+    from sklearn.metrics import davies_bouldin_score
+    from .bag_of_visual_words import pack_descriptions
+    bovw = estimator.named_steps["bovw"]
+    mat, _ = pack_descriptions(bovw.descriptions)
+    labels_ = bovw.clusterer.transform(mat).ravel()
+    all_descriptions = mat.cpu().numpy() if isinstance(mat, torch.Tensor) else np.asarray(mat)
+    dataset_size = all_descriptions.shape[0]
+    sample_size = int(min(dataset_size, CLUSTER_EVAL_SAMPLE_SIZE))
+    scores = []
+    for _ in range(CLUSTER_EVAL_N_SAMPLES):
+        sample_idxs = rs.choice(dataset_size, size=sample_size, replace=False)
+        scores.append(davies_bouldin_score(all_descriptions[sample_idxs], labels_[sample_idxs]))
+    return -1 * np.mean(scores)

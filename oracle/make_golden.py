@@ -9,6 +9,7 @@ What each fixture pins
                    BOVW.transform (np.histogram loop), reference OkapiTransformer, reference
                    create_search_index("cosine" and "l2") + index.search, shim write_index bytes.
   kats.npz         known-answer cases from SURVEY section 4 (histogram quirk Q1, ties, k > ntotal).
+  cluster_score.npz  reference calc_sampled_cluster_score (sampled Davies-Bouldin) on the C1-mini codebook.
 The Faiss arithmetic itself comes from the shim (PARITY UNPINNED, see oracle/__init__.py); everything
 else in these files is produced by reference code.
 """
@@ -73,6 +74,26 @@ def c1_mini(ref, seed=1):
     )
 
 
+def cluster_score(ref, seed=1):
+    """Reference calc_sampled_cluster_score (utils.py:235-290) on the C1-mini pipeline: 10 x davies_bouldin_score
+    over 2000-row samples drawn by the module's RandomState(42), applied to the labels of FaissKMeans.transform."""
+    import types
+    rng = np.random.default_rng(seed)
+    n_img, d, k = 40, 32, 32
+    sizes = np.clip(np.rint(rng.normal(120, 30, n_img)), 20, 300).astype(np.int64)
+    sizes[3] = 1
+    descs = [rng.integers(0, 256, size=(int(s), d), dtype=np.uint8) for s in sizes]
+    km = ref.kmeans_faiss.FaissKMeans(k, n_init=2, max_iter=4)
+    km.fit(np.concatenate(descs, axis=0))
+    bovw = ref.bag_of_visual_words.BOVW(describer=None, n_clusters=k)
+    bovw.descriptions, bovw.clusterer = descs, km
+    est = types.SimpleNamespace(named_steps={"bovw": bovw})
+    ref.utils.rs = np.random.RandomState(42)               # the state a fresh import of utils.py starts from
+    s1 = ref.utils.calc_sampled_cluster_score(est, None)
+    s2 = ref.utils.calc_sampled_cluster_score(est, None)   # the module-level stream keeps advancing
+    return dict(score_first_call=np.float64(s1), score_second_call=np.float64(s2), centroids=km.cluster_centers_)
+
+
 def kats(ref):
     out = {}
     idx = np.array([3, 3, 7, 190, 100, 100], dtype=np.int64).reshape(-1, 1)
@@ -104,6 +125,7 @@ def main():
     OUT.mkdir(parents=True, exist_ok=True)
     np.savez_compressed(OUT / "bovw_c1mini.npz", **c1_mini(ref))
     np.savez_compressed(OUT / "kats.npz", **kats(ref))
+    np.savez_compressed(OUT / "cluster_score.npz", **cluster_score(ref))
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size, "bytes")
 

@@ -512,3 +512,69 @@ def test_transform_csr_matches_reference_pipeline(g):
         assert np.array_equal(got.indptr, want.indptr)
         assert np.array_equal(got.indices, want.indices)
         assert np.array_equal(got.data, want.data)
+
+
+def test_cluster_score_matches_reference_fixture(g):
+    """calc_sampled_cluster_score (utils.py:235-290): same labels + the same RandomState(42) stream -> the
+    reference's own sampled Davies-Bouldin score, first and second call (tests/golden/cluster_score.npz)."""
+    import types
+    from image_search_engine_b200 import BOVW, utils
+    gold = np.load(GOLD / "cluster_score.npz")
+    assert np.array_equal(gold["centroids"], g["centroids"])
+    bovw = BOVW(None, n_clusters=int(g["k"]))
+    bovw.clusterer, bovw.descriptions = _codebook(g), _descs(g)
+    est = types.SimpleNamespace(named_steps={"bovw": bovw})
+    utils.rs = np.random.RandomState(42)
+    utils.CLUSTER_EVAL_SAMPLE_SIZE, utils.CLUSTER_EVAL_N_SAMPLES = 2000, 10
+    s1 = utils.calc_sampled_cluster_score(est, None)
+    s2 = utils.calc_sampled_cluster_score(est, None)
+    assert s1 == pytest.approx(float(gold["score_first_call"]), rel=1e-9)
+    assert s2 == pytest.approx(float(gold["score_second_call"]), rel=1e-9)
+
+
+def test_train_bovw_model_grid_search(tmp_path):
+    """BOVW_HYPERPARAMETERS_SEARCH branch of train_bovw_model (bag_of_visual_words.py:149-181): GridSearchCV over
+    the cluster count with the sampled Davies-Bouldin scorer; the estimators must survive sklearn.clone."""
+    import types
+    from image_search_engine_b200 import faiss_compat, train_bovw_model
+    rng = np.random.default_rng(11)
+    centres = rng.integers(0, 256, size=(12, 32))
+    descs = [np.clip(centres[rng.integers(0, 12, 90)] + rng.normal(0, 6, (90, 32)), 0, 255).astype(np.uint8)
+             for _ in range(30)]
+    cfg = types.SimpleNamespace(NUM_CLUSTERS=10, BOVW_HYPERPARAMETERS_SEARCH=True, MIN_NUM_CLUSTERS=6,
+                                MAX_NUM_CLUSTERS=18, NUM_CLUSTERS_TO_TEST=3, CLUSTER_EVAL_SAMPLE_SIZE=500,
+                                CLUSTER_EVAL_N_SAMPLES=3, BOVW_KMEANS_INDEX_PATH=tmp_path / "km.faiss",
+                                BOVW_INDEX_PATH=tmp_path / "ix.faiss", BOVW_PIPELINE_PATH=tmp_path / "p.joblib")
+    pipeline, index = train_bovw_model(descs, None, cfg)
+    k = pipeline.named_steps["bovw"].n_clusters
+    assert k in (6, 12, 18)
+    assert index.ntotal == 30 and index.d == k
+    assert faiss_compat.read_index(str(tmp_path / "km.faiss")).ntotal == k
+    assert joblib.load(tmp_path / "p.joblib").named_steps["bovw"].n_clusters == k
+
+
+def test_query_batcher_matches_single_queries(g):
+    """Concurrent requests batched into one search return what each request gets on its own (ids equal, exact
+    FP32 distances), whether the batch lands on the small-batch kernel or the tensor-core path."""
+    from image_search_engine_b200 import QueryBatcher, create_search_index, run_image_query
+    rng = np.random.default_rng(3)
+    db = unit_rows(rng, 5000, 64)
+    qs = db[rng.integers(0, 5000, 48)] + 0.05 * rng.standard_normal((48, 64)).astype(np.float32)
+    idx = create_search_index(db.copy(), "l2")
+    paths = [f"img_{i}.jpg" for i in range(5000)]
+    single = [run_image_query(q[None, :], 7, index=idx, images_paths=paths) for q in qs]   # nq = 1: direct-sum path
+    Db, Ib = idx.search(qs, 7)                                                             # one batch of 48
+    for max_wait_ms, lo in ((200.0, 20), (0.0, 1)):
+        with QueryBatcher(idx, paths, max_batch=64, max_wait_ms=max_wait_ms) as qb:
+            futs = [qb.submit(torch.from_numpy(q) if i % 2 else q, 7) for i, q in enumerate(qs)]
+            got = [f.result(timeout=60) for f in futs]
+            assert max(qb.batches) >= lo and sum(qb.batches) == 48
+        # identical to the 48-row batch whatever the batching was (padding keeps one code path) ...
+        assert [[p[2] for p in a] for a in got] == [[paths[i] for i in row] for row in Ib]
+        assert np.array_equal(np.array([[p[0] for p in a] for a in got], np.float32), Db)
+        # ... and equal to the one-at-a-time answers up to near ties between the two L2 formulas
+        ids = np.array([[int(p[2][4:-4]) for p in a] for a in got])
+        ids1 = np.array([[int(p[2][4:-4]) for p in a] for a in single])
+        assert_topk_parity(ids, ids1, qs, db, False, max_mismatch_frac=0.1)
+        np.testing.assert_allclose([[p[0] for p in a] for a in got], [[p[0] for p in a] for a in single],
+                                   rtol=1e-4, atol=1e-5)
