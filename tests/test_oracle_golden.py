@@ -137,3 +137,23 @@ def test_reference_modules_still_match_fixture(g):
     assert np.array_equal(km.transform(g["X"]), g["words"])
     tf = ref.utils.OkapiTransformer().fit(g["hist"]).transform(g["hist"])
     assert np.array_equal(np.asarray(tf.todense()), g["okapi"])
+
+
+def test_cluster_score_fixture_is_davies_bouldin(g):
+    """The committed cluster_score fixture (reference calc_sampled_cluster_score) restated on the CPU: minus the
+    mean of 10 sklearn Davies-Bouldin scores over RandomState(42) samples of 2000 descriptors, labels from the
+    oracle's flat-IP search against the fixture codebook."""
+    from sklearn.metrics import davies_bouldin_score
+    gold = np.load(GOLD / "cluster_score.npz")
+    assert np.array_equal(gold["centroids"], g["centroids"])
+    X = g["X"]
+    idx = fs.IndexFlatIP(32)
+    idx.add(g["centroids"])
+    labels = idx.search(X.astype(np.float32), 1)[1].ravel()
+    rs = np.random.RandomState(42)
+    for key in ("score_first_call", "score_second_call"):
+        scores = []
+        for _ in range(10):
+            s = rs.choice(X.shape[0], size=2000, replace=False)
+            scores.append(davies_bouldin_score(X[s], labels[s]))
+        assert -np.mean(scores) == pytest.approx(float(gold[key]), rel=1e-12)
