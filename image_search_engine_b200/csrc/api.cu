@@ -87,18 +87,36 @@ ISE_EXPORT int ise_split_plan(float* hassign, int64_t k, int64_t n, int32_t* pai
     std::mt19937 mt(1234);
     int32_t ns = 0;
     const float denom = (float)(n - k);
+    // Same draws, same decisions as Faiss's loop `r = mt() / float(mt.max()); if (r < p) break;`.  At k = 65536 a
+    // split probes ~n / (mean cluster size) = 66 k donors and an iteration that empties ~1.7 k clusters spends its
+    // time here, on the host, so the test is reduced to one integer compare per draw: x -> float(x) / M is
+    // monotone, hence `r < p`  <=>  x < T(p) with T(p) the smallest draw whose quotient is not below p (found
+    // by bisection, once per centroid and again for the two entries a split changes).
+    const float rng_max = float(mt.max());
+    auto threshold = [&](float h) -> uint64_t {
+        const float p = (float)((h - 1.0) / denom);
+        uint64_t lo = 0, hi = (uint64_t)1 << 32;            // smallest x in [0, 2^32] with !(x / M < p)
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if ((float)(uint32_t)mid / rng_max < p) lo = mid + 1;
+            else hi = mid;
+        }
+        return lo;
+    };
+    std::vector<uint64_t> thr((size_t)k);
+    for (int64_t c = 0; c < k; c++) thr[(size_t)c] = threshold(hassign[c]);
     for (int64_t ci = 0; ci < k; ci++) {
         if (hassign[ci] != 0) continue;
         int64_t cj = 0;
-        for (;; cj = (cj + 1) % k) {
-            float p = (float)((hassign[cj] - 1.0) / denom);
-            float r = mt() / float(mt.max());
-            if (r < p) break;
+        while ((uint64_t)mt() >= thr[(size_t)cj]) {
+            if (++cj == k) cj = 0;
         }
         pairs[2 * ns] = (int32_t)ci;
         pairs[2 * ns + 1] = (int32_t)cj;
         hassign[ci] = hassign[cj] / 2;
         hassign[cj] -= hassign[ci];
+        thr[(size_t)ci] = threshold(hassign[ci]);
+        thr[(size_t)cj] = threshold(hassign[cj]);
         ns++;
     }
     *nsplit = ns;

@@ -214,15 +214,33 @@ class ShardedKmeans:
                 lops.normalize(cent)
             o = 0.0
             for it in range(cp.niter):
+                timed = x.is_cuda
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timed else None
+                if timed:
+                    ev[0].record()
                 dis, assign = lops.assign(x_train, a_op, cent, metric)
+                if timed:
+                    ev[1].record()
                 accum.zero_()
                 obj.zero_()
                 lops.accumulate(x_train, assign, dis, sums, counts, obj, cent, metric)
+                if timed:
+                    ev[2].record()
                 self._allreduce(accum)     # [k*d sums | k counts] in one NCCL all-reduce
                 self._allreduce(obj)
+                if timed:
+                    ev[3].record()
+                    torch.cuda.current_stream().synchronize()    # finalize reads n_empty back anyway
+                t_fin = time.time()
                 nsplit = lops.finalize(sums, counts, cent, n_train, cp.spherical)
                 o = float(obj.item())
-                stats.append(dict(obj=o, nsplit=nsplit, time=time.time() - t_start))
+                st = dict(obj=o, nsplit=nsplit, time=time.time() - t_start)
+                if timed:
+                    # device time of the three phases of this rank + host wall time of the finalize (mean, Faiss's
+                    # sequential split_clusters plan on the CPU when clusters came out empty, renorm)
+                    st.update(ms_assign=ev[0].elapsed_time(ev[1]), ms_accumulate=ev[1].elapsed_time(ev[2]),
+                              ms_allreduce=ev[2].elapsed_time(ev[3]), ms_finalize_host=(time.time() - t_fin) * 1e3)
+                stats.append(st)
             if cp.nredo > 1:
                 if (lower_is_better and o < best_obj) or (not lower_is_better and o > best_obj):
                     best_cent, best_stats, best_obj = cent.clone(), list(stats), o

@@ -41,6 +41,8 @@ out["c4"] = {"n": n_local * world, "d": d, "k": k, "iters": args.iters, "s_total
              "s_per_iter_incl_setup": (t1 - t0) / args.iters,
              "iter_end_times_s": [s_["time"] for s_ in km.iteration_stats], "obj": [float(o) for o in km.obj],
              "nsplit": [s["nsplit"] for s in km.iteration_stats],
+             "phases_ms_rank0": [{kk: round(s_[kk], 3) for kk in ("ms_assign", "ms_accumulate", "ms_allreduce", "ms_finalize_host")}
+                                 for s_ in km.iteration_stats],
              "allreduce_bytes_per_iter": 4 * (k * d + k) + 8}
 del x, km
 torch.cuda.empty_cache()

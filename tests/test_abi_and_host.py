@@ -35,10 +35,12 @@ def test_split_plan_matches_oracle():
     from image_search_engine_b200 import ops
     from oracle import faiss_shim as fs
     rng = np.random.default_rng(4)
-    for k, n_empty in [(16, 3), (200, 40), (1000, 1)]:
+    # the last case has n >> sum(h): tiny donor probabilities, thousands of RNG draws per split (the regime of a
+    # large codebook) -- the integer-threshold form of the test in ise_split_plan must take the same decisions
+    for k, n_empty, n_over in [(16, 3, 1), (200, 40, 1), (1000, 1, 1), (2000, 60, 20)]:
         h = rng.integers(1, 60, k).astype(np.float32)
         h[rng.choice(k, n_empty, replace=False)] = 0
-        n = int(h.sum())
+        n = int(h.sum()) * n_over
         cent = rng.standard_normal((k, 6)).astype(np.float32)
         cent[h == 0] = 0
         c_ref, h_ref = cent.copy(), h.copy()
