@@ -61,6 +61,12 @@ PROTOTYPES = {
                                   _f64, _f64, _f64, _f64, _c_void_p]),
     "ise_bovw_histogram_csr": (_int, [_c_void_p, _c_void_p, _c_void_p, _i64, _int, _int, _int, _c_void_p, _c_void_p,
                                       _c_void_p, _c_void_p, _int, _f64, _f64, _f64, _f64, _c_void_p]),
+    "ise_scores_topk_workspace_bytes": (_size, [_c_void_p, _i64, _i64, _int]),
+    "ise_scores_topk": (_int, [_c_void_p, _c_void_p, _i64, _i64, _int, _int, _i64, _c_void_p, _c_void_p, _c_void_p,
+                               _size, _c_void_p]),
+    "ise_ivfpq_residual": (_int, [_c_void_p, _c_void_p, _i64, _i64, _int, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "ise_ivfpq_scan": (_int, [_c_void_p, _c_void_p, _i64, _int, _c_void_p, _i64, _c_void_p, _int, _c_void_p, _int, _int,
+                              _c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p]),
     "ise_okapi_tf": (_int, [_c_void_p, _c_void_p, _int, _i64, _int, _f64, _f64, _f64, _f64, _c_void_p,
                             _c_void_p]),
 }

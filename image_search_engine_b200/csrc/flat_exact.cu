@@ -117,6 +117,30 @@ static int64_t exact_slice_len(int64_t nb) {
 }
 static int64_t exact_num_slices(int64_t nb) { return std::max<int64_t>(1, ceil_div64(nb, exact_slice_len(nb))); }
 
+// per-query top-k of a [nq, nb] score matrix: sorted slice lists, then the canonical (score, id) merge.  Scores of
+// +inf (L2) / -inf (IP) are never selected, so short rows are padded with id -1.
+static int select_from_scores(ise_ctx* ctx, const float* scores, int64_t nq, int64_t nb, int metric, int topk,
+                              int64_t id_base, float* out_val, int64_t* out_idx, int64_t* pi, float* pv,
+                              cudaStream_t st) {
+    const int64_t slices = exact_num_slices(nb);
+    const int64_t slen = exact_slice_len(nb);
+    const bool single = slices == 1;
+    float* tv = single ? out_val : pv;
+    int64_t* ti = single ? out_idx : pi;
+    dim3 g2((unsigned)slices, (unsigned)nq);
+    const bool largest = metric == ISE_METRIC_IP;
+    if (topk <= 32) {
+        if (largest) slice_topk_kernel<true, 32><<<g2, kThreads, 0, st>>>(scores, nq, nb, topk, slen, id_base, tv, ti);
+        else slice_topk_kernel<false, 32><<<g2, kThreads, 0, st>>>(scores, nq, nb, topk, slen, id_base, tv, ti);
+    } else {
+        if (largest) slice_topk_kernel<true, 128><<<g2, kThreads, 0, st>>>(scores, nq, nb, topk, slen, id_base, tv, ti);
+        else slice_topk_kernel<false, 128><<<g2, kThreads, 0, st>>>(scores, nq, nb, topk, slen, id_base, tv, ti);
+    }
+    ISE_LAUNCH_CHECK();
+    if (single) return 0;
+    return ise_topk_merge(ctx, pv, pi, (int)slices, nq, topk, metric, out_val, out_idx, (void*)st);
+}
+
 ISE_EXPORT size_t ise_flat_search_exact_workspace_bytes(ise_ctx* ctx, int64_t nq, int64_t nb, int topk) {
     if (!ctx || nq <= 0 || nb <= 0 || topk <= 0) return 0;
     const size_t scores = (size_t)nq * (size_t)nb * sizeof(float);
@@ -138,7 +162,6 @@ ISE_EXPORT int ise_flat_search_exact(ise_ctx* ctx, const float* q, int64_t nq, c
     DeviceGuard guard(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t slices = exact_num_slices(nb);
-    const int64_t slen = exact_slice_len(nb);
     float* scores = reinterpret_cast<float*>(workspace);
     const size_t scores_bytes = (((size_t)nq * nb * sizeof(float)) + 255) & ~size_t(255);
     int64_t* pi = reinterpret_cast<int64_t*>(reinterpret_cast<uint8_t*>(workspace) + scores_bytes);
@@ -151,19 +174,26 @@ ISE_EXPORT int ise_flat_search_exact(ise_ctx* ctx, const float* q, int64_t nq, c
         pair_scores_kernel<false><<<g1, kThreads, d * sizeof(float), st>>>(q, nq, db, nb, d, scores);
     ISE_LAUNCH_CHECK();
 
-    const bool single = slices == 1;
-    float* tv = single ? out_val : pv;
-    int64_t* ti = single ? out_idx : pi;
-    dim3 g2((unsigned)slices, (unsigned)nq);
-    const bool largest = metric == ISE_METRIC_IP;
-    if (topk <= 32) {
-        if (largest) slice_topk_kernel<true, 32><<<g2, kThreads, 0, st>>>(scores, nq, nb, topk, slen, id_base, tv, ti);
-        else slice_topk_kernel<false, 32><<<g2, kThreads, 0, st>>>(scores, nq, nb, topk, slen, id_base, tv, ti);
-    } else {
-        if (largest) slice_topk_kernel<true, 128><<<g2, kThreads, 0, st>>>(scores, nq, nb, topk, slen, id_base, tv, ti);
-        else slice_topk_kernel<false, 128><<<g2, kThreads, 0, st>>>(scores, nq, nb, topk, slen, id_base, tv, ti);
-    }
-    ISE_LAUNCH_CHECK();
-    if (single) return 0;
-    return ise_topk_merge(ctx, pv, pi, (int)slices, nq, topk, metric, out_val, out_idx, stream);
+    return select_from_scores(ctx, scores, nq, nb, metric, topk, id_base, out_val, out_idx, pi, pv, st);
+}
+
+ISE_EXPORT size_t ise_scores_topk_workspace_bytes(ise_ctx* ctx, int64_t nq, int64_t nb, int topk) {
+    if (!ctx || nq <= 0 || nb <= 0 || topk <= 0) return 0;
+    return (size_t)exact_num_slices(nb) * (size_t)nq * (size_t)topk * (sizeof(float) + sizeof(int64_t)) + 256;
+}
+
+ISE_EXPORT int ise_scores_topk(ise_ctx* ctx, const float* scores, int64_t nq, int64_t nb, int metric, int topk,
+                               int64_t id_base, float* out_val, int64_t* out_idx, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+    ISE_CHECK_ARG(ctx != nullptr);
+    ISE_CHECK_ARG(metric == ISE_METRIC_IP || metric == ISE_METRIC_L2);
+    ISE_CHECK_ARG(nq >= 0 && nb > 0 && topk >= 1 && topk <= 128 && nq <= 65535);
+    if (nq == 0) return 0;
+    ISE_CHECK_ARG(scores && out_val && out_idx && workspace);
+    if (workspace_bytes < ise_scores_topk_workspace_bytes(ctx, nq, nb, topk)) ISE_FAIL("workspace too small");
+    DeviceGuard guard(ctx->device);
+    const int64_t slices = exact_num_slices(nb);
+    int64_t* pi = reinterpret_cast<int64_t*>(workspace);
+    float* pv = reinterpret_cast<float*>(pi + (size_t)slices * nq * topk);
+    return select_from_scores(ctx, scores, nq, nb, metric, topk, id_base, out_val, out_idx, pi, pv, (cudaStream_t)stream);
 }

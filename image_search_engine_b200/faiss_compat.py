@@ -216,16 +216,176 @@ class IndexFlatL2(IndexFlat):
 
 
 class IndexIVFPQ:
-    """utils.py:311-325 ("cell-probe") -- off every default path; outside the hot-path scope."""
+    """faiss.IndexIVFPQ as the reference builds it (utils.py:311-325): ``IndexIVFPQ(IndexFlatL2(d), d, 8, 16, 8)``,
+    ``nprobe = 5``, ``train(data)`` then ``add(data)``; L2, by_residual.
 
-    def __init__(self, *a, **kw):
-        raise NotImplementedError("IndexIVFPQ ('cell-probe') is not part of the B200 retrieval core")
+    Training is the hot path's own machinery: level-1 clustering (nlist centroids, niter = 10) and one k-means
+    per sub-quantizer (256 centroids on d/M-dimensional residual slices, niter = 25, seed 1234, at most 65 536
+    training rows) run on the tensor-core assign + update kernels; vectors are encoded with the fused top-1
+    assign; search probes the ``nprobe`` nearest lists and scans their codes with a shared-memory look-up table
+    (``ise_ivfpq_scan``) followed by the canonical top-k selection.  Approximate by construction (8-bit codes):
+    returned distances are sum_m |(q - c_list)_m - pq_m[code_m]|^2 like Faiss's.
+    """
+
+    def __init__(self, quantizer, d, nlist, M, nbits_per_idx, metric=METRIC_L2):
+        if metric != METRIC_L2:
+            raise NotImplementedError("the reference builds IndexIVFPQ with the default L2 metric only")
+        if int(d) % int(M) != 0:
+            raise RuntimeError("The dimension of the vector (d) should be a multiple of the number of "
+                               "subquantizers (M)")
+        if int(nbits_per_idx) != 8:
+            raise NotImplementedError("8-bit codes only (utils.py:321)")
+        self.quantizer, self.d, self.nlist = quantizer, int(d), int(nlist)
+        self.M, self.nbits, self.ksub, self.dsub = int(M), 8, 256, int(d) // int(M)
+        self.nprobe, self.by_residual, self.is_trained, self.metric_type = 1, True, False, METRIC_L2
+        self.niter_coarse, self.pq_cp = 10, ClusteringParameters()
+        self.pq_centroids = None            # [M, ksub, dsub] float32 (device)
+        self._sub_index = None              # one flat L2 index per sub-quantizer (encoding)
+        self._codes = self._ids = self._assign = None    # insertion order
+        self._sorted = None                 # (codes, ids, list_offsets) grouped by list
+        self._lock = threading.RLock()
+
+    @property
+    def ntotal(self) -> int:
+        return 0 if self._ids is None else int(self._ids.shape[0])
+
+    # -- training --
+    def set_trained_state(self, coarse_centroids, pq_centroids) -> None:
+        """Installs externally trained quantizers (lock-step tests against the oracle)."""
+        cc, _ = _to_device(np.ascontiguousarray(coarse_centroids, dtype=np.float32))
+        self.quantizer.reset()
+        self.quantizer.add(cc)
+        pq, _ = _to_device(np.ascontiguousarray(pq_centroids, dtype=np.float32).reshape(self.M * self.ksub, self.dsub))
+        self._install_pq(pq.reshape(self.M, self.ksub, self.dsub))
+
+    def _install_pq(self, pq: torch.Tensor) -> None:
+        self.pq_centroids = pq.contiguous()
+        self._sub_index = []
+        for m in range(self.M):
+            ix = IndexFlatL2(self.dsub)
+            ix.add(self.pq_centroids[m])
+            self._sub_index.append(ix)
+        self.is_trained = True
+
+    def train(self, x) -> None:
+        xd, _ = _to_device(x)
+        xd = xd.to(torch.float32)
+        if xd.shape[1] != self.d:
+            raise AssertionError(f"train: expected (n, {self.d}) array")
+        if not (self.quantizer.ntotal == self.nlist):                      # IndexIVF::train_q1
+            km = Kmeans(self.d, self.nlist, niter=self.niter_coarse, seed=1234)
+            km.train(xd)
+            self.quantizer.reset()
+            self.quantizer.add(km.index._database())
+        nmax = self.pq_cp.max_points_per_centroid * self.ksub              # train_residual: fvecs_maybe_subsample
+        if xd.shape[0] > nmax:
+            perm = ops.rand_perm_prefix(xd.shape[0], self.pq_cp.seed, nmax)
+            xd = xd.index_select(0, torch.from_numpy(perm).to(xd.device))
+        _, assign = self.quantizer._search_device(xd, 1, need_distances=False)
+        res = ops.ivfpq_residual(xd, self.quantizer._database(), assign)
+        pq = torch.empty((self.M, self.ksub, self.dsub), dtype=torch.float32, device=xd.device)
+        for m in range(self.M):                                            # ProductQuantizer::train, Train_default
+            km = Kmeans(self.dsub, self.ksub, niter=self.pq_cp.niter, seed=self.pq_cp.seed)
+            km.train(res[:, m * self.dsub:(m + 1) * self.dsub].contiguous())
+            pq[m] = km.index._database()
+        self._install_pq(pq)
+
+    # -- add / search --
+    def _encode(self, xd: torch.Tensor):
+        _, assign = self.quantizer._search_device(xd, 1, need_distances=False)
+        assign = assign.reshape(-1)
+        res = ops.ivfpq_residual(xd, self.quantizer._database(), assign)
+        codes = torch.empty((xd.shape[0], self.M), dtype=torch.uint8, device=xd.device)
+        for m in range(self.M):
+            _, c = self._sub_index[m]._search_device(res[:, m * self.dsub:(m + 1) * self.dsub].contiguous(), 1,
+                                                     need_distances=False)
+            codes[:, m] = c.reshape(-1).to(torch.uint8)
+        return assign, codes
+
+    def add(self, x) -> None:
+        if not self.is_trained:
+            raise RuntimeError("Error: 'is_trained' failed")
+        xd, _ = _to_device(x)
+        xd = xd.to(torch.float32)
+        if xd.shape[1] != self.d:
+            raise AssertionError(f"add: expected (n, {self.d}) array")
+        assign, codes = self._encode(xd)
+        ids = torch.arange(self.ntotal, self.ntotal + xd.shape[0], dtype=torch.int64, device=xd.device)
+        with self._lock:
+            self._codes = codes if self._codes is None else torch.cat([self._codes, codes])
+            self._assign = assign if self._assign is None else torch.cat([self._assign, assign])
+            self._ids = ids if self._ids is None else torch.cat([self._ids, ids])
+            self._sorted = None
+
+    def _lists(self):
+        with self._lock:
+            if self._sorted is None:
+                order = torch.argsort(self._assign, stable=True)           # lists keep insertion order
+                counts = torch.bincount(self._assign, minlength=self.nlist)
+                off = torch.zeros((self.nlist + 1,), dtype=torch.int64, device=counts.device)
+                off[1:] = torch.cumsum(counts, 0)
+                self._sorted = (self._codes.index_select(0, order).contiguous(), self._ids.index_select(0, order), off)
+            return self._sorted
+
+    def search(self, x, k: int):
+        k = int(k)
+        if k <= 0:
+            raise AssertionError("k must be positive")
+        q, was_cuda = _to_device(x)
+        q = q.to(torch.float32)
+        if q.shape[1] != self.d:
+            raise AssertionError(f"search: expected (n, {self.d}) array")
+        nq = q.shape[0]
+        D = torch.full((nq, k), _FLT_MAX, dtype=torch.float32, device=q.device)
+        I = torch.full((nq, k), -1, dtype=torch.int64, device=q.device)
+        if nq and self.ntotal:
+            if k > ops.MAX_TOPK:
+                raise IseError(f"k = {k} exceeds the fused-selection limit of {ops.MAX_TOPK}")
+            codes, ids, off = self._lists()
+            _, probes = self.quantizer._search_device(q, min(self.nprobe, self.nlist), need_distances=False)
+            for q0 in range(0, nq, 4096):                                  # bounds the [nq, ntotal] distance matrix
+                qs = q[q0:q0 + 4096].contiguous()
+                dist = ops.ivfpq_scan(qs, self.quantizer._database(), probes[q0:q0 + 4096], self.pq_centroids, codes, off)
+                Dv, pos = ops.scores_topk(dist, METRIC_L2, k)
+                ok = pos >= 0
+                I[q0:q0 + 4096] = torch.where(ok, ids[pos.clamp(min=0)], torch.full_like(pos, -1))
+                D[q0:q0 + 4096] = Dv
+        if was_cuda:
+            return D, I
+        return D.cpu().numpy(), I.cpu().numpy()
+
+    def reset(self) -> None:
+        with self._lock:
+            self._codes = self._ids = self._assign = self._sorted = None
+
+    # joblib / pickle: quantizers and codes as host arrays
+    def __getstate__(self):
+        host = lambda t: None if t is None else t.cpu().numpy()
+        return dict(d=self.d, nlist=self.nlist, M=self.M, nprobe=self.nprobe, coarse=self.quantizer.reconstruct_n(),
+                    pq=host(self.pq_centroids), codes=host(self._codes), assign=host(self._assign))
+
+    def __setstate__(self, st):
+        self.__init__(IndexFlatL2(st["d"]), st["d"], st["nlist"], st["M"], 8)
+        self.nprobe = st["nprobe"]
+        if st["pq"] is not None:
+            self.set_trained_state(st["coarse"], st["pq"])
+        if st["codes"] is not None:
+            dev = ops.require_cuda()
+            self._codes = torch.from_numpy(st["codes"]).to(dev)
+            self._assign = torch.from_numpy(st["assign"]).to(dev)
+            self._ids = torch.arange(self._codes.shape[0], dtype=torch.int64, device=dev)
+
+    def __repr__(self):
+        return (f"<image_search_engine_b200.IndexIVFPQ d={self.d} nlist={self.nlist} M={self.M} nprobe={self.nprobe} "
+                f"ntotal={self.ntotal} (HBM resident)>")
 
 
 # ------------------------------------------------------------------------------------------
 # flat index file format (faiss/impl/index_write.cpp), so existing models/*.faiss files open
 # ------------------------------------------------------------------------------------------
 def write_index(index: IndexFlat, fname) -> None:
+    if isinstance(index, IndexIVFPQ):
+        raise NotImplementedError("only flat indexes are written in Faiss's file format; an IndexIVFPQ can be pickled")
     xb = index.reconstruct_n() if index.ntotal else np.zeros((0, index.d), np.float32)
     fourcc = b"IxFI" if index.metric_type == METRIC_INNER_PRODUCT else b"IxF2"
     with open(str(fname), "wb") as f:

@@ -383,6 +383,62 @@ def topk_merge(val_parts: torch.Tensor, idx_parts: torch.Tensor, metric: int):
 
 
 # ------------------------------------------------------------------------------------------
+# IVFPQ ("cell-probe") building blocks
+# ------------------------------------------------------------------------------------------
+def scores_topk(scores: torch.Tensor, metric: int, topk: int, id_base: int = 0):
+    """Per-row top-k of a [nq, nb] float32 score matrix (IP: largest, L2: smallest; +-inf never selected)."""
+    if scores.dtype != torch.float32 or scores.dim() != 2 or not scores.is_contiguous():
+        raise IseError("scores_topk needs a contiguous float32 matrix")
+    if not 1 <= topk <= MAX_TOPK:
+        raise IseError(f"topk must be in [1, {MAX_TOPK}]")
+    nq, nb = scores.shape
+    lib, ctx = _lib.load(), _lib.ctx(_dev(scores))
+    val = torch.empty((nq, topk), dtype=torch.float32, device=scores.device)
+    idx = torch.empty((nq, topk), dtype=torch.int64, device=scores.device)
+    if nq == 0:
+        return val, idx
+    ws_bytes = lib.ise_scores_topk_workspace_bytes(ctx, nq, nb, topk)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=scores.device)
+    _lib.check(lib.ise_scores_topk(ctx, _ptr(scores), nq, nb, int(metric), int(topk), int(id_base), _ptr(val), _ptr(idx),
+                                   _ptr(ws), ws_bytes, _stream()))
+    _count(2)
+    return val, idx
+
+
+def ivfpq_residual(x: torch.Tensor, centroids: torch.Tensor, assign: torch.Tensor) -> torch.Tensor:
+    """x[i] - centroids[assign[i]] (float32)."""
+    if x.dtype != torch.float32 or x.stride(1) != 1 or centroids.dtype != torch.float32 or not centroids.is_contiguous():
+        raise IseError("ivfpq_residual: float32 rows")
+    n, d = x.shape
+    out = torch.empty((n, d), dtype=torch.float32, device=x.device)
+    assign = assign.reshape(-1).contiguous()
+    _lib.check(_lib.load().ise_ivfpq_residual(_lib.ctx(_dev(x)), _ptr(x), x.stride(0) if n > 0 else d, n, d,
+                                              _ptr(centroids), _ptr(assign), _ptr(out), _stream()))
+    _count()
+    return out
+
+
+def ivfpq_scan(q: torch.Tensor, coarse: torch.Tensor, probes: torch.Tensor, pq_centroids: torch.Tensor,
+               codes: torch.Tensor, list_offsets: torch.Tensor) -> torch.Tensor:
+    """Asymmetric distances of every query to the codes of its probed lists: [nq, ntotal] (list-sorted order,
+    +inf where a list is not probed)."""
+    nq, d = q.shape
+    M, ksub, dsub = pq_centroids.shape
+    ntotal = codes.shape[0]
+    if M * dsub != d or codes.dtype != torch.uint8 or codes.shape[1] != M or probes.dtype != torch.int64:
+        raise IseError("ivfpq_scan: inconsistent shapes / dtypes")
+    dist = torch.full((nq, max(ntotal, 1)), float("inf"), dtype=torch.float32, device=q.device)
+    if nq == 0 or ntotal == 0:
+        return dist
+    _lib.check(_lib.load().ise_ivfpq_scan(
+        _lib.ctx(_dev(q)), _ptr(q.contiguous()), nq, d, _ptr(coarse.contiguous()), coarse.shape[0],
+        _ptr(probes.contiguous()), probes.shape[1], _ptr(pq_centroids.contiguous()), M, ksub, _ptr(codes.contiguous()),
+        _ptr(list_offsets.contiguous()), ntotal, _ptr(dist), _stream()))
+    _count()
+    return dist
+
+
+# ------------------------------------------------------------------------------------------
 # k-means update
 # ------------------------------------------------------------------------------------------
 def kmeans_accumulate(x: torch.Tensor, assign: torch.Tensor, dis: torch.Tensor | None, sums: torch.Tensor,

@@ -91,12 +91,18 @@ def create_search_index(data_array, index_type="cosine"):
     """Builds the HBM-resident flat index.
 
     "cosine" -> inner-product index over L2-normalised rows; like the reference (utils.py:302-303)
-    the caller's array is normalised IN PLACE.  "l2" -> squared-L2 index.  "cell-probe" (IVFPQ) is
-    outside the hot path.
+    the caller's array is normalised IN PLACE.  "l2" -> squared-L2 index.  "cell-probe" -> the
+    reference's IndexIVFPQ configuration (approximate; off every default path of the reference).
     """
     num_features = int(data_array.shape[1])
     if index_type == "cell-probe":
-        raise NotImplementedError("'cell-probe' (IndexIVFPQ) is not part of the B200 retrieval core")
+        # utils.py:311-325: 8 coarse centroids, 16 sub-quantizers of 8 bits, 5 probed lists, trained on the data itself
+        index = faiss.IndexIVFPQ(faiss.IndexFlatL2(num_features), num_features, 8, 16, 8)
+        index.nprobe = 5
+        index.train(data_array)
+        index.add(data_array)
+        print(f"There are {index.ntotal} images in the search index.")
+        return index
     if index_type not in ("cosine", "l2"):
         raise ValueError(f"unknown index_type {index_type!r}")
     if isinstance(data_array, torch.Tensor) and data_array.is_cuda:

@@ -202,6 +202,23 @@ int ise_bovw_histogram_csr(ise_ctx* ctx, const int64_t* words, const int64_t* im
 int ise_okapi_tf(ise_ctx* ctx, void* h, int out_dtype, int64_t n_img, int k,
                  double k1, double k2, double b, double avgdl, double* dl_workspace, void* stream);
 
+/* ---- IVFPQ "cell-probe" index (utils.py:311-325: IndexIVFPQ(IndexFlatL2(d), d, 8, 16, 8), nprobe = 5) ---- */
+/* per-query top-k of a device score matrix scores[nq, nb] (IP: largest, L2: smallest; +-inf entries are never
+ * selected, short rows are padded with id -1): the selection stage of ise_flat_search_exact on its own */
+size_t ise_scores_topk_workspace_bytes(ise_ctx* ctx, int64_t nq, int64_t nb, int topk);
+int ise_scores_topk(ise_ctx* ctx, const float* scores, int64_t nq, int64_t nb, int metric, int topk, int64_t id_base,
+                    float* out_val, int64_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
+/* out[i] = x[i] - centroids[assign[i]]  (faiss compute_residual_n; IndexIVFPQ by_residual) */
+int ise_ivfpq_residual(ise_ctx* ctx, const float* x, int64_t ldx, int64_t n, int d, const float* centroids,
+                       const int64_t* assign, float* out, void* stream);
+/* asymmetric-distance scan of the probed inverted lists: dist[nq, ntotal] (list-sorted order, pre-filled with
+ * +inf by the caller) receives sum_m |(q - c_list)_m - pq[m][code_m]|^2 for every code of every probed list.
+ * probes[nq, nprobe] int64 list ids (-1 = none), pq_centroids [M, ksub, d/M], codes [ntotal, M] uint8 sorted by
+ * list, list_offsets [nlist+1]. */
+int ise_ivfpq_scan(ise_ctx* ctx, const float* q, int64_t nq, int d, const float* coarse_centroids, int64_t nlist,
+                   const int64_t* probes, int nprobe, const float* pq_centroids, int M, int ksub,
+                   const uint8_t* codes, const int64_t* list_offsets, int64_t ntotal, float* dist, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

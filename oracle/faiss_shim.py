@@ -264,9 +264,108 @@ class IndexFlatL2(IndexFlat):
         super().__init__(d, METRIC_L2)
 
 
-class IndexIVFPQ:  # utils.py:311-325 "cell-probe": off every default path, out of scope
-    def __init__(self, *a, **kw):
-        raise NotImplementedError("IndexIVFPQ (cell-probe) is outside the hot-path scope")
+# --------------------------------------------------------------------------
+# faiss/impl/ProductQuantizer.cpp + faiss/IndexIVFPQ.cpp (the "cell-probe" branch, utils.py:311-325)
+# Restated from the published algorithm (faiss ~1.7.4): by_residual = true, L2, flat coarse quantizer,
+# one independent k-means (Clustering defaults: niter 25, seed 1234, <= 256 points per centroid) per
+# sub-quantizer, level-1 clustering with niter = 10.  Distances are evaluated with the direct look-up-table
+# form (sum over sub-quantizers of |(q - c)_m - pq_m[code_m]|^2); Faiss's precomputed-table variant is the
+# same quantity regrouped, i.e. equal up to FP32 rounding.  Nothing in the reference pins this path.
+# --------------------------------------------------------------------------
+class ProductQuantizer:
+    def __init__(self, d: int, M: int, nbits: int):
+        if d % M != 0:
+            raise RuntimeError("The dimension of the vector (d) should be a multiple of the number of subquantizers (M)")
+        self.d, self.M, self.nbits = int(d), int(M), int(nbits)
+        self.dsub, self.ksub = self.d // self.M, 1 << self.nbits
+        self.cp = ClusteringParameters()
+        self.centroids = np.zeros((self.M, self.ksub, self.dsub), dtype=np.float32)
+
+    def train(self, x: np.ndarray) -> None:                    # ProductQuantizer::train, Train_default
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        for m in range(self.M):
+            xs = np.ascontiguousarray(x[:, m * self.dsub:(m + 1) * self.dsub])
+            clus = Clustering(self.dsub, self.ksub, self.cp)
+            clus.train(xs, IndexFlatL2(self.dsub))
+            self.centroids[m] = clus.centroids.reshape(self.ksub, self.dsub)
+
+    def compute_codes(self, x: np.ndarray) -> np.ndarray:      # nearest sub-centroid, lowest index on ties
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        codes = np.zeros((x.shape[0], self.M), dtype=np.uint8)
+        for m in range(self.M):
+            xs = np.ascontiguousarray(x[:, m * self.dsub:(m + 1) * self.dsub])
+            codes[:, m] = knn(xs, self.centroids[m], 1, METRIC_L2)[1].ravel().astype(np.uint8)
+        return codes
+
+    def compute_distance_table(self, x: np.ndarray) -> np.ndarray:     # [M, ksub] of one vector: fvec_L2sqr_ny
+        xs = np.asarray(x, dtype=np.float32).reshape(self.M, 1, self.dsub)
+        diff = xs - self.centroids
+        return np.einsum("mkj,mkj->mk", diff, diff, dtype=np.float32)
+
+
+class IndexIVFPQ:
+    def __init__(self, quantizer: IndexFlat, d: int, nlist: int, M: int, nbits_per_idx: int, metric: int = METRIC_L2):
+        if metric != METRIC_L2:
+            raise NotImplementedError("the reference builds IndexIVFPQ with the default L2 metric only")
+        self.quantizer, self.d, self.nlist = quantizer, int(d), int(nlist)
+        self.pq = ProductQuantizer(d, M, nbits_per_idx)
+        self.cp = ClusteringParameters()
+        self.cp.niter = 10                                      # IndexIVF level-1 clustering
+        self.nprobe, self.by_residual, self.is_trained, self.metric_type = 1, True, False, METRIC_L2
+        self.ids = [np.zeros(0, np.int64) for _ in range(self.nlist)]
+        self.codes = [np.zeros((0, self.pq.M), np.uint8) for _ in range(self.nlist)]
+        self.ntotal = 0
+
+    def train(self, x) -> None:
+        x = np.ascontiguousarray(np.asarray(x), dtype=np.float32)
+        if not (self.quantizer.is_trained and self.quantizer.ntotal == self.nlist):     # train_q1
+            clus = Clustering(self.d, self.nlist, self.cp)
+            self.quantizer.reset()
+            clus.train(x, self.quantizer)
+        nmax = self.pq.cp.max_points_per_centroid * self.pq.ksub                         # train_residual
+        if x.shape[0] > nmax:                                                            # fvecs_maybe_subsample
+            x = np.ascontiguousarray(x[rand_perm(x.shape[0], self.pq.cp.seed, prefix=nmax)])
+        assign = self.quantizer.search(x, 1)[1].ravel()
+        self.pq.train(x - self.quantizer._xb[assign])
+        self.is_trained = True
+
+    def add(self, x) -> None:
+        if not self.is_trained:
+            raise RuntimeError("Error: 'is_trained' failed")
+        x = np.ascontiguousarray(np.asarray(x), dtype=np.float32)
+        assign = self.quantizer.search(x, 1)[1].ravel()
+        codes = self.pq.compute_codes(x - self.quantizer._xb[assign])
+        ids = np.arange(self.ntotal, self.ntotal + x.shape[0], dtype=np.int64)
+        for l in range(self.nlist):
+            sel = assign == l
+            self.ids[l] = np.concatenate([self.ids[l], ids[sel]])
+            self.codes[l] = np.concatenate([self.codes[l], codes[sel]])
+        self.ntotal += x.shape[0]
+
+    def search(self, x, k: int):
+        x = np.ascontiguousarray(np.asarray(x), dtype=np.float32)
+        nq, nprobe = x.shape[0], min(self.nprobe, self.nlist)
+        coarse = self.quantizer.search(x, nprobe)[1]
+        D = np.full((nq, k), np.finfo(np.float32).max, dtype=np.float32)
+        I = np.full((nq, k), -1, dtype=np.int64)
+        M = self.pq.M
+        for qi in range(nq):
+            ds, ids = [], []
+            for key in coarse[qi]:
+                if key < 0 or self.ids[key].size == 0:
+                    continue
+                tab = self.pq.compute_distance_table(x[qi] - self.quantizer._xb[key])
+                dis = np.zeros(self.ids[key].size, dtype=np.float32)
+                for m in range(M):                               # dis0 + sum_m table[m][code_m], in this order
+                    dis += tab[m][self.codes[key][:, m]]
+                ds.append(dis)
+                ids.append(self.ids[key])
+            if not ds:
+                continue
+            ds, ids = np.concatenate(ds), np.concatenate(ids)
+            order = np.lexsort((ids, ds))[:k]                    # canonical (distance, id) order
+            D[qi, :order.size], I[qi, :order.size] = ds[order], ids[order]
+        return D, I
 
 
 # --------------------------------------------------------------------------

@@ -109,8 +109,8 @@ def test_search_index_matches_reference_fixture(g):
     assert (Ip2[:, 40:] == -1).all() and np.array_equal(Ip2[:, :10], I if False else Ip2[:, :10])
     m = create_search_index(np.asmatrix(g["feats"].copy()), "l2")          # np.matrix input (quirk Q4)
     assert m.ntotal == 40
-    with pytest.raises(NotImplementedError):
-        create_search_index(g["feats"].copy(), "cell-probe")
+    with pytest.raises(RuntimeError):                                      # 40 rows cannot train 256 PQ centroids
+        create_search_index(g["feats"].copy(), "cell-probe")               # (Faiss raises the same way)
     with pytest.raises(AssertionError):
         idx.search(np.zeros((3, 31), np.float32), 1)
 
@@ -578,3 +578,82 @@ def test_query_batcher_matches_single_queries(g):
         assert_topk_parity(ids, ids1, qs, db, False, max_mismatch_frac=0.1)
         np.testing.assert_allclose([[p[0] for p in a] for a in got], [[p[0] for p in a] for a in single],
                                    rtol=1e-4, atol=1e-5)
+
+
+def _clustered(rng, n, d, n_centres=24, spread=3.0):
+    cent = rng.standard_normal((n_centres, d)).astype(np.float32) * spread
+    return (cent[rng.integers(0, n_centres, n)] + rng.standard_normal((n, d))).astype(np.float32)
+
+
+def test_ivfpq_lockstep_against_oracle():
+    """'cell-probe' index (utils.py:311-325).  Lock-step with the oracle's IndexIVFPQ restatement: the oracle's
+    trained quantizers are installed, then list assignment + PQ codes (fused top-1 assign) and the LUT scan +
+    top-k (ise_ivfpq_scan / ise_scores_topk) must reproduce the oracle's codes, distances and ids."""
+    from image_search_engine_b200 import faiss_compat
+    from oracle import faiss_shim as fs
+    rng = np.random.default_rng(7)
+    n, d, nq, k = 2500, 64, 60, 10
+    x = _clustered(rng, n, d)
+    q = x[rng.integers(0, n, nq)] + 0.1 * rng.standard_normal((nq, d)).astype(np.float32)
+    ref = fs.IndexIVFPQ(fs.IndexFlatL2(d), d, 8, 16, 8)
+    ref.nprobe = 5
+    ref.train(x)
+    ref.add(x)
+    ix = faiss_compat.IndexIVFPQ(faiss_compat.IndexFlatL2(d), d, 8, 16, 8)
+    ix.nprobe = 5
+    ix.set_trained_state(ref.quantizer._xb, ref.pq.centroids)
+    ix.add(x[:1000])
+    ix.add(x[1000:])                                     # incremental adds keep ids = insertion order
+    assert ix.ntotal == n and ix.is_trained
+    # codes / lists vs the oracle (rows in insertion order)
+    ref_assign = np.empty(n, np.int64)
+    ref_codes = np.empty((n, 16), np.uint8)
+    for l in range(8):
+        ref_assign[ref.ids[l]] = l
+        ref_codes[ref.ids[l]] = ref.codes[l]
+    assign, codes = ix._assign.cpu().numpy(), ix._codes.cpu().numpy()
+    assert (assign != ref_assign).mean() <= 0.002           # near ties between two coarse centroids only
+    same_list = assign == ref_assign
+    assert (codes[same_list] != ref_codes[same_list]).mean() <= 0.002
+    # identical codes -> identical search (the oracle's codes are installed to remove the near-tie rows)
+    ix._assign, ix._codes, ix._sorted = torch.from_numpy(ref_assign).cuda(), torch.from_numpy(ref_codes).cuda(), None
+    D, I = ix.search(q, k)
+    Dr, Ir = ref.search(q, k)
+    assert D.dtype == np.float32 and I.dtype == np.int64 and D.shape == (nq, k)
+    np.testing.assert_allclose(D, Dr, rtol=1e-4, atol=1e-4)
+    assert (I != Ir).mean() <= 0.01                          # equal approximate distances may swap neighbours
+    assert (np.diff(D, axis=1) >= 0).all()
+    # k larger than what the probed lists hold: padded with -1 / FLT_MAX like the flat indexes
+    ix.nprobe = 1
+    Dp, Ip = ix.search(q[:3], 128)
+    held = np.bincount(ref_assign, minlength=8)
+    assert ((Ip >= 0).sum(1) <= held.max()).all() and (Dp[Ip < 0] == np.finfo(np.float32).max).all()
+
+
+def test_cell_probe_index_end_to_end():
+    """create_search_index(data, "cell-probe"): trained entirely on the GPU (level-1 k-means + 16 sub-quantizer
+    k-means); approximate, so the check is recall against the exact flat index, next to the oracle's own recall."""
+    from image_search_engine_b200 import create_search_index
+    from oracle import faiss_shim as fs
+    rng = np.random.default_rng(8)
+    n, d, k = 3000, 64, 10
+    x = _clustered(rng, n, d)
+    ix = create_search_index(x.copy(), "cell-probe")
+    assert ix.nprobe == 5 and ix.ntotal == n and ix.d == d
+    D, I = ix.search(x[:200], k)
+    assert (I[:, 0] == np.arange(200)).mean() >= 0.9          # a stored vector finds itself
+    flat = create_search_index(x.copy(), "l2")
+    _, If = flat.search(x[:200], k)
+    recall = np.mean([len(set(a) & set(b)) / k for a, b in zip(I, If)])
+    ref = fs.IndexIVFPQ(fs.IndexFlatL2(d), d, 8, 16, 8)
+    ref.nprobe = 5
+    ref.train(x)
+    ref.add(x)
+    _, Ir = ref.search(x[:200], k)
+    recall_ref = np.mean([len(set(a) & set(b)) / k for a, b in zip(Ir, If)])
+    assert recall >= recall_ref - 0.1, (recall, recall_ref)
+    blob = io.BytesIO()
+    joblib.dump(ix, blob)
+    blob.seek(0)
+    again = joblib.load(blob)
+    assert np.array_equal(again.search(x[:50], k)[1], I[:50])

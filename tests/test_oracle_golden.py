@@ -157,3 +157,28 @@ def test_cluster_score_fixture_is_davies_bouldin(g):
             s = rs.choice(X.shape[0], size=2000, replace=False)
             scores.append(davies_bouldin_score(X[s], labels[s]))
         assert -np.mean(scores) == pytest.approx(float(gold[key]), rel=1e-12)
+
+
+def test_ivfpq_restatement_sanity():
+    """The oracle's IndexIVFPQ (the reference's 'cell-probe' configuration, utils.py:311-325): stored vectors find
+    themselves, results are sorted, all probed lists together return every id once, short results are padded."""
+    rng = np.random.default_rng(5)
+    cent = rng.standard_normal((12, 32)).astype(np.float32) * 3
+    x = (cent[rng.integers(0, 12, 900)] + rng.standard_normal((900, 32))).astype(np.float32)
+    ix = fs.IndexIVFPQ(fs.IndexFlatL2(32), 32, 8, 16, 8)
+    ix.nprobe = 5
+    with pytest.raises(RuntimeError):
+        ix.add(x)                                   # not trained yet
+    ix.train(x)
+    ix.add(x)
+    assert ix.ntotal == 900 and sum(len(i) for i in ix.ids) == 900
+    D, I = ix.search(x[:40], 5)
+    assert (I[:, 0] == np.arange(40)).mean() >= 0.9 and (np.diff(D, axis=1) >= 0).all()
+    ix.nprobe = 8                                   # every list probed: each id appears exactly once
+    D, I = ix.search(x[:2], 900)
+    assert np.array_equal(np.sort(I[0]), np.arange(900))
+    ix.nprobe = 1
+    D, I = ix.search(x[:2], 900)
+    assert (I[0] == -1).any() and (D[0][I[0] == -1] == np.finfo(np.float32).max).all()
+    with pytest.raises(RuntimeError):
+        fs.IndexIVFPQ(fs.IndexFlatL2(30), 30, 8, 16, 8)    # d must be a multiple of M
