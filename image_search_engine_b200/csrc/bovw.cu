@@ -203,7 +203,6 @@ histogram_csr_kernel(const int64_t* __restrict__ words, const int64_t* __restric
     for (int j = threadIdx.x; j < k; j += kThreads) s_cnt[j] = 0;
     if (threadIdx.x == 0) { s_mn = INT_MAX; s_mx = INT_MIN; s_total = 0; }
     __syncthreads();
-    const int cpt = ((k + kThreads - 1) / kThreads + 3) / 4 * 4;     // bins per thread in the compaction (multiple of 4)
     for (int64_t img = blockIdx.x; img < n_img; img += gridDim.x) {
         const int64_t lo = off[img], hi = off[img + 1];
         const int64_t cnt = hi - lo;
@@ -249,32 +248,35 @@ histogram_csr_kernel(const int64_t* __restrict__ words, const int64_t* __restric
                     okapi_weight((double)(threadIdx.x - (kThreads - kTfTable) + 1), k1, k2, b, ratio);
             __syncthreads();
             if (threadIdx.x == 0) { s_mn = INT_MAX; s_mx = INT_MIN; }
-            // ordered compaction: thread t owns bins [t * cpt, t * cpt + cpt)
-            const int c_lo = threadIdx.x * cpt, c_hi = min(k, c_lo + cpt);
+            // ordered compaction, bank-conflict free: warp w owns the contiguous bins [w * per_warp, ...), walks them 32
+            // at a time (lane = bin) and ranks the non-zeros with ballot + popc; a first sweep counts per warp so
+            // that every warp knows where its run starts in the row
+            constexpr int NW = kThreads / 32;
+            const int per_warp = ((k + NW - 1) / NW + 31) / 32 * 32;
+            const int c_lo = wib * per_warp, c_hi = min(k, c_lo + per_warp);
             int mine = 0;
-            for (int c = c_lo; c < c_hi; ++c) mine += s_cnt[c] != 0 ? 1 : 0;
-            int incl = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
+            for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+                const int c = c0 + lane;
+                mine += __popc(__ballot_sync(0xffffffffu, c < c_hi && s_cnt[c] != 0));
             }
-            if (lane == 31) s_warp[wib] = incl;
+            if (lane == 0) s_warp[wib] = mine;
             __syncthreads();
-            int base = 0;
+            int pos = indptr[img];
 #pragma unroll
-            for (int i = 0; i < kThreads / 32; ++i) base += i < wib ? s_warp[i] : 0;
-            int pos = indptr[img] + base + incl - mine;
-            for (int c = c_lo; c < c_hi; ++c) {
-                const int v = s_cnt[c];
+            for (int i = 0; i < NW; ++i) pos += i < wib ? s_warp[i] : 0;
+            for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+                const int c = c0 + lane;
+                const int v = c < c_hi ? s_cnt[c] : 0;
+                const unsigned mask = __ballot_sync(0xffffffffu, v != 0);
                 if (v != 0) {
                     s_cnt[c] = 0;
-                    indices[pos] = c;
+                    const int p = pos + __popc(mask & ((1u << lane) - 1u));
+                    indices[p] = c;
                     double w = (double)v;
                     if (okapi) w = v <= kTfTable ? s_w[v] : okapi_weight_rare((double)v, k1, k2, b, ratio);
-                    data[pos] = (OutT)w;
-                    ++pos;
+                    data[p] = (OutT)w;
                 }
+                pos += __popc(mask);
             }
             __syncthreads();
         }

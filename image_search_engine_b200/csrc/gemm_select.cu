@@ -604,7 +604,15 @@ static int pick_cg(int64_t m, bool split_products) {
     return (split_products && ceil_div64(m, BLOCK_M) >= 4) ? 2 : 1;
 }
 
-static Plan make_plan(const ise_ctx* ctx, int64_t m, int64_t n, bool single_split = false, bool split_products = false) {
+// Optional cap on the bytes of B one work item streams (0 = off).  The CTAs that walk the same column range share
+// every B tile through L2 only while they stay within L2's reach of each other, and ncu showed 30 GB and 104 GB of
+// DRAM reads for the same C3 launch on two boxes.  Capping an item at 32 MB (123 column splits instead of 7) did not
+// help when measured back to back on one box: coarse top-1 36.3 vs 36.4 ms, seeded top-32 41.0 vs 37.8 ms (the extra
+// partial lists cost more than any reuse gained), so the cap stays off (profiles/r01_findings.md section 12).
+constexpr int64_t kL2BytesPerItem = 0;   // 0 = no cap (see below)
+
+static Plan make_plan(const ise_ctx* ctx, int64_t m, int64_t n, int d, bool single_split = false,
+                      bool split_products = false) {
     Plan pl;
     pl.n_mtiles = (int)ceil_div64(m, BLOCK_M);
     pl.n_ntiles = (int)std::max<int64_t>(1, ceil_div64(n, BLOCK_N));
@@ -616,10 +624,15 @@ static Plan make_plan(const ise_ctx* ctx, int64_t m, int64_t n, bool single_spli
     int64_t want = ceil_div64((int64_t)4 * slots, std::max(1, groups));
     int64_t max_by_tiles = std::max<int64_t>(1, pl.n_ntiles / 8);
     int64_t s_hi = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(2 * want, max_by_tiles), 256));
-    if (single_split) s_hi = 1;  // top-1 verification keeps one runner-up per row, so columns are not split
+    // L2 reach: at least this many splits (when more than one row group shares the columns at all)
+    const int64_t tile_bytes = (int64_t)BLOCK_N * ((d + BLOCK_K - 1) / BLOCK_K * BLOCK_K) * 2 * (split_products ? 2 : 1);
+    const int64_t tiles_cap = kL2BytesPerItem > 0 ? std::max<int64_t>(8, kL2BytesPerItem / tile_bytes) : pl.n_ntiles;
+    int64_t s_lo = groups > 1 ? std::min<int64_t>(256, ceil_div64(pl.n_ntiles, tiles_cap)) : 1;
+    s_hi = std::max(s_hi, s_lo);
+    if (single_split) s_lo = s_hi = 1;  // top-1 verification keeps one runner-up per row, so columns are not split
     // pick the split count with the smallest makespan = waves x column tiles per item
-    int64_t best_s = 1, best_cost = -1;
-    for (int64_t s = 1; s <= s_hi; ++s) {
+    int64_t best_s = s_lo, best_cost = -1;
+    for (int64_t s = s_lo; s <= s_hi; ++s) {
         const int64_t tps = ceil_div64(pl.n_ntiles, s);
         const int64_t ns = ceil_div64(pl.n_ntiles, tps);
         const int64_t waves = ceil_div64((int64_t)groups * ns, slots);
@@ -686,7 +699,7 @@ static int dispatch_metric(const ise_ctx* ctx, const CUtensorMap* maps, const Pa
 ISE_EXPORT size_t ise_gemm_select_workspace_bytes(ise_ctx* ctx, int64_t m, int64_t n, int d, int topk) {
     if (!ctx || m <= 0 || topk <= 0) return 0;
     // the split count depends on whether the call will run CTA pairs (lo planes present): size for the larger
-    const int ns = std::max(gs::make_plan(ctx, m, n, false, false).n_splits, gs::make_plan(ctx, m, n, false, true).n_splits);
+    const int ns = std::max(gs::make_plan(ctx, m, n, d, false, false).n_splits, gs::make_plan(ctx, m, n, d, false, true).n_splits);
     if (ns <= 1) return 0;
     return (size_t)ns * (size_t)m * (size_t)topk * (sizeof(float) + sizeof(int64_t)) + 256;
 }
@@ -735,7 +748,7 @@ ISE_EXPORT int ise_gemm_collect(ise_ctx* ctx, const void* a_hi, const void* a_lo
     if (metric == ISE_METRIC_L2) ISE_CHECK_ARG(a_norms && b_norms);
     DeviceGuard guard(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
-    gs::Plan pl = gs::make_plan(ctx, m, n, false, b_lo != nullptr);
+    gs::Plan pl = gs::make_plan(ctx, m, n, d, false, b_lo != nullptr);
     gs::Params p;
     p.m = m; p.n = n; p.d = d;
     p.n_mtiles = pl.n_mtiles; p.n_ntiles = pl.n_ntiles;
@@ -777,7 +790,7 @@ ISE_EXPORT int ise_gemm_select(ise_ctx* ctx, const void* a_hi, const void* a_lo,
     DeviceGuard guard(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
 
-    gs::Plan pl = gs::make_plan(ctx, m, n, flag_count != nullptr, b_lo != nullptr);
+    gs::Plan pl = gs::make_plan(ctx, m, n, d, flag_count != nullptr, b_lo != nullptr);
     gs::Params p;
     p.m = m; p.n = n; p.d = d;
     p.n_mtiles = pl.n_mtiles; p.n_ntiles = pl.n_ntiles;
