@@ -433,7 +433,9 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(q.numel() * 4), "d2h_bytes_per_step": int(C3["nq"] * C3["topk"] * 12)},
             "roofline": {"bound": "tensor", "achieved": flops / (knn_kern_ms * 1e-3) / 1e12, "peak": P["tf_burst"],
                          "unit": "TFLOP/s", "frac": flops / (knn_kern_ms * 1e-3) / 1e12 / P["tf_burst"],
-                         "traffic": None,
+                         "traffic": 104.08e9,
+                         "traffic_source": "ncu r01 final: dram read 103.91 GB + write 0.17 GB for the coarse launch "
+                                           "(29.9 GB on another box with the L2 hit rate at 91 % instead of 72 %)",
                          "kernel": "gemm_select_kernel<1,1,IP,32> coarse (+ sample pre-pass, split re-run of unproven "
                                    "rows, topk_merge_kernel)", "kernel_ms": knn_kern_ms, "search": knn_stats,
                          "peak_source": P["src"] + ", bf16 burst"},
@@ -476,8 +478,8 @@ def run_ours(args):
                           "api": "BOVW.histograms_host(...) -> dense float64 [10k x 4096] (BOVW.transform's format)"},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": ach, "peak": P["tf_burst"], "unit": "TFLOP/s",
-                         "frac": ach / P["tf_burst"], "traffic": 0.2705e9,
-                         "traffic_source": "ncu r01: dram read+write per launch", "kernel": "gemm_select_kernel<2,2,IP,1>",
+                         "frac": ach / P["tf_burst"], "traffic": 272.09e6,
+                         "traffic_source": "ncu r01 final (profiles/r01_final_ncu.md): dram read 258.28 MB + write 13.81 MB per launch", "kernel": "gemm_select_kernel<2,2,IP,1>",
                          "kernel_ms": kern_ms, "search": assign_stats, "kernel_share_of_step": kern_ms / ms_step,
                          "peak_source": P["src"] + ", bf16 burst",
                          # FP32-grade scores need hi*hi + hi*lo(centroids): 2 tcgen05 products per algorithmic FLOP

@@ -45,7 +45,10 @@ __global__ void rescore_kernel(const TA* __restrict__ a, int64_t lda, const floa
         if (threadIdx.x == 0) s_kth = worst;
         __syncthreads();
         const float an = (L2 || flag_count) ? a_norms[row] : 0.f;
-        for (int j = warp; j < kc; j += kWarps) {
+        // collect mode appends candidates to slots [0, row_count): re-score and rank only those (the ranking below is
+        // quadratic in the number of slots looked at -- 1024^2 per row at the full buffer against ~375^2 used)
+        const int kv = row_count ? min(max(row_count[row], 0), kc) : kc;
+        for (int j = warp; j < kv; j += kWarps) {
             const long long id = cand_idx[row * kc + j];
             float out = worst;
             if (id >= 0) {
@@ -76,11 +79,15 @@ __global__ void rescore_kernel(const TA* __restrict__ a, int64_t lda, const floa
         }
         __syncthreads();
         // rank by counting: (score, id) is a strict total order over the real candidates
-        for (int me = threadIdx.x; me < kc; me += kThreads) {
+        for (int r = kv + threadIdx.x; r < topk; r += kThreads) {      // fewer candidates than k: pad the tail
+            val[row * topk + r] = worst;
+            idx[row * topk + r] = -1;
+        }
+        for (int me = threadIdx.x; me < kv; me += kThreads) {
             const float v = s_v[me];
             const long long id = s_i[me];
             int rank = 0;
-            for (int t = 0; t < kc; ++t) {
+            for (int t = 0; t < kv; ++t) {
                 if (t == me) continue;
                 const bool t_first = (id < 0 && s_i[t] < 0) ? (t < me)
                                                             : cand_better<!L2>(s_v[t], s_i[t], v, id);
