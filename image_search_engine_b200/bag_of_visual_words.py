@@ -225,6 +225,10 @@ class BOVW(BaseEstimator):
             descriptions = describe_dataset(self.describer, X, prediction=True)
         dev = ops.require_cuda()
         k = int(self.n_clusters)
+        if k > ops.CSR_MAX_BINS:
+            # codebooks beyond the shared-memory counter budget: dense kernel, CSR conversion on the host
+            H = self.histograms_device(descriptions, okapi=okapi)
+            return sp.csr_matrix(H.cpu().numpy())
         mat, offsets = pack_descriptions(descriptions)
         if isinstance(mat, np.ndarray):
             mat = torch.from_numpy(mat)

@@ -40,11 +40,20 @@ ISE_EXPORT int ise_ctx_create(int device, ise_ctx** out) {
         delete ctx;
         ISE_FAIL("cuTensorMapEncodeTiled not available from the driver");
     }
+    ctx->sync_buf = nullptr;
+    if (cudaMalloc(&ctx->sync_buf, kSyncInts * sizeof(int32_t)) != cudaSuccess) ctx->sync_buf = nullptr;   // optional
     *out = ctx;
     return 0;
 }
 
-ISE_EXPORT void ise_ctx_destroy(ise_ctx* ctx) { delete ctx; }
+ISE_EXPORT void ise_ctx_destroy(ise_ctx* ctx) {
+    if (!ctx) return;
+    if (ctx->sync_buf) {
+        DeviceGuard g(ctx->device);
+        cudaFree(ctx->sync_buf);
+    }
+    delete ctx;
+}
 
 ISE_EXPORT int ise_ctx_sm_count(const ise_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 

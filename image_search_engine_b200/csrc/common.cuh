@@ -20,7 +20,10 @@ struct ise_ctx {
     size_t smem_optin;
     // cuTensorMapEncodeTiled resolved through the runtime (no link-time libcuda dependency)
     void* encode_tiled;
+    // device scratch for the soft lock-step counters of gemm_select (kSyncInts int32, zeroed per launch)
+    int32_t* sync_buf;
 };
+constexpr int kSyncInts = 64 * 1024;
 
 void ise_set_error(const std::string& msg);
 

@@ -50,17 +50,20 @@ constexpr int EPI_WARP0 = 4;
 __host__ __device__ constexpr int epi_halves(int ksel, int pa, int pb) {
     return (ksel == 1 && pa == 1 && pb == 1) ? ISE_EPI_HALVES_COARSE_TOP1 : 1;
 }
-__host__ __device__ constexpr int num_threads(int ksel, int pa, int pb) { return 128 + 128 * epi_halves(ksel, pa, pb); }
+__host__ __device__ constexpr int num_threads(int ksel, int pa, int pb, int mt = 1) {
+    return 128 + 128 * epi_halves(ksel, pa, pb) * mt;
+}
 constexpr int TMEM_COLS = 512;  // 2 accumulator stages x BLOCK_N fp32 columns
 constexpr int AUX_BYTES = 4096;
 constexpr int SMEM_LIMIT = 232448;  // 227 KiB opt-in per CTA on sm_100
 
 // cg = CTAs per MMA (cta_group): with 2, each CTA of the pair stages only half of every B tile
-__host__ __device__ constexpr int stage_bytes(int pa, int pb, int cg = 1) {
-    return pa * A_TILE_BYTES + pb * (B_TILE_BYTES / cg);
+// mt = row tiles per CTA: with 2, one CTA runs two 128-row tiles against every B tile it stages
+__host__ __device__ constexpr int stage_bytes(int pa, int pb, int cg = 1, int mt = 1) {
+    return mt * pa * A_TILE_BYTES + pb * (B_TILE_BYTES / cg);
 }
-__host__ __device__ constexpr int num_stages(int pa, int pb, int cg = 1) {
-    int s = (SMEM_LIMIT - AUX_BYTES - 1024) / stage_bytes(pa, pb, cg);
+__host__ __device__ constexpr int num_stages(int pa, int pb, int cg = 1, int mt = 1) {
+    int s = (SMEM_LIMIT - AUX_BYTES - 1024) / stage_bytes(pa, pb, cg, mt);
     return s > 6 ? 6 : s;
 }
 
@@ -83,6 +86,12 @@ struct Params {
     int32_t* flag_count;    //   coarse error bound are appended here for a full-precision re-run
     float* out_val;    // [n_splits, m, topk]
     int64_t* out_idx;  // [n_splits, m, topk]
+    // soft lock-step (optional): the CTAs that walk one column range in the same round check in every `sync_every`
+    // column tiles and wait (bounded) for the slowest of them, so that every B tile they share is still in L2 when
+    // the last of them asks for it
+    int32_t* sync_cnt;  // [rounds * n_splits, sync_ncp] zero-initialised, or nullptr
+    int sync_every;
+    int sync_ncp;
 };
 
 struct Aux {  // lives after the stage ring in dynamic shared memory
@@ -116,17 +125,26 @@ template <> struct SelList<32> { using type = RegList32; };
 //   Only the leader CTA issues MMAs; TMA completions of both CTAs signal the leader's `full` barrier;
 //   tcgen05.commit multicasts `empty` / `tmem_full` to both CTAs; both epilogues arrive on the leader's
 //   `tmem_empty`.  Each CTA's epilogue reads its own 128 TMEM lanes exactly as in the single-CTA case.
-template <int PA, int PB, bool L2, int KSEL, bool VERIFY, int CG>
-__global__ void __launch_bounds__(num_threads(KSEL, PA, PB), 1)
+// MT = 2 (single CTA, CG == 1): the CTA owns TWO adjacent row tiles and runs both against every B tile it stages
+//   (two 256-column accumulators = all of TMEM, so the accumulators are NOT double buffered: the epilogue of a
+//   column tile and the MMAs of the next one alternate).  Halves the B bytes per MMA cycle like a CTA pair does,
+//   without any cross-CTA signalling; pays off when a tile's MMAs (d / 64 * 512 cycles per row tile) dwarf its
+//   epilogue, i.e. for the large-d coarse search pass, which is bound by the L2 -> shared-memory feed.
+template <int PA, int PB, bool L2, int KSEL, bool VERIFY, int CG, int MT = 1>
+__global__ void __launch_bounds__(num_threads(KSEL, PA, PB, MT), 1)
 gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const Params p) {
-    constexpr int STAGES = num_stages(PA, PB, CG);
-    constexpr int STAGE_BYTES = stage_bytes(PA, PB, CG);
+    static_assert(MT == 1 || (CG == 1 && epi_halves(KSEL, PA, PB) == 1), "two row tiles per CTA: single CTA, one warp per quadrant and tile");
+    constexpr int STAGES = num_stages(PA, PB, CG, MT);
+    constexpr int STAGE_BYTES = stage_bytes(PA, PB, CG, MT);
+    constexpr int A_BLOCK_BYTES = PA * A_TILE_BYTES;      // one row tile's planes inside a stage
+    constexpr int B_OFFSET = MT * A_BLOCK_BYTES;          // B planes follow the MT row tiles
+    constexpr int GRP = CG * MT;                          // row tiles per work item
     constexpr int B_LOAD_BYTES = B_TILE_BYTES / CG;   // this CTA's share of a B tile (one plane)
     constexpr int B_LOAD_ROWS = BLOCK_N / CG;
     constexpr int HALVES = epi_halves(KSEL, PA, PB);
-    constexpr int NUM_EPI_THREADS = 128 * HALVES;
+    constexpr int NUM_EPI_THREADS = 128 * HALVES * MT;
     constexpr int COLS_PER_HALF = BLOCK_N / HALVES;
     static_assert(STAGES >= 2 && STAGES <= 8, "pipeline depth");
 
@@ -168,7 +186,7 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
 
     const int num_kb = (p.d + BLOCK_K - 1) / BLOCK_K;
     // work items are (column split, group of CG adjacent row tiles); a pair walks them together
-    const int n_mgroups = (p.n_mtiles + CG - 1) / CG;
+    const int n_mgroups = (p.n_mtiles + GRP - 1) / GRP;
     const int total_work = n_mgroups * p.n_splits;
     const int w_begin = blockIdx.x / CG, w_step = gridDim.x / CG;
     // PA / PB are the plane SLOTS of a stage; whether a lo plane is really loaded and multiplied is a
@@ -181,12 +199,32 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t it = 0;
-            const uint32_t tx_bytes = A_TILE_BYTES * (1 + (int)use_alo) + B_LOAD_BYTES * (1 + (int)use_blo);
+            const uint32_t tx_bytes = MT * A_TILE_BYTES * (1 + (int)use_alo) + B_LOAD_BYTES * (1 + (int)use_blo);
             for (int w = w_begin; w < total_work; w += w_step) {
-                const int split = w / n_mgroups, mt = (w - split * n_mgroups) * CG + (int)cta_rank;
+                const int split = w / n_mgroups, mt = (w - split * n_mgroups) * GRP + (int)cta_rank;
                 const int nt0 = split * p.tiles_per_split;
                 const int nt1 = min(nt0 + p.tiles_per_split, p.n_ntiles);
+                // this work item's lock-step group: the items of the same split handled in the same round
+                int32_t* cnt = nullptr;
+                int gsize = 0;
+                if (p.sync_cnt != nullptr && leader) {
+                    const int round = (w - w_begin) / w_step;
+                    const int g_lo = max(round * w_step, split * n_mgroups);
+                    const int g_hi = min(min((round + 1) * w_step, (split + 1) * n_mgroups), total_work);
+                    gsize = g_hi - g_lo;
+                    if (gsize > 1) cnt = p.sync_cnt + ((int64_t)round * p.n_splits + split) * p.sync_ncp;
+                }
                 for (int nt = nt0; nt < nt1; ++nt) {
+                    if (cnt != nullptr && (nt - nt0) % p.sync_every == 0) {
+                        const int cp = (nt - nt0) / p.sync_every;
+                        atomicAdd(cnt + cp, 1);
+                        if (cp > 0) {
+                            // wait until every member has at least STARTED the previous block of tiles; bounded, since
+                            // this is a performance hint and co-residency of the group is not guaranteed
+                            const volatile int32_t* prev = cnt + cp - 1;
+                            for (int spin = 0; spin < 400 && *prev < gsize; ++spin) __nanosleep(100);
+                        }
+                    }
                     for (int kb = 0; kb < num_kb; ++kb, ++it) {
                         const int s = it % STAGES;
                         const uint32_t ph = (it / STAGES) & 1;
@@ -195,12 +233,17 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                         const int bcol = nt * BLOCK_N + (int)cta_rank * B_LOAD_ROWS;   // this CTA's half of the tile
                         if (CG == 1) {
                             ptx::mbar_arrive_expect_tx(&aux->full[s], tx_bytes);
-                            ptx::tma_load_2d(st, &tm_a_hi, &aux->full[s], kb * BLOCK_K, mt * BLOCK_M);
-                            if (use_alo)
-                                ptx::tma_load_2d(st + A_TILE_BYTES, &tm_a_lo, &aux->full[s], kb * BLOCK_K, mt * BLOCK_M);
-                            ptx::tma_load_2d(st + PA * A_TILE_BYTES, &tm_b_hi, &aux->full[s], kb * BLOCK_K, bcol);
+#pragma unroll
+                            for (int r = 0; r < MT; ++r) {      // rows past m are zero-filled by TMA
+                                ptx::tma_load_2d(st + r * A_BLOCK_BYTES, &tm_a_hi, &aux->full[s], kb * BLOCK_K,
+                                                 (mt + r) * BLOCK_M);
+                                if (use_alo)
+                                    ptx::tma_load_2d(st + r * A_BLOCK_BYTES + A_TILE_BYTES, &tm_a_lo, &aux->full[s],
+                                                     kb * BLOCK_K, (mt + r) * BLOCK_M);
+                            }
+                            ptx::tma_load_2d(st + B_OFFSET, &tm_b_hi, &aux->full[s], kb * BLOCK_K, bcol);
                             if (use_blo)
-                                ptx::tma_load_2d(st + PA * A_TILE_BYTES + B_LOAD_BYTES, &tm_b_lo, &aux->full[s],
+                                ptx::tma_load_2d(st + B_OFFSET + B_LOAD_BYTES, &tm_b_lo, &aux->full[s],
                                                  kb * BLOCK_K, bcol);
                         } else {
                             // both CTAs' bytes are counted on the LEADER's barrier
@@ -230,8 +273,9 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 const int nt0 = split * p.tiles_per_split;
                 const int nt1 = min(nt0 + p.tiles_per_split, p.n_ntiles);
                 for (int nt = nt0; nt < nt1; ++nt, ++tile) {
-                    const int as = tile & 1;
-                    const uint32_t aph = (tile >> 1) & 1;
+                    // MT == 2: both accumulators belong to this column tile (no double buffering)
+                    const int as = MT == 2 ? 0 : (tile & 1);
+                    const uint32_t aph = MT == 2 ? (tile & 1) : ((tile >> 1) & 1);
                     ptx::mbar_wait(&aux->tmem_empty[as], aph ^ 1);
                     ptx::tc_fence_after();
                     const uint32_t tmem_d = tmem_base + as * BLOCK_N;
@@ -243,8 +287,10 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                         const uint32_t st = smem_base + s * STAGE_BYTES;
                         const uint64_t da_hi = ptx::make_smem_desc_sw128(st);
                         const uint64_t da_lo = ptx::make_smem_desc_sw128(st + A_TILE_BYTES);
-                        const uint64_t db_hi = ptx::make_smem_desc_sw128(st + PA * A_TILE_BYTES);
-                        const uint64_t db_lo = ptx::make_smem_desc_sw128(st + PA * A_TILE_BYTES + B_LOAD_BYTES);
+                        const uint64_t db_hi = ptx::make_smem_desc_sw128(st + B_OFFSET);
+                        const uint64_t db_lo = ptx::make_smem_desc_sw128(st + B_OFFSET + B_LOAD_BYTES);
+                        const uint64_t da1_hi = ptx::make_smem_desc_sw128(st + A_BLOCK_BYTES);                  // MT == 2
+                        const uint64_t da1_lo = ptx::make_smem_desc_sw128(st + A_BLOCK_BYTES + A_TILE_BYTES);
                         const int rem = p.d - kb * BLOCK_K;
                         const int ksteps = rem >= BLOCK_K ? BLOCK_K / UMMA_K : (rem + UMMA_K - 1) / UMMA_K;
                         for (int ks = 0; ks < ksteps; ++ks) {
@@ -254,6 +300,11 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                                 ptx::umma_f16_ss(tmem_d, da_hi + koff, db_hi + koff, idesc, (kb | ks) != 0);
                                 if (use_blo) ptx::umma_f16_ss(tmem_d, da_hi + koff, db_lo + koff, idesc, 1);
                                 if (use_alo) ptx::umma_f16_ss(tmem_d, da_lo + koff, db_hi + koff, idesc, 1);
+                                if (MT == 2) {      // second row tile, accumulator in TMEM columns [256, 512)
+                                    ptx::umma_f16_ss(tmem_d + BLOCK_N, da1_hi + koff, db_hi + koff, idesc, (kb | ks) != 0);
+                                    if (use_blo) ptx::umma_f16_ss(tmem_d + BLOCK_N, da1_hi + koff, db_lo + koff, idesc, 1);
+                                    if (use_alo) ptx::umma_f16_ss(tmem_d + BLOCK_N, da1_lo + koff, db_hi + koff, idesc, 1);
+                                }
                             } else {
                                 ptx::umma_f16_ss_2sm(tmem_d, da_hi + koff, db_hi + koff, idesc, (kb | ks) != 0);
                                 if (use_blo) ptx::umma_f16_ss_2sm(tmem_d, da_hi + koff, db_lo + koff, idesc, 1);
@@ -274,7 +325,8 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         // ===================== epilogue: selection =====================
         const int ew = warp - EPI_WARP0;
         const int q = ew & 3;      // TMEM lane quadrant this warp may read (== warp % 4)
-        const int half = ew >> 2;  // which half of every tile's columns this warp scans
+        const int half = MT == 2 ? 0 : (ew >> 2);  // which half of every tile's columns this warp scans
+        const int rt = MT == 2 ? (ew >> 2) : 0;    // MT == 2: which of the CTA's two row tiles this warp serves
         const int et = threadIdx.x - EPI_WARP0 * 32;
         const float inv = p.a_meta[META_INV_SCALE] * p.b_meta[META_INV_SCALE];
         const float two_inv = 2.f * inv;
@@ -282,7 +334,7 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         if (KSEL == 1 && VERIFY) bound.init(p.a_meta, p.b_meta, p.d);
         uint32_t tile = 0;
         for (int w = w_begin; w < total_work; w += w_step) {
-            const int split = w / n_mgroups, mt = (w - split * n_mgroups) * CG + (int)cta_rank;
+            const int split = w / n_mgroups, mt = (w - split * n_mgroups) * GRP + (int)cta_rank + rt;
             const int nt0 = split * p.tiles_per_split;
             const int nt1 = min(nt0 + p.tiles_per_split, p.n_ntiles);
             const int row_in_tile = q * 32 + lane;
@@ -312,18 +364,18 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             }
 
             for (int nt = nt0; nt < nt1; ++nt, ++tile) {
-                const int as = tile & 1;
-                const uint32_t aph = (tile >> 1) & 1;
+                const int as = MT == 2 ? 0 : (tile & 1);
+                const uint32_t aph = MT == 2 ? (tile & 1) : ((tile >> 1) & 1);
                 const int col0 = nt * BLOCK_N;
                 const int ncols = (int)min((int64_t)BLOCK_N, p.n - col0);
                 if (L2) {
                     for (int c = et; c < BLOCK_N; c += NUM_EPI_THREADS)
-                        aux->bnorm[as][c] = (c < ncols) ? __ldg(p.b_norms + col0 + c) : 0.f;
+                        aux->bnorm[tile & 1][c] = (c < ncols) ? __ldg(p.b_norms + col0 + c) : 0.f;
                     asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_THREADS) : "memory");
                 }
                 ptx::mbar_wait(&aux->tmem_full[as], aph);
                 ptx::tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (MT == 2 ? rt : as) * BLOCK_N;
                 const int c_begin = half * COLS_PER_HALF;
                 const int c_end = min(c_begin + COLS_PER_HALF, ncols);
                 // ROLLED loop over 32-column chunks: one copy of the scan / insertion code (I-cache)
@@ -343,7 +395,7 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                         for (int j = 0; j < 32; ++j) {
                             v[j] = __uint_as_float(r[j]);
                             // maximise 2<a,b> - |b|^2  ==  minimise |a|^2 + |b|^2 - 2<a,b>
-                            if (L2) v[j] = fmaf(v[j], two_inv, -aux->bnorm[as][c + j]);
+                            if (L2) v[j] = fmaf(v[j], two_inv, -aux->bnorm[tile & 1][c + j]);
                         }
 #if ISE_EPI_PREFETCH
                         if (c + 32 < c_end) ptx::tmem_ld_32x32b_x32(taddr + c + 32, r);
@@ -611,13 +663,27 @@ static int pick_cg(int64_t m, bool split_products) {
 // partial lists cost more than any reuse gained), so the cap stays off (profiles/r01_findings.md section 12).
 constexpr int64_t kL2BytesPerItem = 0;   // 0 = no cap (see below)
 
-static Plan make_plan(const ise_ctx* ctx, int64_t m, int64_t n, int d, bool single_split = false,
+// Two row tiles per CTA (MT = 2) for the coarse TOP-1 pass (hi planes only) when the MMAs of a tile pair outlast its
+// epilogue by a wide margin (d >= 1024: >= 16 k MMA cycles against ~2 k of scan) and there are enough row tiles to go
+// round: C3-shaped top-1 30.9 vs 35.5 ms.  The top-k list epilogues lose with it (seeded top-32 40.8 vs 35.4 ms,
+// profiles/r01_findings.md section 13), so they keep one row tile and double-buffered accumulators.
+// ISE_MT2=0 / 1 overrides (A/B measurements).
+static int pick_mt(int64_t m, int d, bool split_products, int topk) {
+    if (split_products || topk != 1) return 1;
+    const char* e = getenv("ISE_MT2");
+    if (e && e[0] == '0') return 1;
+    const bool forced = e && e[0] == '1';
+    return ((forced || d >= 1024) && ceil_div64(m, BLOCK_M) >= 2) ? 2 : 1;
+}
+
+static Plan make_plan(const ise_ctx* ctx, int64_t m, int64_t n, int d, int topk, bool single_split = false,
                       bool split_products = false) {
     Plan pl;
     pl.n_mtiles = (int)ceil_div64(m, BLOCK_M);
     pl.n_ntiles = (int)std::max<int64_t>(1, ceil_div64(n, BLOCK_N));
     const int cg = pick_cg(m, split_products);
-    const int groups = (pl.n_mtiles + cg - 1) / cg;      // work is scheduled per CTA pair
+    const int grp = cg * pick_mt(m, d, split_products, topk);
+    const int groups = (pl.n_mtiles + grp - 1) / grp;    // work is scheduled per CTA pair / per two-tile CTA
     const int slots = std::max(1, ctx->sm_count / cg);
     // enough work items for ~4 waves of the persistent grid, but never less than 8 column tiles per
     // item (a fresh item restarts its selection threshold) and at most 256 partial lists per row
@@ -644,17 +710,45 @@ static Plan make_plan(const ise_ctx* ctx, int64_t m, int64_t n, int d, bool sing
     return pl;
 }
 
-template <int PA, int PB, bool L2, int KSEL, bool VERIFY, int CG>
+
+// soft lock-step set-up: worth it only when one work item streams more B than a slice of L2 can keep around for the
+// slowest CTA of its group
+static void setup_sync(const ise_ctx* ctx, Params& p, int d, bool split_products, int cg, int mt, cudaStream_t st) {
+    p.sync_cnt = nullptr;
+    p.sync_every = 0;
+    p.sync_ncp = 0;
+    const char* e = getenv("ISE_LOCKSTEP");
+    if (!ctx->sync_buf || (e && e[0] == '0')) return;
+    const int64_t tile_bytes = (int64_t)BLOCK_N * ((d + BLOCK_K - 1) / BLOCK_K * BLOCK_K) * 2 * (split_products ? 2 : 1);
+    if (tile_bytes * p.tiles_per_split < (24ll << 20) && !(e && e[0] == '1')) return;
+    const int every = (int)std::max<int64_t>(4, (16ll << 20) / tile_bytes);        // ~16 MB of B between check-ins
+    const int ncp = (p.tiles_per_split + every - 1) / every;
+    const int grp = cg * mt;
+    const int n_mgroups = (p.n_mtiles + grp - 1) / grp;
+    const int64_t total = (int64_t)n_mgroups * p.n_splits;
+    const int slots = std::max(1, ctx->sm_count / cg);
+    const int64_t rounds = ceil_div64(total, std::min<int64_t>(total, slots));
+    const int64_t ints = rounds * p.n_splits * ncp;
+    if (ints > kSyncInts) return;
+    if (cudaMemsetAsync(ctx->sync_buf, 0, (size_t)ints * sizeof(int32_t), st) != cudaSuccess) return;
+    p.sync_cnt = ctx->sync_buf;
+    p.sync_every = every;
+    p.sync_ncp = ncp;
+}
+
+template <int PA, int PB, bool L2, int KSEL, bool VERIFY, int CG, int MT = 1>
 static int launch_cg(const ise_ctx* ctx, const CUtensorMap* maps, const Params& p, cudaStream_t st) {
-    auto kern = gemm_select_kernel<PA, PB, L2, KSEL, VERIFY, CG>;
-    const int smem = num_stages(PA, PB, CG) * stage_bytes(PA, PB, CG) + AUX_BYTES + 1024;
+    auto kern = gemm_select_kernel<PA, PB, L2, KSEL, VERIFY, CG, MT>;
+    const int smem = num_stages(PA, PB, CG, MT) * stage_bytes(PA, PB, CG, MT) + AUX_BYTES + 1024;
     ISE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int groups = (p.n_mtiles + CG - 1) / CG;
+    const int groups = (p.n_mtiles + CG * MT - 1) / (CG * MT);
     const int total = groups * p.n_splits;
+    Params pp = p;
+    setup_sync(ctx, pp, p.d, PB == 2, CG, MT, st);
     const int grid = CG * std::min(total, std::max(1, ctx->sm_count / CG));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3((unsigned)num_threads(KSEL, PA, PB));
+    cfg.blockDim = dim3((unsigned)num_threads(KSEL, PA, PB, MT));
     cfg.dynamicSmemBytes = (size_t)smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -664,12 +758,15 @@ static int launch_cg(const ise_ctx* ctx, const CUtensorMap* maps, const Params& 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    ISE_CUDA(cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], p));
+    ISE_CUDA(cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], pp));
     return 0;
 }
 
 template <int PA, int PB, bool L2, int KSEL, bool VERIFY = false>
 static int launch(const ise_ctx* ctx, const CUtensorMap* maps, const Params& p, cudaStream_t st) {
+    if constexpr (KSEL == 1 && PA == 1 && PB == 1 && epi_halves(KSEL, PA, PB) == 1) {
+        if (pick_mt(p.m, p.d, false, 1) == 2) return launch_cg<PA, PB, L2, KSEL, VERIFY, 1, 2>(ctx, maps, p, st);
+    }
     return pick_cg(p.m, PB == 2) == 2 ? launch_cg<PA, PB, L2, KSEL, VERIFY, 2>(ctx, maps, p, st)
                                       : launch_cg<PA, PB, L2, KSEL, VERIFY, 1>(ctx, maps, p, st);
 }
@@ -699,7 +796,7 @@ static int dispatch_metric(const ise_ctx* ctx, const CUtensorMap* maps, const Pa
 ISE_EXPORT size_t ise_gemm_select_workspace_bytes(ise_ctx* ctx, int64_t m, int64_t n, int d, int topk) {
     if (!ctx || m <= 0 || topk <= 0) return 0;
     // the split count depends on whether the call will run CTA pairs (lo planes present): size for the larger
-    const int ns = std::max(gs::make_plan(ctx, m, n, d, false, false).n_splits, gs::make_plan(ctx, m, n, d, false, true).n_splits);
+    const int ns = std::max(gs::make_plan(ctx, m, n, d, topk, false, false).n_splits, gs::make_plan(ctx, m, n, d, topk, false, true).n_splits);
     if (ns <= 1) return 0;
     return (size_t)ns * (size_t)m * (size_t)topk * (sizeof(float) + sizeof(int64_t)) + 256;
 }
@@ -748,7 +845,7 @@ ISE_EXPORT int ise_gemm_collect(ise_ctx* ctx, const void* a_hi, const void* a_lo
     if (metric == ISE_METRIC_L2) ISE_CHECK_ARG(a_norms && b_norms);
     DeviceGuard guard(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
-    gs::Plan pl = gs::make_plan(ctx, m, n, d, false, b_lo != nullptr);
+    gs::Plan pl = gs::make_plan(ctx, m, n, d, 0, false, b_lo != nullptr);
     gs::Params p;
     p.m = m; p.n = n; p.d = d;
     p.n_mtiles = pl.n_mtiles; p.n_ntiles = pl.n_ntiles;
@@ -790,7 +887,7 @@ ISE_EXPORT int ise_gemm_select(ise_ctx* ctx, const void* a_hi, const void* a_lo,
     DeviceGuard guard(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
 
-    gs::Plan pl = gs::make_plan(ctx, m, n, d, flag_count != nullptr, b_lo != nullptr);
+    gs::Plan pl = gs::make_plan(ctx, m, n, d, topk, flag_count != nullptr, b_lo != nullptr);
     gs::Params p;
     p.m = m; p.n = n; p.d = d;
     p.n_mtiles = pl.n_mtiles; p.n_ntiles = pl.n_ntiles;

@@ -19,6 +19,7 @@ from ._lib import (DTYPE_F32, DTYPE_U8, HIST_BINCOUNT, HIST_NUMPY_COMPAT, METRIC
                    OUT_F64, IseError)
 
 MAX_TOPK = 128
+CSR_MAX_BINS = 12 * 1024     # ise_bovw_histogram_csr keeps one int32 counter per bin in shared memory
 
 # kernel-launch counter (bench.py reports it as gpu_launches)
 _launches = 0
