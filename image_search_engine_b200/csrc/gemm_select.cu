@@ -676,13 +676,26 @@ static int pick_mt(int64_t m, int d, bool split_products, int topk) {
     return ((forced || d >= 1024) && ceil_div64(m, BLOCK_M) >= 2) ? 2 : 1;
 }
 
+// The launch variant (CTAs per MMA, row tiles per CTA) is decided in ONE place: the tensor maps (B box height), the
+// work plan and the kernel instantiation must agree, or a TMA box delivers fewer bytes than the barrier expects.
+struct Variant {
+    int cg, mt;
+};
+static Variant pick_variant(int64_t m, int d, bool split_products, int topk) {
+    Variant v;
+    v.mt = pick_mt(m, d, split_products, topk);
+    v.cg = v.mt == 2 ? 1 : pick_cg(m, split_products);
+    return v;
+}
+
 static Plan make_plan(const ise_ctx* ctx, int64_t m, int64_t n, int d, int topk, bool single_split = false,
                       bool split_products = false) {
     Plan pl;
     pl.n_mtiles = (int)ceil_div64(m, BLOCK_M);
     pl.n_ntiles = (int)std::max<int64_t>(1, ceil_div64(n, BLOCK_N));
-    const int cg = pick_cg(m, split_products);
-    const int grp = cg * pick_mt(m, d, split_products, topk);
+    const Variant var = pick_variant(m, d, split_products, topk);
+    const int cg = var.cg;
+    const int grp = var.cg * var.mt;
     const int groups = (pl.n_mtiles + grp - 1) / grp;    // work is scheduled per CTA pair / per two-tile CTA
     const int slots = std::max(1, ctx->sm_count / cg);
     // enough work items for ~4 waves of the persistent grid, but never less than 8 column tiles per
@@ -764,11 +777,13 @@ static int launch_cg(const ise_ctx* ctx, const CUtensorMap* maps, const Params& 
 
 template <int PA, int PB, bool L2, int KSEL, bool VERIFY = false>
 static int launch(const ise_ctx* ctx, const CUtensorMap* maps, const Params& p, cudaStream_t st) {
+    const Variant var = pick_variant(p.m, p.d, PB == 2, KSEL == 1 ? 1 : 0);
     if constexpr (KSEL == 1 && PA == 1 && PB == 1 && epi_halves(KSEL, PA, PB) == 1) {
-        if (pick_mt(p.m, p.d, false, 1) == 2) return launch_cg<PA, PB, L2, KSEL, VERIFY, 1, 2>(ctx, maps, p, st);
+        if (var.mt == 2) return launch_cg<PA, PB, L2, KSEL, VERIFY, 1, 2>(ctx, maps, p, st);
     }
-    return pick_cg(p.m, PB == 2) == 2 ? launch_cg<PA, PB, L2, KSEL, VERIFY, 2>(ctx, maps, p, st)
-                                      : launch_cg<PA, PB, L2, KSEL, VERIFY, 1>(ctx, maps, p, st);
+    if (var.mt != 1) ISE_FAIL("internal: two-row-tile variant picked for a kernel that has none");
+    return var.cg == 2 ? launch_cg<PA, PB, L2, KSEL, VERIFY, 2>(ctx, maps, p, st)
+                       : launch_cg<PA, PB, L2, KSEL, VERIFY, 1>(ctx, maps, p, st);
 }
 
 template <int PA, int PB, bool L2>
@@ -821,8 +836,8 @@ ISE_EXPORT int ise_topk_merge(ise_ctx* ctx, const float* val_parts, const int64_
 
 // shared argument validation + tensor maps
 static int setup_maps(ise_ctx* ctx, const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi,
-                      const void* b_lo, int64_t ldb, int64_t m, int64_t n, int d, CUtensorMap* maps) {
-    const int b_box = gs::BLOCK_N / gs::pick_cg(m, b_lo != nullptr);   // a CTA of a pair stages half of every B tile
+                      const void* b_lo, int64_t ldb, int64_t m, int64_t n, int d, int topk, CUtensorMap* maps) {
+    const int b_box = gs::BLOCK_N / gs::pick_variant(m, d, b_lo != nullptr, topk).cg;   // a CTA of a pair stages half of every B tile
     ISE_CHECK_ARG(lda >= d && ldb >= d && lda % 8 == 0 && ldb % 8 == 0);
     ISE_CHECK_ARG((reinterpret_cast<uintptr_t>(a_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(b_hi) & 15) == 0);
     if (gs::make_plane_map(ctx, &maps[0], a_hi, m, d, lda, gs::BLOCK_M)) return 1;
@@ -858,7 +873,7 @@ ISE_EXPORT int ise_gemm_collect(ise_ctx* ctx, const void* a_hi, const void* a_lo
     ISE_CUDA(cudaMemsetAsync(cand_idx, 0xFF, (size_t)m * cap * sizeof(int64_t), st));
     ISE_CUDA(cudaMemsetAsync(row_count, 0, (size_t)m * sizeof(int32_t), st));
     CUtensorMap maps[4];
-    if (setup_maps(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, m, n, d, maps)) return 1;
+    if (setup_maps(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, m, n, d, 0, maps)) return 1;
     const int pa = a_lo ? 2 : 1, pb = b_lo ? 2 : 1;
     const bool l2 = metric == ISE_METRIC_L2;
     if (pa == 1 && pb == 1) return l2 ? gs::launch<1, 1, true, 0>(ctx, maps, p, st) : gs::launch<1, 1, false, 0>(ctx, maps, p, st);
@@ -917,7 +932,7 @@ ISE_EXPORT int ise_gemm_select(ise_ctx* ctx, const void* a_hi, const void* a_lo,
 
     const int pa = a_lo ? 2 : 1, pb = b_lo ? 2 : 1;
     CUtensorMap maps[4];
-    if (setup_maps(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, m, n, d, maps)) return 1;
+    if (setup_maps(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, m, n, d, topk, maps)) return 1;
 
     int rc;
     if (pa == 1 && pb == 1) rc = gs::dispatch_metric<1, 1>(ctx, maps, p, metric, st);
