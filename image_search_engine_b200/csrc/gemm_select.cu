@@ -13,6 +13,8 @@
 //                           or thread-local lists while the next tile's MMAs run
 // Replaces Faiss knn_inner_product / knn_L2sqr (sgemm + result handler) behind
 // reference call sites kmeans_faiss.py:41,49 and engine.py:55.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -38,15 +40,14 @@ constexpr int UMMA_K = 16;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
 constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;  // 32 KiB
 constexpr int EPI_WARP0 = 4;
-// One epilogue warp per TMEM lane quadrant.  (Two warps per quadrant, each scanning half of a tile's
-// columns, was measured SLOWER for the d = 128 assign: 1.57-1.67 ms vs 1.43 ms at C2 -- the tile is bound
-// by the TMEM -> register read of the 128 x 256 accumulator, not by issue slots; the code path is kept.)
+// One epilogue warp per TMEM lane quadrant.  Two warps per quadrant (each scanning half of a tile's columns) is a
+// build-time option for the coarse top-1 kernels only (-DISE_EPI_HALVES_COARSE_TOP1=2): measured at the d = 128 C2
+// shape it moves the split products from 1.43 to 1.57-1.67 ms (MMA-bound: nothing to gain, a hand-over to pay) and
+// the one-product coarse pass from 1.07 to 0.99 ms (bound by the L2 -> shared-memory feed, not by the epilogue's TMEM
+// reads: profiles/r01_findings.md section 8), so the default stays at one.
 #ifndef ISE_EPI_HALVES_COARSE_TOP1
 #define ISE_EPI_HALVES_COARSE_TOP1 1
 #endif
-// The COARSE top-1 pass (one product per tile, d <= 128: 1 024 MMA cycles per tile) is bound by the epilogue's
-// instruction stream, not by its TMEM reads (profiles/r01_findings.md section 8), so it gets two warps per
-// quadrant; everything else is MMA-bound and keeps one.
 __host__ __device__ constexpr int epi_halves(int ksel, int pa, int pb) {
     return (ksel == 1 && pa == 1 && pb == 1) ? ISE_EPI_HALVES_COARSE_TOP1 : 1;
 }
