@@ -67,7 +67,12 @@ struct DeviceGuard {
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // meta layout shared by prepare.cu and gemm_select.cu
-enum { META_SCALE = 0, META_INV_SCALE = 1, META_LO_NONZERO = 2, META_ABSMAX = 3, META_MAX_NORM_SQ = 4, META_FLOATS = 8 };
+enum {
+    META_SCALE = 0, META_INV_SCALE = 1, META_LO_NONZERO = 2, META_ABSMAX = 3, META_MAX_NORM_SQ = 4,
+    META_WIDE_MANTISSA = 5,   // != 0: some element has more than 11 significant bits (float32 inputs, absmax pass)
+    META_MIN_NONZERO = 6,     // 0x7f800000 - bits(min |x| over non-zero elements), 0 = none seen (int, via atomicMax)
+    META_FLOATS = 8
+};
 
 #ifdef __CUDACC__
 

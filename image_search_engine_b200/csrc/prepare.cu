@@ -11,9 +11,22 @@ __device__ __forceinline__ float absmax4(float4 v) {
     return fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
 }
 
+// Besides the absolute maximum, the pass records whether every element would be EXACT in one FP16 plane at the
+// power-of-two scale the maximum implies (at most 11 significant bits, and not so small next to the maximum that
+// it would leave FP16's normal range): integer-valued descriptors (SIFT, ORB as float) are, and the conversion
+// pass then skips the lo plane's stores altogether (a quarter of its HBM traffic).
+__device__ __forceinline__ void exact_probe(float v, unsigned& wide, float& mn) {
+    const unsigned b = __float_as_uint(v);
+    wide |= b & 0x1FFFu;                                   // mantissa bits FP16 cannot hold
+    const float a = fabsf(v);
+    mn = (a > 0.f) ? fminf(mn, a) : mn;
+}
+
 __global__ void absmax_f32_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ldx, float* meta) {
     const int lane = threadIdx.x & 31;
     float m = 0.f;
+    unsigned wide = 0u;
+    float mn = 3.402823466e+38f;
     if (ldx == d && ((n * d) % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0)) {
         // contiguous matrix: a flat stream of float4, four independent loads in flight per thread
         const float4* x4 = reinterpret_cast<const float4*>(x);
@@ -24,17 +37,39 @@ __global__ void absmax_f32_kernel(const float* __restrict__ x, int64_t n, int d,
             const float4 a = __ldg(x4 + i), b = __ldg(x4 + i + stride), c = __ldg(x4 + i + 2 * stride),
                          e = __ldg(x4 + i + 3 * stride);
             m = fmaxf(m, fmaxf(fmaxf(absmax4(a), absmax4(b)), fmaxf(absmax4(c), absmax4(e))));
+            const float4 q[4] = {a, b, c, e};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                exact_probe(q[u].x, wide, mn); exact_probe(q[u].y, wide, mn);
+                exact_probe(q[u].z, wide, mn); exact_probe(q[u].w, wide, mn);
+            }
         }
-        for (; i < total; i += stride) m = fmaxf(m, absmax4(__ldg(x4 + i)));
+        for (; i < total; i += stride) {
+            const float4 a = __ldg(x4 + i);
+            m = fmaxf(m, absmax4(a));
+            exact_probe(a.x, wide, mn); exact_probe(a.y, wide, mn); exact_probe(a.z, wide, mn); exact_probe(a.w, wide, mn);
+        }
     } else {
         const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
         const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
         for (int64_t r = warp; r < n; r += nwarps) {
             const float* row = x + r * ldx;
-            for (int c = lane; c < d; c += 32) m = fmaxf(m, fabsf(__ldg(row + c)));
+            for (int c = lane; c < d; c += 32) {
+                const float v = __ldg(row + c);
+                m = fmaxf(m, fabsf(v));
+                exact_probe(v, wide, mn);
+            }
         }
     }
     m = warp_max(m);
+    wide = __reduce_or_sync(0xffffffffu, wide);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    if (lane == 0) {
+        if (wide) meta[META_WIDE_MANTISSA] = 1.f;
+        if (mn < 3.402823466e+38f)
+            atomicMax(reinterpret_cast<int*>(meta + META_MIN_NONZERO), 0x7f800000 - __float_as_int(mn));
+    }
     // non-negative finite floats order like their bit patterns; NaN/Inf are rejected by the host API
     if (lane == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(meta + META_ABSMAX), __float_as_int(m));
 }
@@ -121,6 +156,12 @@ __global__ void prepare_planes_f32x4_kernel(const float* __restrict__ x, int64_t
         meta[META_SCALE] = scale;
         meta[META_INV_SCALE] = 1.f / scale;
     }
+    // every element exact in the hi plane (<= 11 significant bits, scaled value in FP16's normal range): the lo plane
+    // is all zeros, META_LO_NONZERO stays 0 and nobody will ever read it -- do not write it
+    const int mn_code = reinterpret_cast<const int*>(meta)[META_MIN_NONZERO];
+    const float mn_abs = mn_code ? __int_as_float(0x7f800000 - mn_code) : 1.f;
+    const bool exact = meta[META_WIDE_MANTISSA] == 0.f && mn_abs * scale >= 6.103515625e-05f;
+    if (exact) lo = nullptr;
     bool any_lo = false;
     float max_ss = 0.f;
     const int d4 = d >> 2, dp4 = (int)(ldp >> 2);
@@ -142,6 +183,16 @@ __global__ void prepare_planes_f32x4_kernel(const float* __restrict__ x, int64_t
                 if (r >= n) continue;
                 ss[i] = fmaf(v[i].x, v[i].x, ss[i]); ss[i] = fmaf(v[i].y, v[i].y, ss[i]);
                 ss[i] = fmaf(v[i].z, v[i].z, ss[i]); ss[i] = fmaf(v[i].w, v[i].w, ss[i]);
+                if (exact) {
+                    // one packed conversion per two elements, no residual: the float -> half conversions (not HBM)
+                    // bound this kernel when every element goes through three of them
+                    const __half2 ha = __floats2half2_rn(v[i].x * scale, v[i].y * scale);
+                    const __half2 hb = __floats2half2_rn(v[i].z * scale, v[i].w * scale);
+                    uint2 hv;
+                    hv.x = *reinterpret_cast<const uint32_t*>(&ha); hv.y = *reinterpret_cast<const uint32_t*>(&hb);
+                    reinterpret_cast<uint2*>(hi + r * ldp)[c] = hv;
+                    continue;
+                }
                 __half h0, h1, h2, h3, l0, l1, l2, l3;
                 split_f16(v[i].x * scale, h0, l0); split_f16(v[i].y * scale, h1, l1);
                 split_f16(v[i].z * scale, h2, l2); split_f16(v[i].w * scale, h3, l3);

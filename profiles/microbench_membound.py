@@ -48,7 +48,9 @@ def rec(name, ms, nbytes):
     print(f"{name:58s} {ms*1e3:8.1f} us  {gbs:7.0f} GB/s  {gbs/P:5.2f} of {P:.0f}")
 
 
-rec("prepare f32 (absmax + planes hi/lo + norms)", t(lambda: ops.prepare_operand(X)), n * d * (4 + 4 + 4))
+rec("prepare f32, integer-valued (absmax + hi plane + norms; 10 B/element moved)", t(lambda: ops.prepare_operand(X)), n * d * 10)
+Xf = X + 0.37
+rec("prepare f32, general (absmax + hi/lo planes + norms; 12 B/element moved)", t(lambda: ops.prepare_operand(Xf)), n * d * 12)
 rec("prepare u8 (one plane + norms)", t(lambda: ops.prepare_operand(Xu8)), n * d * (1 + 2))
 rec("histogram f64 numpy-compat + okapi", t(lambda: ops.bovw_histogram(words, off, k, mode=HIST_NUMPY_COMPAT, okapi=True, out=out64)), n * 8 + n_img * k * 8)
 rec("histogram f64 bincount", t(lambda: ops.bovw_histogram(words, off, k, mode=HIST_BINCOUNT, out=out64)), n * 8 + n_img * k * 8)

@@ -388,3 +388,41 @@ def test_privatised_accumulate_equals_oracle_and_plain(dev, monkeypatch, n, d, k
         assert np.array_equal(c, counts_ref), which
         np.testing.assert_allclose(s, sums_ref, rtol=2e-5, atol=2e-5 * np.abs(sums_ref).max(), err_msg=which)
         assert abs(o - obj_ref) <= 1e-5 * abs(obj_ref) + 1e-3, (which, o, obj_ref)
+
+
+def test_exact_inputs_skip_the_lo_plane_and_nobody_reads_it(dev):
+    """Integer-valued float32 descriptors are exact in the FP16 hi plane: prepare does not even write the lo plane
+    (META_LO_NONZERO stays 0) and gemm_select must never load it.  The allocator block the lo plane lands in is
+    poisoned with NaNs first, so any read of it would surface in the scores."""
+    from image_search_engine_b200 import ops
+    from image_search_engine_b200._lib import METRIC_IP, METRIC_L2
+    rng = np.random.default_rng(12)
+    x = torch.from_numpy(sift_like(rng, 40000, 128)).to(dev)
+    c = torch.from_numpy(unit_rows(rng, 1000, 128)).to(dev)
+    b = ops.prepare_operand(c)
+    for _ in range(2):
+        poison = torch.full((40000, 128), float("nan"), dtype=torch.float16, device=dev)
+        poison2 = torch.full((40000, 128), float("nan"), dtype=torch.float16, device=dev)
+        del poison, poison2                                    # blocks return to the caching allocator ...
+        a = ops.prepare_operand(x)                             # ... and are handed out again for hi / lo
+        assert a.lo is not None and float(a.meta[2]) == 0.0
+    assert bool(torch.isnan(a.lo.float()).any()), "the lo plane was written although the input is exact"
+    assert not bool(torch.isnan(a.hi.float()).any())
+    a_hi_only = ops.Operand(a.hi, None, a.norms, a.meta, a.n, a.d, a.ldp)
+    for metric in (METRIC_IP, METRIC_L2):
+        v2, i2 = ops.gemm_select(a, b, metric, 1)              # PA = 2 plane slots, lo skipped at run time
+        v1, i1 = ops.gemm_select(a_hi_only, b, metric, 1)
+        assert torch.equal(i1, i2) and torch.equal(v1, v2) and not bool(torch.isnan(v2).any())
+    # non-exact data still gets its lo plane
+    y = torch.randn((5000, 128), device=dev)
+    ay = ops.prepare_operand(y)
+    assert float(ay.meta[2]) == 1.0 and not bool(torch.isnan(ay.lo.float()).any())
+    # a value far below the maximum leaves FP16's normal range once scaled: the input no longer counts as exact and
+    # the lo plane is written again (zeros here: such a value underflows in both planes, which the coarse error
+    # bound accounts for)
+    z = x[:4096].clone()
+    z[0, 0] = 2.0 ** -40
+    poison = torch.full((4096, 128), float("nan"), dtype=torch.float16, device=dev)
+    del poison
+    az = ops.prepare_operand(z)
+    assert not bool(torch.isnan(az.lo.float()).any())
