@@ -647,13 +647,19 @@ struct Plan {
 // CTA and carries 8-12 MMAs, and pairs win 4-6 % (C2 assign 1.36 vs 1.41 ms, C3 split top-1 92 vs 98 ms);
 // for the coarse pass (hi planes only, 4 MMAs per 32 KB stage) the cross-CTA signalling round trip is
 // exposed and pairs lose 3-20 %, so the coarse pass stays single-CTA.
-static int pick_cg(int64_t m, bool split_products) {
+static int pick_cg(int64_t m, bool split_products, int d = 0, int topk = 1) {
 #ifdef ISE_FORCE_CG1
     return 1;
 #endif
 #ifdef ISE_FORCE_CG2
     split_products = true;
 #endif
+    // coarse top-k / collect passes at large d: with the soft lock-step keeping the column range in L2, halving the
+    // B bytes per MMA cycle pays (C3 seeded top-32 35.5 -> 33.0 ms); ISE_CG2_COARSE=0 / 1 overrides
+    if (!split_products && topk != 1) {
+        const char* e = getenv("ISE_CG2_COARSE");
+        if (e ? e[0] == '1' : d >= 1024) split_products = true;
+    }
     return (split_products && ceil_div64(m, BLOCK_M) >= 4) ? 2 : 1;
 }
 
@@ -685,7 +691,7 @@ struct Variant {
 static Variant pick_variant(int64_t m, int d, bool split_products, int topk) {
     Variant v;
     v.mt = pick_mt(m, d, split_products, topk);
-    v.cg = v.mt == 2 ? 1 : pick_cg(m, split_products);
+    v.cg = v.mt == 2 ? 1 : pick_cg(m, split_products, d, topk);
     return v;
 }
 
