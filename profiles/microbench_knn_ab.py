@@ -23,3 +23,4 @@ def t(fn, n=3):
     return e0.elapsed_time(e1) / n
 print("coarse k=32 seeded: %.2f ms" % t(lambda: ops.gemm_select(hi(a), hi(b), METRIC_IP, 32, row_seed=seed)), flush=True)
 print("search_topk verified: %.2f ms" % t(lambda: ops.search_topk(q, a, db, b, METRIC_IP, 10)), flush=True)
+print("stats:", ops.last_search_stats)
