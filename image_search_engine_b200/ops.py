@@ -492,8 +492,8 @@ def bovw_histogram(words: torch.Tensor, img_offsets: torch.Tensor, k: int, *, mo
     elif tuple(out.shape) != (n_img, k) or out.dtype != out_dtype or not out.is_contiguous():
         raise IseError("bovw_histogram: out must be a contiguous [n_img, k] tensor of out_dtype")
     _lib.check(_lib.load().ise_bovw_histogram(
-        _lib.ctx(_dev(img_offsets)), _ptr(words), _ptr(img_offsets), n_img, int(k), int(mode), od, _ptr(out),
-        1 if okapi else 0, float(k1), float(k2), float(b), float(avgdl), _stream()))
+        _lib.ctx(_dev(img_offsets)), _ptr(words), int(words.numel()), _ptr(img_offsets), n_img, int(k), int(mode), od,
+        _ptr(out), 1 if okapi else 0, float(k1), float(k2), float(b), float(avgdl), _stream()))
     _count()
     return out
 

@@ -183,8 +183,9 @@ int ise_kmeans_apply_splits(ise_ctx* ctx, float* centroids, int64_t k, int d,
  * bit-exactly (float64 edge arithmetic); BINCOUNT is bincount(idx, minlength=k).
  * okapi != 0 fuses OkapiTransformer.transform: tf*k1/(tf*k1 + k2*(1-b+b*dl/avgdl)) with
  * dl = row sum, avgdl = mean dl over this batch when the argument is < 0, else the given value (a batch
- * fed in several launches passes the whole batch's mean); zeros stay zero. */
-int ise_bovw_histogram(ise_ctx* ctx, const int64_t* words, const int64_t* img_offsets, int64_t n_img,
+ * fed in several launches passes the whole batch's mean); zeros stay zero.  n_words = length of words[] (its
+ * ratio to n_img picks the warp-per-image kernel for short images); 0 = unknown. */
+int ise_bovw_histogram(ise_ctx* ctx, const int64_t* words, int64_t n_words, const int64_t* img_offsets, int64_t n_img,
                        int k, int mode, int out_dtype, void* out,
                        int okapi, double k1, double k2, double b, double avgdl, void* stream);
 /* Same histogram (+ fused Okapi), as a CSR matrix with sorted column indices -- what

@@ -426,3 +426,39 @@ def test_exact_inputs_skip_the_lo_plane_and_nobody_reads_it(dev):
     del poison
     az = ops.prepare_operand(z)
     assert not bool(torch.isnan(az.lo.float()).any())
+
+
+@pytest.mark.parametrize("k,mode_name,out_dtype", [(4096, "numpy", torch.float64), (512, "bincount", torch.float64),
+                                                   (1001, "numpy", torch.float32), (4096, "numpy", torch.float32)])
+def test_warp_per_image_histogram_equals_cta_kernel(dev, monkeypatch, k, mode_name, out_dtype):
+    """Short images with float64 rows go through the warp-per-image kernel; it must equal the CTA-per-image kernel bit
+    for bit and np.histogram row by row (empty, one-word and over-long images included; the float32 cases pin the
+    CTA kernel the same way)."""
+    from image_search_engine_b200 import ops
+    from image_search_engine_b200._lib import HIST_BINCOUNT, HIST_NUMPY_COMPAT
+    rng = np.random.default_rng(k)
+    sizes = rng.integers(0, 220, 2000)
+    sizes[:4] = [0, 1, 2500, 130]                      # empty / single / longer than the register window / > 128
+    off = np.zeros(len(sizes) + 1, np.int64)
+    np.cumsum(sizes, out=off[1:])
+    words = rng.integers(0, k, int(off[-1]))
+    words[off[2]:off[2] + 60] = 5                      # tf beyond the 32-entry Okapi table
+    wd, od = torch.from_numpy(words).to(dev), torch.from_numpy(off).to(dev)
+    mode = HIST_NUMPY_COMPAT if mode_name == "numpy" else HIST_BINCOUNT
+    res = {}
+    for which in ("warp", "cta"):
+        if which == "cta":
+            monkeypatch.setenv("ISE_HIST_CTA", "1")
+        else:
+            monkeypatch.delenv("ISE_HIST_CTA", raising=False)
+        res[which] = (ops.bovw_histogram(wd, od, k, mode=mode, out_dtype=out_dtype),
+                      ops.bovw_histogram(wd, od, k, mode=mode, out_dtype=out_dtype, okapi=True, k1=1.3, k2=0.8, b=0.7))
+    assert torch.equal(res["warp"][0], res["cta"][0])
+    assert torch.equal(res["warp"][1], res["cta"][1])
+    H = res["warp"][0].cpu().numpy()
+    for i in (0, 1, 2, 3, 17, 1999):
+        seg = words[off[i]:off[i + 1]]
+        want = np.zeros(k) if seg.size == 0 else (np.histogram(seg, bins=k)[0] if mode_name == "numpy"
+                                                   else np.bincount(seg, minlength=k))
+        assert np.array_equal(H[i], want.astype(H.dtype)), i
+    assert (H.sum(1) == sizes).all()
