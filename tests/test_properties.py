@@ -102,3 +102,34 @@ def test_chunkit_partitions_in_order(n, num):
     seq = list(range(n))
     pieces = chunkIt(seq, num)
     assert [x for p in pieces for x in p] == seq
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.integers(2, 70000), st.integers(0, 2**31 - 2), st.integers(1, 2**20), st.integers(0, 2**31 - 1))
+def test_division_free_bin_estimate_matches_numpy_histogram(k, lo, span, seed):
+    """The histogram kernels bin ids with (x - first) * (k / denom) + numpy's own edge corrections instead of
+    numpy's ((x - first) / denom) * k (bovw.cu: NumpyBins).  Restated here in float64 NumPy and compared with
+    np.histogram over random id ranges, codebook sizes and ids (edges, duplicates, both ends included)."""
+    rng = np.random.default_rng(seed)
+    hi = min(lo + span, 2**31 - 1)
+    ids = rng.integers(lo, hi + 1, 300)
+    ids[:2] = [lo, hi]
+    ids = np.concatenate([ids, ids[:20]])
+    want = np.histogram(ids, bins=k)[0]
+    mn, mx = int(ids.min()), int(ids.max())
+    first, last = (mn - 0.5, mx + 0.5) if mn == mx else (float(mn), float(mx))
+    denom = last - first
+    step = denom / k
+    kscale = k / denom
+    x = ids.astype(np.float64)
+
+    def edge(i):
+        return np.where(i == k, last, i.astype(np.float64) * step + first)
+
+    idx = ((x - first) * kscale).astype(np.int64)
+    idx[idx == k] -= 1
+    idx[x < edge(idx)] -= 1
+    inc = (x >= edge(idx + 1)) & (idx != k - 1)
+    idx[inc] += 1
+    assert idx.min() >= 0 and idx.max() < k
+    assert np.array_equal(np.bincount(idx, minlength=k), want)
