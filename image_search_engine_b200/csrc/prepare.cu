@@ -144,8 +144,12 @@ __device__ __forceinline__ void split_f16(float s, __half& h, __half& l) {
 // columns per step (one 128-bit load, one 64-bit store per plane) and every warp keeps ROWS rows in flight --
 // one row per warp iteration leaves ~32 KB of loads in flight per SM, which is what held the first version at
 // 0.6 of HBM peak (profiles/r01_findings.md section 9).
-template <int ROWS>
-__global__ void prepare_planes_f32x4_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ldx,
+// EXACT selects which of the two cases a launch handles; the host launches BOTH instantiations back to back and each
+// returns at once unless the absmax pass proved (EXACT) / did not prove (!EXACT) that one FP16 plane holds every
+// element exactly -- the decision lives on the device, and the light exact path is not held to the register budget
+// of the general one (89 registers -> 2 CTAs per SM when they shared a kernel).
+template <int ROWS, bool EXACT>
+__global__ void __launch_bounds__(kThreads, EXACT ? 5 : 3) prepare_planes_f32x4_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ldx,
                                             __half* __restrict__ hi, __half* __restrict__ lo, int64_t ldp,
                                             float* __restrict__ norms, float* meta) {
     const int lane = threadIdx.x & 31;
@@ -161,7 +165,8 @@ __global__ void prepare_planes_f32x4_kernel(const float* __restrict__ x, int64_t
     const int mn_code = reinterpret_cast<const int*>(meta)[META_MIN_NONZERO];
     const float mn_abs = mn_code ? __int_as_float(0x7f800000 - mn_code) : 1.f;
     const bool exact = meta[META_WIDE_MANTISSA] == 0.f && mn_abs * scale >= 6.103515625e-05f;
-    if (exact) lo = nullptr;
+    if (exact != EXACT) return;
+    if (EXACT) lo = nullptr;
     bool any_lo = false;
     float max_ss = 0.f;
     const int d4 = d >> 2, dp4 = (int)(ldp >> 2);
@@ -183,7 +188,7 @@ __global__ void prepare_planes_f32x4_kernel(const float* __restrict__ x, int64_t
                 if (r >= n) continue;
                 ss[i] = fmaf(v[i].x, v[i].x, ss[i]); ss[i] = fmaf(v[i].y, v[i].y, ss[i]);
                 ss[i] = fmaf(v[i].z, v[i].z, ss[i]); ss[i] = fmaf(v[i].w, v[i].w, ss[i]);
-                if (exact) {
+                if (EXACT) {
                     // one packed conversion per two elements, no residual: the float -> half conversions (not HBM)
                     // bound this kernel when every element goes through three of them
                     const __half2 ha = __floats2half2_rn(v[i].x * scale, v[i].y * scale);
@@ -351,8 +356,11 @@ ISE_EXPORT int ise_prepare_planes(ise_ctx* ctx, const void* x, int dtype, int64_
         if (d % 4 == 0 && ldx % 4 == 0 && al16) {
             constexpr int ROWS = 4;
             const int g4 = grid_for_rows(ctx, ceil_div64(n, ROWS));
-            prepare_planes_f32x4_kernel<ROWS><<<g4, kThreads, 0, st>>>((const float*)x, n, d, ldx, (__half*)hi, (__half*)lo,
-                                                                       ldp, norms, meta);
+            prepare_planes_f32x4_kernel<ROWS, true><<<g4, kThreads, 0, st>>>((const float*)x, n, d, ldx, (__half*)hi,
+                                                                             (__half*)lo, ldp, norms, meta);
+            ISE_LAUNCH_CHECK();
+            prepare_planes_f32x4_kernel<ROWS, false><<<g4, kThreads, 0, st>>>((const float*)x, n, d, ldx, (__half*)hi,
+                                                                              (__half*)lo, ldp, norms, meta);
         } else {
             prepare_planes_kernel<float><<<grid, kThreads, 0, st>>>((const float*)x, n, d, ldx, (__half*)hi,
                                                                     (__half*)lo, ldp, norms, meta, false);

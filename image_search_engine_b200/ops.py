@@ -124,7 +124,7 @@ def prepare_operand(x: torch.Tensor, *, keep_lo: bool | None = None) -> Operand:
     _lib.check(_lib.load().ise_prepare_planes(
         _lib.ctx(dev), _ptr(x), dt, n, d, x.stride(0) if n > 0 else d, _ptr(hi), _ptr(lo), ldp, _ptr(norms),
         _ptr(meta), _stream()))
-    _count(2 if dt == DTYPE_F32 else 1)
+    _count(3 if dt == DTYPE_F32 else 1)   # absmax + the exact / general conversion kernels (one of them returns at once)
     return Operand(hi, lo, norms, meta, n, d, ldp)
 
 
