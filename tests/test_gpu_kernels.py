@@ -253,7 +253,9 @@ def test_kmeans_update_and_split(dev):
 @pytest.mark.parametrize("metric_ip", [True, False])
 @pytest.mark.parametrize("nq,nb,d,k", [(300, 20000, 128, 10), (64, 5000, 2048, 10), (500, 70000, 96, 5),
                                         (80000, 1024, 512, 1), (200, 30000, 64, 100), (150, 70000, 128, 40),
-                                        (300, 200000, 64, 100)])
+                                        (300, 200000, 64, 100),
+                                        # d >= 1024 with >= 4 row tiles: CTA pairs for the coarse top-k / collect pass
+                                        (600, 20000, 1024, 10), (600, 70000, 1024, 40)])
 def test_verified_coarse_search_equals_split(dev, metric_ip, nq, nb, d, k):
     """Default index search = 1-product coarse pass + exact re-score + proof; must agree with the
     3-product split path and with the oracle."""
