@@ -108,3 +108,60 @@ def test_shard_bounds():
     assert list(shard_bounds(10, 4)) == [0, 3, 6, 8, 10]
     assert list(shard_bounds(8, 8)) == list(range(9))
     assert shard_bounds(10_000_000, 8)[-1] == 10_000_000
+
+
+def test_query_batcher_host_logic():
+    """QueryBatcher's batching / padding / future plumbing with a NumPy stand-in for the index (no GPU): every
+    request gets its own top-n, batches are padded to Faiss's BLAS threshold so one code path serves them all,
+    a failing search fails its requests and not the server thread."""
+    from image_search_engine_b200.engine import QueryBatcher
+
+    class FakeIndex:
+        def __init__(self, db):
+            self.db, self.calls = db, []
+
+        def search(self, q, k):
+            self.calls.append(q.shape[0])
+            if np.isnan(q).any():
+                raise RuntimeError("bad query")
+            d = ((q[:, None, :] - self.db[None]) ** 2).sum(-1)
+            I = np.argsort(d, axis=1, kind="stable")[:, :k]
+            return np.take_along_axis(d, I, 1).astype(np.float32), I.astype(np.int64)
+
+    rng = np.random.default_rng(0)
+    db = rng.standard_normal((50, 8)).astype(np.float32)
+    idx = FakeIndex(db)
+    paths = [f"p{i}" for i in range(50)]
+    with QueryBatcher(idx, paths, max_batch=64, max_wait_ms=150.0) as qb:
+        futs = [qb.submit(db[i] + 0.01, 3 + i % 2) for i in range(7)]
+        got = [f.result(timeout=30) for f in futs]
+        assert sum(qb.batches) == 7
+        bad = qb.submit(np.full(8, np.nan, np.float32), 3)
+        with pytest.raises(RuntimeError):
+            bad.result(timeout=30)
+        assert qb.query(db[11], 1)[0][2] == "p11"            # the server thread survived the failed batch
+    assert all(c >= 20 for c in idx.calls)                    # padded to distance_compute_blas_threshold
+    for i, preds in enumerate(got):
+        assert len(preds) == 3 + i % 2 and preds[0][2] == f"p{i}" and preds[0][1] is None
+        assert [p[0] for p in preds] == sorted(p[0] for p in preds)
+
+
+def test_cluster_score_host_logic_matches_reference_fixture():
+    """utils.calc_sampled_cluster_score with the oracle's flat-IP search standing in for the GPU quantiser: same
+    RandomState(42) stream and sklearn calls as the reference -> the reference's own scores (golden fixture)."""
+    import types
+    from pathlib import Path
+    from image_search_engine_b200 import utils
+    from oracle import faiss_shim as fs
+    gold_dir = Path(__file__).parent / "golden"
+    gold, g = np.load(gold_dir / "cluster_score.npz"), np.load(gold_dir / "bovw_c1mini.npz")
+    oidx = fs.IndexFlatIP(32)
+    oidx.add(gold["centroids"])
+    clusterer = types.SimpleNamespace(transform=lambda X: oidx.search(np.asarray(X, dtype=np.float32), 1)[1])
+    off = g["offsets"]
+    descs = [g["X"][off[i]:off[i + 1]] for i in range(len(off) - 1)]
+    est = types.SimpleNamespace(named_steps={"bovw": types.SimpleNamespace(descriptions=descs, clusterer=clusterer)})
+    utils.rs = np.random.RandomState(42)
+    utils.CLUSTER_EVAL_SAMPLE_SIZE, utils.CLUSTER_EVAL_N_SAMPLES = 2000, 10
+    assert utils.calc_sampled_cluster_score(est, None) == pytest.approx(float(gold["score_first_call"]), rel=1e-12)
+    assert utils.calc_sampled_cluster_score(est, None) == pytest.approx(float(gold["score_second_call"]), rel=1e-12)
