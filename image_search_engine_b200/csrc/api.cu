@@ -91,9 +91,42 @@ ISE_EXPORT int ise_rand_perm_prefix(int64_t n, int64_t seed, int64_t m, int64_t*
 
 // faiss/Clustering.cpp split_clusters(): the RNG stream is consumed one draw per probed donor, so the
 // plan is inherently sequential; it only runs when an iteration produced empty clusters.
+namespace {
+// std::mt19937-compatible generator whose tempered outputs are produced 624 at a time into a flat buffer, so that
+// the donor scan below is a tight compare loop over an array instead of a call (with its refill check) per draw.
+struct BlockMT19937 {
+    static constexpr int N = 624, M = 397;
+    uint32_t st[N];
+    uint32_t out[N];
+    int pos = N;
+    explicit BlockMT19937(uint32_t seed) {
+        st[0] = seed;
+        for (int i = 1; i < N; ++i) st[i] = 1812433253u * (st[i - 1] ^ (st[i - 1] >> 30)) + (uint32_t)i;
+    }
+    static uint32_t twist(uint32_t u, uint32_t v) {
+        const uint32_t y = (u & 0x80000000u) | (v & 0x7fffffffu);
+        return (y >> 1) ^ ((v & 1u) ? 0x9908b0dfu : 0u);
+    }
+    void refill() {
+        for (int i = 0; i < N - M; ++i) st[i] = st[i + M] ^ twist(st[i], st[i + 1]);
+        for (int i = N - M; i < N - 1; ++i) st[i] = st[i + M - N] ^ twist(st[i], st[i + 1]);
+        st[N - 1] = st[M - 1] ^ twist(st[N - 1], st[0]);
+        for (int i = 0; i < N; ++i) {
+            uint32_t y = st[i];
+            y ^= y >> 11;
+            y ^= (y << 7) & 0x9d2c5680u;
+            y ^= (y << 15) & 0xefc60000u;
+            y ^= y >> 18;
+            out[i] = y;
+        }
+        pos = 0;
+    }
+};
+}  // namespace
+
 ISE_EXPORT int ise_split_plan(float* hassign, int64_t k, int64_t n, int32_t* pairs, int32_t* nsplit) {
     ISE_CHECK_ARG(hassign != nullptr && pairs != nullptr && nsplit != nullptr && k > 0 && n > k);
-    std::mt19937 mt(1234);
+    BlockMT19937 mt(1234);
     int32_t ns = 0;
     const float denom = (float)(n - k);
     // Same draws, same decisions as Faiss's loop `r = mt() / float(mt.max()); if (r < p) break;`.  At k = 65536 a
@@ -101,7 +134,7 @@ ISE_EXPORT int ise_split_plan(float* hassign, int64_t k, int64_t n, int32_t* pai
     // time here, on the host, so the test is reduced to one integer compare per draw: x -> float(x) / M is
     // monotone, hence `r < p`  <=>  x < T(p) with T(p) the smallest draw whose quotient is not below p (found
     // by bisection, once per centroid and again for the two entries a split changes).
-    const float rng_max = float(mt.max());
+    const float rng_max = 4294967295.0f;      // float(std::mt19937::max())
     auto threshold = [&](float h) -> uint64_t {
         const float p = (float)((h - 1.0) / denom);
         uint64_t lo = 0, hi = (uint64_t)1 << 32;            // smallest x in [0, 2^32] with !(x / M < p)
@@ -117,8 +150,12 @@ ISE_EXPORT int ise_split_plan(float* hassign, int64_t k, int64_t n, int32_t* pai
     for (int64_t ci = 0; ci < k; ci++) {
         if (hassign[ci] != 0) continue;
         int64_t cj = 0;
-        while ((uint64_t)mt() >= thr[(size_t)cj]) {
-            if (++cj == k) cj = 0;
+        for (bool found = false; !found;) {
+            if (mt.pos == BlockMT19937::N) mt.refill();
+            while (mt.pos < BlockMT19937::N) {
+                if ((uint64_t)mt.out[mt.pos++] < thr[(size_t)cj]) { found = true; break; }
+                if (++cj == k) cj = 0;
+            }
         }
         pairs[2 * ns] = (int32_t)ci;
         pairs[2 * ns + 1] = (int32_t)cj;
