@@ -41,6 +41,8 @@ PROTOTYPES = {
     "ise_flat_search_exact_workspace_bytes": (_size, [_c_void_p, _i64, _i64, _int]),
     "ise_flat_search_exact": (_int, [_c_void_p, _c_void_p, _i64, _c_void_p, _i64, _int, _int, _int, _i64,
                                      _c_void_p, _c_void_p, _c_void_p, _size, _c_void_p]),
+    "ise_pair_scores": (_int, [_c_void_p, _c_void_p, _i64, _c_void_p, _i64, _int, _int, _c_void_p, _c_void_p]),
+    "ise_scores_mask": (_int, [_c_void_p, _c_void_p, _i64, _i64, _c_void_p, _int, _i64, _int, _c_void_p]),
     "ise_rescore_topk": (_int, [_c_void_p, _c_void_p, _int, _i64, _c_void_p, _i64, _i64, _i64, _int, _int, _int, _i64,
                                 _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "ise_rescore_select": (_int, [_c_void_p, _c_void_p, _int, _i64, _c_void_p, _c_void_p, _c_void_p, _i64, _c_void_p,
@@ -67,6 +69,9 @@ PROTOTYPES = {
     "ise_ivfpq_residual": (_int, [_c_void_p, _c_void_p, _i64, _i64, _int, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "ise_ivfpq_scan": (_int, [_c_void_p, _c_void_p, _i64, _int, _c_void_p, _i64, _c_void_p, _int, _c_void_p, _int, _int,
                               _c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p]),
+    "ise_okapi_csr": (_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _i64, _f64, _f64, _f64, _f64, _c_void_p, _int,
+                             _c_void_p, _c_void_p]),
+    "ise_tfidf_finish": (_int, [_c_void_p, _c_void_p, _int, _i64, _int, _c_void_p, _int, _c_void_p]),
     "ise_okapi_tf": (_int, [_c_void_p, _c_void_p, _int, _i64, _int, _f64, _f64, _f64, _f64, _c_void_p,
                             _c_void_p]),
 }

@@ -12,6 +12,7 @@ gives the intended word-id histogram.  ``transform`` ignores X when ``self.descr
 """
 from __future__ import annotations
 
+import threading
 from pathlib import Path
 
 import joblib
@@ -99,10 +100,23 @@ class BOVW(BaseEstimator):
         self.hist_mode = hist_mode
 
     def __getstate__(self):
-        state = super().__getstate__()
-        for key in ("_pipe_cache", "_csr_cache", "_csr_bufs"):   # CUDA streams / events / staging buffers are not persisted
+        # copy first: on Python >= 3.11 BaseEstimator.__getstate__ hands back the LIVE __dict__, and popping from it
+        # would drop the caches of the estimator being pickled
+        state = dict(super().__getstate__())
+        for key in ("_pipe_cache", "_csr_cache", "_csr_bufs", "_pipe_lock"):   # CUDA streams / events / staging buffers / locks are not persisted
             state.pop(key, None)
         return state
+
+    def _lock(self):
+        """Guards the cached staging buffers, pinned result buffers, side streams and events of the pipelined host
+        paths (histograms_host / transform_csr): the reference serves queries from a threaded Flask server
+        (engine.py:137) and fans transform out over joblib threads (bag_of_visual_words.py:108-113), so two threads
+        may call the same BOVW at once; the pipelines are then serialised per object instead of overwriting each
+        other's buffers."""
+        lk = self.__dict__.get("_pipe_lock")
+        if lk is None:
+            lk = self.__dict__.setdefault("_pipe_lock", threading.RLock())
+        return lk
 
     def fit(self, X, y=None):
         self.descriptions = describe_dataset(self.describer, X)
@@ -124,6 +138,11 @@ class BOVW(BaseEstimator):
 
     def histograms_host(self, descriptions, out: torch.Tensor, *, okapi: OkapiTransformer | None = None,
                         n_chunks: int = 8) -> np.ndarray:
+        with self._lock():
+            return self._histograms_host(descriptions, out, okapi=okapi, n_chunks=n_chunks)
+
+    def _histograms_host(self, descriptions, out: torch.Tensor, *, okapi: OkapiTransformer | None = None,
+                         n_chunks: int = 8) -> np.ndarray:
         """Host descriptors in, host histogram matrix out, with the three legs overlapped: the images are
         cut into ``n_chunks`` groups and chunk i+1's H2D copy, chunk i's kernels and chunk i-1's D2H copy
         run concurrently on three streams (PCIe is full duplex).  ``out`` must be a pinned CPU tensor
@@ -211,6 +230,10 @@ class BOVW(BaseEstimator):
         return ops.bovw_histogram_csr(words, off, int(self.n_clusters), out_dtype=out_dtype, **self._csr_kwargs(okapi))
 
     def transform_csr(self, X=None, *, okapi: OkapiTransformer | None = None, n_chunks: int = 8, copy: bool = True):
+        with self._lock():
+            return self._transform_csr(X, okapi=okapi, n_chunks=n_chunks, copy=copy)
+
+    def _transform_csr(self, X=None, *, okapi: OkapiTransformer | None = None, n_chunks: int = 8, copy: bool = True):
         """Host descriptors in, scipy CSR float64 (n_images, n_clusters) out == OkapiTransformer().transform(
         BOVW.transform(X)) of the reference (``okapi=None``: the plain histogram as CSR).  The host -> device copy
         of the descriptors is cut into ``n_chunks`` pieces overlapped with the quantisation of the previous
@@ -337,9 +360,18 @@ def load_cluster_model(n_clusters, index=None):
     return FaissKMeans(n_clusters=n_clusters, index=index)
 
 
-def train_bovw_model(images_paths, describer, config):
-    """Offline index build (bag_of_visual_words.py:137-204).  ``config`` supplies NUM_CLUSTERS, the three artefact
-    paths and, with BOVW_HYPERPARAMETERS_SEARCH, the cluster-count grid (:149-181)."""
+def train_bovw_model(images_paths, describer, config=None):
+    """Offline index build (bag_of_visual_words.py:137-204), same two-argument call as the reference
+    (indexer.py:37).  ``config`` supplies NUM_CLUSTERS, the three artefact paths and, with
+    BOVW_HYPERPARAMETERS_SEARCH, the cluster-count grid (:149-181); when omitted it is the host application's own
+    ``config.Config()``, which is what the reference's module-level ``config = Config()`` (:37) resolves to."""
+    if config is None:
+        try:
+            from config import Config      # the application's backend/config.py, like bag_of_visual_words.py:32,37
+        except Exception as exc:
+            raise RuntimeError("train_bovw_model(images_paths, describer): no `config` module with a `Config` class "
+                               "on sys.path (the reference's backend/config.py); pass config= explicitly") from exc
+        config = Config()
     print(f"Received {len(images_paths)} images to process")
     pipeline = Pipeline([("bovw", BOVW(describer, n_clusters=config.NUM_CLUSTERS)), ("tfidf", OkapiTransformer())])
     if getattr(config, "BOVW_HYPERPARAMETERS_SEARCH", False):
@@ -365,6 +397,7 @@ def train_bovw_model(images_paths, describer, config):
     # GPU-resident build: histogram + Okapi fused, float32 rows, normalise + add without leaving HBM
     H = bovw.histograms_device(bovw.descriptions, okapi=tfidf, out_dtype=torch.float32)
     tfidf.fit(H)
+    tfidf.finish_device_(H)    # opt-in corrected mode (OkapiTransformer(compat=False)): idf + row norm; no-op by default
     print("Saving KMeans index", bovw.clusterer.index)
     faiss.write_index(bovw.clusterer.index, str(config.BOVW_KMEANS_INDEX_PATH))
     index = create_search_index(H)

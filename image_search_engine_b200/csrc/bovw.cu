@@ -461,6 +461,94 @@ __global__ void okapi_dense_kernel(T* __restrict__ h, int64_t n_img, int k, doub
     }
 }
 
+// ---- OkapiTransformer.transform on a CSR matrix (utils.py:153-202 operates on X.data exactly like this) ----
+// one warp per row: document length = sum of the row's stored values
+__global__ void csr_row_sum_kernel(const int64_t* __restrict__ indptr, const double* __restrict__ data, int64_t n_rows,
+                                   double* __restrict__ dl, double* __restrict__ total) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    double mine = 0.0;
+    for (int64_t r = warp; r < n_rows; r += nwarps) {
+        const int64_t lo = indptr[r], hi = indptr[r + 1];
+        double acc = 0.0;
+        for (int64_t j = lo + lane; j < hi; j += 32) acc += data[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) { dl[r] = acc; mine += acc; }
+    }
+    if (lane == 0 && mine != 0.0) atomicAdd(total, mine);
+}
+
+// weights in place; idf != nullptr / norm != 0 = the opt-in corrected tf-idf mode (the reference computes idf in fit
+// and declares norm="l2" but applies neither, utils.py:112-151)
+__global__ void csr_okapi_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                 double* __restrict__ data, int64_t n_rows, double k1, double k2, double b,
+                                 double avgdl_in, const double* __restrict__ dl, const double* __restrict__ total,
+                                 const double* __restrict__ idf, int norm) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    const double avgdl = avgdl_in >= 0.0 ? avgdl_in : __ddiv_rn(*total, (double)n_rows);
+    for (int64_t r = warp; r < n_rows; r += nwarps) {
+        const int64_t lo = indptr[r], hi = indptr[r + 1];
+        const double ratio = __ddiv_rn(dl[r], avgdl);
+        double nrm = 0.0;
+        for (int64_t j = lo + lane; j < hi; j += 32) {
+            double w = okapi_weight(data[j], k1, k2, b, ratio);     // 0 stays 0 (0 / positive)
+            if (idf) w *= idf[indices[j]];
+            data[j] = w;
+            nrm += norm == 2 ? w * w : fabs(w);
+        }
+        if (norm) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+            if (norm == 2) nrm = sqrt(nrm);
+            if (nrm > 0.0) {
+                __syncwarp();
+                for (int64_t j = lo + lane; j < hi; j += 32) data[j] = data[j] / nrm;
+            }
+        }
+    }
+}
+
+// dense counterpart of the opt-in mode (GPU-resident index build): h[i, j] *= idf[j], then row normalisation
+template <typename T>
+__global__ void tfidf_finish_kernel(T* __restrict__ h, int64_t n_img, int k, const double* __restrict__ idf, int norm) {
+    __shared__ double s_part[kThreads / 32];
+    __shared__ double s_nrm;
+    for (int64_t img = blockIdx.x; img < n_img; img += gridDim.x) {
+        T* row = h + img * (int64_t)k;
+        double nrm = 0.0;
+        for (int j = threadIdx.x; j < k; j += kThreads) {
+            double w = (double)row[j];
+            if (w != 0.0) {
+                if (idf) { w *= idf[j]; row[j] = (T)w; }
+                nrm += norm == 2 ? w * w : fabs(w);
+            }
+        }
+        if (norm) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+            if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = nrm;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double t = 0.0;
+                for (int i = 0; i < kThreads / 32; ++i) t += s_part[i];
+                s_nrm = norm == 2 ? sqrt(t) : t;
+            }
+            __syncthreads();
+            const double t = s_nrm;
+            if (t > 0.0)
+                for (int j = threadIdx.x; j < k; j += kThreads) {
+                    const double w = (double)row[j];
+                    if (w != 0.0) row[j] = (T)(w / t);
+                }
+            __syncthreads();
+        }
+    }
+}
+
 }  // namespace
 
 ISE_EXPORT int ise_bovw_histogram(ise_ctx* ctx, const int64_t* words, int64_t n_words, const int64_t* img_offsets,
@@ -570,6 +658,40 @@ ISE_EXPORT int ise_bovw_histogram_csr(ise_ctx* ctx, const int64_t* words, const 
     else
         histogram_csr_kernel<float, 1><<<grid, kThreads, shm, st>>>(words, img_offsets, n_img, k, mode, row_nnz, indptr,
                                                                     indices, (float*)data, okapi, k1, k2, b, avgdl);
+    ISE_LAUNCH_CHECK();
+    return 0;
+}
+
+ISE_EXPORT int ise_okapi_csr(ise_ctx* ctx, const int64_t* indptr, const int32_t* indices, double* data, int64_t n_rows,
+                             double k1, double k2, double b, double avgdl, const double* idf, int norm,
+                             double* dl_workspace, void* stream) {
+    ISE_CHECK_ARG(ctx && n_rows >= 0 && norm >= 0 && norm <= 2);
+    if (n_rows == 0) return 0;
+    ISE_CHECK_ARG(indptr && data && dl_workspace && (indices || !idf));
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    double* dl = dl_workspace;
+    double* total = dl_workspace + n_rows;
+    ISE_CUDA(cudaMemsetAsync(total, 0, sizeof(double), st));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(n_rows, kThreads / 32), (int64_t)ctx->sm_count * 16));
+    csr_row_sum_kernel<<<grid, kThreads, 0, st>>>(indptr, data, n_rows, dl, total);
+    ISE_LAUNCH_CHECK();
+    csr_okapi_kernel<<<grid, kThreads, 0, st>>>(indptr, indices, data, n_rows, k1, k2, b, avgdl, dl, total, idf, norm);
+    ISE_LAUNCH_CHECK();
+    return 0;
+}
+
+ISE_EXPORT int ise_tfidf_finish(ise_ctx* ctx, void* h, int out_dtype, int64_t n_img, int k, const double* idf, int norm,
+                                void* stream) {
+    ISE_CHECK_ARG(ctx && n_img >= 0 && k >= 1 && norm >= 0 && norm <= 2);
+    ISE_CHECK_ARG(out_dtype == ISE_OUT_F32 || out_dtype == ISE_OUT_F64);
+    if (n_img == 0 || (!idf && !norm)) return 0;
+    ISE_CHECK_ARG(h != nullptr);
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (int)std::min<int64_t>(n_img, (int64_t)ctx->sm_count * 16);
+    if (out_dtype == ISE_OUT_F64) tfidf_finish_kernel<double><<<grid, kThreads, 0, st>>>((double*)h, n_img, k, idf, norm);
+    else tfidf_finish_kernel<float><<<grid, kThreads, 0, st>>>((float*)h, n_img, k, idf, norm);
     ISE_LAUNCH_CHECK();
     return 0;
 }

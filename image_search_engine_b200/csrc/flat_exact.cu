@@ -110,6 +110,16 @@ __global__ void slice_topk_kernel(const float* __restrict__ scores, int64_t nq, 
     }
 }
 
+// k > 128: the selected entries of a pass are masked (+-inf is never selected) so the next pass returns the next
+// best 128 in the same canonical (score, id) order
+__global__ void scores_mask_kernel(float* __restrict__ scores, int64_t nq, int64_t nb, const int64_t* __restrict__ idx,
+                                   int kk, int64_t id_base, float fill) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nq * kk) return;
+    const int64_t id = idx[t];
+    if (id >= 0) scores[(t / kk) * nb + (id - id_base)] = fill;
+}
+
 }  // namespace
 
 static int64_t exact_slice_len(int64_t nb) {
@@ -196,4 +206,36 @@ ISE_EXPORT int ise_scores_topk(ise_ctx* ctx, const float* scores, int64_t nq, in
     int64_t* pi = reinterpret_cast<int64_t*>(workspace);
     float* pv = reinterpret_cast<float*>(pi + (size_t)slices * nq * topk);
     return select_from_scores(ctx, scores, nq, nb, metric, topk, id_base, out_val, out_idx, pi, pv, (cudaStream_t)stream);
+}
+
+ISE_EXPORT int ise_pair_scores(ise_ctx* ctx, const float* q, int64_t nq, const float* db, int64_t nb, int d, int metric,
+                               float* scores, void* stream) {
+    ISE_CHECK_ARG(ctx != nullptr);
+    ISE_CHECK_ARG(metric == ISE_METRIC_IP || metric == ISE_METRIC_L2);
+    ISE_CHECK_ARG(nq >= 0 && nb > 0 && d > 0 && nq <= 65535 && (size_t)d * sizeof(float) <= 48 * 1024);
+    if (nq == 0) return 0;
+    ISE_CHECK_ARG(q && db && scores);
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 g1((unsigned)std::min<int64_t>(ceil_div64(nb, kWarps), (int64_t)ctx->sm_count * 8), (unsigned)nq);
+    if (metric == ISE_METRIC_L2)
+        pair_scores_kernel<true><<<g1, kThreads, d * sizeof(float), st>>>(q, nq, db, nb, d, scores);
+    else
+        pair_scores_kernel<false><<<g1, kThreads, d * sizeof(float), st>>>(q, nq, db, nb, d, scores);
+    ISE_LAUNCH_CHECK();
+    return 0;
+}
+
+ISE_EXPORT int ise_scores_mask(ise_ctx* ctx, float* scores, int64_t nq, int64_t nb, const int64_t* idx, int kk,
+                               int64_t id_base, int metric, void* stream) {
+    ISE_CHECK_ARG(ctx && nq >= 0 && nb > 0 && kk >= 1);
+    ISE_CHECK_ARG(metric == ISE_METRIC_IP || metric == ISE_METRIC_L2);
+    if (nq == 0) return 0;
+    ISE_CHECK_ARG(scores && idx);
+    DeviceGuard guard(ctx->device);
+    const int64_t total = nq * kk;
+    const float fill = metric == ISE_METRIC_IP ? -INFINITY : INFINITY;
+    scores_mask_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(scores, nq, nb, idx, kk, id_base, fill);
+    ISE_LAUNCH_CHECK();
+    return 0;
 }

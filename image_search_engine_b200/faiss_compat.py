@@ -164,7 +164,9 @@ class IndexFlat:
             return D, I
         kk = min(k, ops.MAX_TOPK)
         if k > ops.MAX_TOPK and self._ntotal > ops.MAX_TOPK:
-            raise IseError(f"k = {k} exceeds the fused-selection limit of {ops.MAX_TOPK}")
+            # beyond the fused-selection limit: exact pair scores + repeated masked selection passes (any k, like Faiss)
+            qf = q if q.dtype == torch.float32 else q.to(torch.float32)
+            return ops.search_exact_any_k(qf.contiguous(), self._database(), self.metric_type, k)
         if nq < distance_compute_blas_threshold:
             qf = q if q.dtype == torch.float32 else q.to(torch.float32)
             D, I = ops.flat_search_exact(qf.contiguous(), self._database(), self.metric_type, kk)
@@ -339,14 +341,12 @@ class IndexIVFPQ:
         D = torch.full((nq, k), _FLT_MAX, dtype=torch.float32, device=q.device)
         I = torch.full((nq, k), -1, dtype=torch.int64, device=q.device)
         if nq and self.ntotal:
-            if k > ops.MAX_TOPK:
-                raise IseError(f"k = {k} exceeds the fused-selection limit of {ops.MAX_TOPK}")
             codes, ids, off = self._lists()
             _, probes = self.quantizer._search_device(q, min(self.nprobe, self.nlist), need_distances=False)
             for q0 in range(0, nq, 4096):                                  # bounds the [nq, ntotal] distance matrix
                 qs = q[q0:q0 + 4096].contiguous()
                 dist = ops.ivfpq_scan(qs, self.quantizer._database(), probes[q0:q0 + 4096], self.pq_centroids, codes, off)
-                Dv, pos = ops.scores_topk(dist, METRIC_L2, k)
+                Dv, pos = ops.scores_topk_any_k_(dist, METRIC_L2, k)
                 ok = pos >= 0
                 I[q0:q0 + 4096] = torch.where(ok, ids[pos.clamp(min=0)], torch.full_like(pos, -1))
                 D[q0:q0 + 4096] = Dv

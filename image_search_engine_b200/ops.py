@@ -370,6 +370,57 @@ def flat_search_exact(q: torch.Tensor, db: torch.Tensor, metric: int, topk: int,
     return val, idx
 
 
+def search_exact_any_k(q: torch.Tensor, db: torch.Tensor, metric: int, k: int, id_base: int = 0,
+                       max_score_bytes: int = 1 << 30):
+    """Flat search for k beyond the fused-selection limit (Faiss's IndexFlat.search takes any k): the exact FP32
+    pair scores of a query chunk are materialised once, then ceil(k / 128) selection passes each return the next
+    best 128 -- the entries already returned are masked -- in the canonical (score, id) order.  CUDA cores only;
+    an edge path (the reference asks for k = 20, engine.py:55)."""
+    if q.dtype != torch.float32 or db.dtype != torch.float32 or not q.is_contiguous() or not db.is_contiguous():
+        raise IseError("search_exact_any_k needs contiguous float32 tensors")
+    dev = _dev(q)
+    lib, ctx = _lib.load(), _lib.ctx(dev)
+    nq, d = q.shape
+    nb = db.shape[0]
+    k_eff = min(int(k), nb)
+    pad = -3.4028234663852886e38 if metric == METRIC_IP else 3.4028234663852886e38
+    val = torch.full((nq, k), pad, dtype=torch.float32, device=q.device)
+    idx = torch.full((nq, k), -1, dtype=torch.int64, device=q.device)
+    if nq == 0 or nb == 0:
+        return val, idx
+    chunk = int(max(1, min(nq, 65535, max_score_bytes // (4 * nb))))
+    for q0 in range(0, nq, chunk):
+        qs = q[q0:q0 + chunk]
+        n = qs.shape[0]
+        scores = torch.empty((n, nb), dtype=torch.float32, device=q.device)
+        _lib.check(lib.ise_pair_scores(ctx, _ptr(qs), n, _ptr(db), nb, d, int(metric), _ptr(scores), _stream()))
+        _count()
+        val[q0:q0 + n], idx[q0:q0 + n] = scores_topk_any_k_(scores, metric, k, id_base)
+    return val, idx
+
+
+def scores_topk_any_k_(scores: torch.Tensor, metric: int, k: int, id_base: int = 0):
+    """Per-row top-k of a score matrix for any k: ceil(k / 128) selection passes, masking what a pass returned
+    (``scores`` is consumed).  Rows shorter than k are padded with id -1 / -+FLT_MAX like Faiss."""
+    nq, nb = scores.shape
+    pad = -3.4028234663852886e38 if metric == METRIC_IP else 3.4028234663852886e38
+    if k <= MAX_TOPK:
+        return scores_topk(scores, metric, k, id_base)
+    val = torch.full((nq, k), pad, dtype=torch.float32, device=scores.device)
+    idx = torch.full((nq, k), -1, dtype=torch.int64, device=scores.device)
+    k_eff = min(int(k), nb)
+    lib, ctx = _lib.load(), _lib.ctx(_dev(scores))
+    for k0 in range(0, k_eff, MAX_TOPK):
+        kk = min(MAX_TOPK, k_eff - k0)
+        v, i = scores_topk(scores, metric, kk, id_base)
+        val[:, k0:k0 + kk] = v
+        idx[:, k0:k0 + kk] = i
+        if k0 + kk < k_eff:
+            _lib.check(lib.ise_scores_mask(ctx, _ptr(scores), nq, nb, _ptr(i), kk, int(id_base), int(metric), _stream()))
+            _count()
+    return val, idx
+
+
 def topk_merge(val_parts: torch.Tensor, idx_parts: torch.Tensor, metric: int):
     """[g, m, k] sorted partial lists -> ([m, k], [m, k])."""
     g, m, k = val_parts.shape
@@ -536,4 +587,35 @@ def okapi_tf_(h: torch.Tensor, k1: float = 1.0, k2: float = 1.0, b: float = 0.75
     _lib.check(_lib.load().ise_okapi_tf(_lib.ctx(_dev(h)), _ptr(h), od, n_img, k, float(k1), float(k2), float(b),
                                         float(avgdl), _ptr(ws), _stream()))
     _count(2)
+    return h
+
+
+def okapi_csr_(indptr: torch.Tensor, indices: torch.Tensor | None, data: torch.Tensor, k1: float = 1.0, k2: float = 1.0,
+               b: float = 0.75, avgdl: float = -1.0, idf: torch.Tensor | None = None, norm: int = 0):
+    """OkapiTransformer.transform on the data array of a CSR matrix, in place (O(nnz)).  idf / norm: the opt-in
+    corrected tf-idf mode (see include/ise.h)."""
+    if indptr.dtype != torch.int64 or data.dtype != torch.float64 or not data.is_contiguous():
+        raise IseError("okapi_csr_: int64 indptr, contiguous float64 data")
+    if indices is not None and indices.dtype != torch.int32:
+        raise IseError("okapi_csr_: int32 indices")
+    if idf is not None and (idf.dtype != torch.float64 or indices is None):
+        raise IseError("okapi_csr_: idf must be float64 and needs the column indices")
+    n_rows = indptr.numel() - 1
+    ws = torch.empty((n_rows + 1,), dtype=torch.float64, device=data.device)
+    _lib.check(_lib.load().ise_okapi_csr(_lib.ctx(_dev(data)), _ptr(indptr), _ptr(indices), _ptr(data), n_rows, float(k1),
+                                         float(k2), float(b), float(avgdl), _ptr(idf), int(norm), _ptr(ws), _stream()))
+    _count(2)
+    return data
+
+
+def tfidf_finish_(h: torch.Tensor, idf: torch.Tensor | None, norm: int):
+    """h[i, j] *= idf[j], then l1 / l2 row normalisation, in place (dense half of the opt-in tf-idf mode)."""
+    if h.dtype not in (torch.float32, torch.float64) or h.dim() != 2 or not h.is_contiguous():
+        raise IseError("tfidf_finish_: contiguous float32/float64 matrix")
+    if idf is not None and (idf.dtype != torch.float64 or idf.numel() != h.shape[1]):
+        raise IseError("tfidf_finish_: idf must be float64 [k]")
+    od = OUT_F64 if h.dtype == torch.float64 else OUT_F32
+    _lib.check(_lib.load().ise_tfidf_finish(_lib.ctx(_dev(h)), _ptr(h), od, h.shape[0], h.shape[1], _ptr(idf), int(norm),
+                                            _stream()))
+    _count()
     return h

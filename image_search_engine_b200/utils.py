@@ -28,21 +28,27 @@ def chunkIt(seq, num):
 class OkapiTransformer(TransformerMixin, BaseEstimator):
     """BM25/Okapi term-frequency weighting of a count matrix.
 
-    Behaviour kept from the reference:
+    Behaviour kept from the reference, the default ``compat=True``:
       * ``fit`` computes idf = log((n - df + 0.5) / (df + 0.5)) and stores it, but ``transform`` never
         applies it, nor the ``norm`` parameter -- the output is tf*k1 / (tf*k1 + k2*(1 - b + b*dl/avgdl));
       * ``avgdl`` is the mean document length of the batch being transformed, so a single query row
         always sees dl/avgdl == 1;
       * host inputs come back as a float64 scipy CSR matrix.
-    A CUDA tensor input is weighted in place and returned as a tensor (GPU-resident index build).
+    ``compat=False`` is the opt-in corrected mode the reference's parameters promise: the tf weights are
+    multiplied by the fitted idf (when ``use_idf``) and every row is then l1 / l2 normalised (``norm``).
+
+    Host inputs are weighted as CSR: only the non-zeros travel to the device and back (O(nnz), the reference
+    works on ``X.data`` the same way, utils.py:180-200).  A CUDA tensor input is weighted in place and returned
+    as a tensor (GPU-resident index build).
     """
 
-    def __init__(self, *, norm="l2", use_idf=True, k1=1, k2=1, b=0.75):
+    def __init__(self, *, norm="l2", use_idf=True, k1=1, k2=1, b=0.75, compat=True):
         self.norm = norm
         self.use_idf = use_idf
         self.k1 = k1
         self.k2 = k2
         self.b = b
+        self.compat = compat
 
     def fit(self, X, y=None):
         if self.use_idf:
@@ -59,18 +65,55 @@ class OkapiTransformer(TransformerMixin, BaseEstimator):
                                       dtype=np.float64)
         return self
 
+    def _norm_code(self):
+        if getattr(self, "compat", True) or self.norm is None:
+            return 0
+        if self.norm not in ("l1", "l2"):
+            raise ValueError(f"norm must be 'l1', 'l2' or None, got {self.norm!r}")
+        return 1 if self.norm == "l1" else 2
+
+    def _idf_device(self, dev):
+        if getattr(self, "compat", True) or not self.use_idf:
+            return None
+        return torch.from_numpy(np.ascontiguousarray(self.idf_, dtype=np.float64)).to(dev)
+
+    def finish_device_(self, H: torch.Tensor) -> torch.Tensor:
+        """Second half of the opt-in mode on an [n, k] CUDA matrix already holding the Okapi tf weights (the
+        histogram kernels fuse those): idf scaling + row normalisation.  No-op with ``compat=True``."""
+        norm, idf = self._norm_code(), self._idf_device(H.device)
+        if norm or idf is not None:
+            ops.tfidf_finish_(H, idf, norm)
+        return H
+
     def transform(self, X, copy=True):
         if isinstance(X, torch.Tensor) and X.is_cuda:
             H = X.clone() if copy else X
-            return ops.okapi_tf_(H, self.k1, self.k2, self.b)
-        dense = X.toarray() if sp.issparse(X) else np.asarray(X)
-        if dense.ndim != 2:
-            raise ValueError("Expected a 2-D count matrix")
-        dense = np.ascontiguousarray(dense, dtype=np.float64)
+            ops.okapi_tf_(H, self.k1, self.k2, self.b)
+            return self.finish_device_(H)
+        if sp.issparse(X):
+            M = X.tocsr()
+            if M is X and copy:
+                M = M.copy()
+            if M.dtype not in (np.float64, np.float32):
+                M = M.astype(np.float64)
+        else:
+            dense = np.asarray(X)
+            if dense.ndim != 2:
+                raise ValueError("Expected a 2-D count matrix")
+            M = sp.csr_matrix(dense, dtype=np.float64)
+        if M.nnz == 0:
+            return M
         dev = ops.require_cuda()
-        H = torch.from_numpy(dense).to(dev)
-        ops.okapi_tf_(H, self.k1, self.k2, self.b)
-        return sp.csr_matrix(H.cpu().numpy())
+        norm = self._norm_code()
+        idf = self._idf_device(dev)
+        data = torch.from_numpy(np.ascontiguousarray(M.data, dtype=np.float64)).to(dev, non_blocking=True)
+        indptr = torch.from_numpy(np.ascontiguousarray(M.indptr, dtype=np.int64)).to(dev, non_blocking=True)
+        indices = None
+        if idf is not None:
+            indices = torch.from_numpy(np.ascontiguousarray(M.indices, dtype=np.int32)).to(dev, non_blocking=True)
+        ops.okapi_csr_(indptr, indices, data, self.k1, self.k2, self.b, idf=idf, norm=norm)
+        M.data[...] = data.cpu().numpy()      # float32 matrices keep their dtype (computed in float64)
+        return M
 
     def __sklearn_is_fitted__(self):
         # stateless at transform time; lets sklearn >= 1.4 Pipeline.transform run (SURVEY quirk Q8)

@@ -129,6 +129,15 @@ int ise_flat_search_exact(ise_ctx* ctx, const float* q, int64_t nq, const float*
                           int metric, int topk, int64_t id_base, float* out_val, int64_t* out_idx,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* The two stages of ise_flat_search_exact on their own, for k > 128 (Faiss's IndexFlat.search takes any k,
+ * engine.py:55): scores[nq, nb] = direct FP32 <q,y> / sum (q-y)^2 of every pair; ise_scores_mask overwrites the entries a
+ * selection pass returned (idx[nq, kk], -1 = padding) with -+inf so that the next ise_scores_topk pass yields the next
+ * best kk in the same canonical (score, id) order. */
+int ise_pair_scores(ise_ctx* ctx, const float* q, int64_t nq, const float* db, int64_t nb, int d, int metric,
+                    float* scores, void* stream);
+int ise_scores_mask(ise_ctx* ctx, float* scores, int64_t nq, int64_t nb, const int64_t* idx, int kk,
+                    int64_t id_base, int metric, void* stream);
+
 /* Exact FP32 re-score + re-rank of already selected candidates (CUDA cores).  The tensor-core
  * accumulator truncates, which shows in returned distances (not in which candidates are picked); this
  * recomputes val[m,topk] for the ids in idx[m,topk] from the original rows with Faiss's formulas
@@ -202,6 +211,19 @@ int ise_bovw_histogram_csr(ise_ctx* ctx, const int64_t* words, const int64_t* im
  * avgdl < 0 => mean row sum of this batch (utils.py:196).  dl_workspace: device double[n_img + 1]. */
 int ise_okapi_tf(ise_ctx* ctx, void* h, int out_dtype, int64_t n_img, int k,
                  double k1, double k2, double b, double avgdl, double* dl_workspace, void* stream);
+
+/* OkapiTransformer.transform on a CSR matrix, O(nnz) (utils.py:153-202 works on X.data exactly like this): data[nnz]
+ * float64 in place, indptr int64[n_rows + 1], indices int32[nnz] (needed with idf only).  dl = row sums, avgdl < 0 =>
+ * mean dl of this batch.  idf (nullable, double[k]) and norm (0 none, 1 l1, 2 l2) are the OPT-IN corrected tf-idf
+ * mode: the reference computes idf in fit (utils.py:119-151) and declares norm="l2" (:112) but applies neither, so
+ * the drop-in default passes NULL / 0.  dl_workspace: device double[n_rows + 1]. */
+int ise_okapi_csr(ise_ctx* ctx, const int64_t* indptr, const int32_t* indices, double* data, int64_t n_rows,
+                  double k1, double k2, double b, double avgdl, const double* idf, int norm,
+                  double* dl_workspace, void* stream);
+/* dense counterpart of the opt-in mode for the GPU-resident index build: h[i, j] *= idf[j] (nullable), then row
+ * normalisation (norm as above), in place on an [n_img, k] f32 / f64 matrix already weighted by ise_okapi_tf */
+int ise_tfidf_finish(ise_ctx* ctx, void* h, int out_dtype, int64_t n_img, int k, const double* idf, int norm,
+                     void* stream);
 
 /* ---- IVFPQ "cell-probe" index (utils.py:311-325: IndexIVFPQ(IndexFlatL2(d), d, 8, 16, 8), nprobe = 5) ---- */
 /* per-query top-k of a device score matrix scores[nq, nb] (IP: largest, L2: smallest; +-inf entries are never

@@ -165,3 +165,62 @@ def test_cluster_score_host_logic_matches_reference_fixture():
     utils.CLUSTER_EVAL_SAMPLE_SIZE, utils.CLUSTER_EVAL_N_SAMPLES = 2000, 10
     assert utils.calc_sampled_cluster_score(est, None) == pytest.approx(float(gold["score_first_call"]), rel=1e-12)
     assert utils.calc_sampled_cluster_score(est, None) == pytest.approx(float(gold["score_second_call"]), rel=1e-12)
+
+
+def test_train_bovw_model_keeps_the_reference_signature(monkeypatch):
+    """indexer.py:37 calls train_bovw_model(images_paths, describer): config must be optional and, when omitted,
+    resolve to the host application's own config.Config() like bag_of_visual_words.py:32,37 does."""
+    import inspect
+    import sys
+    import types
+    from image_search_engine_b200 import train_bovw_model
+    params = list(inspect.signature(train_bovw_model).parameters.values())
+    assert [p.name for p in params[:2]] == ["images_paths", "describer"]
+    assert all(p.default is not inspect.Parameter.empty for p in params[2:])
+    # no `config` module on sys.path -> a clear error, not a TypeError about a missing argument
+    monkeypatch.setitem(sys.modules, "config", None)
+    with pytest.raises(RuntimeError, match="config"):
+        train_bovw_model(np.zeros((0, 1)), None)
+    # an application config module is picked up (the call then proceeds to the pipeline and needs data / a GPU)
+    seen = {}
+
+    class Config:
+        NUM_CLUSTERS = 3
+
+        def __init__(self):
+            seen["made"] = True
+    monkeypatch.setitem(sys.modules, "config", types.SimpleNamespace(Config=Config))
+    with pytest.raises(Exception):
+        train_bovw_model(np.zeros((0, 1)), None)
+    assert seen.get("made")
+
+
+def test_bovw_pickle_does_not_strip_the_live_estimator():
+    """BaseEstimator.__getstate__ returns the live __dict__ on Python >= 3.11: pickling must not delete the cached
+    pipelines of the estimator being pickled, and must not persist them either."""
+    import pickle
+    from image_search_engine_b200 import BOVW
+    b = BOVW(None, n_clusters=5)
+    b.__dict__["_pipe_cache"] = {"key": "x"}
+    b.__dict__["_csr_bufs"] = {"cap": 1}
+    b._lock()
+    blob = pickle.dumps(b)
+    assert "_pipe_cache" in b.__dict__ and "_csr_bufs" in b.__dict__ and "_pipe_lock" in b.__dict__
+    c = pickle.loads(blob)
+    assert c.n_clusters == 5 and not {"_pipe_cache", "_csr_bufs", "_pipe_lock"} & set(c.__dict__)
+    with c._lock():          # re-created lazily, re-entrant
+        with c._lock():
+            pass
+
+
+def test_okapi_params_and_opt_in_flags():
+    from sklearn.base import clone
+    from image_search_engine_b200 import OkapiTransformer
+    ok = OkapiTransformer()
+    assert ok.get_params() == dict(norm="l2", use_idf=True, k1=1, k2=1, b=0.75, compat=True)
+    assert ok._norm_code() == 0                        # reference behaviour: norm is declared, never applied
+    ok2 = clone(OkapiTransformer(compat=False, norm="l1"))
+    assert ok2._norm_code() == 1 and OkapiTransformer(compat=False)._norm_code() == 2
+    assert OkapiTransformer(compat=False, norm=None)._norm_code() == 0
+    with pytest.raises(ValueError):
+        OkapiTransformer(compat=False, norm="max")._norm_code()
