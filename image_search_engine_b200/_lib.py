@@ -29,12 +29,16 @@ PROTOTYPES = {
     "ise_ctx_sm_count": (_int, [_c_void_p]),
     "ise_rand_perm_prefix": (_int, [_i64, _i64, _i64, _c_void_p]),
     "ise_split_plan": (_int, [_c_void_p, _i64, _i64, _c_void_p, C.POINTER(C.c_int32)]),
+    "ise_split_plan_warm": (_int, [_i64]),
     "ise_prepare_planes": (_int, [_c_void_p, _c_void_p, _int, _i64, _int, _i64, _c_void_p, _c_void_p, _i64,
                                   _c_void_p, _c_void_p, _c_void_p]),
+    "ise_prepare_rows": (_int, [_c_void_p, _c_void_p, _int, _i64, _int, _i64, _c_void_p, _c_void_p, _i64,
+                                _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "ise_scan_f32": (_int, [_c_void_p, _c_void_p, _i64, _int, _i64, _c_void_p, _c_void_p]),
     "ise_normalize_l2": (_int, [_c_void_p, _c_void_p, _i64, _int, _c_void_p]),
     "ise_gemm_select_workspace_bytes": (_size, [_c_void_p, _i64, _i64, _int, _int]),
     "ise_gemm_select": (_int, [_c_void_p,
-                               _c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p,
+                               _c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _c_void_p,
                                _c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p,
                                _i64, _i64, _int, _int, _int, _i64, _c_void_p, _c_void_p, _c_void_p,
                                _c_void_p, _c_void_p, _c_void_p, _size, _c_void_p]),
@@ -45,11 +49,11 @@ PROTOTYPES = {
     "ise_scores_mask": (_int, [_c_void_p, _c_void_p, _i64, _i64, _c_void_p, _int, _i64, _int, _c_void_p]),
     "ise_rescore_topk": (_int, [_c_void_p, _c_void_p, _int, _i64, _c_void_p, _i64, _i64, _i64, _int, _int, _int, _i64,
                                 _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
-    "ise_rescore_select": (_int, [_c_void_p, _c_void_p, _int, _i64, _c_void_p, _c_void_p, _c_void_p, _i64, _c_void_p,
+    "ise_rescore_select": (_int, [_c_void_p, _c_void_p, _int, _i64, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _i64, _c_void_p,
                                   _c_void_p, _i64, _i64, _int, _int, _int, _int, _i64, _c_void_p, _c_void_p, _c_void_p,
                                   _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "ise_gemm_collect": (_int, [_c_void_p,
-                                _c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p,
+                                _c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _c_void_p,
                                 _c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p,
                                 _i64, _i64, _int, _int, _i64, _c_void_p, _int,
                                 _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
@@ -57,6 +61,9 @@ PROTOTYPES = {
                               _c_void_p]),
     "ise_kmeans_accumulate": (_int, [_c_void_p, _c_void_p, _int, _i64, _int, _i64, _c_void_p, _c_void_p,
                                      _c_void_p, _i64, _int, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "ise_kmeans_accumulate_workspace_bytes": (_size, [_c_void_p, _i64, _i64]),
+    "ise_kmeans_accumulate_sorted": (_int, [_c_void_p, _c_void_p, _int, _i64, _int, _i64, _c_void_p, _c_void_p, _i64, _int,
+                                            _c_void_p, _c_void_p, _c_void_p, _c_void_p, _size, _c_void_p]),
     "ise_kmeans_mean": (_int, [_c_void_p, _c_void_p, _c_void_p, _i64, _int, _c_void_p, _c_void_p, _c_void_p]),
     "ise_kmeans_apply_splits": (_int, [_c_void_p, _c_void_p, _i64, _int, _c_void_p, C.c_int32, _c_void_p]),
     "ise_bovw_histogram": (_int, [_c_void_p, _c_void_p, _i64, _c_void_p, _i64, _int, _int, _int, _c_void_p, _int,

@@ -1,5 +1,10 @@
 // Context, error plumbing and the host-side sequential-RNG helpers of libise.
+#include <stdlib.h>
+
+#include <atomic>
+#include <mutex>
 #include <random>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -124,14 +129,69 @@ struct BlockMT19937 {
 };
 }  // namespace
 
-ISE_EXPORT int ise_split_plan(float* hassign, int64_t k, int64_t n, int32_t* pairs, int32_t* nsplit) {
-    ISE_CHECK_ARG(hassign != nullptr && pairs != nullptr && nsplit != nullptr && k > 0 && n > k);
+// ---- sparse index of the split_clusters RNG stream ---------------------------------------------------------------
+// split_clusters seeds a FRESH mt19937(1234) on every call, so the stream of draws is the same for every iteration of
+// every training run in the process.  A probed donor cj is accepted when r = float(x) / 2^32 < p = (h[cj] - 1) / (n - k);
+// with a large codebook p is tiny for every cluster (sum_j p_j = 1), so only "small" draws can ever accept: a draw
+// x >= 2^24 gives r >= 2^-8 and is rejected whenever p_max <= 2^-8.  The stream is therefore generated ONCE per
+// process and only the positions / values of its small draws are kept (1 in 256: 12 bytes per 256 draws); a plan then
+// walks ~k / 256 candidates per split instead of ~k draws, and later iterations reuse the index (k = 65536, 1.7 k
+// splits: 111 M draws -> 0.43 M candidate checks).  Same draws, same order, same float predicate as Faiss's loop.
+namespace {
+struct SplitStreamIndex {
+    static constexpr uint32_t kSmall = 1u << 24;
+    static constexpr int64_t kStep = 4 << 20;             // draws generated per extension step
+    std::mutex mu;
+    BlockMT19937 mt{1234};
+    int64_t generated = 0;                                // draws consumed from mt so far
+    std::vector<int64_t> pos;                             // stream positions of the small draws, ascending
+    std::vector<uint32_t> val;
+    std::thread warm;
+    std::atomic<bool> stop{false};
+    // caller holds mu
+    void extend_to(int64_t target) {
+        while (generated < target) {
+            if (mt.pos == BlockMT19937::N) mt.refill();
+            const int take = (int)std::min<int64_t>(BlockMT19937::N - mt.pos, target - generated);
+            const uint32_t* o = mt.out + mt.pos;
+            for (int i = 0; i < take; ++i)
+                if (o[i] < kSmall) { pos.push_back(generated + i); val.push_back(o[i]); }
+            mt.pos += take;
+            generated += take;
+        }
+    }
+    ~SplitStreamIndex() {
+        stop.store(true);
+        if (warm.joinable()) warm.join();
+    }
+};
+SplitStreamIndex g_split_stream;
+}  // namespace
+
+// Non-blocking: generate the first n_draws of the stream in a background thread (k-means training calls this when it
+// starts on a large codebook, so the index exists by the time an iteration needs a plan).
+ISE_EXPORT int ise_split_plan_warm(int64_t n_draws) {
+    ISE_CHECK_ARG(n_draws >= 0);
+    SplitStreamIndex& ix = g_split_stream;
+    std::lock_guard<std::mutex> lk(ix.mu);
+    if (ix.generated >= n_draws || ix.warm.joinable()) return 0;       // one warm-up thread per process
+    ix.warm = std::thread([n_draws]() {
+        SplitStreamIndex& s = g_split_stream;
+        for (;;) {
+            std::lock_guard<std::mutex> g(s.mu);
+            if (s.stop.load() || s.generated >= n_draws) return;
+            s.extend_to(std::min<int64_t>(n_draws, s.generated + SplitStreamIndex::kStep));
+        }
+    });
+    return 0;
+}
+
+// the original form: one integer compare per draw against per-centroid thresholds (any donor probabilities)
+static int split_plan_dense(float* hassign, int64_t k, int64_t n, int32_t* pairs, int32_t* nsplit) {
     BlockMT19937 mt(1234);
     int32_t ns = 0;
     const float denom = (float)(n - k);
-    // Same draws, same decisions as Faiss's loop `r = mt() / float(mt.max()); if (r < p) break;`.  At k = 65536 a
-    // split probes ~n / (mean cluster size) = 66 k donors and an iteration that empties ~1.7 k clusters spends its
-    // time here, on the host, so the test is reduced to one integer compare per draw: x -> float(x) / M is
+    // Same draws, same decisions as Faiss's loop `r = mt() / float(mt.max()); if (r < p) break;`: x -> float(x) / M is
     // monotone, hence `r < p`  <=>  x < T(p) with T(p) the smallest draw whose quotient is not below p (found
     // by bisection, once per centroid and again for the two entries a split changes).
     const float rng_max = 4294967295.0f;      // float(std::mt19937::max())
@@ -163,6 +223,55 @@ ISE_EXPORT int ise_split_plan(float* hassign, int64_t k, int64_t n, int32_t* pai
         hassign[cj] -= hassign[ci];
         thr[(size_t)ci] = threshold(hassign[ci]);
         thr[(size_t)cj] = threshold(hassign[cj]);
+        ns++;
+    }
+    *nsplit = ns;
+    return 0;
+}
+
+ISE_EXPORT int ise_split_plan(float* hassign, int64_t k, int64_t n, int32_t* pairs, int32_t* nsplit) {
+    ISE_CHECK_ARG(hassign != nullptr && pairs != nullptr && nsplit != nullptr && k > 0 && n > k);
+    const float denom = (float)(n - k);
+    const float rng_max = 4294967295.0f;      // float(std::mt19937::max()) == 2^32
+    float h_max = 0.f;
+    bool any_empty = false;
+    for (int64_t c = 0; c < k; c++) {
+        h_max = std::max(h_max, hassign[c]);
+        any_empty |= hassign[c] == 0;
+    }
+    if (!any_empty) { *nsplit = 0; return 0; }
+    // donor probabilities only shrink while the plan runs (a split halves the donor), so p_max is known up front
+    const float p_max = (float)((h_max - 1.0) / denom);
+    if (!(p_max <= 0.00390625f) || getenv("ISE_SPLIT_PLAN_DENSE"))     // 2^-8: a draw >= 2^24 could accept
+        return split_plan_dense(hassign, k, n, pairs, nsplit);
+    if (!(h_max > 1.f)) ISE_FAIL("no cluster has more than one point: split_clusters would never terminate");
+    SplitStreamIndex& ix = g_split_stream;
+    std::lock_guard<std::mutex> lk(ix.mu);
+    int32_t ns = 0;
+    int64_t g = 0;                 // stream position of the next draw
+    size_t cur = 0;                // first index entry with pos >= g
+    for (int64_t ci = 0; ci < k; ci++) {
+        if (hassign[ci] != 0) continue;
+        int64_t cj = -1;
+        while (cj < 0) {
+            if (cur == ix.pos.size()) {             // out of candidates: generate more of the stream
+                ix.extend_to(ix.generated + SplitStreamIndex::kStep);
+                continue;
+            }
+            const int64_t P = ix.pos[cur];
+            const uint32_t x = ix.val[cur];
+            ++cur;
+            const int64_t c = (P - g) % k;          // the donor this draw is compared with
+            const float p = (float)((hassign[c] - 1.0) / denom);
+            if ((float)x / rng_max < p) {           // Faiss: r = mt() / float(mt.max()); if (r < p) break;
+                cj = c;
+                g = P + 1;
+            }
+        }
+        pairs[2 * ns] = (int32_t)ci;
+        pairs[2 * ns + 1] = (int32_t)cj;
+        hassign[ci] = hassign[cj] / 2;
+        hassign[cj] -= hassign[ci];
         ns++;
     }
     *nsplit = ns;

@@ -71,6 +71,7 @@ enum {
     META_SCALE = 0, META_INV_SCALE = 1, META_LO_NONZERO = 2, META_ABSMAX = 3, META_MAX_NORM_SQ = 4,
     META_WIDE_MANTISSA = 5,   // != 0: some element has more than 11 significant bits (float32 inputs, absmax pass)
     META_MIN_NONZERO = 6,     // 0x7f800000 - bits(min |x| over non-zero elements), 0 = none seen (int, via atomicMax)
+    META_NONFINITE = 7,       // != 0: the conversion pass met a NaN or an Inf (Faiss refuses such training sets)
     META_FLOATS = 8
 };
 
@@ -103,15 +104,22 @@ __device__ __forceinline__ bool cand_better(float va, int64_t ia, float vb, int6
 // the truncating FP32 accumulation adds <= (d/16 + 4) 2^-23 |a||b|; FP16 underflow (scaled elements below
 // 2^-14 round with absolute error <= 2^-25) adds <= 2^-25/scale * sqrt(d) * |other operand|.
 struct CoarseBound {
-    float kappa, uf_a, uf_b, nb_max;
+    float kappa, uf_a, uf_b, nb_max, sq_, ca_;
     __device__ __forceinline__ void init(const float* a_meta, const float* b_meta, int d) {
         const float ca = a_meta[META_LO_NONZERO] != 0.f ? 4.8828125e-4f : 0.f;   // 2^-11
         const float cb = b_meta[META_LO_NONZERO] != 0.f ? 4.8828125e-4f : 0.f;
         kappa = 1.02f * (ca + cb) + 2.4e-7f + (float)(d / 16 + 4) * 1.1920929e-7f;
         const float sq = sqrtf((float)d) * 5.9604645e-8f;                         // 2 * 2^-25 * sqrt(d)
+        sq_ = sq;
+        ca_ = ca;
         uf_a = ca != 0.f ? sq * a_meta[META_INV_SCALE] : 0.f;                     // times |b|
         uf_b = cb != 0.f ? sq * b_meta[META_INV_SCALE] : 0.f;                     // times |a|
         nb_max = sqrtf(b_meta[META_MAX_NORM_SQ]);
+    }
+    // row operands prepared with a per-row scale (ise_prepare_rows): the FP16-underflow term of the A planes follows
+    // the row's own scale instead of the tensor's
+    __device__ __forceinline__ void set_a_inv_scale(float a_inv) {
+        uf_a = ca_ != 0.f ? sq_ * a_inv : 0.f;
     }
     // every coarse inner product of a row with squared norm `an` is within eps(an) of the exact one
     __device__ __forceinline__ float eps(float an) const {

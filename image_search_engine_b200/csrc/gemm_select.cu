@@ -81,6 +81,7 @@ struct Params {
     const float* b_meta;
     const float* a_norms;
     const float* b_norms;
+    const float* a_row_inv; // optional [m]: per-row 1 / scale of the A planes (single-pass row preparation); overrides a_meta's
     const float* row_seed;  // optional [m]: a per-row score every kept candidate must beat (real units)
     int32_t* row_count;     // collect mode (KSEL == 0): per-row append counters, out_* are [m, topk] buffers
     int32_t* flag_rows;     // optional (top-1 only): rows whose winner is not provably unique under the
@@ -329,8 +330,8 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         const int half = MT == 2 ? 0 : (ew >> 2);  // which half of every tile's columns this warp scans
         const int rt = MT == 2 ? (ew >> 2) : 0;    // MT == 2: which of the CTA's two row tiles this warp serves
         const int et = threadIdx.x - EPI_WARP0 * 32;
-        const float inv = p.a_meta[META_INV_SCALE] * p.b_meta[META_INV_SCALE];
-        const float two_inv = 2.f * inv;
+        const float b_inv = p.b_meta[META_INV_SCALE];
+        const float a_inv_tensor = p.a_meta[META_INV_SCALE];
         CoarseBound bound;
         if (KSEL == 1 && VERIFY) bound.init(p.a_meta, p.b_meta, p.d);
         uint32_t tile = 0;
@@ -340,6 +341,11 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             const int nt1 = min(nt0 + p.tiles_per_split, p.n_ntiles);
             const int row_in_tile = q * 32 + lane;
             const int64_t row = (int64_t)mt * BLOCK_M + row_in_tile;
+            // accumulator -> real units: 1 / (scale of this row's A planes * scale of the B planes)
+            const float a_inv = (p.a_row_inv != nullptr && row < p.m) ? __ldg(p.a_row_inv + row) : a_inv_tensor;
+            const float inv = a_inv * b_inv;
+            const float two_inv = 2.f * inv;
+            if (KSEL == 1 && VERIFY) bound.set_a_inv_scale(a_inv);
 
             // top-1 state: best score / id, the best score among the OTHER columns of the chunk that
             // holds the best (sib) and among all other chunks (m2): max(sib, m2) is the exact runner-up
@@ -350,7 +356,7 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             if (KSEL == 0) {
                 if (row < p.m) {
                     const float sr = __ldg(p.row_seed + row);
-                    collect_thr = L2 ? (__ldg(p.a_norms + row) - sr) : sr * (p.a_meta[META_SCALE] * p.b_meta[META_SCALE]);
+                    collect_thr = L2 ? (__ldg(p.a_norms + row) - sr) : sr / inv;   // scales are powers of two: exact
                 }
             }
             if (KSEL > 1) {
@@ -359,7 +365,7 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 float seed = -CUDART_INF_F;
                 if (p.row_seed != nullptr && row < p.m) {
                     const float sr = __ldg(p.row_seed + row);
-                    seed = L2 ? (__ldg(p.a_norms + row) - sr) : sr * (p.a_meta[META_SCALE] * p.b_meta[META_SCALE]);
+                    seed = L2 ? (__ldg(p.a_norms + row) - sr) : sr / inv;           // scales are powers of two: exact
                 }
                 list.init(p.topk, seed);
             }
@@ -855,7 +861,7 @@ static int setup_maps(ise_ctx* ctx, const void* a_hi, const void* a_lo, int64_t 
 }
 
 ISE_EXPORT int ise_gemm_collect(ise_ctx* ctx, const void* a_hi, const void* a_lo, int64_t lda, const float* a_meta,
-                                const float* a_norms, const void* b_hi, const void* b_lo, int64_t ldb,
+                                const float* a_norms, const float* a_row_inv, const void* b_hi, const void* b_lo, int64_t ldb,
                                 const float* b_meta, const float* b_norms, int64_t m, int64_t n, int d, int metric,
                                 int64_t id_base, const float* row_seed, int cap, float* cand_val, int64_t* cand_idx,
                                 int32_t* row_count, void* stream) {
@@ -874,6 +880,7 @@ ISE_EXPORT int ise_gemm_collect(ise_ctx* ctx, const void* a_hi, const void* a_lo
     p.tiles_per_split = pl.tiles_per_split; p.n_splits = pl.n_splits;
     p.topk = cap; p.id_base = id_base;
     p.a_meta = a_meta; p.b_meta = b_meta; p.a_norms = a_norms; p.b_norms = b_norms;
+    p.a_row_inv = a_row_inv;
     p.row_seed = row_seed; p.row_count = row_count; p.flag_rows = nullptr; p.flag_count = nullptr;
     p.out_val = cand_val; p.out_idx = cand_idx;
     // empty slots read as id -1 / count 0
@@ -890,7 +897,7 @@ ISE_EXPORT int ise_gemm_collect(ise_ctx* ctx, const void* a_hi, const void* a_lo
 }
 
 ISE_EXPORT int ise_gemm_select(ise_ctx* ctx, const void* a_hi, const void* a_lo, int64_t lda, const float* a_meta,
-                               const float* a_norms, const void* b_hi, const void* b_lo, int64_t ldb,
+                               const float* a_norms, const float* a_row_inv, const void* b_hi, const void* b_lo, int64_t ldb,
                                const float* b_meta, const float* b_norms, int64_t m, int64_t n, int d, int metric,
                                int topk, int64_t id_base, const float* row_seed, int32_t* flag_rows,
                                int32_t* flag_count, float* out_val, int64_t* out_idx, void* workspace,
@@ -916,6 +923,7 @@ ISE_EXPORT int ise_gemm_select(ise_ctx* ctx, const void* a_hi, const void* a_lo,
     p.tiles_per_split = pl.tiles_per_split; p.n_splits = pl.n_splits;
     p.topk = topk; p.id_base = id_base;
     p.a_meta = a_meta; p.b_meta = b_meta; p.a_norms = a_norms; p.b_norms = b_norms;
+    p.a_row_inv = a_row_inv;
     p.row_seed = row_seed;
     p.row_count = nullptr;
     p.flag_rows = flag_rows;

@@ -244,6 +244,181 @@ accumulate_priv_kernel(const T* __restrict__ x, int64_t n, int d, int64_t ldx, c
     }
 }
 
+// =====================================================================================================================
+// Sorted-gather update (the default): no atomics per row at all.
+//   (A) count_kernel      histogram of the assignment ids (shared-memory privatised when k fits)        8 B / row
+//   (B) scan_kernel       exclusive scan -> segment starts; counts[c] += (float)cnt[c]                   O(k)
+//   (C) scatter_kernel    counting sort: (key, row) pairs grouped by centroid                            8 + 8 B / row
+//   (D) gather_reduce     the sorted list is cut into fixed chunks of kSegRows rows, one worker (a group of d / 4 lanes,
+//                         a whole warp at d >= 128) per chunk: rows are gathered with 128-bit loads, kGatherRows in
+//                         flight, and summed in REGISTERS while the centroid id does not change; a run that ends is
+//                         flushed with one red.global.add.v4.f32 per lane.  4 d + 8 B / row, perfectly balanced
+//                         whatever the cluster sizes, ~1.3 flushes per 64 rows at C2 instead of 64.
+// The objective terms (<x, c> or |x - c|^2 in exact FP32) ride along in (D): the centroid row is loaded once per run.
+// =====================================================================================================================
+constexpr int kSegRows = 64;
+constexpr int kGatherRows = 8;
+constexpr int kCountSmemBins = 12 * 1024;
+
+__global__ void count_kernel(const int64_t* __restrict__ assign, int64_t n, int k, int32_t* __restrict__ cnt) {
+    extern __shared__ int s_bins[];
+    const bool smem = k <= kCountSmemBins;
+    if (smem) {
+        for (int j = threadIdx.x; j < k; j += blockDim.x) s_bins[j] = 0;
+        __syncthreads();
+    }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // two ids per 128-bit load
+    const bool al = (reinterpret_cast<uintptr_t>(assign) & 15) == 0;
+    const int64_t n2 = al ? n / 2 : 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+        const longlong2 a = __ldg(reinterpret_cast<const longlong2*>(assign) + i);
+        if (a.x >= 0 && a.x < k) { if (smem) atomicAdd(&s_bins[a.x], 1); else atomicAdd(cnt + a.x, 1); }
+        if (a.y >= 0 && a.y < k) { if (smem) atomicAdd(&s_bins[a.y], 1); else atomicAdd(cnt + a.y, 1); }
+    }
+    for (int64_t i = 2 * n2 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int64_t a = __ldg(assign + i);
+        if (a >= 0 && a < k) { if (smem) atomicAdd(&s_bins[a], 1); else atomicAdd(cnt + a, 1); }
+    }
+    if (smem) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < k; j += blockDim.x) {
+            const int v = s_bins[j];
+            if (v) atomicAdd(cnt + j, v);
+        }
+    }
+}
+
+// single CTA: offs[0..k] = exclusive scan of cnt; cursor = copy of the starts; counts += cnt (float, like hassign)
+__global__ void scan_counts_kernel(const int32_t* __restrict__ cnt, int k, int32_t* __restrict__ offs,
+                                   int32_t* __restrict__ cursor, float* __restrict__ counts) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < k; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int v = i < k ? cnt[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[wib] = incl;
+        __syncthreads();
+        int wbase = 0;
+        for (int w = 0; w < wib; ++w) wbase += s_warp[w];
+        const int carry = s_carry;
+        if (i < k) {
+            const int start = carry + wbase + incl - v;
+            offs[i] = start;
+            cursor[i] = start;
+            if (v) counts[i] += (float)v;
+        }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = carry + wbase + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offs[k] = s_carry;
+}
+
+__global__ void scatter_kernel(const int64_t* __restrict__ assign, int64_t n, int k, int32_t* __restrict__ cursor,
+                               int2* __restrict__ sorted) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int64_t a = __ldg(assign + i);
+        if (a < 0 || a >= k) continue;
+        const int pos = atomicAdd(cursor + a, 1);
+        sorted[pos] = make_int2((int)a, (int)i);
+    }
+}
+
+template <typename T> struct RowVec;
+template <> struct RowVec<float> {
+    static __device__ __forceinline__ float4 ld(const float* row, int c4) { return __ldg(reinterpret_cast<const float4*>(row) + c4); }
+};
+template <> struct RowVec<uint8_t> {
+    static __device__ __forceinline__ float4 ld(const uint8_t* row, int c4) {
+        const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(row) + c4);
+        return make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w);
+    }
+};
+
+// G = lanes per worker (power of two, 32 / G workers per warp); a worker owns columns [4 * (cb + lg), +4) of its rows for
+// the column block cb (d > 128: the chunk is walked once per 128-column block, the rows come back from L1 / L2)
+template <typename T, int G>
+__global__ void __launch_bounds__(256)
+gather_reduce_kernel(const T* __restrict__ x, int d, int64_t ldx, const int2* __restrict__ sorted,
+                     const int32_t* __restrict__ n_sorted_ptr, const float* __restrict__ cent, int metric, float* __restrict__ sums, double* __restrict__ obj) {
+    __shared__ double s_obj[8];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int lg = lane & (G - 1);                       // lane within the worker
+    const int64_t worker = ((int64_t)blockIdx.x * 8 + wib) * (32 / G) + lane / G;
+    const int64_t n_workers = (int64_t)gridDim.x * 8 * (32 / G);
+    const int64_t n_sorted = *n_sorted_ptr;             // rows with a valid id (all of them after an assign pass)
+    const int64_t n_chunks = (n_sorted + kSegRows - 1) / kSegRows;
+    const int d4 = d >> 2;
+    float objp = 0.f;
+    double objd = 0.0;
+    for (int64_t chunk = worker; chunk < n_chunks; chunk += n_workers) {
+        const int64_t i0 = chunk * kSegRows, i1 = min(n_sorted, i0 + kSegRows);
+        for (int cb = 0; cb < d4; cb += G) {
+            const int c4 = cb + lg;
+            const bool col_ok = c4 < d4;
+            int cur = -1;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), cc = acc;
+            for (int64_t i = i0; i < i1; i += kGatherRows) {
+                int2 kr[kGatherRows];
+                float4 v[kGatherRows];
+#pragma unroll
+                for (int u = 0; u < kGatherRows; ++u)
+                    kr[u] = i + u < i1 ? __ldg(sorted + i + u) : make_int2(-1, 0);
+#pragma unroll
+                for (int u = 0; u < kGatherRows; ++u)
+                    if (kr[u].x >= 0 && col_ok) v[u] = RowVec<T>::ld(x + (int64_t)kr[u].y * ldx, c4);
+#pragma unroll
+                for (int u = 0; u < kGatherRows; ++u) {
+                    if (kr[u].x < 0) continue;
+                    if (kr[u].x != cur) {
+                        if (cur >= 0 && col_ok) red_add_v4(sums + (int64_t)cur * d + 4 * c4, acc);
+                        cur = kr[u].x;
+                        acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (cent && col_ok) cc = __ldg(reinterpret_cast<const float4*>(cent + (int64_t)cur * d) + c4);
+                    }
+                    if (!col_ok) continue;
+                    acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+                    if (cent) {
+                        if (metric == ISE_METRIC_IP) {
+                            objp = fmaf(v[u].x, cc.x, objp); objp = fmaf(v[u].y, cc.y, objp);
+                            objp = fmaf(v[u].z, cc.z, objp); objp = fmaf(v[u].w, cc.w, objp);
+                        } else {
+                            const float e0 = v[u].x - cc.x, e1 = v[u].y - cc.y, e2 = v[u].z - cc.z, e3 = v[u].w - cc.w;
+                            objp = fmaf(e0, e0, objp); objp = fmaf(e1, e1, objp);
+                            objp = fmaf(e2, e2, objp); objp = fmaf(e3, e3, objp);
+                        }
+                    }
+                }
+            }
+            if (cur >= 0 && col_ok) red_add_v4(sums + (int64_t)cur * d + 4 * c4, acc);
+        }
+        objd += (double)objp;            // FP32 partial of one chunk's 64 rows x 4 columns, FP64 from there on
+        objp = 0.f;
+    }
+    if (obj && cent) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) objd += __shfl_xor_sync(0xffffffffu, objd, o);
+        if (lane == 0) s_obj[wib] = objd;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int i = 0; i < 8; ++i) t += s_obj[i];
+            if (t != 0.0) atomicAdd(obj, t);
+        }
+    }
+}
+
 __global__ void mean_kernel(const float* __restrict__ sums, const float* __restrict__ counts, int64_t k, int d,
                             float* __restrict__ centroids, int32_t* __restrict__ n_empty) {
     const int lane = threadIdx.x & 31;
@@ -336,6 +511,71 @@ ISE_EXPORT int ise_kmeans_accumulate(ise_ctx* ctx, const void* x, int dtype, int
     else
         accumulate_kernel<uint8_t><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const uint8_t*)x, n, d, ldx, assign,
                                                                                dis, centroids, metric, sums, counts, obj);
+    ISE_LAUNCH_CHECK();
+    return 0;
+}
+
+ISE_EXPORT size_t ise_kmeans_accumulate_workspace_bytes(ise_ctx* ctx, int64_t n, int64_t k) {
+    if (!ctx || n <= 0 || k <= 0) return 0;
+    // cnt[k] | offs[k + 1] | cursor[k] (int32) | sorted[n] (int2), 16-byte aligned sections
+    return (size_t)(((3 * k + 1) * 4 + 15) & ~(int64_t)15) + (size_t)n * sizeof(int2) + 256;
+}
+
+template <typename T>
+static void launch_gather(const T* x, int d, int64_t ldx, const int2* sorted, int64_t n, const int32_t* n_sorted, const float* cent, int metric,
+                          float* sums, double* obj, int sm_count, cudaStream_t st) {
+    const int d4 = d / 4;
+    int g = 1;
+    while (g < d4 && g < 32) g <<= 1;
+    const int64_t chunks = ceil_div64(n, kSegRows);
+    const int64_t workers_per_cta = 8 * (32 / g);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(chunks, workers_per_cta), (int64_t)sm_count * 8));
+    switch (g) {
+        case 1: gather_reduce_kernel<T, 1><<<grid, 256, 0, st>>>(x, d, ldx, sorted, n_sorted, cent, metric, sums, obj); break;
+        case 2: gather_reduce_kernel<T, 2><<<grid, 256, 0, st>>>(x, d, ldx, sorted, n_sorted, cent, metric, sums, obj); break;
+        case 4: gather_reduce_kernel<T, 4><<<grid, 256, 0, st>>>(x, d, ldx, sorted, n_sorted, cent, metric, sums, obj); break;
+        case 8: gather_reduce_kernel<T, 8><<<grid, 256, 0, st>>>(x, d, ldx, sorted, n_sorted, cent, metric, sums, obj); break;
+        case 16: gather_reduce_kernel<T, 16><<<grid, 256, 0, st>>>(x, d, ldx, sorted, n_sorted, cent, metric, sums, obj); break;
+        default: gather_reduce_kernel<T, 32><<<grid, 256, 0, st>>>(x, d, ldx, sorted, n_sorted, cent, metric, sums, obj); break;
+    }
+}
+
+ISE_EXPORT int ise_kmeans_accumulate_sorted(ise_ctx* ctx, const void* x, int dtype, int64_t n, int d, int64_t ldx,
+                                            const int64_t* assign, const float* centroids, int64_t k, int metric,
+                                            float* sums, float* counts, double* obj, void* workspace,
+                                            size_t workspace_bytes, void* stream) {
+    ISE_CHECK_ARG(ctx && n >= 0 && d > 0 && ldx >= d && k > 0 && k < ((int64_t)1 << 31) && n < ((int64_t)1 << 31));
+    ISE_CHECK_ARG(dtype == ISE_DTYPE_F32 || dtype == ISE_DTYPE_U8);
+    ISE_CHECK_ARG(metric == ISE_METRIC_IP || metric == ISE_METRIC_L2);
+    if (n == 0) return 0;
+    ISE_CHECK_ARG(x && assign && sums && counts && workspace);
+    // rows are gathered as 4-column vectors: 16-byte (float32) / 4-byte (uint8) aligned rows
+    const bool vec_ok = d % 4 == 0 && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(sums) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(x) & (dtype == ISE_DTYPE_F32 ? 15 : 3)) == 0 &&
+                        (!centroids || (reinterpret_cast<uintptr_t>(centroids) & 15) == 0);
+    if (!vec_ok)
+        return ise_kmeans_accumulate(ctx, x, dtype, n, d, ldx, assign, nullptr, centroids, 0, metric, sums, counts, obj, stream);
+    if (workspace_bytes < ise_kmeans_accumulate_workspace_bytes(ctx, n, k)) ISE_FAIL("workspace too small");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t* cnt = reinterpret_cast<int32_t*>((reinterpret_cast<uintptr_t>(workspace) + 15) & ~uintptr_t(15));
+    int32_t* offs = cnt + k;
+    int32_t* cursor = offs + k + 1;
+    int2* sorted = reinterpret_cast<int2*>(reinterpret_cast<uint8_t*>(cnt) + (((3 * k + 1) * 4 + 15) & ~(int64_t)15));
+    ISE_CUDA(cudaMemsetAsync(cnt, 0, (size_t)k * sizeof(int32_t), st));
+    const int grid_n = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(n, 256 * 4), (int64_t)ctx->sm_count * 8));
+    const size_t shm = k <= kCountSmemBins ? (size_t)k * sizeof(int) : 0;
+    count_kernel<<<k <= kCountSmemBins ? std::min(grid_n, ctx->sm_count * 4) : grid_n, 256, shm, st>>>(assign, n, (int)k, cnt);
+    ISE_LAUNCH_CHECK();
+    scan_counts_kernel<<<1, 1024, 0, st>>>(cnt, (int)k, offs, cursor, counts);
+    ISE_LAUNCH_CHECK();
+    scatter_kernel<<<grid_n, 256, 0, st>>>(assign, n, (int)k, cursor, sorted);
+    ISE_LAUNCH_CHECK();
+    // rows with ids outside [0, k) are left out, like the atomic kernels skip negative ids: the sorted list holds offs[k]
+    // entries; the gather kernel is sized for n and reads the real length from the scan result
+    // (n_sorted == n whenever every row was assigned, which is what the assign kernel guarantees)
+    if (dtype == ISE_DTYPE_F32) launch_gather<float>((const float*)x, d, ldx, sorted, n, offs + k, centroids, metric, sums, obj, ctx->sm_count, st);
+    else launch_gather<uint8_t>((const uint8_t*)x, d, ldx, sorted, n, offs + k, centroids, metric, sums, obj, ctx->sm_count, st);
     ISE_LAUNCH_CHECK();
     return 0;
 }

@@ -1,5 +1,7 @@
 // Operand preparation: FP32 / uint8 rows -> scaled FP16 hi/lo planes + exact FP32 row norms,
 // and faiss.normalize_L2.  HBM-bound streaming kernels: one warp per row, 128-bit loads.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -18,6 +20,7 @@ __device__ __forceinline__ float absmax4(float4 v) {
 __device__ __forceinline__ void exact_probe(float v, unsigned& wide, float& mn) {
     const unsigned b = __float_as_uint(v);
     wide |= b & 0x1FFFu;                                   // mantissa bits FP16 cannot hold
+    wide |= ((b & 0x7F800000u) == 0x7F800000u) ? 0x80000000u : 0u;   // NaN / Inf: reported through META_NONFINITE
     const float a = fabsf(v);
     mn = (a > 0.f) ? fminf(mn, a) : mn;
 }
@@ -66,6 +69,7 @@ __global__ void absmax_f32_kernel(const float* __restrict__ x, int64_t n, int d,
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
     if (lane == 0) {
+        if (wide & 0x80000000u) meta[META_NONFINITE] = 1.f;
         if (wide) meta[META_WIDE_MANTISSA] = 1.f;
         if (mn < 3.402823466e+38f)
             atomicMax(reinterpret_cast<int*>(meta + META_MIN_NONZERO), 0x7f800000 - __float_as_int(mn));
@@ -224,6 +228,119 @@ __global__ void __launch_bounds__(kThreads, EXACT ? 5 : 3) prepare_planes_f32x4_
     if (__any_sync(0xffffffffu, any_lo) && lane == 0) meta[META_LO_NONZERO] = 1.f;
 }
 
+// ---- single-pass preparation of ROW operands (descriptors / queries) ------------------------------------------------
+// The per-tensor scale of the kernels above needs the absolute maximum first, i.e. a second read of the matrix
+// (10 B moved per element for 6 B of algorithmic traffic at the C2 assign step).  A row operand does not need a common
+// scale: the selection epilogue owns one row per thread and multiplies the accumulator by that row's 1 / scale, and an
+// arg-max is invariant to it anyway.  So a warp reads its rows ONCE, takes each row's own absolute maximum with a
+// shuffle reduction, and converts from registers: 4 B read + 2 B (+ 2 B when the row is not exact in one FP16 plane)
+// written per element.  Rows whose lo part is all zero skip the lo store (integer-valued SIFT / ORB-as-float: all of
+// them); they are recorded in lo_skipped[] and zeroed by lo_fixup_kernel only if some other row did need its lo plane.
+// NaN / Inf are detected on the way (meta[NONFINITE]) so that k-means training needs no separate validation pass.
+template <int ROWS, int NV>
+__global__ void __launch_bounds__(kThreads)
+prepare_rows_f32_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ldx, __half* __restrict__ hi,
+                        __half* __restrict__ lo, int64_t ldp, float* __restrict__ norms, float* __restrict__ row_inv,
+                        uint8_t* __restrict__ lo_skipped, float* meta) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { meta[META_SCALE] = 1.f; meta[META_INV_SCALE] = 1.f; }
+    const int d4 = d >> 2, dp4 = (int)(ldp >> 2);
+    bool any_lo_written = false, bad = false;
+    float max_ss = 0.f, max_abs = 0.f;
+    for (int64_t r0 = warp * ROWS; r0 < n; r0 += nwarps * ROWS) {
+        float4 v[ROWS][NV];
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i)
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const int c = lane + 32 * j;
+                v[i][j] = (r0 + i < n && c < d4) ? __ldg(reinterpret_cast<const float4*>(x + (r0 + i) * ldx) + c)
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) {
+            const int64_t r = r0 + i;
+            float ss = 0.f, am = 0.f;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const float4 t = v[i][j];
+                ss = fmaf(t.x, t.x, ss); ss = fmaf(t.y, t.y, ss); ss = fmaf(t.z, t.z, ss); ss = fmaf(t.w, t.w, ss);
+                am = fmaxf(am, absmax4(t));
+                // fmaxf drops NaN: test every element (x - x is NaN for NaN and +-Inf, 0 otherwise)
+                bad |= ((t.x - t.x) + (t.y - t.y) + (t.z - t.z) + (t.w - t.w)) != 0.f;
+            }
+            ss = warp_sum(ss);
+            am = warp_max(am);
+            if (r >= n) continue;                               // warp-uniform
+            const float scale = scale_from_absmax(am);
+            uint32_t hv[NV][2], lv[NV][2];                      // packed half2 pairs
+            bool row_lo = false;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const float4 t = v[i][j];
+                __half h0, h1, h2, h3, l0, l1, l2, l3;
+                split_f16(t.x * scale, h0, l0); split_f16(t.y * scale, h1, l1);
+                split_f16(t.z * scale, h2, l2); split_f16(t.w * scale, h3, l3);
+                const __half2 ha = __halves2half2(h0, h1), hb = __halves2half2(h2, h3);
+                const __half2 la = __halves2half2(l0, l1), lb = __halves2half2(l2, l3);
+                hv[j][0] = *reinterpret_cast<const uint32_t*>(&ha);
+                hv[j][1] = *reinterpret_cast<const uint32_t*>(&hb);
+                lv[j][0] = *reinterpret_cast<const uint32_t*>(&la);
+                lv[j][1] = *reinterpret_cast<const uint32_t*>(&lb);
+                row_lo |= ((lv[j][0] | lv[j][1]) & 0x7FFF7FFFu) != 0u;
+            }
+            row_lo = __any_sync(0xffffffffu, row_lo);
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const int c = lane + 32 * j;
+                if (c < dp4) {                                  // pad columns [d, ldp) come out as zeros
+                    reinterpret_cast<uint2*>(hi + r * ldp)[c] = make_uint2(hv[j][0], hv[j][1]);
+                    if (lo && row_lo)
+                        reinterpret_cast<uint2*>(lo + r * ldp)[c] = make_uint2(lv[j][0], lv[j][1]);
+                }
+            }
+            if (lane == 0) {
+                if (norms) norms[r] = ss;
+                row_inv[r] = 1.f / scale;
+                if (lo_skipped) lo_skipped[r] = (lo && !row_lo) ? 1 : 0;
+            }
+            any_lo_written |= row_lo;
+            max_ss = fmaxf(max_ss, ss);
+            max_abs = fmaxf(max_abs, am);
+        }
+    }
+    if (lane == 0) {
+        if (max_ss > 0.f) atomicMax(reinterpret_cast<int*>(meta + META_MAX_NORM_SQ), __float_as_int(max_ss));
+        if (max_abs > 0.f) atomicMax(reinterpret_cast<int*>(meta + META_ABSMAX), __float_as_int(max_abs));
+        if (any_lo_written) meta[META_LO_NONZERO] = 1.f;
+    }
+    if (__any_sync(0xffffffffu, bad) && lane == 0) meta[META_NONFINITE] = 1.f;
+}
+
+// rows that skipped their (all-zero) lo store get it now -- only when the tensor as a whole has a lo plane in use
+__global__ void lo_fixup_kernel(__half* __restrict__ lo, int64_t n, int64_t ldp, const uint8_t* __restrict__ lo_skipped,
+                                const float* __restrict__ meta) {
+    if (meta[META_LO_NONZERO] == 0.f) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+    for (int64_t r0 = warp * 32; r0 < n; r0 += nwarps * 32) {
+        const unsigned mask = __ballot_sync(0xffffffffu, r0 + lane < n && lo_skipped[r0 + lane] != 0);
+        for (unsigned m = mask; m; m &= m - 1) {
+            uint2* row = reinterpret_cast<uint2*>(lo + (r0 + __ffs(m) - 1) * ldp);
+            for (int c = lane; c < (int)(ldp >> 2); c += 32) row[c] = make_uint2(0u, 0u);
+        }
+    }
+}
+
+__global__ void fill_row_inv_kernel(float* __restrict__ row_inv, int64_t n, float* meta) {
+    const float inv = meta[META_INV_SCALE];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        row_inv[i] = inv;
+}
+
 // Fast path, uint8 rows (ORB / BRISK bytes) with d % 16 == 0 and d / 16 a power of two <= 32, contiguous rows and
 // planes: the matrix is a flat stream of 16-byte groups; a lane converts one group (16 columns: one 128-bit
 // load, two 128-bit stores), and the LPR = d / 16 lanes that share a row reduce its norm with shuffles.
@@ -376,6 +493,60 @@ ISE_EXPORT int ise_prepare_planes(ise_ctx* ctx, const void* x, int dtype, int64_
                                                                       (__half*)lo, ldp, norms, meta, true);
         }
     }
+    ISE_LAUNCH_CHECK();
+    return 0;
+}
+
+// Row-operand preparation (descriptors, queries): one pass, per-row power-of-two scales returned as row_inv[n] =
+// 1 / scale.  Shapes the single-pass kernel does not cover (uint8 rows: already one pass with scale 1; float32 rows
+// with d % 4 != 0, unaligned, or d > 512) go through ise_prepare_planes and get a constant row_inv.
+ISE_EXPORT int ise_prepare_rows(ise_ctx* ctx, const void* x, int dtype, int64_t n, int d, int64_t ldx, void* hi, void* lo,
+                                int64_t ldp, float* norms, float* row_inv, uint8_t* lo_skipped, float* meta, void* stream) {
+    ISE_CHECK_ARG(ctx && meta && row_inv);
+    ISE_CHECK_ARG(n >= 0 && d > 0 && ldx >= d && ldp >= d && ldp % 8 == 0);
+    ISE_CHECK_ARG(dtype == ISE_DTYPE_F32 || dtype == ISE_DTYPE_U8);
+    ISE_CHECK_ARG(lo == nullptr || lo_skipped != nullptr);
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) {
+        ISE_CUDA(cudaMemsetAsync(meta, 0, META_FLOATS * sizeof(float), st));
+        return 0;
+    }
+    ISE_CHECK_ARG(x && hi);
+    const bool al16 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15) == 0;
+    if (dtype == ISE_DTYPE_F32 && d % 4 == 0 && ldx % 4 == 0 && al16 && ldp <= 512 && !getenv("ISE_PREPARE_TWO_PASS")) {
+        ISE_CUDA(cudaMemsetAsync(meta, 0, META_FLOATS * sizeof(float), st));
+        constexpr int ROWS = 4;
+        const int g4 = grid_for_rows(ctx, ceil_div64(n, ROWS));
+        const int nv = (int)((ldp / 4 + 31) / 32);
+#define ISE_ROWS_ARGS (const float*)x, n, d, ldx, (__half*)hi, (__half*)lo, ldp, norms, row_inv, lo_skipped, meta
+        if (nv <= 1) prepare_rows_f32_kernel<ROWS, 1><<<g4, kThreads, 0, st>>>(ISE_ROWS_ARGS);
+        else if (nv == 2) prepare_rows_f32_kernel<ROWS, 2><<<g4, kThreads, 0, st>>>(ISE_ROWS_ARGS);
+        else prepare_rows_f32_kernel<2, 4><<<grid_for_rows(ctx, ceil_div64(n, 2)), kThreads, 0, st>>>(ISE_ROWS_ARGS);
+#undef ISE_ROWS_ARGS
+        ISE_LAUNCH_CHECK();
+        if (lo) {
+            lo_fixup_kernel<<<grid_for_rows(ctx, ceil_div64(n, 32)), kThreads, 0, st>>>((__half*)lo, n, ldp, lo_skipped, meta);
+            ISE_LAUNCH_CHECK();
+        }
+        return 0;
+    }
+    if (ise_prepare_planes(ctx, x, dtype, n, d, ldx, hi, lo, ldp, norms, meta, stream)) return 1;
+    fill_row_inv_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(n, 256), 1024), 256, 0, st>>>(row_inv, n, meta);
+    ISE_LAUNCH_CHECK();
+    return 0;
+}
+
+// the absmax pass on its own: meta[ABSMAX], meta[NONFINITE] (+ the exactness probes) of a float32 matrix.  Used to
+// validate a training set that is about to be sub-sampled (Clustering::train checks ALL of its input for NaN / Inf).
+ISE_EXPORT int ise_scan_f32(ise_ctx* ctx, const float* x, int64_t n, int d, int64_t ldx, float* meta, void* stream) {
+    ISE_CHECK_ARG(ctx && meta && n >= 0 && d > 0 && ldx >= d);
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    ISE_CUDA(cudaMemsetAsync(meta, 0, META_FLOATS * sizeof(float), st));
+    if (n == 0) return 0;
+    ISE_CHECK_ARG(x != nullptr);
+    absmax_f32_kernel<<<grid_for_rows(ctx, n), kThreads, 0, st>>>(x, n, d, ldx, meta);
     ISE_LAUNCH_CHECK();
     return 0;
 }

@@ -29,7 +29,7 @@ __global__ void rescore_kernel(const TA* __restrict__ a, int64_t lda, const floa
                                const float* __restrict__ cand_val, const int64_t* __restrict__ cand_idx,
                                float* __restrict__ val, int64_t* __restrict__ idx,
                                const float* __restrict__ a_meta, const float* __restrict__ b_meta,
-                               const float* __restrict__ row_seed, const int32_t* __restrict__ row_count,
+                               const float* __restrict__ a_row_inv, const float* __restrict__ row_seed, const int32_t* __restrict__ row_count,
                                int32_t* __restrict__ flag_rows, int32_t* __restrict__ flag_count) {
     extern __shared__ float s_a[];          // the row of A as float32
     __shared__ float s_v[kMaxK];
@@ -45,6 +45,7 @@ __global__ void rescore_kernel(const TA* __restrict__ a, int64_t lda, const floa
         if (threadIdx.x == 0) s_kth = worst;
         __syncthreads();
         const float an = (L2 || flag_count) ? a_norms[row] : 0.f;
+        if (flag_count && a_row_inv) bound.set_a_inv_scale(a_row_inv[row]);    // row operand with per-row plane scales
         // collect mode appends candidates to slots [0, row_count): re-score and rank only those (the ranking below is
         // quadratic in the number of slots looked at -- 1024^2 per row at the full buffer against ~375^2 used)
         const int kv = row_count ? min(max(row_count[row], 0), kc) : kc;
@@ -190,7 +191,8 @@ __global__ void rescore_top1_kernel(const TA* __restrict__ a, int64_t lda, const
 static int launch_rescore(ise_ctx* ctx, const void* a, int a_dtype, int64_t lda, const float* b, int64_t ldb,
                           int64_t m, int64_t n, int d, int metric, int kc, int topk, int64_t id_base,
                           const float* a_norms, const float* b_norms, const float* cand_val, const int64_t* cand_idx,
-                          float* val, int64_t* idx, const float* a_meta, const float* b_meta, const float* row_seed,
+                          float* val, int64_t* idx, const float* a_meta, const float* b_meta, const float* a_row_inv,
+                          const float* row_seed,
                           const int32_t* row_count, int32_t* flag_rows, int32_t* flag_count, void* stream) {
     ISE_CHECK_ARG(ctx != nullptr);
     ISE_CHECK_ARG(metric == ISE_METRIC_IP || metric == ISE_METRIC_L2);
@@ -222,7 +224,7 @@ static int launch_rescore(ise_ctx* ctx, const void* a, int a_dtype, int64_t lda,
     const int grid = (int)std::min<int64_t>(m, (int64_t)ctx->sm_count * 16);
     const size_t shm = (size_t)((d + 3) / 4 * 4) * sizeof(float);
 #define ISE_RESCORE_ARGS lda, b, ldb, m, n, d, kc, topk, id_base, a_norms, b_norms, cand_val, cand_idx, val, idx, \
-                         a_meta, b_meta, row_seed, row_count, flag_rows, flag_count
+                         a_meta, b_meta, a_row_inv, row_seed, row_count, flag_rows, flag_count
     if (a_dtype == ISE_DTYPE_F32) {
         if (l2) rescore_kernel<float, true><<<grid, kThreads, shm, st>>>((const float*)a, ISE_RESCORE_ARGS);
         else rescore_kernel<float, false><<<grid, kThreads, shm, st>>>((const float*)a, ISE_RESCORE_ARGS);
@@ -240,17 +242,17 @@ ISE_EXPORT int ise_rescore_topk(ise_ctx* ctx, const void* a, int a_dtype, int64_
                                 const float* a_norms, const float* b_norms, float* val, int64_t* idx,
                                 void* stream) {
     return launch_rescore(ctx, a, a_dtype, lda, b, ldb, m, n, d, metric, topk, topk, id_base, a_norms, b_norms,
-                          nullptr, idx, val, idx, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
+                          nullptr, idx, val, idx, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
 }
 
 ISE_EXPORT int ise_rescore_select(ise_ctx* ctx, const void* a, int a_dtype, int64_t lda, const float* a_meta,
-                                  const float* a_norms, const float* b, int64_t ldb, const float* b_meta,
+                                  const float* a_norms, const float* a_row_inv, const float* b, int64_t ldb, const float* b_meta,
                                   const float* b_norms, int64_t m, int64_t n, int d, int metric, int kc, int topk,
                                   int64_t id_base, const float* row_seed, const int32_t* row_count,
                                   const float* cand_val, const int64_t* cand_idx, float* out_val, int64_t* out_idx,
                                   int32_t* flag_rows, int32_t* flag_count, void* stream) {
     ISE_CHECK_ARG(flag_rows && flag_count);
     return launch_rescore(ctx, a, a_dtype, lda, b, ldb, m, n, d, metric, kc, topk, id_base, a_norms, b_norms, cand_val,
-                          cand_idx, out_val, out_idx, a_meta, b_meta, row_seed, row_count, flag_rows, flag_count,
-                          stream);
+                          cand_idx, out_val, out_idx, a_meta, b_meta, a_row_inv, row_seed, row_count, flag_rows,
+                          flag_count, stream);
 }

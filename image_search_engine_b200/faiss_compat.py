@@ -172,7 +172,7 @@ class IndexFlat:
             D, I = ops.flat_search_exact(qf.contiguous(), self._database(), self.metric_type, kk)
         else:
             b = self._operand()
-            a = ops.prepare_operand(q)
+            a = ops.prepare_operand(q, rows=True)
             D, I = ops.search_topk(q, a, self._database(), b, self.metric_type, kk, precision=self.precision,
                                    need_distances=need_distances)
         if kk < k:
@@ -483,15 +483,15 @@ class Kmeans:
         if n < k:
             raise RuntimeError("Number of training points (%d) should be at least as large as number of "
                                "clusters (%d)" % (n, k))
-        if xd.dtype == torch.float32 and not bool(torch.isfinite(xd).all()):
-            raise RuntimeError("input contains NaN's or Inf's")
-        t0 = time.time()
         if n > k * cp.max_points_per_centroid:
+            # Clustering::train validates ALL of its input before sub-sampling; without sub-sampling the check rides
+            # on the operand conversion pass below
+            if xd.dtype == torch.float32 and ops.has_nonfinite(xd):
+                raise RuntimeError("input contains NaN's or Inf's")
             nsub = k * cp.max_points_per_centroid
             perm = ops.rand_perm_prefix(n, cp.seed, nsub)
             xd = xd.index_select(0, torch.from_numpy(perm).to(xd.device))
             n = nsub
-        metric = METRIC_INNER_PRODUCT if cp.spherical else METRIC_L2
         self.index = IndexFlatIP(d) if cp.spherical else IndexFlatL2(d)
         if n == k:
             cent = xd.to(torch.float32).clone()
@@ -500,64 +500,14 @@ class Kmeans:
             self.obj = np.array([0.0])
             self.index.add(cent)
             return 0.0
-
-        a_op = ops.compact_operand(ops.prepare_operand(xd))
-        dev = xd.device
-        if init_centroids is not None:
-            ic = np.ascontiguousarray(init_centroids, dtype=np.float32)
-            assert ic.shape[1] == d
-            ic = ic[:k]
-        else:
-            ic = np.zeros((0, d), np.float32)
-        n_input = ic.shape[0]
-        lower_is_better = not cp.spherical
-        best_obj = float("inf") if lower_is_better else float("-inf")
-        best_cent, best_stats = None, []
-        stats: list[dict] = []
-        accum = torch.empty((k * d + k,), dtype=torch.float32, device=dev)
-        sums, counts = accum[: k * d].view(k, d), accum[k * d:]
-        objbuf = torch.zeros((1,), dtype=torch.float64, device=dev)
-        n_empty = torch.zeros((1,), dtype=torch.int32, device=dev)
-        cent = torch.empty((k, d), dtype=torch.float32, device=dev)
-        t_search = 0.0
-        for redo in range(cp.nredo):
-            if n_input:
-                cent[:n_input] = torch.from_numpy(ic).to(dev)
-            if n_input < k:
-                cent[n_input:] = self._initial_rows(xd, n, cp.seed + 1 + redo * 15486557, n_input, k)
-            self._post_process(cent)
-            obj = 0.0
-            for it in range(cp.niter):
-                b_op = ops.prepare_operand(cent)
-                # ids from the tensor cores; the objective terms are recomputed exactly inside the update
-                dis, assign = ops.search_topk(xd, a_op, cent, b_op, metric, 1, precision=self.precision,
-                                              need_distances=False)
-                accum.zero_()
-                objbuf.zero_()
-                ops.kmeans_accumulate(xd, assign, None, sums, counts, objbuf, centroids=cent, metric=metric)
-                if self.trace is not None:
-                    self.trace.append(dict(redo=redo, it=it, centroids_in=cent.clone(), assign=assign.clone(),
-                                           dis=dis.clone()))
-                ops.kmeans_mean(sums, counts, cent, n_empty)
-                obj = float(objbuf.item())          # one tiny sync per iteration
-                nsplit = 0
-                if int(n_empty.item()) > 0:
-                    pairs, _ = ops.split_plan(counts.cpu().numpy(), n)
-                    nsplit = pairs.shape[0]
-                    ops.kmeans_apply_splits(cent, torch.from_numpy(pairs).to(dev))
-                cs = counts.double()
-                imb = float((cs * cs).sum() * k / (cs.sum() ** 2)) if cp.verbose else float("nan")
-                stats.append(dict(obj=obj, time=time.time() - t0, time_search=t_search, imbalance_factor=imb,
-                                  nsplit=nsplit))
-                self._post_process(cent)
-                if self.trace is not None:
-                    self.trace[-1]["centroids_out"] = cent.clone()
-                    self.trace[-1]["nsplit"] = nsplit
-            if cp.nredo > 1:
-                if (lower_is_better and obj < best_obj) or (not lower_is_better and obj > best_obj):
-                    best_cent, best_stats, best_obj = cent.clone(), list(stats), obj
-        if cp.nredo > 1:
-            cent, stats = best_cent, best_stats
+        from .parallel import DeviceOps, lloyd_train      # the Lloyd loop is shared with the multi-GPU ShardedKmeans
+        if k >= 1024:
+            ops.split_plan_warm(min(k * 2048, 1 << 28))
+        # row operand: one pass, per-row scales; the same pass rejects NaN / Inf like Clustering::train does
+        a_op = ops.compact_operand(ops.prepare_operand(xd, rows=True), reject_nonfinite=True)
+        cent, stats = lloyd_train(cp, d, k, xd, n, a_op, DeviceOps(),
+                                  init_rows=lambda seed, n_input: self._initial_rows(xd, n, seed, n_input, k),
+                                  init_centroids=init_centroids, trace=self.trace, precision=self.precision)
         self.index.add(cent)
         self.centroids = cent.cpu().numpy().reshape(k, d)
         self.iteration_stats = stats

@@ -77,6 +77,12 @@ def split_plan(hassign: np.ndarray, n: int) -> tuple[np.ndarray, np.ndarray]:
     return pairs[: 2 * ns.value].reshape(-1, 2).copy(), h
 
 
+def split_plan_warm(n_draws: int) -> None:
+    """Starts generating the sparse index of split_clusters' mt19937(1234) stream in a background thread (no-op
+    when it already covers n_draws); k-means training on a large codebook calls this up front."""
+    _lib.check(_lib.load().ise_split_plan_warm(int(n_draws)))
+
+
 # ------------------------------------------------------------------------------------------
 # operands
 # ------------------------------------------------------------------------------------------
@@ -92,10 +98,25 @@ class Operand:
     ldp: int
     sample: "Operand | None" = None        # strided 1/64 row sample (hi plane only): seeds for k <= 16
     sample_dense: "Operand | None" = None  # strided 1/16 row sample: seeds for the collect mode (k > 16)
+    row_inv: torch.Tensor | None = None    # [n] float32, ROW operands only: 1 / (power-of-two scale of the row's planes)
+
+    def rows(self, sel: torch.Tensor) -> "Operand":
+        """Sub-operand of the selected rows (planes gathered, not re-prepared)."""
+        return Operand(self.hi.index_select(0, sel), None if self.lo is None else self.lo.index_select(0, sel),
+                       self.norms.index_select(0, sel), self.meta, int(sel.numel()), self.d, self.ldp,
+                       row_inv=None if self.row_inv is None else self.row_inv.index_select(0, sel))
+
+    def hi_only(self) -> "Operand":
+        return Operand(self.hi, None, self.norms, self.meta, self.n, self.d, self.ldp, row_inv=self.row_inv)
 
 
-def prepare_operand(x: torch.Tensor, *, keep_lo: bool | None = None) -> Operand:
+def prepare_operand(x: torch.Tensor, *, keep_lo: bool | None = None, rows: bool = False) -> Operand:
     """x: [n, d] float32 or uint8 CUDA tensor (row-major, last dim contiguous).
+
+    ``rows=True`` marks a ROW operand (the descriptors of an assign, the queries of a search -- never the codebook /
+    database side): float32 rows are then converted in ONE pass with a power-of-two scale per row
+    (``Operand.row_inv``), which halves the HBM traffic of the preparation (no absmax pre-pass, no lo store for rows
+    that are exact in one FP16 plane) and also reports NaN / Inf through ``meta[7]``.
 
     No host synchronisation: float32 inputs always get a lo plane and the device-side
     ``meta[lo_nonzero]`` flag tells gemm_select at run time whether to load / multiply it (integer
@@ -121,6 +142,18 @@ def prepare_operand(x: torch.Tensor, *, keep_lo: bool | None = None) -> Operand:
     lo = torch.empty((n, ldp), dtype=torch.float16, device=x.device) if want_lo else None
     norms = torch.empty((n,), dtype=torch.float32, device=x.device)
     meta = torch.empty((8,), dtype=torch.float32, device=x.device)
+    if n == 0:                  # an empty operand (e.g. a rank that owns no rows): nothing to convert
+        _lib.ctx(dev)
+        meta.zero_()
+        return Operand(hi, None, norms, meta, 0, d, ldp)
+    if rows and dt == DTYPE_F32:
+        row_inv = torch.empty((n,), dtype=torch.float32, device=x.device)
+        skipped = torch.empty((n,), dtype=torch.uint8, device=x.device) if want_lo else None
+        _lib.check(_lib.load().ise_prepare_rows(
+            _lib.ctx(dev), _ptr(x), dt, n, d, x.stride(0), _ptr(hi), _ptr(lo), ldp, _ptr(norms), _ptr(row_inv),
+            _ptr(skipped), _ptr(meta), _stream()))
+        _count(2 if want_lo else 1)
+        return Operand(hi, lo, norms, meta, n, d, ldp, row_inv=row_inv)
     _lib.check(_lib.load().ise_prepare_planes(
         _lib.ctx(dev), _ptr(x), dt, n, d, x.stride(0) if n > 0 else d, _ptr(hi), _ptr(lo), ldp, _ptr(norms),
         _ptr(meta), _stream()))
@@ -149,11 +182,29 @@ def attach_sample(op: Operand) -> Operand:
     return op
 
 
-def compact_operand(op: Operand) -> Operand:
-    """Drops an all-zero lo plane (one 4-byte D2H readback): smaller smem stages, deeper pipeline."""
-    if op.lo is not None and op.n > 0 and float(op.meta[2].item()) == 0.0:
-        op.lo = None
+def compact_operand(op: Operand, *, reject_nonfinite: bool = False) -> Operand:
+    """Drops an all-zero lo plane (one 32-byte D2H readback of ``meta``): smaller smem stages, deeper pipeline.
+    The same readback carries the NaN / Inf flag of the conversion pass (``reject_nonfinite``: raise like
+    faiss.Kmeans.train does -- no separate validation pass over the data)."""
+    if op.n > 0:
+        meta = op.meta.cpu()
+        if reject_nonfinite and float(meta[7]) != 0.0:
+            raise RuntimeError("input contains NaN's or Inf's")
+        if op.lo is not None and float(meta[2]) == 0.0:
+            op.lo = None
     return op
+
+
+def has_nonfinite(x: torch.Tensor) -> bool:
+    """True when a float32 matrix holds a NaN or an Inf (one read-only pass, one 4-byte readback)."""
+    if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
+        raise IseError("has_nonfinite: row-major float32 matrix")
+    if x.shape[0] == 0:
+        return False
+    meta = torch.empty((8,), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().ise_scan_f32(_lib.ctx(_dev(x)), _ptr(x), x.shape[0], x.shape[1], x.stride(0), _ptr(meta), _stream()))
+    _count()
+    return float(meta[7].item()) != 0.0
 
 
 def normalize_l2_(x: torch.Tensor) -> torch.Tensor:
@@ -177,6 +228,8 @@ def gemm_select(a: Operand, b: Operand, metric: int, topk: int, id_base: int = 0
         raise IseError(f"topk must be in [1, {MAX_TOPK}]")
     if b.n == 0:
         raise IseError("empty column operand")
+    if b.row_inv is not None:
+        raise IseError("the column operand (codebook / database) must be prepared with rows=False")
     dev = _dev(a.hi)
     lib, ctx = _lib.load(), _lib.ctx(dev)
     val = torch.empty((a.n, topk), dtype=torch.float32, device=a.hi.device)
@@ -189,7 +242,7 @@ def gemm_select(a: Operand, b: Operand, metric: int, topk: int, id_base: int = 0
     ws_bytes = lib.ise_gemm_select_workspace_bytes(ctx, a.n, b.n, a.d, topk)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=a.hi.device) if ws_bytes else None
     _lib.check(lib.ise_gemm_select(
-        ctx, _ptr(a.hi), _ptr(a_lo), a.ldp, _ptr(a.meta), _ptr(a.norms),
+        ctx, _ptr(a.hi), _ptr(a_lo), a.ldp, _ptr(a.meta), _ptr(a.norms), _ptr(a.row_inv),
         _ptr(b.hi), _ptr(b_lo), b.ldp, _ptr(b.meta), _ptr(b.norms),
         a.n, b.n, a.d, int(metric), int(topk), int(id_base), _ptr(row_seed),
         _ptr(flags[0] if flags else None), _ptr(flags[1] if flags else None), _ptr(val), _ptr(idx), _ptr(ws),
@@ -227,7 +280,7 @@ def gemm_collect(a: Operand, b: Operand, metric: int, row_seed: torch.Tensor, ca
     if a_lo is not None and b_lo is None:
         b_lo = torch.zeros_like(b.hi)
     _lib.check(_lib.load().ise_gemm_collect(
-        _lib.ctx(_dev(a.hi)), _ptr(a.hi), _ptr(a_lo), a.ldp, _ptr(a.meta), _ptr(a.norms),
+        _lib.ctx(_dev(a.hi)), _ptr(a.hi), _ptr(a_lo), a.ldp, _ptr(a.meta), _ptr(a.norms), _ptr(a.row_inv),
         _ptr(b.hi), _ptr(b_lo), b.ldp, _ptr(b.meta), _ptr(b.norms), a.n, b.n, a.d, int(metric), int(id_base),
         _ptr(row_seed), int(cap), _ptr(cv), _ptr(ci), _ptr(cnt), _stream()))
     _count()
@@ -249,7 +302,7 @@ def rescore_select(a_raw: torch.Tensor, b_raw: torch.Tensor, a_op: Operand, b_op
         return val, idx, flag_rows, flag_count
     _lib.check(_lib.load().ise_rescore_select(
         _lib.ctx(_dev(cand_idx)), _ptr(a_raw), DTYPE_F32 if a_raw.dtype == torch.float32 else DTYPE_U8,
-        a_raw.stride(0), _ptr(a_op.meta), _ptr(a_op.norms), _ptr(b_raw), b_raw.stride(0), _ptr(b_op.meta),
+        a_raw.stride(0), _ptr(a_op.meta), _ptr(a_op.norms), _ptr(a_op.row_inv), _ptr(b_raw), b_raw.stride(0), _ptr(b_op.meta),
         _ptr(b_op.norms), m, b_raw.shape[0], a_raw.shape[1], int(metric), kc, int(topk), int(id_base),
         _ptr(row_seed), _ptr(row_count), _ptr(cand_val.contiguous()), _ptr(cand_idx.contiguous()), _ptr(val), _ptr(idx), _ptr(flag_rows),
         _ptr(flag_count), _stream()))
@@ -283,16 +336,14 @@ def search_topk(q_raw: torch.Tensor, a_op: Operand, db_raw: torch.Tensor, b_op: 
     """
     nb = b_op.n
     kc = 32 if k <= 16 else MAX_TOPK
-    a_hi = Operand(a_op.hi, None, a_op.norms, a_op.meta, a_op.n, a_op.d, a_op.ldp)
-    b_hi = Operand(b_op.hi, None, b_op.norms, b_op.meta, b_op.n, b_op.d, b_op.ldp)
+    a_hi, b_hi = a_op.hi_only(), b_op.hi_only()
 
     def rerun_rows(rows, cnt, D, I):
         """Re-runs the flagged rows with the split products (planes gathered, not re-prepared)."""
         nflag = int(cnt.item())                       # 4-byte readback: how many rows need the split path
         if nflag:
             sel = rows[:nflag].to(torch.int64)
-            sub = Operand(a_op.hi.index_select(0, sel), None if a_op.lo is None else a_op.lo.index_select(0, sel),
-                          a_op.norms.index_select(0, sel), a_op.meta, nflag, a_op.d, a_op.ldp)
+            sub = a_op.rows(sel)
             D2, I2 = gemm_select(sub, b_op, metric, k, id_base)
             if need_distances:
                 rescore_topk_(q_raw.index_select(0, sel), db_raw, sub, b_op, metric, D2, I2, id_base)
@@ -508,6 +559,28 @@ def kmeans_accumulate(x: torch.Tensor, assign: torch.Tensor, dis: torch.Tensor |
         _lib.ctx(_dev(x)), _ptr(x), dt, n, d, x.stride(0) if n > 0 else d, _ptr(assign), _ptr(dis),
         _ptr(centroids), int(sums.shape[0]), int(metric), _ptr(sums), _ptr(counts), _ptr(obj), _stream()))
     _count()
+
+
+def kmeans_accumulate_sorted(x: torch.Tensor, assign: torch.Tensor, sums: torch.Tensor, counts: torch.Tensor,
+                             obj: torch.Tensor | None, centroids: torch.Tensor | None = None, metric: int = METRIC_IP,
+                             workspace: torch.Tensor | None = None):
+    """Atomics-free update: counting sort of the rows by centroid + chunked gather-reduce (see include/ise.h).
+    ``workspace``: optional persistent uint8 tensor (grown by the caller across iterations)."""
+    if x.dtype not in (torch.float32, torch.uint8):
+        raise IseError("kmeans_accumulate_sorted: float32 or uint8 rows")
+    dt = DTYPE_F32 if x.dtype == torch.float32 else DTYPE_U8
+    n, d = x.shape
+    k = int(sums.shape[0])
+    assign = assign.reshape(-1)
+    lib, ctx = _lib.load(), _lib.ctx(_dev(x))
+    need = lib.ise_kmeans_accumulate_workspace_bytes(ctx, n, k)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty((max(need, 1),), dtype=torch.uint8, device=x.device)
+    _lib.check(lib.ise_kmeans_accumulate_sorted(
+        ctx, _ptr(x), dt, n, d, x.stride(0) if n > 0 else d, _ptr(assign), _ptr(centroids), k, int(metric), _ptr(sums),
+        _ptr(counts), _ptr(obj), _ptr(workspace), workspace.numel(), _stream()))
+    _count(4)
+    return workspace
 
 
 def kmeans_mean(sums: torch.Tensor, counts: torch.Tensor, centroids: torch.Tensor, n_empty: torch.Tensor):

@@ -65,6 +65,11 @@ def bind_to_gpu_numa(device_index: int) -> list[int] | None:
 class DeviceOps:
     """libise-backed local compute (the product path)."""
 
+    def __init__(self):
+        self._acc_ws = None       # persistent workspace of the sorted-gather update
+        self._stat = None         # 16 device bytes: float64 objective | int32 number of empty clusters
+        self._stat_host = None    # pinned mirror: ONE 16-byte readback per iteration
+
     def device(self):
         return ops.require_cuda()
 
@@ -75,29 +80,45 @@ class DeviceOps:
             t = t.to(torch.float32)
         return t.to(dev, non_blocking=True)
 
-    def prepare(self, x, reuse=False):
-        op = ops.prepare_operand(x)
-        return ops.compact_operand(op) if reuse else op
+    def prepare(self, x, reuse=False, rows=False, reject_nonfinite=False):
+        """rows=True: the row side of a contraction (descriptors / queries): single-pass, per-row scales.
+        reuse=True: one 32-byte readback drops an all-zero lo plane (and can reject NaN / Inf input)."""
+        op = ops.prepare_operand(x, rows=rows)
+        return ops.compact_operand(op, reject_nonfinite=reject_nonfinite) if reuse else op
 
-    def assign(self, x, a_op, cent, metric):
-        return ops.search_topk(x, a_op, cent, ops.prepare_operand(cent), metric, 1, need_distances=False)
+    def new_buffers(self, k, d, dev):
+        """(accum [k*d + k] float32 = the all-reduce payload, sums view, counts view, obj float64[1])."""
+        accum = torch.empty((k * d + k,), dtype=torch.float32, device=dev)
+        self._stat = torch.zeros((16,), dtype=torch.uint8, device=dev)
+        self._stat_host = torch.zeros((16,), dtype=torch.uint8, pin_memory=True)
+        return accum, accum[:k * d].view(k, d), accum[k * d:], self._stat[:8].view(torch.float64)
+
+    def assign(self, x, a_op, cent, metric, precision="verified"):
+        return ops.search_topk(x, a_op, cent, ops.prepare_operand(cent), metric, 1, precision=precision,
+                               need_distances=False)
 
     def accumulate(self, x, assign, dis, sums, counts, obj, cent=None, metric=METRIC_IP):
-        ops.kmeans_accumulate(x, assign, None if cent is not None else dis, sums, counts, obj, centroids=cent,
-                              metric=metric)
+        # ids from the tensor cores; the objective terms are recomputed in exact FP32 inside the update
+        self._acc_ws = ops.kmeans_accumulate_sorted(x, assign, sums, counts, obj, centroids=cent, metric=metric,
+                                                    workspace=self._acc_ws)
 
-    def finalize(self, sums, counts, cent, n_global, spherical):
-        """mean -> split empties (host plan, sequential Faiss RNG) -> renorm.  Returns nsplit."""
-        n_empty = torch.zeros((1,), dtype=torch.int32, device=cent.device)
+    def finalize(self, sums, counts, cent, n_global, spherical, obj):
+        """mean -> split empties (host plan, sequential Faiss RNG) -> renorm.  Returns (nsplit, objective): the
+        objective and the number of empty clusters come back in ONE 16-byte copy, the only host synchronisation
+        of an iteration."""
+        n_empty = self._stat[8:12].view(torch.int32)
         ops.kmeans_mean(sums, counts, cent, n_empty)
+        self._stat_host.copy_(self._stat, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        o = float(self._stat_host[:8].view(torch.float64)[0])
         nsplit = 0
-        if int(n_empty.item()) > 0:
+        if int(self._stat_host[8:12].view(torch.int32)[0]) > 0:
             pairs, _ = ops.split_plan(counts.cpu().numpy(), n_global)
             nsplit = pairs.shape[0]
             ops.kmeans_apply_splits(cent, torch.from_numpy(pairs).to(cent.device))
         if spherical:
             ops.normalize_l2_(cent)
-        return nsplit
+        return nsplit, o
 
     def normalize(self, cent):
         ops.normalize_l2_(cent)
@@ -129,6 +150,79 @@ def shard_bounds(n: int, world: int) -> np.ndarray:
     b = np.zeros(world + 1, dtype=np.int64)
     np.cumsum(sizes, out=b[1:])
     return b
+
+
+def lloyd_train(cp, d, k, x_train, n_train, a_op, lops, *, init_rows, init_centroids=None, allreduce=None,
+                trace=None, precision="verified"):
+    """The Lloyd iterations of faiss Clustering::train (SURVEY appendix A.2, steps 4a-4g) over this process's rows;
+    shared by faiss_compat.Kmeans (one GPU, ``allreduce=None``) and ShardedKmeans (rows split over ranks: ``allreduce``
+    sums the [k*d | k] buffer and the objective across ranks, after which every rank runs the identical finalize).
+
+    ``init_rows(seed)`` -> [k - n_input, d] float32: rows perm[n_input:k] of rand_perm(n_train, seed) (A.2 step 4).
+    Returns (centroids [k, d] on the device, iteration stats)."""
+    dev = x_train.device
+    metric = METRIC_IP if cp.spherical else METRIC_L2
+    if init_centroids is not None:
+        ic = np.ascontiguousarray(init_centroids, dtype=np.float32)[:k]
+        assert ic.shape[1] == d
+    else:
+        ic = np.zeros((0, d), np.float32)
+    n_input = ic.shape[0]
+    accum, sums, counts, obj = lops.new_buffers(k, d, dev)
+    cent = torch.empty((k, d), dtype=torch.float32, device=dev)
+    lower_is_better = not cp.spherical
+    best_obj = float("inf") if lower_is_better else float("-inf")
+    best_cent, best_stats, stats = None, [], []
+    timed = x_train.is_cuda
+    t_start = time.time()
+    for redo in range(cp.nredo):
+        if n_input:
+            cent[:n_input] = torch.from_numpy(ic).to(dev)
+        if n_input < k:
+            cent[n_input:] = init_rows(cp.seed + 1 + redo * 15486557, n_input)
+        if cp.spherical:
+            lops.normalize(cent)
+        o = 0.0
+        for it in range(cp.niter):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timed else None
+            if timed:
+                ev[0].record()
+            dis, assign = lops.assign(x_train, a_op, cent, metric, precision)
+            if timed:
+                ev[1].record()
+            accum.zero_()
+            obj.zero_()
+            lops.accumulate(x_train, assign, dis, sums, counts, obj, cent, metric)
+            if trace is not None:
+                trace.append(dict(redo=redo, it=it, centroids_in=cent.clone(), assign=assign.clone(), dis=dis.clone()))
+            if timed:
+                ev[2].record()
+            if allreduce is not None:
+                allreduce(accum)     # [k*d sums | k counts] in one NCCL all-reduce
+                allreduce(obj)
+            if timed:
+                ev[3].record()
+            t_fin = time.time()
+            nsplit, o = lops.finalize(sums, counts, cent, n_train, cp.spherical, obj)
+            st = dict(obj=o, nsplit=nsplit, time=time.time() - t_start, time_search=0.0, imbalance_factor=float("nan"))
+            if cp.verbose:
+                cs = counts.double()
+                st["imbalance_factor"] = float((cs * cs).sum() * k / (cs.sum() ** 2))
+            if timed:
+                # device time of the three phases of this rank (finalize synchronised the stream) + host wall time of the
+                # finalize (mean, 16-byte readback, Faiss's sequential split_clusters plan when clusters came out empty, renorm)
+                st.update(ms_assign=ev[0].elapsed_time(ev[1]), ms_accumulate=ev[1].elapsed_time(ev[2]),
+                          ms_allreduce=ev[2].elapsed_time(ev[3]), ms_finalize_host=(time.time() - t_fin) * 1e3)
+            stats.append(st)
+            if trace is not None:
+                trace[-1]["centroids_out"] = cent.clone()
+                trace[-1]["nsplit"] = nsplit
+        if cp.nredo > 1:
+            if (lower_is_better and o < best_obj) or (not lower_is_better and o > best_obj):
+                best_cent, best_stats, best_obj = cent.clone(), list(stats), o
+    if cp.nredo > 1:
+        cent, stats = best_cent, best_stats
+    return cent, stats
 
 
 class ShardedKmeans:
@@ -192,7 +286,6 @@ class ShardedKmeans:
             n_train = nsub
         else:
             x_train, n_train = x, n_glob
-        metric = METRIC_IP if cp.spherical else METRIC_L2
         if n_train == k:
             # Clustering::train: as many points as centroids -> the points ARE the centroids, one fake iteration
             cent = self._gather_rows(x, start, np.arange(n_glob, dtype=np.int64))
@@ -203,64 +296,17 @@ class ShardedKmeans:
                 self.index = IndexFlatIP(d) if cp.spherical else IndexFlatL2(d)
                 self.index.add(cent)
             return 0.0
-        a_op = lops.prepare(x_train, reuse=True)
-        if init_centroids is not None:
-            ic = np.ascontiguousarray(init_centroids, dtype=np.float32)[:k]
-        else:
-            ic = np.zeros((0, d), np.float32)
-        n_input = ic.shape[0]
-        dev = x.device
-        accum = torch.empty((k * d + k,), dtype=torch.float32, device=dev)
-        sums, counts = accum[:k * d].view(k, d), accum[k * d:]
-        obj = torch.zeros((1,), dtype=torch.float64, device=dev)
-        cent = torch.empty((k, d), dtype=torch.float32, device=dev)
-        lower_is_better = not cp.spherical
-        best_obj = float("inf") if lower_is_better else float("-inf")
-        best_cent, best_stats, stats = None, [], []
-        t_start = time.time()
-        for redo in range(cp.nredo):
-            if n_input:
-                cent[:n_input] = torch.from_numpy(ic).to(dev)
-            if n_input < k:
-                perm = ops.rand_perm_prefix(n_train, cp.seed + 1 + redo * 15486557, k)[n_input:k]
-                gids = sub_ids[perm] if sub_ids is not None else perm
-                cent[n_input:] = self._gather_rows(x, start, gids)
-            if cp.spherical:
-                lops.normalize(cent)
-            o = 0.0
-            for it in range(cp.niter):
-                timed = x.is_cuda
-                ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timed else None
-                if timed:
-                    ev[0].record()
-                dis, assign = lops.assign(x_train, a_op, cent, metric)
-                if timed:
-                    ev[1].record()
-                accum.zero_()
-                obj.zero_()
-                lops.accumulate(x_train, assign, dis, sums, counts, obj, cent, metric)
-                if timed:
-                    ev[2].record()
-                self._allreduce(accum)     # [k*d sums | k counts] in one NCCL all-reduce
-                self._allreduce(obj)
-                if timed:
-                    ev[3].record()
-                    torch.cuda.current_stream().synchronize()    # finalize reads n_empty back anyway
-                t_fin = time.time()
-                nsplit = lops.finalize(sums, counts, cent, n_train, cp.spherical)
-                o = float(obj.item())
-                st = dict(obj=o, nsplit=nsplit, time=time.time() - t_start)
-                if timed:
-                    # device time of the three phases of this rank + host wall time of the finalize (mean, Faiss's
-                    # sequential split_clusters plan on the CPU when clusters came out empty, renorm)
-                    st.update(ms_assign=ev[0].elapsed_time(ev[1]), ms_accumulate=ev[1].elapsed_time(ev[2]),
-                              ms_allreduce=ev[2].elapsed_time(ev[3]), ms_finalize_host=(time.time() - t_fin) * 1e3)
-                stats.append(st)
-            if cp.nredo > 1:
-                if (lower_is_better and o < best_obj) or (not lower_is_better and o > best_obj):
-                    best_cent, best_stats, best_obj = cent.clone(), list(stats), o
-        if cp.nredo > 1:
-            cent, stats = best_cent, best_stats
+        if isinstance(lops, DeviceOps) and k >= 1024:
+            ops.split_plan_warm(min(k * 2048, 1 << 28))
+        a_op = lops.prepare(x_train, reuse=True, rows=True, reject_nonfinite=True)
+
+        def init_rows(seed, n_input):
+            perm = ops.rand_perm_prefix(n_train, seed, k)[n_input:k]
+            gids = sub_ids[perm] if sub_ids is not None else perm
+            return self._gather_rows(x, start, gids)
+
+        cent, stats = lloyd_train(cp, d, k, x_train, n_train, a_op, lops, init_rows=init_rows,
+                                  init_centroids=init_centroids, allreduce=self._allreduce if world > 1 else None)
         self.centroids = cent.cpu().numpy()
         self.iteration_stats = stats
         self.obj = np.array([s["obj"] for s in stats])
@@ -296,7 +342,7 @@ class ShardedIndexFlat:
         self.id_base = int(sizes[:rank].sum())
         self.ntotal = int(sizes.sum())
         self._local = x
-        self._b_op = self.lops.prepare(x, reuse=True)
+        self._b_op = self.lops.prepare(x, reuse=True, rows=False)
         if isinstance(self.lops, DeviceOps):
             ops.attach_sample(self._b_op)
 
@@ -318,7 +364,7 @@ class ShardedIndexFlat:
             D = torch.full((nq, k), pad, dtype=torch.float32, device=qd.device)
             I = torch.full((nq, k), -1, dtype=torch.int64, device=qd.device)
         else:
-            D, I = self.lops.search(qd, self.lops.prepare(qd), self._local, self._b_op, self.metric_type, k, self.id_base)
+            D, I = self.lops.search(qd, self.lops.prepare(qd, rows=True), self._local, self._b_op, self.metric_type, k, self.id_base)
         if world == 1:
             return D, I
         per = -(-nq // world)                       # queries per merging rank (last slices padded)

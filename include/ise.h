@@ -65,6 +65,10 @@ int ise_rand_perm_prefix(int64_t n, int64_t seed, int64_t m, int64_t* out_host);
  * ordered list of (empty ci, donor cj) pairs with RandomGenerator(1234).  pairs_host: int32[2*k].
  * Returns the number of splits in *nsplit. */
 int ise_split_plan(float* hassign_host, int64_t k, int64_t n, int32_t* pairs_host, int32_t* nsplit);
+/* split_clusters re-seeds mt19937(1234) on every call, so libise keeps a process-wide sparse index of that stream
+ * (the draws small enough to ever accept a donor); this starts generating its first n_draws entries in a background
+ * thread and returns at once.  Optional: ise_split_plan extends the index itself when it runs past it. */
+int ise_split_plan_warm(int64_t n_draws);
 
 /* ---- operand preparation --------------------------------------------------------------
  * The distance contractions run on the tcgen05 tensor cores as FP16 "hi + lo" split
@@ -78,6 +82,21 @@ int ise_split_plan(float* hassign_host, int64_t k, int64_t n, int32_t* pairs_hos
 int ise_prepare_planes(ise_ctx* ctx, const void* x, int dtype, int64_t n, int d, int64_t ldx,
                        void* hi, void* lo, int64_t ldp, float* norms, float* meta, void* stream);
 
+/* ROW operands (descriptor rows of an assign, query rows of a search) in ONE pass over x: every row gets its own
+ * power-of-two scale (row_inv[n] = 1 / scale; meta's scale fields are 1), so no absmax pre-pass is needed -- the
+ * selection epilogue owns one row per thread and rescales its accumulator by that row's factor.  Rows whose lo part is
+ * all zero skip the lo store (lo_skipped[n]: device scratch bytes, required when lo != NULL).  meta[7] != 0 reports
+ * NaN / Inf in x (faiss.Kmeans.train refuses such input, kmeans_faiss.py:41).  Pass row_inv as a_row_inv to
+ * ise_gemm_select / ise_gemm_collect / ise_rescore_select.  Replaces the host-side `X.astype(np.float32)` of
+ * kmeans_faiss.py:41,49 for the row side. */
+int ise_prepare_rows(ise_ctx* ctx, const void* x, int dtype, int64_t n, int d, int64_t ldx,
+                     void* hi, void* lo, int64_t ldp, float* norms, float* row_inv, uint8_t* lo_skipped,
+                     float* meta, void* stream);
+
+/* One read-only pass over a float32 matrix: meta[3] = max |x|, meta[7] != 0 when it holds a NaN or an Inf (Faiss's
+ * Clustering::train validates ALL of its input before sub-sampling it, kmeans_faiss.py:41). */
+int ise_scan_f32(ise_ctx* ctx, const float* x, int64_t n, int d, int64_t ldx, float* meta, void* stream);
+
 /* faiss.normalize_L2 (utils.py:303, engine.py:53, siamese/test_index.py:53): in place,
  * x *= 1/sqrtf(sum x^2) for rows with non-zero norm. */
 int ise_normalize_l2(ise_ctx* ctx, float* x, int64_t n, int d, void* stream);
@@ -90,6 +109,7 @@ int ise_normalize_l2(ise_ctx* ctx, float* x, int64_t n, int d, void* stream);
  * Output rows are sorted best-first; when topk > n the tail is id -1 / -+FLT_MAX like Faiss.
  * a_lo / b_lo may be NULL when the corresponding meta says lo_nonzero == 0 (exact operand).
  * a_norms / b_norms are required for L2 only.  out ids = column + id_base.
+ * a_row_inv (nullable): per-row 1 / scale of the A planes from ise_prepare_rows (overrides a_meta's scale).
  * row_seed (nullable, topk > 1): per-row score of a column known to exist (IP score / L2 distance, e.g. the
  * best hit in a column sample); only columns strictly better than it are kept, so lists may come back
  * shorter than topk (padded with id -1).  It removes nearly all selection traffic from the epilogue.
@@ -103,6 +123,7 @@ int ise_normalize_l2(ise_ctx* ctx, float* x, int64_t n, int d, void* stream);
 size_t ise_gemm_select_workspace_bytes(ise_ctx* ctx, int64_t m, int64_t n, int d, int topk);
 int ise_gemm_select(ise_ctx* ctx,
                     const void* a_hi, const void* a_lo, int64_t lda, const float* a_meta, const float* a_norms,
+                    const float* a_row_inv,
                     const void* b_hi, const void* b_lo, int64_t ldb, const float* b_meta, const float* b_norms,
                     int64_t m, int64_t n, int d, int metric, int topk, int64_t id_base,
                     const float* row_seed, int32_t* flag_rows, int32_t* flag_count,
@@ -116,6 +137,7 @@ int ise_gemm_select(ise_ctx* ctx,
  * ise_gemm_select. */
 int ise_gemm_collect(ise_ctx* ctx,
                      const void* a_hi, const void* a_lo, int64_t lda, const float* a_meta, const float* a_norms,
+                     const float* a_row_inv,
                      const void* b_hi, const void* b_lo, int64_t ldb, const float* b_meta, const float* b_norms,
                      int64_t m, int64_t n, int d, int metric, int64_t id_base, const float* row_seed, int cap,
                      float* cand_val, int64_t* cand_idx, int32_t* row_count, void* stream);
@@ -157,7 +179,7 @@ int ise_rescore_topk(ise_ctx* ctx, const void* a, int a_dtype, int64_t lda, cons
  * row_seed (nullable): the seed the coarse call was given; it then also bounds the unseen columns.
  * row_count (nullable): candidates come from ise_gemm_collect (unsorted, kc = cap <= 1024). */
 int ise_rescore_select(ise_ctx* ctx, const void* a, int a_dtype, int64_t lda, const float* a_meta,
-                       const float* a_norms, const float* b, int64_t ldb, const float* b_meta,
+                       const float* a_norms, const float* a_row_inv, const float* b, int64_t ldb, const float* b_meta,
                        const float* b_norms, int64_t m, int64_t n, int d, int metric, int kc, int topk,
                        int64_t id_base, const float* row_seed, const int32_t* row_count,
                        const float* cand_val, const int64_t* cand_idx,
@@ -179,6 +201,16 @@ int ise_topk_merge(ise_ctx* ctx, const float* val_parts, const int64_t* idx_part
 int ise_kmeans_accumulate(ise_ctx* ctx, const void* x, int dtype, int64_t n, int d, int64_t ldx,
                           const int64_t* assign, const float* dis, const float* centroids, int64_t k, int metric,
                           float* sums, float* counts, double* obj, void* stream);
+/* Same contract, atomics-free: the rows are grouped by centroid with a counting sort (ids -> histogram -> scan ->
+ * scatter of (centroid, row) pairs), the sorted list is cut into fixed 64-row chunks and each chunk is gathered with
+ * 128-bit loads and summed in registers, one vector reduction per lane per run of equal ids (C2: ~1.3 per 64 rows
+ * instead of 64).  Objective always recomputed from `centroids` (nullable: no objective).  Falls back to
+ * ise_kmeans_accumulate for rows that are not 4-column aligned.  workspace: ise_kmeans_accumulate_workspace_bytes. */
+size_t ise_kmeans_accumulate_workspace_bytes(ise_ctx* ctx, int64_t n, int64_t k);
+int ise_kmeans_accumulate_sorted(ise_ctx* ctx, const void* x, int dtype, int64_t n, int d, int64_t ldx,
+                                 const int64_t* assign, const float* centroids, int64_t k, int metric,
+                                 float* sums, float* counts, double* obj,
+                                 void* workspace, size_t workspace_bytes, void* stream);
 /* centroids = sums / counts for non-empty clusters (empty rows stay zero); n_empty[0] = #empty */
 int ise_kmeans_mean(ise_ctx* ctx, const float* sums, const float* counts, int64_t k, int d,
                     float* centroids, int32_t* n_empty, void* stream);

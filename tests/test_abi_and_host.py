@@ -224,3 +224,40 @@ def test_okapi_params_and_opt_in_flags():
     assert OkapiTransformer(compat=False, norm=None)._norm_code() == 0
     with pytest.raises(ValueError):
         OkapiTransformer(compat=False, norm="max")._norm_code()
+
+
+def test_split_plan_sparse_stream_index_equals_dense_scan(monkeypatch):
+    """Large codebook regime (k = 65 536, C4): the plan walks the cached sparse index of the mt19937(1234) stream; it
+    must take exactly the decisions of the draw-by-draw scan (ISE_SPLIT_PLAN_DENSE=1), on a cold index, on a warm
+    one, after the background warm-up, and when a later call needs more of the stream than an earlier one."""
+    import time
+    from image_search_engine_b200 import _lib, ops
+    rng = np.random.default_rng(65536)
+    k = 65536
+    h = rng.poisson(150, k).astype(np.float32) + 2
+    h[rng.choice(k, 40, replace=False)] *= 20                     # a few big clusters (still p_max < 2^-8)
+    n = 10_000_000
+
+    def plan(n_empty, dense):
+        hh = h.copy()
+        hh[np.random.default_rng(n_empty).choice(k, n_empty, replace=False)] = 0
+        if dense:
+            monkeypatch.setenv("ISE_SPLIT_PLAN_DENSE", "1")
+        else:
+            monkeypatch.delenv("ISE_SPLIT_PLAN_DENSE", raising=False)
+        t0 = time.perf_counter()
+        pairs, h_new = ops.split_plan(hh, n)
+        return pairs, h_new, time.perf_counter() - t0
+
+    p_small, h_small, t_cold = plan(30, dense=False)             # cold index: generates ~2 M draws
+    _lib.check(_lib.load().ise_split_plan_warm(40_000_000))       # background warm-up, returns at once
+    p_big, h_big, _ = plan(400, dense=False)                      # needs ~26 M draws: extends / waits for the warm-up
+    p_big2, h_big2, t_warm = plan(400, dense=False)               # fully cached now
+    d_small, dh_small, _ = plan(30, dense=True)
+    d_big, dh_big, t_dense = plan(400, dense=True)
+    assert p_small.shape == (30, 2) and p_big.shape == (400, 2)
+    assert np.array_equal(p_small, d_small) and np.array_equal(h_small, dh_small)
+    assert np.array_equal(p_big, d_big) and np.array_equal(h_big, dh_big)
+    assert np.array_equal(p_big, p_big2) and np.array_equal(h_big, h_big2)
+    print(f"split plan, k=65536, 400 splits: dense scan {t_dense * 1e3:.1f} ms, cached sparse index {t_warm * 1e3:.2f} ms")
+    assert t_warm < t_dense

@@ -393,8 +393,8 @@ def test_empty_and_degenerate_inputs(g):
     assert D.shape == (25, 200) and (I[:, 40:] == -1).all() and (I[:, 0] == np.arange(25)).all()
     big = faiss_compat.IndexFlatIP(8)
     big.add(np.random.default_rng(0).standard_normal((500, 8)).astype(np.float32))
-    with pytest.raises(IseError):
-        big.search(np.zeros((30, 8), np.float32), 129)                      # beyond the fused top-k limit
+    D, I = big.search(np.zeros((30, 8), np.float32), 129)                   # beyond the fused top-k limit: any k works
+    assert D.shape == (30, 129) and (I >= 0).all() and (I[0] == np.arange(129)).all()   # all-equal scores: id order
     one = faiss_compat.IndexFlatL2(1)                                       # d = 1 (padded to 8 internally)
     one.add(np.arange(100, dtype=np.float32).reshape(-1, 1))
     D, I = one.search(np.full((25, 1), 41.3, np.float32), 3)

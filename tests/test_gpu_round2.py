@@ -174,3 +174,166 @@ def test_sharded_index_small_batches_and_empty_shard():
     empty.add_local(np.zeros((0, 40), np.float32))
     D, I = empty.search(q, 5)
     assert (I.cpu().numpy() == -1).all() and (D.cpu().numpy() == np.finfo(np.float32).max).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# single-pass row preparation (per-row power-of-two scales) and the atomics-free k-means update
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d", [128, 32, 100, 256, 512, 640, 30])
+def test_prepare_rows_single_pass(d):
+    """Row operands: every row is scaled by its own power of two; hi + lo reconstruct the row to ~22 bits, norms are the
+    exact FP32 sums, pad columns are zero, NaN / Inf are reported.  d = 640 (> 512) and d = 30 (not a multiple of 4)
+    fall back to the two-pass kernels and must satisfy the same contract."""
+    from image_search_engine_b200 import ops
+    dev = ops.require_cuda()
+    rng = np.random.default_rng(d)
+    x = (rng.standard_normal((3001, d)) * np.exp2(rng.integers(-12, 12, (3001, 1)))).astype(np.float32)
+    x[5] = 0                                              # an all-zero row keeps scale 1
+    op = ops.prepare_operand(torch.from_numpy(x).to(dev), rows=True)
+    assert op.row_inv is not None and op.lo is not None
+    inv = op.row_inv.cpu().numpy()
+    assert (inv == np.exp2(np.round(np.log2(inv)))).all()                  # powers of two
+    scaled_max = np.abs(x).max(1) / inv
+    single_pass = d % 4 == 0 and d <= 512
+    if single_pass:
+        nz = np.abs(x).max(1) > 0
+        assert ((scaled_max[nz] >= 8192) & (scaled_max[nz] < 16384)).all() and inv[5] == 1.0
+        assert float(op.meta[0]) == 1.0 and float(op.meta[1]) == 1.0
+    rec = (op.hi.float() + op.lo.float()).cpu().numpy()[:, :d] * inv[:, None]
+    assert (np.abs(rec - x) <= np.abs(x).max(1, keepdims=True) * 2.0 ** -21 + 1e-30).all()
+    assert (op.hi.cpu().numpy()[:, d:] == 0).all()
+    np.testing.assert_allclose(op.norms.cpu().numpy(), (x.astype(np.float64) ** 2).sum(1), rtol=2e-6)
+    assert float(op.meta[2]) == 1.0 and float(op.meta[7]) == 0.0
+    np.testing.assert_allclose(float(op.meta[4]), (x.astype(np.float64) ** 2).sum(1).max(), rtol=2e-6)
+    for bad in (np.nan, np.inf, -np.inf):
+        y = x.copy()
+        y[1234, d // 2] = bad
+        assert float(ops.prepare_operand(torch.from_numpy(y).to(dev), rows=True).meta[7]) != 0.0
+        assert ops.has_nonfinite(torch.from_numpy(y).to(dev)) and not ops.has_nonfinite(torch.from_numpy(x).to(dev))
+
+
+def test_prepare_rows_exact_rows_skip_their_lo_store():
+    """Integer-valued rows are exact in one plane: no lo store at all when every row is (LO_NONZERO stays 0); when
+    only SOME rows are, the skipped rows' lo parts are zeroed by the fix-up so the plane can be read as a whole."""
+    from image_search_engine_b200 import ops
+    dev = ops.require_cuda()
+    rng = np.random.default_rng(77)
+    s = sift_like(rng, 20000, 128)
+    for _ in range(2):
+        poison = torch.full((20000, 128), float("nan"), dtype=torch.float16, device=dev)
+        del poison
+        op = ops.prepare_operand(torch.from_numpy(s).to(dev), rows=True)
+    assert float(op.meta[2]) == 0.0
+    inv = op.row_inv.cpu().numpy()
+    assert np.array_equal(op.hi.float().cpu().numpy() * inv[:, None], s)
+    assert ops.compact_operand(op).lo is None
+    mixed = s.copy()
+    mixed[::7] += rng.standard_normal((len(mixed[::7]), 128)).astype(np.float32) * 0.37
+    for _ in range(2):
+        poison = torch.full((20000, 128), float("nan"), dtype=torch.float16, device=dev)
+        del poison
+        om = ops.prepare_operand(torch.from_numpy(mixed).to(dev), rows=True)
+    assert float(om.meta[2]) == 1.0
+    lo = om.lo.float().cpu().numpy()
+    assert not np.isnan(lo).any()
+    exact_rows = np.ones(20000, bool)
+    exact_rows[::7] = False
+    assert (lo[exact_rows] == 0).all() and (np.abs(lo[~exact_rows]).max(1) > 0).all()
+    rec = (om.hi.float().cpu().numpy() + lo) * om.row_inv.cpu().numpy()[:, None]
+    assert (np.abs(rec - mixed) <= np.abs(mixed).max(1, keepdims=True) * 2.0 ** -21).all()
+
+
+@pytest.mark.parametrize("metric_ip", [True, False])
+@pytest.mark.parametrize("m,n,d,k,kind", [(3000, 4096, 128, 1, "sift"), (2000, 700, 64, 1, "scaled"), (500, 30000, 96, 10, "scaled"),
+                                           (300, 70000, 128, 40, "unit"), (150, 5000, 512, 100, "scaled")])
+def test_row_scaled_operands_through_the_search_paths(metric_ip, m, n, d, k, kind):
+    """gemm_select / gemm_collect / rescore_select with per-row scales on the A side: rows of wildly different magnitude
+    (2^-10 .. 2^10) must come out with the oracle's ids and real-unit distances."""
+    from image_search_engine_b200 import ops
+    from image_search_engine_b200._lib import METRIC_IP, METRIC_L2
+    from oracle import faiss_shim as fs
+    dev = ops.require_cuda()
+    rng = np.random.default_rng(m + n + d + k)
+    db = unit_rows(rng, n, d)
+    if kind == "sift":
+        q = sift_like(rng, m, d)
+    else:
+        q = db[rng.integers(0, n, m)] + 0.05 * rng.standard_normal((m, d)).astype(np.float32)
+        if kind == "scaled":
+            q = (q * np.exp2(rng.integers(-10, 10, (m, 1)))).astype(np.float32)
+    qd, dbd = torch.from_numpy(q).to(dev), torch.from_numpy(db).to(dev)
+    a = ops.prepare_operand(qd, rows=True)
+    b = ops.attach_sample(ops.prepare_operand(dbd))
+    metric = METRIC_IP if metric_ip else METRIC_L2
+    Dr, Ir = fs.knn(q, db, k, fs.METRIC_INNER_PRODUCT if metric_ip else fs.METRIC_L2)
+    for precision in ("verified", "split"):
+        D, I = ops.search_topk(qd, a, dbd, b, metric, k, precision=precision)
+        assert_topk_parity(I.cpu().numpy(), Ir, q, db, metric_ip, max_mismatch_frac=0.05)
+        scale_tol = 1e-4 * np.abs(Dr).max(1, keepdims=True) + 1e-6
+        assert (np.abs(D.cpu().numpy() - Dr) <= 1e-4 * np.abs(Dr) + scale_tol).all(), precision
+    # raw kernel output (no exact re-score): the accumulator is rescaled by the row's own factor
+    val, idx = ops.gemm_select(a, b, metric, min(k, 32))
+    kk = min(k, 32)
+    tol = 2e-3 * (np.abs(Dr[:, :kk]) + (np.linalg.norm(q, axis=1, keepdims=True) ** 2 if not metric_ip else 0)) + 1e-6
+    assert (np.abs(val.cpu().numpy() - Dr[:, :kk]) <= tol).all()
+
+
+@pytest.mark.parametrize("metric_ip", [True, False])
+@pytest.mark.parametrize("n,d,k,kind", [(50000, 128, 4096, "sift"), (30000, 32, 512, "orb"), (20000, 64, 300, "float"),
+                                          (9000, 256, 1000, "float"), (6000, 100, 64, "float"), (40000, 128, 20000, "sift"),
+                                          (3000, 8, 16, "float"), (5000, 2048, 40, "float"), (700, 30, 9, "float")])
+def test_sorted_gather_accumulate_equals_oracle(metric_ip, n, d, k, kind):
+    """Counting sort + chunked gather-reduce vs a float64 scatter-add: counts exact, sums / objective within FP32
+    reassociation.  k = 20000 takes the global-atomic histogram (no shared-memory bins); d = 30 (rows not 4-column
+    aligned) falls back to the atomic kernel; two calls into the same buffers add up (shards / ranks)."""
+    from image_search_engine_b200 import ops
+    from image_search_engine_b200._lib import METRIC_IP, METRIC_L2
+    dev = ops.require_cuda()
+    rng = np.random.default_rng(n + d + k)
+    x = orb_like_(rng, n, d) if kind == "orb" else sift_like(rng, n, d) if kind == "sift" else \
+        rng.standard_normal((n, d)).astype(np.float32)
+    assign = rng.integers(0, max(1, k - 3), n).astype(np.int64)      # last 3 clusters stay empty
+    assign[: n // 10] = assign[0]                                     # one big cluster: long runs, many chunks
+    cent = unit_rows(rng, k, d)
+    xf = x.astype(np.float32)
+    sums_ref = np.zeros((k, d), np.float64)
+    np.add.at(sums_ref, assign, xf.astype(np.float64))
+    counts_ref = np.bincount(assign, minlength=k).astype(np.float32)
+    c64 = cent.astype(np.float64)[assign]
+    obj_ref = float((xf * c64).sum()) if metric_ip else float(((xf - c64) ** 2).sum())
+    xd, ad, cd = torch.from_numpy(x).to(dev), torch.from_numpy(assign).to(dev), torch.from_numpy(cent).to(dev)
+    accum = torch.zeros(k * d + k, device=dev)
+    sums, counts = accum[:k * d].view(k, d), accum[k * d:]
+    obj = torch.zeros(1, dtype=torch.float64, device=dev)
+    metric = METRIC_IP if metric_ip else METRIC_L2
+    ws = ops.kmeans_accumulate_sorted(xd, ad, sums, counts, obj, centroids=cd, metric=metric)
+    assert np.array_equal(counts.cpu().numpy(), counts_ref)
+    np.testing.assert_allclose(sums.cpu().numpy(), sums_ref, rtol=2e-5, atol=2e-5 * np.abs(sums_ref).max())
+    assert abs(float(obj.item()) - obj_ref) <= 1e-5 * abs(obj_ref) + 1e-3
+    half = n // 2                                                      # second call: buffers accumulate, workspace reused
+    accum.zero_()
+    obj.zero_()
+    ws = ops.kmeans_accumulate_sorted(xd[:half], ad[:half], sums, counts, obj, centroids=cd, metric=metric, workspace=ws)
+    ops.kmeans_accumulate_sorted(xd[half:], ad[half:], sums, counts, obj, centroids=cd, metric=metric, workspace=ws)
+    assert np.array_equal(counts.cpu().numpy(), counts_ref)
+    np.testing.assert_allclose(sums.cpu().numpy(), sums_ref, rtol=2e-5, atol=2e-5 * np.abs(sums_ref).max())
+    assert abs(float(obj.item()) - obj_ref) <= 1e-5 * abs(obj_ref) + 1e-3
+
+
+def orb_like_(rng, n, d):
+    return rng.integers(0, 256, size=(n, d), dtype=np.uint8)
+
+
+def test_kmeans_train_rejects_nonfinite_and_warms_the_split_stream():
+    from image_search_engine_b200 import FaissKMeans
+    rng = np.random.default_rng(9)
+    x = sift_like(rng, 6000, 32)
+    FaissKMeans(16, n_init=1, max_iter=2).fit(x)
+    y = x.copy()
+    y[4321, 7] = np.nan
+    with pytest.raises(RuntimeError, match="NaN"):
+        FaissKMeans(16, n_init=1, max_iter=2).fit(y)
+    big = np.tile(x, (2, 1))                                       # 12000 rows > 256 * 16: the sub-sampled path validates ALL rows
+    big[11999, 0] = np.inf
+    with pytest.raises(RuntimeError, match="NaN"):
+        FaissKMeans(16, n_init=1, max_iter=2).fit(big)

@@ -23,10 +23,14 @@ class OracleOps:
         t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
         return t if t.dtype in (torch.float32, torch.uint8) else t.to(torch.float32)
 
-    def prepare(self, x, reuse=False):
+    def prepare(self, x, reuse=False, rows=False, reject_nonfinite=False):
         return x
 
-    def assign(self, x, a_op, cent, metric):
+    def new_buffers(self, k, d, dev):
+        accum = torch.empty((k * d + k,), dtype=torch.float32)
+        return accum, accum[:k * d].view(k, d), accum[k * d:], torch.zeros((1,), dtype=torch.float64)
+
+    def assign(self, x, a_op, cent, metric, precision="verified"):
         D, I = fs.knn(a_op.numpy().astype(np.float32), cent.numpy(), 1, metric)
         return torch.from_numpy(D), torch.from_numpy(I)
 
@@ -36,7 +40,7 @@ class OracleOps:
         np.add.at(sums.numpy(), a, x.numpy().astype(np.float32))
         obj += float(dis.numpy().astype(np.float64).sum())
 
-    def finalize(self, sums, counts, cent, n_global, spherical):
+    def finalize(self, sums, counts, cent, n_global, spherical, obj):
         c, h = cent.numpy(), counts.numpy().copy()
         c[:] = 0
         nz = h != 0
@@ -44,7 +48,7 @@ class OracleOps:
         ns = fs.split_clusters(c.shape[1], c.shape[0], n_global, h, c)
         if spherical:
             fs.normalize_L2(c)
-        return ns
+        return ns, float(obj.item())
 
     def normalize(self, cent):
         fs.normalize_L2(cent.numpy())
