@@ -1,6 +1,11 @@
 // Context, error plumbing and the host-side sequential-RNG helpers of libise.
 #include <stdlib.h>
+#include <string.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <random>
@@ -275,5 +280,99 @@ ISE_EXPORT int ise_split_plan(float* hassign, int64_t k, int64_t n, int32_t* pai
         ns++;
     }
     *nsplit = ns;
+    return 0;
+}
+
+// ---- ragged ingestion: list of per-image descriptor arrays -> one packed (pinned) matrix ------------------------------
+// The reference's input contract is a Python list with one (n_i, d) array per image (descriptors.py:104-139); its
+// run_clustering does one single-threaded np.concatenate (bag_of_visual_words.py:128).  This is the same copy,
+// spread over host threads, straight into the caller's pinned staging buffer, optionally narrowing float32 -> uint8
+// on the way when every value is an integer in [0, 255] (OpenCV SIFT / ORB-as-float descriptors are): a quarter of
+// the host -> device bytes, and the device path widens uint8 for free.
+namespace {
+// returns false as soon as a value is not exactly representable as uint8
+inline bool narrow_f32_to_u8_scalar(const float* src, uint8_t* dst, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) {
+        const float v = src[i];
+        if (!(v >= 0.f && v <= 255.f)) return false;
+        const int q = (int)v;
+        if ((float)q != v) return false;
+        dst[i] = (uint8_t)q;
+    }
+    return true;
+}
+
+#if defined(__x86_64__)
+// 32 floats per step: truncate, compare back (exact integers only), range-check via the packed saturations
+__attribute__((target("avx2"))) bool narrow_f32_to_u8_avx2(const float* src, uint8_t* dst, int64_t n) {
+    int64_t i = 0;
+    const __m256i perm = _mm256_setr_epi32(0, 4, 1, 5, 2, 6, 3, 7);
+    for (; i + 32 <= n; i += 32) {
+        const __m256 a = _mm256_loadu_ps(src + i), b = _mm256_loadu_ps(src + i + 8);
+        const __m256 c = _mm256_loadu_ps(src + i + 16), e = _mm256_loadu_ps(src + i + 24);
+        const __m256i qa = _mm256_cvttps_epi32(a), qb = _mm256_cvttps_epi32(b);
+        const __m256i qc = _mm256_cvttps_epi32(c), qe = _mm256_cvttps_epi32(e);
+        // exact integer <=> converting back gives the same float (NaN / out-of-range values fail the compare)
+        __m256 ok = _mm256_and_ps(_mm256_and_ps(_mm256_cmp_ps(_mm256_cvtepi32_ps(qa), a, _CMP_EQ_OQ),
+                                                _mm256_cmp_ps(_mm256_cvtepi32_ps(qb), b, _CMP_EQ_OQ)),
+                                  _mm256_and_ps(_mm256_cmp_ps(_mm256_cvtepi32_ps(qc), c, _CMP_EQ_OQ),
+                                                _mm256_cmp_ps(_mm256_cvtepi32_ps(qe), e, _CMP_EQ_OQ)));
+        // [0, 255] <=> no bit above the low byte
+        const __m256i hi_bits = _mm256_or_si256(_mm256_or_si256(qa, qb), _mm256_or_si256(qc, qe));
+        const __m256i in_range = _mm256_cmpeq_epi32(_mm256_srli_epi32(hi_bits, 8), _mm256_setzero_si256());
+        if (_mm256_movemask_ps(_mm256_and_ps(ok, _mm256_castsi256_ps(in_range))) != 0xFF) return false;
+        const __m256i w0 = _mm256_packus_epi32(qa, qb), w1 = _mm256_packus_epi32(qc, qe);   // per 128-bit lane
+        const __m256i bytes = _mm256_permutevar8x32_epi32(_mm256_packus_epi16(w0, w1), perm);
+        _mm256_storeu_si256(reinterpret_cast<__m256i*>(dst + i), bytes);
+    }
+    return narrow_f32_to_u8_scalar(src + i, dst + i, n - i);
+}
+#endif
+
+inline bool narrow_f32_to_u8(const float* src, uint8_t* dst, int64_t n) {
+#if defined(__x86_64__)
+    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    if (have_avx2) return narrow_f32_to_u8_avx2(src, dst, n);
+#endif
+    return narrow_f32_to_u8_scalar(src, dst, n);
+}
+}  // namespace
+
+ISE_EXPORT int ise_pack_rows(const void* const* srcs, const int64_t* offsets, int64_t i0, int64_t i1, int d,
+                             int src_dtype, int dst_dtype, void* dst_base, int nthreads, int* ok_out) {
+    ISE_CHECK_ARG(srcs && offsets && dst_base && ok_out && d > 0 && i0 >= 0 && i1 >= i0);
+    ISE_CHECK_ARG(src_dtype == ISE_DTYPE_F32 || src_dtype == ISE_DTYPE_U8);
+    ISE_CHECK_ARG(dst_dtype == ISE_DTYPE_F32 || dst_dtype == ISE_DTYPE_U8);
+    ISE_CHECK_ARG(!(src_dtype == ISE_DTYPE_U8 && dst_dtype == ISE_DTYPE_F32));     // widening happens on the device
+    *ok_out = 1;
+    if (i1 == i0) return 0;
+    const size_t src_elt = src_dtype == ISE_DTYPE_F32 ? 4 : 1, dst_elt = dst_dtype == ISE_DTYPE_F32 ? 4 : 1;
+    const int64_t total_rows = offsets[i1] - offsets[i0];
+    int nt = std::max(1, std::min<int>(nthreads, 64));
+    if (total_rows * d < (int64_t)1 << 16) nt = 1;
+    std::atomic<int> ok{1};
+    auto work = [&](int t) {
+        // contiguous image ranges balanced by row count
+        const int64_t r_lo = offsets[i0] + total_rows * t / nt, r_hi = offsets[i0] + total_rows * (t + 1) / nt;
+        int64_t a = std::lower_bound(offsets + i0, offsets + i1, r_lo) - offsets;
+        int64_t b = std::lower_bound(offsets + i0, offsets + i1, r_hi) - offsets;
+        if (t == nt - 1) b = i1;
+        for (int64_t i = a; i < b && ok.load(std::memory_order_relaxed); ++i) {
+            const int64_t rows = offsets[i + 1] - offsets[i];
+            if (rows <= 0) continue;
+            uint8_t* dst = (uint8_t*)dst_base + (size_t)offsets[i] * d * dst_elt;
+            if (src_dtype == dst_dtype) memcpy(dst, srcs[i], (size_t)rows * d * src_elt);
+            else if (!narrow_f32_to_u8((const float*)srcs[i], dst, rows * d)) ok.store(0);
+        }
+    };
+    if (nt == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        th.reserve(nt);
+        for (int t = 0; t < nt; ++t) th.emplace_back(work, t);
+        for (auto& x : th) x.join();
+    }
+    *ok_out = ok.load();
     return 0;
 }

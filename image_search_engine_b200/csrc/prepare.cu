@@ -237,6 +237,38 @@ __global__ void __launch_bounds__(kThreads, EXACT ? 5 : 3) prepare_planes_f32x4_
 // written per element.  Rows whose lo part is all zero skip the lo store (integer-valued SIFT / ORB-as-float: all of
 // them); they are recorded in lo_skipped[] and zeroed by lo_fixup_kernel only if some other row did need its lo plane.
 // NaN / Inf are detected on the way (meta[NONFINITE]) so that k-means training needs no separate validation pass.
+// sums of R per-lane values over the warp with R + log2(32 / R) - 1 shuffles instead of 5 R: every step halves the
+// number of values a lane still carries (the upper half of the lanes keeps the upper half of the rows).  Returns the
+// total of row `multi_row<R>(lane)`; the lanes with (lane & (32 / R - 1)) == 0 are the designated writers.
+template <int R>
+__device__ __forceinline__ float multi_sum(float (&a)[R], int lane) {
+    int width = 16;
+#pragma unroll
+    for (int n = R; n > 1; n >>= 1, width >>= 1) {
+        const bool up = (lane & width) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const float send = up ? a[i] : a[i + n / 2];
+            const float keep = up ? a[i + n / 2] : a[i];
+            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, width);
+        }
+    }
+    for (; width > 0; width >>= 1) a[0] += __shfl_xor_sync(0xffffffffu, a[0], width);
+    return a[0];
+}
+template <int R>
+__device__ __forceinline__ int multi_row(int lane) {
+    int row = 0, width = 16;
+#pragma unroll
+    for (int n = R; n > 1; n >>= 1, width >>= 1) row += (lane & width) ? n / 2 : 0;
+    return row;
+}
+
+// scaled value exactly representable in one FP16 plane?  (<= 11 significant bits, inside FP16's normal range, or zero)
+__device__ __forceinline__ bool f16_inexact(float t) {
+    return ((__float_as_uint(t) & 0x1FFFu) != 0u) | ((fabsf(t) < 6.103515625e-05f) & (t != 0.f));
+}
+
 template <int ROWS, int NV>
 __global__ void __launch_bounds__(kThreads)
 prepare_rows_f32_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ldx, __half* __restrict__ hi,
@@ -247,8 +279,11 @@ prepare_rows_f32_kernel(const float* __restrict__ x, int64_t n, int d, int64_t l
     const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
     if (blockIdx.x == 0 && threadIdx.x == 0) { meta[META_SCALE] = 1.f; meta[META_INV_SCALE] = 1.f; }
     const int d4 = d >> 2, dp4 = (int)(ldp >> 2);
+    const int my_row = multi_row<ROWS>(lane);
+    const bool writer = (lane & (32 / ROWS - 1)) == 0;
     bool any_lo_written = false, bad = false;
-    float max_ss = 0.f, max_abs = 0.f;
+    float max_ss = 0.f;
+    unsigned max_abs_bits = 0u;
     for (int64_t r0 = warp * ROWS; r0 < n; r0 += nwarps * ROWS) {
         float4 v[ROWS][NV];
 #pragma unroll
@@ -259,61 +294,86 @@ prepare_rows_f32_kernel(const float* __restrict__ x, int64_t n, int d, int64_t l
                 v[i][j] = (r0 + i < n && c < d4) ? __ldg(reinterpret_cast<const float4*>(x + (r0 + i) * ldx) + c)
                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+        float ss[ROWS];
+        unsigned am[ROWS];
 #pragma unroll
         for (int i = 0; i < ROWS; ++i) {
-            const int64_t r = r0 + i;
-            float ss = 0.f, am = 0.f;
+            float s = 0.f, a = 0.f;
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
                 const float4 t = v[i][j];
-                ss = fmaf(t.x, t.x, ss); ss = fmaf(t.y, t.y, ss); ss = fmaf(t.z, t.z, ss); ss = fmaf(t.w, t.w, ss);
-                am = fmaxf(am, absmax4(t));
+                s = fmaf(t.x, t.x, s); s = fmaf(t.y, t.y, s); s = fmaf(t.z, t.z, s); s = fmaf(t.w, t.w, s);
+                a = fmaxf(a, absmax4(t));
                 // fmaxf drops NaN: test every element (x - x is NaN for NaN and +-Inf, 0 otherwise)
                 bad |= ((t.x - t.x) + (t.y - t.y) + (t.z - t.z) + (t.w - t.w)) != 0.f;
             }
-            ss = warp_sum(ss);
-            am = warp_max(am);
+            ss[i] = s;
+            am[i] = __reduce_max_sync(0xffffffffu, __float_as_uint(a));    // non-negative floats order like their bits
+        }
+        const float row_ss = multi_sum<ROWS>(ss, lane);                    // total of row r0 + my_row
+        if (writer && r0 + my_row < n) {
+            if (norms) norms[r0 + my_row] = row_ss;
+            max_ss = fmaxf(max_ss, row_ss);
+        }
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) {
+            const int64_t r = r0 + i;
             if (r >= n) continue;                               // warp-uniform
-            const float scale = scale_from_absmax(am);
-            uint32_t hv[NV][2], lv[NV][2];                      // packed half2 pairs
-            bool row_lo = false;
+            const float scale = scale_from_absmax(__uint_as_float(am[i]));
+            max_abs_bits = max(max_abs_bits, am[i]);
+            bool inexact = false;
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
                 const float4 t = v[i][j];
-                __half h0, h1, h2, h3, l0, l1, l2, l3;
-                split_f16(t.x * scale, h0, l0); split_f16(t.y * scale, h1, l1);
-                split_f16(t.z * scale, h2, l2); split_f16(t.w * scale, h3, l3);
-                const __half2 ha = __halves2half2(h0, h1), hb = __halves2half2(h2, h3);
-                const __half2 la = __halves2half2(l0, l1), lb = __halves2half2(l2, l3);
-                hv[j][0] = *reinterpret_cast<const uint32_t*>(&ha);
-                hv[j][1] = *reinterpret_cast<const uint32_t*>(&hb);
-                lv[j][0] = *reinterpret_cast<const uint32_t*>(&la);
-                lv[j][1] = *reinterpret_cast<const uint32_t*>(&lb);
-                row_lo |= ((lv[j][0] | lv[j][1]) & 0x7FFF7FFFu) != 0u;
+                inexact |= f16_inexact(t.x * scale) | f16_inexact(t.y * scale) | f16_inexact(t.z * scale) |
+                           f16_inexact(t.w * scale);
             }
-            row_lo = __any_sync(0xffffffffu, row_lo);
+            const bool row_lo = __any_sync(0xffffffffu, inexact);
+            if (!row_lo) {
+                // the common case for descriptors (integer-valued SIFT, ORB as float): one packed conversion per two
+                // elements, no residual
 #pragma unroll
-            for (int j = 0; j < NV; ++j) {
-                const int c = lane + 32 * j;
-                if (c < dp4) {                                  // pad columns [d, ldp) come out as zeros
-                    reinterpret_cast<uint2*>(hi + r * ldp)[c] = make_uint2(hv[j][0], hv[j][1]);
-                    if (lo && row_lo)
-                        reinterpret_cast<uint2*>(lo + r * ldp)[c] = make_uint2(lv[j][0], lv[j][1]);
+                for (int j = 0; j < NV; ++j) {
+                    const int c = lane + 32 * j;
+                    if (c < dp4) {
+                        const float4 t = v[i][j];
+                        const __half2 ha = __floats2half2_rn(t.x * scale, t.y * scale);
+                        const __half2 hb = __floats2half2_rn(t.z * scale, t.w * scale);
+                        reinterpret_cast<uint2*>(hi + r * ldp)[c] =
+                            make_uint2(*reinterpret_cast<const uint32_t*>(&ha), *reinterpret_cast<const uint32_t*>(&hb));
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NV; ++j) {
+                    const int c = lane + 32 * j;
+                    if (c < dp4) {                              // pad columns [d, ldp) come out as zeros
+                        const float4 t = v[i][j];
+                        __half h0, h1, h2, h3, l0, l1, l2, l3;
+                        split_f16(t.x * scale, h0, l0); split_f16(t.y * scale, h1, l1);
+                        split_f16(t.z * scale, h2, l2); split_f16(t.w * scale, h3, l3);
+                        const __half2 ha = __halves2half2(h0, h1), hb = __halves2half2(h2, h3);
+                        const __half2 la = __halves2half2(l0, l1), lb = __halves2half2(l2, l3);
+                        reinterpret_cast<uint2*>(hi + r * ldp)[c] =
+                            make_uint2(*reinterpret_cast<const uint32_t*>(&ha), *reinterpret_cast<const uint32_t*>(&hb));
+                        if (lo)
+                            reinterpret_cast<uint2*>(lo + r * ldp)[c] =
+                                make_uint2(*reinterpret_cast<const uint32_t*>(&la), *reinterpret_cast<const uint32_t*>(&lb));
+                    }
                 }
             }
             if (lane == 0) {
-                if (norms) norms[r] = ss;
                 row_inv[r] = 1.f / scale;
                 if (lo_skipped) lo_skipped[r] = (lo && !row_lo) ? 1 : 0;
             }
             any_lo_written |= row_lo;
-            max_ss = fmaxf(max_ss, ss);
-            max_abs = fmaxf(max_abs, am);
         }
     }
+    max_ss = warp_max(max_ss);
     if (lane == 0) {
         if (max_ss > 0.f) atomicMax(reinterpret_cast<int*>(meta + META_MAX_NORM_SQ), __float_as_int(max_ss));
-        if (max_abs > 0.f) atomicMax(reinterpret_cast<int*>(meta + META_ABSMAX), __float_as_int(max_abs));
+        if (max_abs_bits != 0u && max_abs_bits < 0x7F800000u)
+            atomicMax(reinterpret_cast<int*>(meta + META_ABSMAX), (int)max_abs_bits);
         if (any_lo_written) meta[META_LO_NONZERO] = 1.f;
     }
     if (__any_sync(0xffffffffu, bad) && lane == 0) meta[META_NONFINITE] = 1.f;

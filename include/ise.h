@@ -70,6 +70,15 @@ int ise_split_plan(float* hassign_host, int64_t k, int64_t n, int32_t* pairs_hos
  * thread and returns at once.  Optional: ise_split_plan extends the index itself when it runs past it. */
 int ise_split_plan_warm(int64_t n_draws);
 
+/* Ragged ingestion (pure CPU, multi-threaded): the reference's input contract is a Python list with one (n_i, d)
+ * row-major array per image (descriptors.py:104-139), concatenated by one single-threaded np.concatenate
+ * (bag_of_visual_words.py:128).  Copies images [i0, i1) -- srcs[i] = HOST pointer of image i, offsets[n_img + 1] =
+ * cumulative row counts -- to dst_base + offsets[i] * d * sizeof(dst element), i.e. straight into the caller's (pinned)
+ * packed matrix.  src F32 -> dst U8 narrows on the way and sets *ok = 0 (dst undefined) unless every value is an
+ * integer in [0, 255] (OpenCV SIFT / ORB-as-float descriptors are): a quarter of the host -> device bytes. */
+int ise_pack_rows(const void* const* srcs_host, const int64_t* offsets_host, int64_t i0, int64_t i1, int d,
+                  int src_dtype, int dst_dtype, void* dst_base_host, int nthreads, int* ok);
+
 /* ---- operand preparation --------------------------------------------------------------
  * The distance contractions run on the tcgen05 tensor cores as FP16 "hi + lo" split
  * products (hi*hi + hi*lo + lo*hi, FP32 accumulate) which carries ~22-24 mantissa bits:

@@ -51,6 +51,8 @@ def rec(name, ms, nbytes):
 rec("prepare f32, integer-valued (absmax + hi plane + norms; 10 B/element moved)", t(lambda: ops.prepare_operand(X)), n * d * 10)
 Xf = X + 0.37
 rec("prepare f32, general (absmax + hi/lo planes + norms; 12 B/element moved)", t(lambda: ops.prepare_operand(Xf)), n * d * 12)
+rec("prepare ROWS f32, integer-valued (single pass: 4 B read + hi plane + norms; 6 B/element)", t(lambda: ops.prepare_operand(X, rows=True)), n * d * 6)
+rec("prepare ROWS f32, general (single pass: 4 B read + hi/lo planes + norms; 8 B/element)", t(lambda: ops.prepare_operand(Xf, rows=True)), n * d * 8)
 rec("prepare u8 (one plane + norms)", t(lambda: ops.prepare_operand(Xu8)), n * d * (1 + 2))
 rec("histogram f64 numpy-compat + okapi", t(lambda: ops.bovw_histogram(words, off, k, mode=HIST_NUMPY_COMPAT, okapi=True, out=out64)), n * 8 + n_img * k * 8)
 rec("histogram f64 bincount", t(lambda: ops.bovw_histogram(words, off, k, mode=HIST_BINCOUNT, out=out64)), n * 8 + n_img * k * 8)
@@ -58,6 +60,11 @@ rec("histogram f32 numpy-compat + okapi", t(lambda: ops.bovw_histogram(words, of
 rec("okapi_tf_ dense f64 in place (row sums + weights)", t(lambda: ops.okapi_tf_(out64)), n_img * k * 8 * 2)
 rec("kmeans_accumulate f32 (+ exact objective)", t(lambda: ops.kmeans_accumulate(X, words, None, sums, counts, obj, centroids=cent)), n * (4 * d + 8))
 rec("kmeans_accumulate u8", t(lambda: ops.kmeans_accumulate(Xu8, words, None, sums, counts, obj, centroids=cent)), n * (d + 8))
+ws = [None]
+def _sorted(x):
+    ws[0] = ops.kmeans_accumulate_sorted(x, words, sums, counts, obj, centroids=cent, workspace=ws[0])
+rec("kmeans_accumulate_sorted f32 (counting sort + gather-reduce, + exact objective)", t(lambda: _sorted(X)), n * (4 * d + 8))
+rec("kmeans_accumulate_sorted u8", t(lambda: _sorted(Xu8)), n * (d + 8))
 val = torch.empty((n, 1), dtype=torch.float32, device=dev)
 rec("rescore top-1 (exact distances of the winners)", t(lambda: ops.rescore_topk_(X, cent, a, b, METRIC_IP, val, words)), n * (4 * d + 12))
 Y = X.clone()
@@ -66,4 +73,4 @@ big = torch.empty((256 << 20,), dtype=torch.float32, device=dev)
 big2 = torch.empty_like(big)
 rec("(reference) torch copy 1 GiB -> 1 GiB", t(lambda: big2.copy_(big)), big.numel() * 8)
 rec("(reference) cudaMemset 1 GiB", t(lambda: big.zero_()), big.numel() * 4)
-json.dump(rows, open("gpurun_out/membound.json", "w"), indent=1)
+json.dump(rows, open("gpurun_out/r02_membound.json", "w"), indent=1)

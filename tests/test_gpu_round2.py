@@ -200,7 +200,9 @@ def test_prepare_rows_single_pass(d):
         assert ((scaled_max[nz] >= 8192) & (scaled_max[nz] < 16384)).all() and inv[5] == 1.0
         assert float(op.meta[0]) == 1.0 and float(op.meta[1]) == 1.0
     rec = (op.hi.float() + op.lo.float()).cpu().numpy()[:, :d] * inv[:, None]
-    assert (np.abs(rec - x) <= np.abs(x).max(1, keepdims=True) * 2.0 ** -21 + 1e-30).all()
+    # ~22 bits relative to the magnitude the scale was chosen for: the row's own maximum (single pass) or the tensor's
+    ref_mag = np.abs(x).max(1, keepdims=True) if single_pass else np.abs(x).max()
+    assert (np.abs(rec - x) <= ref_mag * 2.0 ** -21 + 1e-30).all()
     assert (op.hi.cpu().numpy()[:, d:] == 0).all()
     np.testing.assert_allclose(op.norms.cpu().numpy(), (x.astype(np.float64) ** 2).sum(1), rtol=2e-6)
     assert float(op.meta[2]) == 1.0 and float(op.meta[7]) == 0.0
@@ -337,3 +339,42 @@ def test_kmeans_train_rejects_nonfinite_and_warms_the_split_stream():
     big[11999, 0] = np.inf
     with pytest.raises(RuntimeError, match="NaN"):
         FaissKMeans(16, n_init=1, max_iter=2).fit(big)
+
+
+def test_transform_csr_from_a_python_list_of_arrays():
+    """The reference's input contract is a list with one (n_i, d) array per image: it is packed by the C list walker +
+    ise_pack_rows into a persistent pinned buffer -- uint8 on the wire when every value is an integer in [0, 255] --
+    and must give exactly the matrix of the pre-packed path, for ragged lists with empty images too."""
+    from image_search_engine_b200 import BOVW, FaissKMeans, OkapiTransformer, faiss_compat
+    from image_search_engine_b200.bag_of_visual_words import _pack_list_into, pack_descriptions
+    rng = np.random.default_rng(15)
+    k, d = 512, 128
+    gi = faiss_compat.IndexFlatIP(d)
+    gi.add(unit_rows(rng, k, d))
+    bovw = BOVW(None, n_clusters=k)
+    bovw.clusterer = FaissKMeans(k, index=gi)
+    ok = OkapiTransformer()
+    sizes = rng.integers(0, 160, 300)
+    sizes[7] = 0
+    ints = [sift_like(rng, int(s), d) for s in sizes]                       # integer-valued float32 -> uint8 on the wire
+    general = [a + np.float32(0.25) for a in ints]                          # not integers -> float32 on the wire
+    bytes_ = [a.astype(np.uint8) for a in ints]                             # ORB-style uint8 input
+    for descs, wire in ((ints, torch.uint8), (general, torch.float32), (bytes_, torch.uint8)):
+        bufs = {}
+        packed = _pack_list_into(descs, bufs)
+        assert packed is not None and packed.matrix.dtype == wire and packed.matrix.is_pinned()
+        mat, off = pack_descriptions(descs)
+        assert np.array_equal(packed.offsets, off)
+        assert np.array_equal(packed.matrix.numpy().astype(np.float32), np.asarray(mat, dtype=np.float32))
+        packed2 = _pack_list_into(descs, bufs)                              # the pinned buffer is reused
+        assert packed2.matrix.data_ptr() == packed.matrix.data_ptr()
+        want = bovw.transform_csr(pack_descriptions(descs, pin=True), okapi=ok, n_chunks=4).toarray()
+        got = bovw.transform_csr(descs, okapi=ok, n_chunks=4).toarray()
+        assert np.array_equal(got, want)
+    assert np.array_equal(bovw.transform_csr(ints, okapi=ok, n_chunks=4).toarray(),
+                          bovw.transform_csr(bytes_, okapi=ok, n_chunks=4).toarray())
+    # lists the packer does not understand (mixed dtypes, float64) take the generic path and still work
+    mixed = [a.astype(np.float64) if i % 2 else a for i, a in enumerate(ints)]
+    assert _pack_list_into(mixed, {}) is None
+    assert np.array_equal(bovw.transform_csr(mixed, okapi=ok, n_chunks=4).toarray(),
+                          bovw.transform_csr(ints, okapi=ok, n_chunks=4).toarray())
