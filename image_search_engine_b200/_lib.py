@@ -63,7 +63,7 @@ PROTOTYPES = {
     "ise_kmeans_accumulate": (_int, [_c_void_p, _c_void_p, _int, _i64, _int, _i64, _c_void_p, _c_void_p,
                                      _c_void_p, _i64, _int, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "ise_kmeans_accumulate_workspace_bytes": (_size, [_c_void_p, _i64, _i64]),
-    "ise_kmeans_accumulate_sorted": (_int, [_c_void_p, _c_void_p, _int, _i64, _int, _i64, _c_void_p, _c_void_p, _i64, _int,
+    "ise_kmeans_accumulate_sorted": (_int, [_c_void_p, _c_void_p, _int, _i64, _int, _i64, _c_void_p, _c_void_p, _c_void_p, _i64, _int,
                                             _c_void_p, _c_void_p, _c_void_p, _c_void_p, _size, _c_void_p]),
     "ise_kmeans_mean": (_int, [_c_void_p, _c_void_p, _c_void_p, _i64, _int, _c_void_p, _c_void_p, _c_void_p]),
     "ise_kmeans_apply_splits": (_int, [_c_void_p, _c_void_p, _i64, _int, _c_void_p, C.c_int32, _c_void_p]),
@@ -85,7 +85,7 @@ PROTOTYPES = {
 }
 
 METRIC_IP, METRIC_L2 = 0, 1
-DTYPE_F32, DTYPE_U8 = 0, 1
+DTYPE_F32, DTYPE_U8, DTYPE_F16 = 0, 1, 2
 HIST_NUMPY_COMPAT, HIST_BINCOUNT = 0, 1
 OUT_F32, OUT_F64 = 0, 1
 

@@ -152,6 +152,8 @@ struct SplitStreamIndex {
     std::vector<int64_t> pos;                             // stream positions of the small draws, ascending
     std::vector<uint32_t> val;
     std::thread warm;
+    bool warm_running = false;                            // guarded by mu
+    int64_t warm_target = 0;                              // guarded by mu
     std::atomic<bool> stop{false};
     // caller holds mu
     void extend_to(int64_t target) {
@@ -174,18 +176,26 @@ SplitStreamIndex g_split_stream;
 }  // namespace
 
 // Non-blocking: generate the first n_draws of the stream in a background thread (k-means training calls this when it
-// starts on a large codebook, so the index exists by the time an iteration needs a plan).
+// starts on a large codebook, so the index exists by the time an iteration needs a plan).  A later call with a larger
+// target raises the running thread's target, or starts a new thread when the previous one has finished.
 ISE_EXPORT int ise_split_plan_warm(int64_t n_draws) {
     ISE_CHECK_ARG(n_draws >= 0);
     SplitStreamIndex& ix = g_split_stream;
     std::lock_guard<std::mutex> lk(ix.mu);
-    if (ix.generated >= n_draws || ix.warm.joinable()) return 0;       // one warm-up thread per process
-    ix.warm = std::thread([n_draws]() {
+    if (ix.generated >= n_draws) return 0;
+    ix.warm_target = std::max(ix.warm_target, n_draws);
+    if (ix.warm_running) return 0;
+    if (ix.warm.joinable()) ix.warm.join();      // finished earlier (it cleared warm_running under mu and needs mu no more)
+    ix.warm_running = true;
+    ix.warm = std::thread([]() {
         SplitStreamIndex& s = g_split_stream;
         for (;;) {
             std::lock_guard<std::mutex> g(s.mu);
-            if (s.stop.load() || s.generated >= n_draws) return;
-            s.extend_to(std::min<int64_t>(n_draws, s.generated + SplitStreamIndex::kStep));
+            if (s.stop.load() || s.generated >= s.warm_target) {
+                s.warm_running = false;
+                return;
+            }
+            s.extend_to(std::min<int64_t>(s.warm_target, s.generated + SplitStreamIndex::kStep));
         }
     });
     return 0;

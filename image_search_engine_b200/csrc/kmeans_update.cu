@@ -260,9 +260,9 @@ constexpr int kSegRows = 64;
 constexpr int kGatherRows = 8;
 constexpr int kCountSmemBins = 12 * 1024;
 
-__global__ void count_kernel(const int64_t* __restrict__ assign, int64_t n, int k, int32_t* __restrict__ cnt) {
+__global__ void count_kernel(const int64_t* __restrict__ assign, int64_t n, int k, int32_t* __restrict__ cnt, int use_smem) {
     extern __shared__ int s_bins[];
-    const bool smem = k <= kCountSmemBins;
+    const bool smem = use_smem != 0;
     if (smem) {
         for (int j = threadIdx.x; j < k; j += blockDim.x) s_bins[j] = 0;
         __syncthreads();
@@ -289,69 +289,107 @@ __global__ void count_kernel(const int64_t* __restrict__ assign, int64_t n, int 
     }
 }
 
-// single CTA: offs[0..k] = exclusive scan of cnt; cursor = copy of the starts; counts += cnt (float, like hassign)
-__global__ void scan_counts_kernel(const int32_t* __restrict__ cnt, int k, int32_t* __restrict__ offs,
-                                   int32_t* __restrict__ cursor, float* __restrict__ counts) {
+// single CTA: offs[0..k] = exclusive scan of cnt; cursor = copy of the starts; counts += cnt (float, like hassign).
+// Every thread owns a contiguous run of ceil(k / 1024) bins (serial), the 1024 run totals are scanned with two levels of
+// warp shuffles: three barriers in all, whatever k.
+__global__ void __launch_bounds__(1024)
+scan_counts_kernel(const int32_t* __restrict__ cnt, int k, int32_t* __restrict__ offs, int32_t* __restrict__ cursor,
+                   float* __restrict__ counts) {
     __shared__ int s_warp[32];
-    __shared__ int s_carry;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_carry = 0;
+    const int per = (k + 1023) / 1024;
+    const int lo = min(k, (int)threadIdx.x * per), hi = min(k, lo + per);
+    int total = 0;
+    for (int i = lo; i < hi; ++i) total += cnt[i];
+    int incl = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[wib] = incl;
     __syncthreads();
-    for (int base = 0; base < k; base += blockDim.x) {
-        const int i = base + threadIdx.x;
-        const int v = i < k ? cnt[i] : 0;
-        int incl = v;
+    if (wib == 0) {
+        int w = s_warp[lane];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+            const int t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += t;
         }
-        if (lane == 31) s_warp[wib] = incl;
-        __syncthreads();
-        int wbase = 0;
-        for (int w = 0; w < wib; ++w) wbase += s_warp[w];
-        const int carry = s_carry;
-        if (i < k) {
-            const int start = carry + wbase + incl - v;
-            offs[i] = start;
-            cursor[i] = start;
-            if (v) counts[i] += (float)v;
-        }
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) s_carry = carry + wbase + incl;
-        __syncthreads();
+        s_warp[lane] = w;                       // inclusive scan of the warp totals
     }
-    if (threadIdx.x == 0) offs[k] = s_carry;
+    __syncthreads();
+    int run = (wib ? s_warp[wib - 1] : 0) + incl - total;       // exclusive prefix of this thread's run
+    for (int i = lo; i < hi; ++i) {
+        const int v = cnt[i];
+        offs[i] = run;
+        cursor[i] = run;
+        if (v) counts[i] += (float)v;
+        run += v;
+    }
+    if (threadIdx.x == 1023) offs[k] = s_warp[31];
 }
 
+// row_inv given (rows will be gathered from an FP16 plane): the row's scale travels with its pair, so the gather reads it
+// as a stream instead of one more random 4-byte access per row
 __global__ void scatter_kernel(const int64_t* __restrict__ assign, int64_t n, int k, int32_t* __restrict__ cursor,
-                               int2* __restrict__ sorted) {
+                               int2* __restrict__ sorted, const float* __restrict__ row_inv,
+                               float* __restrict__ sorted_inv) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const int64_t a = __ldg(assign + i);
         if (a < 0 || a >= k) continue;
         const int pos = atomicAdd(cursor + a, 1);
         sorted[pos] = make_int2((int)a, (int)i);
+        if (row_inv) sorted_inv[pos] = __ldg(row_inv + i);
     }
 }
 
+// element types a row can be gathered as: FP32 rows, uint8 rows, or -- when the operand is EXACT in one FP16 plane
+// (integer-valued SIFT, ORB: ise_prepare_rows wrote no lo plane) -- the FP16 hi plane itself, half the bytes of the
+// FP32 rows: value = half * row_inv[row], both exact, so the sums are the same numbers.
 template <typename T> struct RowVec;
 template <> struct RowVec<float> {
-    static __device__ __forceinline__ float4 ld(const float* row, int c4) { return __ldg(reinterpret_cast<const float4*>(row) + c4); }
+    static constexpr bool kScaled = false;
+    typedef float4 raw;
+    static __device__ __forceinline__ raw ld(const float* row, int c4) { return __ldg(reinterpret_cast<const float4*>(row) + c4); }
+    static __device__ __forceinline__ float4 cvt(raw r, float) { return r; }
 };
 template <> struct RowVec<uint8_t> {
-    static __device__ __forceinline__ float4 ld(const uint8_t* row, int c4) {
-        const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(row) + c4);
-        return make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w);
+    static constexpr bool kScaled = false;
+    typedef uchar4 raw;
+    static __device__ __forceinline__ raw ld(const uint8_t* row, int c4) { return __ldg(reinterpret_cast<const uchar4*>(row) + c4); }
+    static __device__ __forceinline__ float4 cvt(raw u, float) { return make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w); }
+};
+template <> struct RowVec<__half> {
+    static constexpr bool kScaled = true;      // FP16 hi plane: per-row power-of-two scale
+    typedef uint2 raw;
+    static __device__ __forceinline__ raw ld(const __half* row, int c4) { return __ldg(reinterpret_cast<const uint2*>(row) + c4); }
+    static __device__ __forceinline__ float4 cvt(raw r, float inv) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+        return make_float4(a.x * inv, a.y * inv, b.x * inv, b.y * inv);
     }
 };
 
-// G = lanes per worker (power of two, 32 / G workers per warp); a worker owns columns [4 * (cb + lg), +4) of its rows for
-// the column block cb (d > 128: the chunk is walked once per 128-column block, the rows come back from L1 / L2)
-template <typename T, int G>
+// G = lanes per worker (4, 8, 16 or 32; 32 / G workers per warp), U = rows in flight per worker (<= G, sized so that a
+// warp keeps ~4 KB of row loads in flight: measured effective latency under load is ~3 us, i.e. ~100 KB per SM are
+// needed to fill HBM).  A worker owns one 64-row chunk at a time: its lanes load the chunk's (centroid, row) pairs
+// ONCE, coalesced, 64 / G per lane, and every row's pair is then broadcast from its holder with a shuffle -- no
+// per-row key registers, no per-row index loads.  A lane owns columns [4 (cb + lg), +4) of the rows for the
+// column block cb (d > 4 G: the chunk is walked once per column block; the rows come back from L1 / L2).
+__device__ __forceinline__ float run_dot(float4 a, float4 c) {
+    return fmaf(a.w, c.w, fmaf(a.z, c.z, fmaf(a.y, c.y, a.x * c.x)));
+}
+
+template <typename T, int G, int U>
 __global__ void __launch_bounds__(256)
 gather_reduce_kernel(const T* __restrict__ x, int d, int64_t ldx, const int2* __restrict__ sorted,
-                     const int32_t* __restrict__ n_sorted_ptr, const float* __restrict__ cent, int metric, float* __restrict__ sums, double* __restrict__ obj) {
+                     const float* __restrict__ sorted_inv, const int32_t* __restrict__ n_sorted_ptr,
+                     const float* __restrict__ cent, int metric, float* __restrict__ sums, double* __restrict__ obj) {
+    static_assert(U <= G && kSegRows % G == 0, "rows in flight per worker");
+    constexpr int PER = kSegRows / G;                    // (centroid, row) pairs held per lane
+    constexpr bool SC = RowVec<T>::kScaled;
     __shared__ double s_obj[8];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int lg = lane & (G - 1);                       // lane within the worker
@@ -360,51 +398,74 @@ gather_reduce_kernel(const T* __restrict__ x, int d, int64_t ldx, const int2* __
     const int64_t n_sorted = *n_sorted_ptr;             // rows with a valid id (all of them after an assign pass)
     const int64_t n_chunks = (n_sorted + kSegRows - 1) / kSegRows;
     const int d4 = d >> 2;
-    float objp = 0.f;
     double objd = 0.0;
-    for (int64_t chunk = worker; chunk < n_chunks; chunk += n_workers) {
-        const int64_t i0 = chunk * kSegRows, i1 = min(n_sorted, i0 + kSegRows);
+    // inner-product objective: sum_rows <x, c> = <sum_rows x, c>, so it costs four FMAs per RUN (at the flush), not per
+    // row; the L2 objective sum |x - c|^2 stays per row
+    const bool ip_obj = cent != nullptr && metric == ISE_METRIC_IP, l2_obj = cent != nullptr && metric != ISE_METRIC_IP;
+    // all workers of a warp run the same number of iterations (shuffles are warp-wide): idle workers carry empty chunks
+    const int64_t iters = (n_chunks + n_workers - 1) / n_workers;
+    for (int64_t itn = 0; itn < iters; ++itn) {
+        const int64_t chunk = worker + itn * n_workers;
+        const int64_t i0 = chunk * kSegRows;
+        int key[PER], ridx[PER];
+        float sinv[SC ? PER : 1];
+#pragma unroll
+        for (int p = 0; p < PER; ++p) {
+            const int64_t i = i0 + p * G + lg;
+            const bool ok = chunk < n_chunks && i < n_sorted;
+            const int2 kr = ok ? __ldg(sorted + i) : make_int2(-1, 0);
+            key[p] = kr.x;
+            ridx[p] = kr.y;
+            if (SC) sinv[p] = ok ? __ldg(sorted_inv + i) : 1.f;
+        }
+        float objp = 0.f;
         for (int cb = 0; cb < d4; cb += G) {
             const int c4 = cb + lg;
             const bool col_ok = c4 < d4;
             int cur = -1;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), cc = acc;
-            for (int64_t i = i0; i < i1; i += kGatherRows) {
-                int2 kr[kGatherRows];
-                float4 v[kGatherRows];
 #pragma unroll
-                for (int u = 0; u < kGatherRows; ++u)
-                    kr[u] = i + u < i1 ? __ldg(sorted + i + u) : make_int2(-1, 0);
+            for (int p = 0; p < PER; ++p) {
 #pragma unroll
-                for (int u = 0; u < kGatherRows; ++u)
-                    if (kr[u].x >= 0 && col_ok) v[u] = RowVec<T>::ld(x + (int64_t)kr[u].y * ldx, c4);
+                for (int jb = 0; jb < G; jb += U) {
+                    typename RowVec<T>::raw v[U];
 #pragma unroll
-                for (int u = 0; u < kGatherRows; ++u) {
-                    if (kr[u].x < 0) continue;
-                    if (kr[u].x != cur) {
-                        if (cur >= 0 && col_ok) red_add_v4(sums + (int64_t)cur * d + 4 * c4, acc);
-                        cur = kr[u].x;
-                        acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (cent && col_ok) cc = __ldg(reinterpret_cast<const float4*>(cent + (int64_t)cur * d) + c4);
+                    for (int u = 0; u < U; ++u) {
+                        const int kq = __shfl_sync(0xffffffffu, key[p], jb + u, G);
+                        const int r = __shfl_sync(0xffffffffu, ridx[p], jb + u, G);
+                        if (kq >= 0 && col_ok) v[u] = RowVec<T>::ld(x + (int64_t)r * ldx, c4);
                     }
-                    if (!col_ok) continue;
-                    acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
-                    if (cent) {
-                        if (metric == ISE_METRIC_IP) {
-                            objp = fmaf(v[u].x, cc.x, objp); objp = fmaf(v[u].y, cc.y, objp);
-                            objp = fmaf(v[u].z, cc.z, objp); objp = fmaf(v[u].w, cc.w, objp);
-                        } else {
-                            const float e0 = v[u].x - cc.x, e1 = v[u].y - cc.y, e2 = v[u].z - cc.z, e3 = v[u].w - cc.w;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int kq = __shfl_sync(0xffffffffu, key[p], jb + u, G);
+                        const float iv = SC ? __shfl_sync(0xffffffffu, sinv[SC ? p : 0], jb + u, G) : 1.f;
+                        if (kq < 0) continue;
+                        if (kq != cur) {
+                            if (cur >= 0 && col_ok) {
+                                red_add_v4(sums + (int64_t)cur * d + 4 * c4, acc);
+                                if (ip_obj) objp += run_dot(acc, cc);
+                            }
+                            cur = kq;
+                            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (cent && col_ok) cc = __ldg(reinterpret_cast<const float4*>(cent + (int64_t)cur * d) + c4);
+                        }
+                        if (!col_ok) continue;
+                        const float4 t = RowVec<T>::cvt(v[u], iv);
+                        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+                        if (l2_obj) {
+                            const float e0 = t.x - cc.x, e1 = t.y - cc.y, e2 = t.z - cc.z, e3 = t.w - cc.w;
                             objp = fmaf(e0, e0, objp); objp = fmaf(e1, e1, objp);
                             objp = fmaf(e2, e2, objp); objp = fmaf(e3, e3, objp);
                         }
                     }
                 }
             }
-            if (cur >= 0 && col_ok) red_add_v4(sums + (int64_t)cur * d + 4 * c4, acc);
+            if (cur >= 0 && col_ok) {
+                red_add_v4(sums + (int64_t)cur * d + 4 * c4, acc);
+                if (ip_obj) objp += run_dot(acc, cc);
+            }
         }
         objd += (double)objp;            // FP32 partial of one chunk's 64 rows x 4 columns, FP64 from there on
-        objp = 0.f;
     }
     if (obj && cent) {
 #pragma unroll
@@ -517,44 +578,49 @@ ISE_EXPORT int ise_kmeans_accumulate(ise_ctx* ctx, const void* x, int dtype, int
 
 ISE_EXPORT size_t ise_kmeans_accumulate_workspace_bytes(ise_ctx* ctx, int64_t n, int64_t k) {
     if (!ctx || n <= 0 || k <= 0) return 0;
-    // cnt[k] | offs[k + 1] | cursor[k] (int32) | sorted[n] (int2), 16-byte aligned sections
-    return (size_t)(((3 * k + 1) * 4 + 15) & ~(int64_t)15) + (size_t)n * sizeof(int2) + 256;
+    // cnt[k] | offs[k + 1] | cursor[k] (int32) | sorted[n] (int2) | sorted_inv[n] (float), 16-byte aligned sections
+    return (size_t)(((3 * k + 1) * 4 + 15) & ~(int64_t)15) + (size_t)n * (sizeof(int2) + sizeof(float)) + 256;
 }
 
-template <typename T>
-static void launch_gather(const T* x, int d, int64_t ldx, const int2* sorted, int64_t n, const int32_t* n_sorted, const float* cent, int metric,
-                          float* sums, double* obj, int sm_count, cudaStream_t st) {
+template <typename T, int UMAX>
+static void launch_gather(const T* x, int d, int64_t ldx, const int2* sorted, const float* sorted_inv, int64_t n,
+                          const int32_t* n_sorted, const float* cent, int metric, float* sums, double* obj, int sm_count,
+                          cudaStream_t st) {
     const int d4 = d / 4;
-    int g = 1;
+    int g = 4;
     while (g < d4 && g < 32) g <<= 1;
     const int64_t chunks = ceil_div64(n, kSegRows);
     const int64_t workers_per_cta = 8 * (32 / g);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(chunks, workers_per_cta), (int64_t)sm_count * 8));
+#define ISE_GATHER(G) gather_reduce_kernel<T, G, (UMAX < G ? UMAX : G)><<<grid, 256, 0, st>>>(x, d, ldx, sorted, sorted_inv, n_sorted, cent, metric, sums, obj)
     switch (g) {
-        case 1: gather_reduce_kernel<T, 1><<<grid, 256, 0, st>>>(x, d, ldx, sorted, n_sorted, cent, metric, sums, obj); break;
-        case 2: gather_reduce_kernel<T, 2><<<grid, 256, 0, st>>>(x, d, ldx, sorted, n_sorted, cent, metric, sums, obj); break;
-        case 4: gather_reduce_kernel<T, 4><<<grid, 256, 0, st>>>(x, d, ldx, sorted, n_sorted, cent, metric, sums, obj); break;
-        case 8: gather_reduce_kernel<T, 8><<<grid, 256, 0, st>>>(x, d, ldx, sorted, n_sorted, cent, metric, sums, obj); break;
-        case 16: gather_reduce_kernel<T, 16><<<grid, 256, 0, st>>>(x, d, ldx, sorted, n_sorted, cent, metric, sums, obj); break;
-        default: gather_reduce_kernel<T, 32><<<grid, 256, 0, st>>>(x, d, ldx, sorted, n_sorted, cent, metric, sums, obj); break;
+        case 4: ISE_GATHER(4); break;
+        case 8: ISE_GATHER(8); break;
+        case 16: ISE_GATHER(16); break;
+        default: ISE_GATHER(32); break;
     }
+#undef ISE_GATHER
 }
 
 ISE_EXPORT int ise_kmeans_accumulate_sorted(ise_ctx* ctx, const void* x, int dtype, int64_t n, int d, int64_t ldx,
-                                            const int64_t* assign, const float* centroids, int64_t k, int metric,
-                                            float* sums, float* counts, double* obj, void* workspace,
-                                            size_t workspace_bytes, void* stream) {
+                                            const float* row_inv, const int64_t* assign, const float* centroids,
+                                            int64_t k, int metric, float* sums, float* counts, double* obj,
+                                            void* workspace, size_t workspace_bytes, void* stream) {
     ISE_CHECK_ARG(ctx && n >= 0 && d > 0 && ldx >= d && k > 0 && k < ((int64_t)1 << 31) && n < ((int64_t)1 << 31));
-    ISE_CHECK_ARG(dtype == ISE_DTYPE_F32 || dtype == ISE_DTYPE_U8);
+    ISE_CHECK_ARG(dtype == ISE_DTYPE_F32 || dtype == ISE_DTYPE_U8 || dtype == ISE_DTYPE_F16);
     ISE_CHECK_ARG(metric == ISE_METRIC_IP || metric == ISE_METRIC_L2);
+    ISE_CHECK_ARG(dtype != ISE_DTYPE_F16 || row_inv != nullptr);      // FP16 hi planes carry per-row scales
     if (n == 0) return 0;
     ISE_CHECK_ARG(x && assign && sums && counts && workspace);
-    // rows are gathered as 4-column vectors: 16-byte (float32) / 4-byte (uint8) aligned rows
+    // rows are gathered as 4-column vectors: 16-byte (float32) / 8-byte (FP16 plane) / 4-byte (uint8) aligned rows
+    const uintptr_t amask = dtype == ISE_DTYPE_F32 ? 15 : (dtype == ISE_DTYPE_F16 ? 7 : 3);
     const bool vec_ok = d % 4 == 0 && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(sums) & 15) == 0 &&
-                        (reinterpret_cast<uintptr_t>(x) & (dtype == ISE_DTYPE_F32 ? 15 : 3)) == 0 &&
+                        (reinterpret_cast<uintptr_t>(x) & amask) == 0 &&
                         (!centroids || (reinterpret_cast<uintptr_t>(centroids) & 15) == 0);
-    if (!vec_ok)
+    if (!vec_ok) {
+        if (dtype == ISE_DTYPE_F16) ISE_FAIL("FP16 plane rows must be 8-byte aligned with d % 4 == 0");
         return ise_kmeans_accumulate(ctx, x, dtype, n, d, ldx, assign, nullptr, centroids, 0, metric, sums, counts, obj, stream);
+    }
     if (workspace_bytes < ise_kmeans_accumulate_workspace_bytes(ctx, n, k)) ISE_FAIL("workspace too small");
     DeviceGuard guard(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
@@ -562,20 +628,26 @@ ISE_EXPORT int ise_kmeans_accumulate_sorted(ise_ctx* ctx, const void* x, int dty
     int32_t* offs = cnt + k;
     int32_t* cursor = offs + k + 1;
     int2* sorted = reinterpret_cast<int2*>(reinterpret_cast<uint8_t*>(cnt) + (((3 * k + 1) * 4 + 15) & ~(int64_t)15));
+    float* sorted_inv = reinterpret_cast<float*>(sorted + n);
     ISE_CUDA(cudaMemsetAsync(cnt, 0, (size_t)k * sizeof(int32_t), st));
     const int grid_n = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(n, 256 * 4), (int64_t)ctx->sm_count * 8));
-    const size_t shm = k <= kCountSmemBins ? (size_t)k * sizeof(int) : 0;
-    count_kernel<<<k <= kCountSmemBins ? std::min(grid_n, ctx->sm_count * 4) : grid_n, 256, shm, st>>>(assign, n, (int)k, cnt);
+    // shared-memory bins pay only when a CTA sees many more ids than there are bins
+    const bool smem_bins = k <= kCountSmemBins && n / ctx->sm_count >= 8 * k;
+    count_kernel<<<smem_bins ? std::min(grid_n, ctx->sm_count) : grid_n, 256, smem_bins ? (size_t)k * sizeof(int) : 0, st>>>(
+        assign, n, (int)k, cnt, smem_bins ? 1 : 0);
     ISE_LAUNCH_CHECK();
     scan_counts_kernel<<<1, 1024, 0, st>>>(cnt, (int)k, offs, cursor, counts);
     ISE_LAUNCH_CHECK();
-    scatter_kernel<<<grid_n, 256, 0, st>>>(assign, n, (int)k, cursor, sorted);
+    scatter_kernel<<<grid_n, 256, 0, st>>>(assign, n, (int)k, cursor, sorted, dtype == ISE_DTYPE_F16 ? row_inv : nullptr, sorted_inv);
     ISE_LAUNCH_CHECK();
-    // rows with ids outside [0, k) are left out, like the atomic kernels skip negative ids: the sorted list holds offs[k]
-    // entries; the gather kernel is sized for n and reads the real length from the scan result
-    // (n_sorted == n whenever every row was assigned, which is what the assign kernel guarantees)
-    if (dtype == ISE_DTYPE_F32) launch_gather<float>((const float*)x, d, ldx, sorted, n, offs + k, centroids, metric, sums, obj, ctx->sm_count, st);
-    else launch_gather<uint8_t>((const uint8_t*)x, d, ldx, sorted, n, offs + k, centroids, metric, sums, obj, ctx->sm_count, st);
+    // rows with ids outside [0, k) are left out, like the atomic kernels skip negative ids: the sorted list holds
+    // offs[k] entries, which the gather kernel reads on the device (== n after an assign pass)
+    if (dtype == ISE_DTYPE_F32)
+        launch_gather<float, 8>((const float*)x, d, ldx, sorted, nullptr, n, offs + k, centroids, metric, sums, obj, ctx->sm_count, st);
+    else if (dtype == ISE_DTYPE_F16)
+        launch_gather<__half, 16>((const __half*)x, d, ldx, sorted, sorted_inv, n, offs + k, centroids, metric, sums, obj, ctx->sm_count, st);
+    else
+        launch_gather<uint8_t, 16>((const uint8_t*)x, d, ldx, sorted, nullptr, n, offs + k, centroids, metric, sums, obj, ctx->sm_count, st);
     ISE_LAUNCH_CHECK();
     return 0;
 }

@@ -264,13 +264,17 @@ __device__ __forceinline__ int multi_row(int lane) {
     return row;
 }
 
-// scaled value exactly representable in one FP16 plane?  (<= 11 significant bits, inside FP16's normal range, or zero)
-__device__ __forceinline__ bool f16_inexact(float t) {
-    return ((__float_as_uint(t) & 0x1FFFu) != 0u) | ((fabsf(t) < 6.103515625e-05f) & (t != 0.f));
-}
-
+// The first version of this kernel ran at 0.56-0.60 of HBM peak and ncu showed why: 146 warp instructions per row
+// (ilogbf / ldexpf / a division for the scale, a float NaN test per element, a multiply + three compares per element for
+// the exactness test) -- issue-bound, not memory-bound.  Everything that is per-row-uniform is integer bit arithmetic
+// now, and the per-element work is four integer min/max/or + one FMA:
+//   * |x| as an unsigned bit pattern orders like the value and keeps NaN / Inf visible (>= 0x7F800000), so one integer
+//     max gives both the row's absolute maximum (-> its power-of-two scale: exponent arithmetic) and the non-finite flag;
+//   * an element is exact in one FP16 plane iff its low 13 mantissa bits are zero (scaling by a power of two does not
+//     change them) and it does not fall below FP16's normal range once scaled: min over (|x| bits - 1) against one
+//     per-row threshold (zero wraps to 0xFFFFFFFF and never counts).
 template <int ROWS, int NV>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 prepare_rows_f32_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ldx, __half* __restrict__ hi,
                         __half* __restrict__ lo, int64_t ldp, float* __restrict__ norms, float* __restrict__ row_inv,
                         uint8_t* __restrict__ lo_skipped, float* meta) {
@@ -281,7 +285,7 @@ prepare_rows_f32_kernel(const float* __restrict__ x, int64_t n, int d, int64_t l
     const int d4 = d >> 2, dp4 = (int)(ldp >> 2);
     const int my_row = multi_row<ROWS>(lane);
     const bool writer = (lane & (32 / ROWS - 1)) == 0;
-    bool any_lo_written = false, bad = false;
+    bool any_lo_written = false;
     float max_ss = 0.f;
     unsigned max_abs_bits = 0u;
     for (int64_t r0 = warp * ROWS; r0 < n; r0 += nwarps * ROWS) {
@@ -295,20 +299,26 @@ prepare_rows_f32_kernel(const float* __restrict__ x, int64_t n, int d, int64_t l
                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         float ss[ROWS];
-        unsigned am[ROWS];
+        unsigned am[ROWS], mant[ROWS], minm1[ROWS];
 #pragma unroll
         for (int i = 0; i < ROWS; ++i) {
-            float s = 0.f, a = 0.f;
+            float s = 0.f;
+            unsigned a = 0u, m = 0u, mn = 0xFFFFFFFFu;
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
                 const float4 t = v[i][j];
+                const unsigned b0 = __float_as_uint(t.x), b1 = __float_as_uint(t.y), b2 = __float_as_uint(t.z),
+                               b3 = __float_as_uint(t.w);
+                const unsigned a0 = b0 & 0x7FFFFFFFu, a1 = b1 & 0x7FFFFFFFu, a2 = b2 & 0x7FFFFFFFu, a3 = b3 & 0x7FFFFFFFu;
                 s = fmaf(t.x, t.x, s); s = fmaf(t.y, t.y, s); s = fmaf(t.z, t.z, s); s = fmaf(t.w, t.w, s);
-                a = fmaxf(a, absmax4(t));
-                // fmaxf drops NaN: test every element (x - x is NaN for NaN and +-Inf, 0 otherwise)
-                bad |= ((t.x - t.x) + (t.y - t.y) + (t.z - t.z) + (t.w - t.w)) != 0.f;
+                a = max(max(a, a0), max(a1, max(a2, a3)));
+                m |= b0 | b1 | b2 | b3;
+                mn = min(min(mn, a0 - 1u), min(a1 - 1u, min(a2 - 1u, a3 - 1u)));
             }
             ss[i] = s;
-            am[i] = __reduce_max_sync(0xffffffffu, __float_as_uint(a));    // non-negative floats order like their bits
+            mant[i] = m;
+            minm1[i] = mn;
+            am[i] = __reduce_max_sync(0xffffffffu, a);
         }
         const float row_ss = multi_sum<ROWS>(ss, lane);                    // total of row r0 + my_row
         if (writer && r0 + my_row < n) {
@@ -319,15 +329,15 @@ prepare_rows_f32_kernel(const float* __restrict__ x, int64_t n, int d, int64_t l
         for (int i = 0; i < ROWS; ++i) {
             const int64_t r = r0 + i;
             if (r >= n) continue;                               // warp-uniform
-            const float scale = scale_from_absmax(__uint_as_float(am[i]));
-            max_abs_bits = max(max_abs_bits, am[i]);
-            bool inexact = false;
-#pragma unroll
-            for (int j = 0; j < NV; ++j) {
-                const float4 t = v[i][j];
-                inexact |= f16_inexact(t.x * scale) | f16_inexact(t.y * scale) | f16_inexact(t.z * scale) |
-                           f16_inexact(t.w * scale);
-            }
+            max_abs_bits = max(max_abs_bits, am[i]);            // >= 0x7F800000 <=> the row holds a NaN or an Inf
+            // scale = 2^sh puts the row maximum in [2^13, 2^14): sh = 13 - (biased exponent - 127), clamped like
+            // scale_from_absmax; an all-zero row keeps scale 1
+            int sh = 140 - (int)(am[i] >> 23);
+            sh = max(-100, min(100, sh));
+            if (am[i] == 0u) sh = 0;
+            const float scale = __uint_as_float((unsigned)(127 + sh) << 23);
+            const unsigned small_thr = (unsigned)(127 - 14 - sh) << 23;       // bits of 2^-14 / scale
+            const bool inexact = ((mant[i] & 0x1FFFu) != 0u) | (minm1[i] < small_thr - 1u);
             const bool row_lo = __any_sync(0xffffffffu, inexact);
             if (!row_lo) {
                 // the common case for descriptors (integer-valued SIFT, ORB as float): one packed conversion per two
@@ -363,7 +373,7 @@ prepare_rows_f32_kernel(const float* __restrict__ x, int64_t n, int d, int64_t l
                 }
             }
             if (lane == 0) {
-                row_inv[r] = 1.f / scale;
+                row_inv[r] = __uint_as_float((unsigned)(127 - sh) << 23);
                 if (lo_skipped) lo_skipped[r] = (lo && !row_lo) ? 1 : 0;
             }
             any_lo_written |= row_lo;
@@ -372,11 +382,10 @@ prepare_rows_f32_kernel(const float* __restrict__ x, int64_t n, int d, int64_t l
     max_ss = warp_max(max_ss);
     if (lane == 0) {
         if (max_ss > 0.f) atomicMax(reinterpret_cast<int*>(meta + META_MAX_NORM_SQ), __float_as_int(max_ss));
-        if (max_abs_bits != 0u && max_abs_bits < 0x7F800000u)
-            atomicMax(reinterpret_cast<int*>(meta + META_ABSMAX), (int)max_abs_bits);
+        if (max_abs_bits >= 0x7F800000u) meta[META_NONFINITE] = 1.f;
+        else if (max_abs_bits != 0u) atomicMax(reinterpret_cast<int*>(meta + META_ABSMAX), (int)max_abs_bits);
         if (any_lo_written) meta[META_LO_NONZERO] = 1.f;
     }
-    if (__any_sync(0xffffffffu, bad) && lane == 0) meta[META_NONFINITE] = 1.f;
 }
 
 // rows that skipped their (all-zero) lo store get it now -- only when the tensor as a whole has a lo plane in use
@@ -576,12 +585,10 @@ ISE_EXPORT int ise_prepare_rows(ise_ctx* ctx, const void* x, int dtype, int64_t 
     const bool al16 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15) == 0;
     if (dtype == ISE_DTYPE_F32 && d % 4 == 0 && ldx % 4 == 0 && al16 && ldp <= 512 && !getenv("ISE_PREPARE_TWO_PASS")) {
         ISE_CUDA(cudaMemsetAsync(meta, 0, META_FLOATS * sizeof(float), st));
-        constexpr int ROWS = 4;
-        const int g4 = grid_for_rows(ctx, ceil_div64(n, ROWS));
         const int nv = (int)((ldp / 4 + 31) / 32);
 #define ISE_ROWS_ARGS (const float*)x, n, d, ldx, (__half*)hi, (__half*)lo, ldp, norms, row_inv, lo_skipped, meta
-        if (nv <= 1) prepare_rows_f32_kernel<ROWS, 1><<<g4, kThreads, 0, st>>>(ISE_ROWS_ARGS);
-        else if (nv == 2) prepare_rows_f32_kernel<ROWS, 2><<<g4, kThreads, 0, st>>>(ISE_ROWS_ARGS);
+        if (nv <= 1) prepare_rows_f32_kernel<4, 1><<<grid_for_rows(ctx, ceil_div64(n, 4)), kThreads, 0, st>>>(ISE_ROWS_ARGS);
+        else if (nv == 2) prepare_rows_f32_kernel<4, 2><<<grid_for_rows(ctx, ceil_div64(n, 4)), kThreads, 0, st>>>(ISE_ROWS_ARGS);
         else prepare_rows_f32_kernel<2, 4><<<grid_for_rows(ctx, ceil_div64(n, 2)), kThreads, 0, st>>>(ISE_ROWS_ARGS);
 #undef ISE_ROWS_ARGS
         ISE_LAUNCH_CHECK();

@@ -563,21 +563,27 @@ def kmeans_accumulate(x: torch.Tensor, assign: torch.Tensor, dis: torch.Tensor |
 
 def kmeans_accumulate_sorted(x: torch.Tensor, assign: torch.Tensor, sums: torch.Tensor, counts: torch.Tensor,
                              obj: torch.Tensor | None, centroids: torch.Tensor | None = None, metric: int = METRIC_IP,
-                             workspace: torch.Tensor | None = None):
+                             workspace: torch.Tensor | None = None, exact_op: "Operand | None" = None):
     """Atomics-free update: counting sort of the rows by centroid + chunked gather-reduce (see include/ise.h).
-    ``workspace``: optional persistent uint8 tensor (grown by the caller across iterations)."""
+    ``workspace``: optional persistent uint8 tensor (grown by the caller across iterations).
+    ``exact_op``: the row operand of ``x`` when it is EXACT in its FP16 hi plane (``lo is None`` after
+    ``compact_operand``, per-row scales): the rows are then gathered from that plane -- the same values at half the
+    bytes of the float32 rows."""
     if x.dtype not in (torch.float32, torch.uint8):
         raise IseError("kmeans_accumulate_sorted: float32 or uint8 rows")
-    dt = DTYPE_F32 if x.dtype == torch.float32 else DTYPE_U8
     n, d = x.shape
     k = int(sums.shape[0])
     assign = assign.reshape(-1)
+    src, dt, ld, row_inv = x, (DTYPE_F32 if x.dtype == torch.float32 else DTYPE_U8), (x.stride(0) if n > 0 else d), None
+    if (exact_op is not None and x.dtype == torch.float32 and exact_op.lo is None and exact_op.row_inv is not None
+            and exact_op.n == n and d % 4 == 0):
+        src, dt, ld, row_inv = exact_op.hi, _lib.DTYPE_F16, exact_op.ldp, exact_op.row_inv
     lib, ctx = _lib.load(), _lib.ctx(_dev(x))
     need = lib.ise_kmeans_accumulate_workspace_bytes(ctx, n, k)
     if workspace is None or workspace.numel() < need:
         workspace = torch.empty((max(need, 1),), dtype=torch.uint8, device=x.device)
     _lib.check(lib.ise_kmeans_accumulate_sorted(
-        ctx, _ptr(x), dt, n, d, x.stride(0) if n > 0 else d, _ptr(assign), _ptr(centroids), k, int(metric), _ptr(sums),
+        ctx, _ptr(src), dt, n, d, ld, _ptr(row_inv), _ptr(assign), _ptr(centroids), k, int(metric), _ptr(sums),
         _ptr(counts), _ptr(obj), _ptr(workspace), workspace.numel(), _stream()))
     _count(4)
     return workspace

@@ -97,10 +97,11 @@ class DeviceOps:
         return ops.search_topk(x, a_op, cent, ops.prepare_operand(cent), metric, 1, precision=precision,
                                need_distances=False)
 
-    def accumulate(self, x, assign, dis, sums, counts, obj, cent=None, metric=METRIC_IP):
-        # ids from the tensor cores; the objective terms are recomputed in exact FP32 inside the update
+    def accumulate(self, x, assign, dis, sums, counts, obj, cent=None, metric=METRIC_IP, a_op=None):
+        # ids from the tensor cores; the objective terms are recomputed in exact FP32 inside the update; descriptors
+        # that are exact in their FP16 hi plane (integer-valued SIFT, ORB as float) are gathered from that plane
         self._acc_ws = ops.kmeans_accumulate_sorted(x, assign, sums, counts, obj, centroids=cent, metric=metric,
-                                                    workspace=self._acc_ws)
+                                                    workspace=self._acc_ws, exact_op=a_op)
 
     def finalize(self, sums, counts, cent, n_global, spherical, obj):
         """mean -> split empties (host plan, sequential Faiss RNG) -> renorm.  Returns (nsplit, objective): the
@@ -192,7 +193,7 @@ def lloyd_train(cp, d, k, x_train, n_train, a_op, lops, *, init_rows, init_centr
                 ev[1].record()
             accum.zero_()
             obj.zero_()
-            lops.accumulate(x_train, assign, dis, sums, counts, obj, cent, metric)
+            lops.accumulate(x_train, assign, dis, sums, counts, obj, cent, metric, a_op)
             if trace is not None:
                 trace.append(dict(redo=redo, it=it, centroids_in=cent.clone(), assign=assign.clone(), dis=dis.clone()))
             if timed:
@@ -202,7 +203,8 @@ def lloyd_train(cp, d, k, x_train, n_train, a_op, lops, *, init_rows, init_centr
                 allreduce(obj)
             if timed:
                 ev[3].record()
-            t_fin = time.time()
+                torch.cuda.current_stream().synchronize()     # finalize reads the statistics back anyway; this keeps the
+            t_fin = time.time()                               # device phases out of its host wall time
             nsplit, o = lops.finalize(sums, counts, cent, n_train, cp.spherical, obj)
             st = dict(obj=o, nsplit=nsplit, time=time.time() - t_start, time_search=0.0, imbalance_factor=float("nan"))
             if cp.verbose:

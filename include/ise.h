@@ -37,6 +37,8 @@ extern "C" {
 /* element type of raw descriptor rows (descriptors.py:216-258: ORB/BRISK uint8, SIFT float32) */
 #define ISE_DTYPE_F32 0
 #define ISE_DTYPE_U8 1
+/* rows of an FP16 hi plane written by ise_prepare_rows (ise_kmeans_accumulate_sorted only) */
+#define ISE_DTYPE_F16 2
 
 /* histogram binning: np.histogram(idx, bins=k) over [min,max] (bag_of_visual_words.py:103,
  * SURVEY quirk Q1) or the intended bincount(idx, minlength=k) */
@@ -213,10 +215,14 @@ int ise_kmeans_accumulate(ise_ctx* ctx, const void* x, int dtype, int64_t n, int
 /* Same contract, atomics-free: the rows are grouped by centroid with a counting sort (ids -> histogram -> scan ->
  * scatter of (centroid, row) pairs), the sorted list is cut into fixed 64-row chunks and each chunk is gathered with
  * 128-bit loads and summed in registers, one vector reduction per lane per run of equal ids (C2: ~1.3 per 64 rows
- * instead of 64).  Objective always recomputed from `centroids` (nullable: no objective).  Falls back to
+ * instead of 64).  dtype ISE_DTYPE_F16: x is the FP16 hi plane of ise_prepare_rows (pitch ldx halves) and row_inv its
+ * per-row 1 / scale -- valid when the operand is exact in that plane (meta lo_nonzero == 0: integer-valued SIFT, ORB),
+ * and half the gather traffic of the FP32 rows; row_inv is NULL otherwise.
+ * Objective always recomputed from `centroids` (nullable: no objective).  Falls back to
  * ise_kmeans_accumulate for rows that are not 4-column aligned.  workspace: ise_kmeans_accumulate_workspace_bytes. */
 size_t ise_kmeans_accumulate_workspace_bytes(ise_ctx* ctx, int64_t n, int64_t k);
 int ise_kmeans_accumulate_sorted(ise_ctx* ctx, const void* x, int dtype, int64_t n, int d, int64_t ldx,
+                                 const float* row_inv,
                                  const int64_t* assign, const float* centroids, int64_t k, int metric,
                                  float* sums, float* counts, double* obj,
                                  void* workspace, size_t workspace_bytes, void* stream);

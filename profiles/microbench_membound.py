@@ -51,6 +51,10 @@ def rec(name, ms, nbytes):
 rec("prepare f32, integer-valued (absmax + hi plane + norms; 10 B/element moved)", t(lambda: ops.prepare_operand(X)), n * d * 10)
 Xf = X + 0.37
 rec("prepare f32, general (absmax + hi/lo planes + norms; 12 B/element moved)", t(lambda: ops.prepare_operand(Xf)), n * d * 12)
+import os
+os.environ["ISE_PREP_ROWS"] = "4"
+rec("prepare ROWS f32, integer-valued, 4 rows in flight per warp (A/B)", t(lambda: ops.prepare_operand(X, rows=True)), n * d * 6)
+os.environ.pop("ISE_PREP_ROWS")
 rec("prepare ROWS f32, integer-valued (single pass: 4 B read + hi plane + norms; 6 B/element)", t(lambda: ops.prepare_operand(X, rows=True)), n * d * 6)
 rec("prepare ROWS f32, general (single pass: 4 B read + hi/lo planes + norms; 8 B/element)", t(lambda: ops.prepare_operand(Xf, rows=True)), n * d * 8)
 rec("prepare u8 (one plane + norms)", t(lambda: ops.prepare_operand(Xu8)), n * d * (1 + 2))
@@ -65,6 +69,10 @@ def _sorted(x):
     ws[0] = ops.kmeans_accumulate_sorted(x, words, sums, counts, obj, centroids=cent, workspace=ws[0])
 rec("kmeans_accumulate_sorted f32 (counting sort + gather-reduce, + exact objective)", t(lambda: _sorted(X)), n * (4 * d + 8))
 rec("kmeans_accumulate_sorted u8", t(lambda: _sorted(Xu8)), n * (d + 8))
+a_rows = ops.compact_operand(ops.prepare_operand(X, rows=True))
+def _sorted_h():
+    ws[0] = ops.kmeans_accumulate_sorted(X, words, sums, counts, obj, centroids=cent, workspace=ws[0], exact_op=a_rows)
+rec("kmeans_accumulate_sorted, rows gathered from the exact FP16 hi plane (2 d + 12 B/row)", t(_sorted_h), n * (2 * d + 12))
 val = torch.empty((n, 1), dtype=torch.float32, device=dev)
 rec("rescore top-1 (exact distances of the winners)", t(lambda: ops.rescore_topk_(X, cent, a, b, METRIC_IP, val, words)), n * (4 * d + 12))
 Y = X.clone()

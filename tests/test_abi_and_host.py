@@ -250,6 +250,8 @@ def test_split_plan_sparse_stream_index_equals_dense_scan(monkeypatch):
         return pairs, h_new, time.perf_counter() - t0
 
     p_small, h_small, t_cold = plan(30, dense=False)             # cold index: generates ~2 M draws
+    _lib.check(_lib.load().ise_split_plan_warm(1_000_000))        # a finished warm-up must not block a later, larger one
+    time.sleep(0.2)
     _lib.check(_lib.load().ise_split_plan_warm(40_000_000))       # background warm-up, returns at once
     p_big, h_big, _ = plan(400, dense=False)                      # needs ~26 M draws: extends / waits for the warm-up
     p_big2, h_big2, t_warm = plan(400, dense=False)               # fully cached now

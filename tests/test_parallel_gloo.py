@@ -34,7 +34,7 @@ class OracleOps:
         D, I = fs.knn(a_op.numpy().astype(np.float32), cent.numpy(), 1, metric)
         return torch.from_numpy(D), torch.from_numpy(I)
 
-    def accumulate(self, x, assign, dis, sums, counts, obj, cent=None, metric=None):
+    def accumulate(self, x, assign, dis, sums, counts, obj, cent=None, metric=None, a_op=None):
         a = assign.numpy().ravel()
         np.add.at(counts.numpy(), a, np.float32(1))
         np.add.at(sums.numpy(), a, x.numpy().astype(np.float32))
