@@ -303,6 +303,23 @@ def run_c4(args, torch, dist, dev, rank, world, barrier, max_over_ranks, ops, P)
     ar_steady = float(np.median(ar_ms[1:] or ar_ms))
     as_ms = [max_over_ranks(v) for v in phases["ms_assign"]]            # collectives: every rank takes part
     a_ms = float(np.median(as_ms[1:] or as_ms))
+    # the collective on its own: the per-iteration figure above (event after the update -> event after the all-reduce)
+    # also contains the time this rank WAITS for the slowest rank's assign to finish (rank skew), which is what made the
+    # round-1 numbers look erratic (0.3 - 3.6 ms for the same 33.8 MB); here: same buffer size, ranks aligned by a barrier
+    ar_pure = None
+    if world > 1:
+        buf = torch.zeros((C4["k"] * C4["d"] + C4["k"],), dtype=torch.float32, device=dev)
+        for _ in range(2):
+            dist.all_reduce(buf)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            dist.all_reduce(buf)
+        e1.record()
+        torch.cuda.synchronize()
+        ar_pure = max_over_ranks(e0.elapsed_time(e1) / 5)
+        del buf
     # ---- parity: (1) every rank ends with bit-identical centroids (the finalize is deterministic, no broadcast);
     #      (2) >= 256 sampled rows of this rank re-assigned by the oracle against the trained 65 536-centroid codebook
     cent = torch.from_numpy(km.centroids).to(dev)
@@ -344,10 +361,10 @@ def run_c4(args, torch, dist, dev, rank, world, barrier, max_over_ranks, ops, P)
                "ms_per_iter": it_ms, "ms_per_iter_steady": float(np.median(steady)),
                "phases_ms_rank0": {p_: [round(v, 3) for v in phases[p_]] for p_ in phases},
                "nsplit": [s["nsplit"] for s in st],
-               "allreduce": {"bytes_per_iter": ar_bytes, "ms": ar_ms, "ms_steady": ar_steady,
-                             "algbw_gbs": (ar_bytes / (ar_steady * 1e-3) / 1e9) if (world > 1 and ar_steady > 0) else None,
-                             "busbw_gbs": (ar_bytes * 2 * (world - 1) / world / (ar_steady * 1e-3) / 1e9)
-                             if (world > 1 and ar_steady > 0) else None},
+               "allreduce": {"bytes_per_iter": ar_bytes, "ms_in_loop_incl_rank_skew": ar_ms,
+                             "ms_in_loop_steady": ar_steady, "ms_collective_alone": ar_pure,
+                             "algbw_gbs": (ar_bytes / (ar_pure * 1e-3) / 1e9) if ar_pure else None,
+                             "busbw_gbs": (ar_bytes * 2 * (world - 1) / world / (ar_pure * 1e-3) / 1e9) if ar_pure else None},
                "Mdescriptors_per_s_steady": C4["n"] / (float(np.median(steady)) * 1e-3) / 1e6,
                "assign_roofline": {"bound": "tensor", "achieved": flops / world / (a_ms * 1e-3) / 1e12, "peak": P["tf_burst"],
                                    "unit": "TFLOP/s per GPU", "frac": flops / world / (a_ms * 1e-3) / 1e12 / P["tf_burst"],
