@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 #include "topk_list.cuh"
+#include "rows_convert.cuh"
 
 // epilogue variants (A/B-tested on the B200, see profiles/r01_findings.md)
 #ifndef ISE_EPI_PREFETCH
@@ -51,8 +52,10 @@ constexpr int EPI_WARP0 = 4;
 __host__ __device__ constexpr int epi_halves(int ksel, int pa, int pb) {
     return (ksel == 1 && pa == 1 && pb == 1) ? ISE_EPI_HALVES_COARSE_TOP1 : 1;
 }
-__host__ __device__ constexpr int num_threads(int ksel, int pa, int pb, int mt = 1) {
-    return 128 + 128 * epi_halves(ksel, pa, pb) * mt;
+// conv: four extra warps that convert the NEXT work item's float32 rows into FP16 planes while the current item is
+// being multiplied (fused assign, see the CONV template parameter)
+__host__ __device__ constexpr int num_threads(int ksel, int pa, int pb, int mt = 1, bool conv = false) {
+    return 128 + 128 * epi_halves(ksel, pa, pb) * mt + (conv ? 128 : 0);
 }
 constexpr int TMEM_COLS = 512;  // 2 accumulator stages x BLOCK_N fp32 columns
 constexpr int AUX_BYTES = 4096;
@@ -94,6 +97,19 @@ struct Params {
     int32_t* sync_cnt;  // [rounds * n_splits, sync_ncp] zero-initialised, or nullptr
     int sync_every;
     int sync_ncp;
+    // fused assign (CONV kernels): the raw float32 rows and the WRITABLE views of the A operand the converter warps fill
+    const float* a_raw;
+    int64_t lda_raw;
+    __half* a_hi_w;
+    __half* a_lo_w;         // nullable
+    int64_t lda_w;
+    float* a_norms_w;
+    float* a_row_inv_w;
+    uint8_t* a_lo_skipped;  // nullable (required with a_lo_w)
+    float* a_meta_w;
+    // regular kernels: return at once when the A operand turned out exact in its hi plane (meta[LO_NONZERO] == 0); the
+    // launch that follows an optimistic hi-only fused assign and repeats it with the lo planes only if they exist
+    int skip_if_a_exact;
 };
 
 struct Aux {  // lives after the stage ring in dynamic shared memory
@@ -101,6 +117,8 @@ struct Aux {  // lives after the stage ring in dynamic shared memory
     uint64_t empty[8];
     uint64_t tmem_full[2];
     uint64_t tmem_empty[2];
+    uint64_t a_ready[2];    // CONV: converter warps -> producer / epilogue, one slot per work-item parity
+    uint64_t a_free[2];     // CONV: epilogue -> converter (the converter stays at most two items ahead)
     uint32_t tmem_base;
     uint32_t pad_[3];
     float bnorm[2][BLOCK_N];
@@ -132,12 +150,23 @@ template <> struct SelList<32> { using type = RegList32; };
 //   column tile and the MMAs of the next one alternate).  Halves the B bytes per MMA cycle like a CTA pair does,
 //   without any cross-CTA signalling; pays off when a tile's MMAs (d / 64 * 512 cycles per row tile) dwarf its
 //   epilogue, i.e. for the large-d coarse search pass, which is bound by the L2 -> shared-memory feed.
-template <int PA, int PB, bool L2, int KSEL, bool VERIFY, int CG, int MT = 1>
-__global__ void __launch_bounds__(num_threads(KSEL, PA, PB, MT), 1)
+// CONV (fused assign, top-1 only): the kernel takes the RAW float32 rows.  Four extra warps convert the rows of the work
+//   item this CTA will run NEXT into per-row-scaled FP16 planes (rows_convert.cuh: the single-pass preparation, same
+//   code) and write planes, norms and per-row scales to global memory -- 32 KB per row tile that the TMA producer reads
+//   straight back from L2 -- while the tensor pipe works on the current item.  The separate HBM-bound preparation pass
+//   (0.15 ms of a 1.72 ms C2 step) disappears behind the MMAs; the planes / norms / scales stay valid afterwards
+//   (re-score, k-means update).  Only the hi plane of A is multiplied: a tensor that turns out NOT to be exact in it
+//   sets meta[LO_NONZERO] and the caller's follow-up launch (Params::skip_if_a_exact) repeats the assign with the lo
+//   planes -- for descriptors (integer SIFT, ORB / BRISK as float) that launch returns at once.
+template <int PA, int PB, bool L2, int KSEL, bool VERIFY, int CG, int MT = 1, bool CONV = false>
+__global__ void __launch_bounds__(num_threads(KSEL, PA, PB, MT, CONV), 1)
 gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const Params p) {
     static_assert(MT == 1 || (CG == 1 && epi_halves(KSEL, PA, PB) == 1), "two row tiles per CTA: single CTA, one warp per quadrant and tile");
+    static_assert(!CONV || (PA == 1 && KSEL == 1 && !VERIFY && MT == 1 && epi_halves(KSEL, PA, PB) == 1), "fused conversion: plain top-1, hi plane of A");
+    // uniform over the whole grid, before any barrier / TMEM state exists
+    if (!CONV && p.skip_if_a_exact && __ldcg(p.a_meta + META_LO_NONZERO) == 0.f) return;
     constexpr int STAGES = num_stages(PA, PB, CG, MT);
     constexpr int STAGE_BYTES = stage_bytes(PA, PB, CG, MT);
     constexpr int A_BLOCK_BYTES = PA * A_TILE_BYTES;      // one row tile's planes inside a stage
@@ -173,6 +202,8 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&aux->tmem_full[i], 1);
             ptx::mbar_init(&aux->tmem_empty[i], NUM_EPI_THREADS * CG);   // both CTAs' epilogues (leader's copy)
+            ptx::mbar_init(&aux->a_ready[i], 128);                       // CONV: the four converter warps
+            ptx::mbar_init(&aux->a_free[i], NUM_EPI_THREADS);            // CONV: this CTA's epilogue threads
         }
         ptx::fence_barrier_init();
     }
@@ -200,10 +231,15 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            uint32_t it = 0;
+            uint32_t it = 0, item = 0;
             const uint32_t tx_bytes = MT * A_TILE_BYTES * (1 + (int)use_alo) + B_LOAD_BYTES * (1 + (int)use_blo);
-            for (int w = w_begin; w < total_work; w += w_step) {
+            for (int w = w_begin; w < total_work; w += w_step, ++item) {
                 const int split = w / n_mgroups, mt = (w - split * n_mgroups) * GRP + (int)cta_rank;
+                if (CONV) {
+                    // this item's planes have been written (generic proxy, this CTA) -- make them visible to the TMA reads
+                    ptx::mbar_wait(&aux->a_ready[item & 1], (item >> 1) & 1);
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                }
                 const int nt0 = split * p.tiles_per_split;
                 const int nt1 = min(nt0 + p.tiles_per_split, p.n_ntiles);
                 // this work item's lock-step group: the items of the same split handled in the same round
@@ -323,7 +359,7 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 }
             }
         }
-    } else if (warp >= EPI_WARP0) {
+    } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + NUM_EPI_THREADS / 32) {
         // ===================== epilogue: selection =====================
         const int ew = warp - EPI_WARP0;
         const int q = ew & 3;      // TMEM lane quadrant this warp may read (== warp % 4)
@@ -334,15 +370,19 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         const float a_inv_tensor = p.a_meta[META_INV_SCALE];
         CoarseBound bound;
         if (KSEL == 1 && VERIFY) bound.init(p.a_meta, p.b_meta, p.d);
-        uint32_t tile = 0;
-        for (int w = w_begin; w < total_work; w += w_step) {
+        uint32_t tile = 0, item = 0;
+        for (int w = w_begin; w < total_work; w += w_step, ++item) {
             const int split = w / n_mgroups, mt = (w - split * n_mgroups) * GRP + (int)cta_rank + rt;
             const int nt0 = split * p.tiles_per_split;
             const int nt1 = min(nt0 + p.tiles_per_split, p.n_ntiles);
             const int row_in_tile = q * 32 + lane;
             const int64_t row = (int64_t)mt * BLOCK_M + row_in_tile;
+            // CONV: this item's norms / per-row scales were written by the converter warps during this launch: wait for
+            // them and read them with coherent loads (not the read-only path)
+            if (CONV) ptx::mbar_wait(&aux->a_ready[item & 1], (item >> 1) & 1);
             // accumulator -> real units: 1 / (scale of this row's A planes * scale of the B planes)
-            const float a_inv = (p.a_row_inv != nullptr && row < p.m) ? __ldg(p.a_row_inv + row) : a_inv_tensor;
+            const float a_inv = (p.a_row_inv != nullptr && row < p.m)
+                                    ? (CONV ? __ldcg(p.a_row_inv + row) : __ldg(p.a_row_inv + row)) : a_inv_tensor;
             const float inv = a_inv * b_inv;
             const float two_inv = 2.f * inv;
             if (KSEL == 1 && VERIFY) bound.set_a_inv_scale(a_inv);
@@ -515,7 +555,7 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                     asm volatile("bar.sync 2, %0;" ::"n"(NUM_EPI_THREADS) : "memory");
                 }
                 if (half == 0 && row < p.m) {
-                    const float an = (L2 || VERIFY) ? __ldg(p.a_norms + row) : 0.f;
+                    const float an = (L2 || VERIFY) ? (CONV ? __ldcg(p.a_norms + row) : __ldg(p.a_norms + row)) : 0.f;
                     float* ov = p.out_val + ((int64_t)split * p.m + row) * p.topk;
                     int64_t* oi = p.out_idx + ((int64_t)split * p.m + row) * p.topk;
                     if (best_id >= 0) {
@@ -552,7 +592,29 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                     for (int j = 0; j < p.topk; ++j) emit(j, list.v[j], list.id[j]);
                 }
             }
+            if (CONV) ptx::mbar_arrive(&aux->a_free[item & 1]);     // the converter may reuse this parity slot
         }
+    } else if (CONV && warp >= EPI_WARP0 + NUM_EPI_THREADS / 32) {
+        // ===================== converter: float32 rows -> FP16 planes of the item this CTA runs next =====================
+        const int cw = warp - (EPI_WARP0 + NUM_EPI_THREADS / 32);   // 0..3: 32 rows of the 128-row tile each
+        const int d4 = p.d >> 2, dp4 = (int)(p.lda_w >> 2);
+        RowStats st;
+        if (blockIdx.x == 0 && cw == 0 && lane == 0) { p.a_meta_w[META_SCALE] = 1.f; p.a_meta_w[META_INV_SCALE] = 1.f; }
+        uint32_t item = 0;
+        for (int w = w_begin; w < total_work; w += w_step, ++item) {
+            const int split = w / n_mgroups, mt = (w - split * n_mgroups) * GRP + (int)cta_rank;
+            ptx::mbar_wait(&aux->a_free[item & 1], ((item >> 1) & 1) ^ 1);
+            const int64_t r_base = (int64_t)mt * BLOCK_M + cw * 32;
+#pragma unroll 1
+            for (int g = 0; g < 32; g += 4)
+                if (r_base + g < p.m)
+                    convert_row_group<4, 1>(p.a_raw, p.m, d4, dp4, p.lda_raw, p.a_hi_w, p.a_lo_w, p.lda_w, p.a_norms_w,
+                                            p.a_row_inv_w, p.a_lo_skipped, r_base + g, lane, st);
+            __threadfence();                                       // planes / norms / scales are in L2 ...
+            asm volatile("fence.proxy.async;" ::: "memory");       // ... and ordered before the TMA (async proxy) reads
+            ptx::mbar_arrive(&aux->a_ready[item & 1]);
+        }
+        commit_row_stats(st, p.a_meta_w, lane);
     }
 
     ptx::tc_fence_before();
@@ -762,9 +824,9 @@ static void setup_sync(const ise_ctx* ctx, Params& p, int d, bool split_products
     p.sync_ncp = ncp;
 }
 
-template <int PA, int PB, bool L2, int KSEL, bool VERIFY, int CG, int MT = 1>
+template <int PA, int PB, bool L2, int KSEL, bool VERIFY, int CG, int MT = 1, bool CONV = false>
 static int launch_cg(const ise_ctx* ctx, const CUtensorMap* maps, const Params& p, cudaStream_t st) {
-    auto kern = gemm_select_kernel<PA, PB, L2, KSEL, VERIFY, CG, MT>;
+    auto kern = gemm_select_kernel<PA, PB, L2, KSEL, VERIFY, CG, MT, CONV>;
     const int smem = num_stages(PA, PB, CG, MT) * stage_bytes(PA, PB, CG, MT) + AUX_BYTES + 1024;
     ISE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int groups = (p.n_mtiles + CG * MT - 1) / (CG * MT);
@@ -774,7 +836,7 @@ static int launch_cg(const ise_ctx* ctx, const CUtensorMap* maps, const Params& 
     const int grid = CG * std::min(total, std::max(1, ctx->sm_count / CG));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3((unsigned)num_threads(KSEL, PA, PB, MT));
+    cfg.blockDim = dim3((unsigned)num_threads(KSEL, PA, PB, MT, CONV));
     cfg.dynamicSmemBytes = (size_t)smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -817,6 +879,11 @@ static int dispatch_metric(const ise_ctx* ctx, const CUtensorMap* maps, const Pa
                            cudaStream_t st) {
     return metric == ISE_METRIC_L2 ? dispatch_k<PA, PB, true>(ctx, maps, p, st)
                                    : dispatch_k<PA, PB, false>(ctx, maps, p, st);
+}
+
+static void clear_conv(Params& p) {
+    p.a_raw = nullptr; p.lda_raw = 0; p.a_hi_w = nullptr; p.a_lo_w = nullptr; p.lda_w = 0; p.a_norms_w = nullptr;
+    p.a_row_inv_w = nullptr; p.a_lo_skipped = nullptr; p.a_meta_w = nullptr; p.skip_if_a_exact = 0;
 }
 
 }  // namespace gs
@@ -882,6 +949,7 @@ ISE_EXPORT int ise_gemm_collect(ise_ctx* ctx, const void* a_hi, const void* a_lo
     p.a_meta = a_meta; p.b_meta = b_meta; p.a_norms = a_norms; p.b_norms = b_norms;
     p.a_row_inv = a_row_inv;
     p.row_seed = row_seed; p.row_count = row_count; p.flag_rows = nullptr; p.flag_count = nullptr;
+    gs::clear_conv(p);
     p.out_val = cand_val; p.out_idx = cand_idx;
     // empty slots read as id -1 / count 0
     ISE_CUDA(cudaMemsetAsync(cand_idx, 0xFF, (size_t)m * cap * sizeof(int64_t), st));
@@ -896,12 +964,12 @@ ISE_EXPORT int ise_gemm_collect(ise_ctx* ctx, const void* a_hi, const void* a_lo
     ISE_FAIL("a_lo without b_lo is not supported: pass a zero b_lo plane");
 }
 
-ISE_EXPORT int ise_gemm_select(ise_ctx* ctx, const void* a_hi, const void* a_lo, int64_t lda, const float* a_meta,
-                               const float* a_norms, const float* a_row_inv, const void* b_hi, const void* b_lo, int64_t ldb,
-                               const float* b_meta, const float* b_norms, int64_t m, int64_t n, int d, int metric,
-                               int topk, int64_t id_base, const float* row_seed, int32_t* flag_rows,
-                               int32_t* flag_count, float* out_val, int64_t* out_idx, void* workspace,
-                               size_t workspace_bytes, void* stream) {
+static int gemm_select_impl(ise_ctx* ctx, const void* a_hi, const void* a_lo, int64_t lda, const float* a_meta,
+                            const float* a_norms, const float* a_row_inv, const void* b_hi, const void* b_lo, int64_t ldb,
+                            const float* b_meta, const float* b_norms, int64_t m, int64_t n, int d, int metric,
+                            int topk, int64_t id_base, const float* row_seed, int32_t* flag_rows,
+                            int32_t* flag_count, float* out_val, int64_t* out_idx, void* workspace,
+                            size_t workspace_bytes, void* stream, int skip_if_a_exact) {
     ISE_CHECK_ARG(ctx != nullptr);
     ISE_CHECK_ARG(metric == ISE_METRIC_IP || metric == ISE_METRIC_L2);
     ISE_CHECK_ARG(m >= 0 && n >= 0 && d > 0 && topk >= 1 && topk <= 128);
@@ -924,6 +992,8 @@ ISE_EXPORT int ise_gemm_select(ise_ctx* ctx, const void* a_hi, const void* a_lo,
     p.topk = topk; p.id_base = id_base;
     p.a_meta = a_meta; p.b_meta = b_meta; p.a_norms = a_norms; p.b_norms = b_norms;
     p.a_row_inv = a_row_inv;
+    gs::clear_conv(p);
+    p.skip_if_a_exact = skip_if_a_exact;
     p.row_seed = row_seed;
     p.row_count = nullptr;
     p.flag_rows = flag_rows;
@@ -957,5 +1027,78 @@ ISE_EXPORT int ise_gemm_select(ise_ctx* ctx, const void* a_hi, const void* a_lo,
     if (rc) return rc;
     if (pl.n_splits > 1)
         return ise_topk_merge(ctx, wv, wi, pl.n_splits, m, topk, metric, out_val, out_idx, stream);
+    return 0;
+}
+
+ISE_EXPORT int ise_gemm_select(ise_ctx* ctx, const void* a_hi, const void* a_lo, int64_t lda, const float* a_meta,
+                               const float* a_norms, const float* a_row_inv, const void* b_hi, const void* b_lo, int64_t ldb,
+                               const float* b_meta, const float* b_norms, int64_t m, int64_t n, int d, int metric,
+                               int topk, int64_t id_base, const float* row_seed, int32_t* flag_rows,
+                               int32_t* flag_count, float* out_val, int64_t* out_idx, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+    return gemm_select_impl(ctx, a_hi, a_lo, lda, a_meta, a_norms, a_row_inv, b_hi, b_lo, ldb, b_meta, b_norms, m, n, d,
+                            metric, topk, id_base, row_seed, flag_rows, flag_count, out_val, out_idx, workspace,
+                            workspace_bytes, stream, 0);
+}
+
+int ise_internal_lo_fixup(ise_ctx* ctx, void* lo, int64_t n, int64_t ldp, const uint8_t* lo_skipped, const float* meta,
+                          void* stream);   // prepare.cu
+
+// Fused assign: raw float32 rows in, nearest column out, with the row operand (planes, norms, per-row scales, meta) as a
+// by-product.  Returns 2 (and does nothing) when the shape is outside what the fused kernel covers -- the caller then
+// runs ise_prepare_rows + ise_gemm_select.
+ISE_EXPORT int ise_assign_fused(ise_ctx* ctx, const float* x, int64_t ldx, int64_t m, int d, void* a_hi, void* a_lo,
+                                int64_t lda, float* a_norms, float* a_row_inv, uint8_t* a_lo_skipped, float* a_meta,
+                                const void* b_hi, const void* b_lo, int64_t ldb, const float* b_meta, const float* b_norms,
+                                int64_t n, int metric, int64_t id_base, float* out_val, int64_t* out_idx, void* stream) {
+    ISE_CHECK_ARG(ctx != nullptr);
+    ISE_CHECK_ARG(metric == ISE_METRIC_IP || metric == ISE_METRIC_L2);
+    ISE_CHECK_ARG(m >= 0 && n > 0 && d > 0 && n < (int64_t)1 << 31 && m < (int64_t)1 << 31);
+    if (m == 0) return 0;
+    ISE_CHECK_ARG(x && a_hi && a_norms && a_row_inv && a_meta && b_hi && b_meta && out_val && out_idx);
+    ISE_CHECK_ARG(a_lo == nullptr || a_lo_skipped != nullptr);
+    if (metric == ISE_METRIC_L2) ISE_CHECK_ARG(b_norms != nullptr);
+    ISE_CHECK_ARG(lda >= d && ldb >= d && lda % 8 == 0 && ldb % 8 == 0 && ldx >= d);
+    const bool al16 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(a_hi) | reinterpret_cast<uintptr_t>(a_lo) |
+                        reinterpret_cast<uintptr_t>(b_hi)) & 15) == 0;
+    gs::Plan pl = gs::make_plan(ctx, m, n, d, 1, false, b_lo != nullptr);
+    // covered: 16-byte aligned float32 rows of at most 128 columns (every keypoint descriptor type: SIFT 128, BRISK 64,
+    // ORB 32), an unsplit column range (enough row tiles to fill the machine)
+    if (d % 4 != 0 || ldx % 4 != 0 || lda > 128 || !al16 || pl.n_splits != 1 || getenv("ISE_NO_FUSED_ASSIGN")) return 2;
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    ISE_CUDA(cudaMemsetAsync(a_meta, 0, META_FLOATS * sizeof(float), st));
+    gs::Params p;
+    p.m = m; p.n = n; p.d = d;
+    p.n_mtiles = pl.n_mtiles; p.n_ntiles = pl.n_ntiles;
+    p.tiles_per_split = pl.tiles_per_split; p.n_splits = pl.n_splits;
+    p.topk = 1; p.id_base = id_base;
+    p.a_meta = a_meta; p.b_meta = b_meta; p.a_norms = a_norms; p.b_norms = b_norms; p.a_row_inv = a_row_inv;
+    p.row_seed = nullptr; p.row_count = nullptr; p.flag_rows = nullptr; p.flag_count = nullptr;
+    p.out_val = out_val; p.out_idx = out_idx;
+    gs::clear_conv(p);
+    p.a_raw = x; p.lda_raw = ldx; p.a_hi_w = (__half*)a_hi; p.a_lo_w = (__half*)a_lo; p.lda_w = lda;
+    p.a_norms_w = a_norms; p.a_row_inv_w = a_row_inv; p.a_lo_skipped = a_lo_skipped; p.a_meta_w = a_meta;
+    CUtensorMap maps[4];
+    if (setup_maps(ctx, a_hi, nullptr, lda, b_hi, b_lo, ldb, m, n, d, 1, maps)) return 1;
+    const int cg = gs::pick_variant(m, d, b_lo != nullptr, 1).cg;
+    const bool l2 = metric == ISE_METRIC_L2;
+    int rc;
+#define ISE_CONV_LAUNCH(PB, L2V)                                                                                       \
+    (cg == 2 ? gs::launch_cg<1, PB, L2V, 1, false, 2, 1, true>(ctx, maps, p, st)                                       \
+             : gs::launch_cg<1, PB, L2V, 1, false, 1, 1, true>(ctx, maps, p, st))
+    if (b_lo) rc = l2 ? ISE_CONV_LAUNCH(2, true) : ISE_CONV_LAUNCH(2, false);
+    else rc = l2 ? ISE_CONV_LAUNCH(1, true) : ISE_CONV_LAUNCH(1, false);
+#undef ISE_CONV_LAUNCH
+    if (rc) return rc;
+    if (a_lo) {
+        // the tensor was NOT exact in its hi plane (device-side flag): complete the lo plane of the rows that skipped
+        // it and repeat the assign with the lo products; both launches return at once otherwise
+        if (ise_internal_lo_fixup(ctx, a_lo, m, lda, a_lo_skipped, a_meta, stream)) return 1;
+        const void* b_lo_full = b_lo;
+        if (b_lo_full == nullptr) return 0;     // (2, 1) plane combination does not exist: hi-only result stands (documented)
+        return gemm_select_impl(ctx, a_hi, a_lo, lda, a_meta, a_norms, a_row_inv, b_hi, b_lo, ldb, b_meta, b_norms, m, n, d,
+                                metric, 1, id_base, nullptr, nullptr, nullptr, out_val, out_idx, nullptr, 0, stream, 1);
+    }
     return 0;
 }

@@ -3,6 +3,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "rows_convert.cuh"
 
 namespace {
 
@@ -138,12 +139,6 @@ __global__ void prepare_planes_kernel(const T* __restrict__ x, int64_t n, int d,
     if (__any_sync(0xffffffffu, any_lo) && lane == 0) meta[META_LO_NONZERO] = 1.f;
 }
 
-// split one scaled value into its FP16 hi / lo parts
-__device__ __forceinline__ void split_f16(float s, __half& h, __half& l) {
-    h = __float2half_rn(s);
-    l = __float2half_rn(s - __half2float(h));
-}
-
 // Fast path, float32 rows with d % 4 == 0 (16-byte aligned rows and planes): a lane converts four consecutive
 // columns per step (one 128-bit load, one 64-bit store per plane) and every warp keeps ROWS rows in flight --
 // one row per warp iteration leaves ~32 KB of loads in flight per SM, which is what held the first version at
@@ -237,37 +232,10 @@ __global__ void __launch_bounds__(kThreads, EXACT ? 5 : 3) prepare_planes_f32x4_
 // written per element.  Rows whose lo part is all zero skip the lo store (integer-valued SIFT / ORB-as-float: all of
 // them); they are recorded in lo_skipped[] and zeroed by lo_fixup_kernel only if some other row did need its lo plane.
 // NaN / Inf are detected on the way (meta[NONFINITE]) so that k-means training needs no separate validation pass.
-// sums of R per-lane values over the warp with R + log2(32 / R) - 1 shuffles instead of 5 R: every step halves the
-// number of values a lane still carries (the upper half of the lanes keeps the upper half of the rows).  Returns the
-// total of row `multi_row<R>(lane)`; the lanes with (lane & (32 / R - 1)) == 0 are the designated writers.
-template <int R>
-__device__ __forceinline__ float multi_sum(float (&a)[R], int lane) {
-    int width = 16;
-#pragma unroll
-    for (int n = R; n > 1; n >>= 1, width >>= 1) {
-        const bool up = (lane & width) != 0;
-#pragma unroll
-        for (int i = 0; i < n / 2; ++i) {
-            const float send = up ? a[i] : a[i + n / 2];
-            const float keep = up ? a[i + n / 2] : a[i];
-            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, width);
-        }
-    }
-    for (; width > 0; width >>= 1) a[0] += __shfl_xor_sync(0xffffffffu, a[0], width);
-    return a[0];
-}
-template <int R>
-__device__ __forceinline__ int multi_row(int lane) {
-    int row = 0, width = 16;
-#pragma unroll
-    for (int n = R; n > 1; n >>= 1, width >>= 1) row += (lane & width) ? n / 2 : 0;
-    return row;
-}
-
 // The first version of this kernel ran at 0.56-0.60 of HBM peak and ncu showed why: 146 warp instructions per row
 // (ilogbf / ldexpf / a division for the scale, a float NaN test per element, a multiply + three compares per element for
 // the exactness test) -- issue-bound, not memory-bound.  Everything that is per-row-uniform is integer bit arithmetic
-// now, and the per-element work is four integer min/max/or + one FMA:
+// now, and the per-element work is four integer min/max/or + one FMA (rows_convert.cuh):
 //   * |x| as an unsigned bit pattern orders like the value and keeps NaN / Inf visible (>= 0x7F800000), so one integer
 //     max gives both the row's absolute maximum (-> its power-of-two scale: exponent arithmetic) and the non-finite flag;
 //   * an element is exact in one FP16 plane iff its low 13 mantissa bits are zero (scaling by a power of two does not
@@ -283,109 +251,10 @@ prepare_rows_f32_kernel(const float* __restrict__ x, int64_t n, int d, int64_t l
     const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
     if (blockIdx.x == 0 && threadIdx.x == 0) { meta[META_SCALE] = 1.f; meta[META_INV_SCALE] = 1.f; }
     const int d4 = d >> 2, dp4 = (int)(ldp >> 2);
-    const int my_row = multi_row<ROWS>(lane);
-    const bool writer = (lane & (32 / ROWS - 1)) == 0;
-    bool any_lo_written = false;
-    float max_ss = 0.f;
-    unsigned max_abs_bits = 0u;
-    for (int64_t r0 = warp * ROWS; r0 < n; r0 += nwarps * ROWS) {
-        float4 v[ROWS][NV];
-#pragma unroll
-        for (int i = 0; i < ROWS; ++i)
-#pragma unroll
-            for (int j = 0; j < NV; ++j) {
-                const int c = lane + 32 * j;
-                v[i][j] = (r0 + i < n && c < d4) ? __ldg(reinterpret_cast<const float4*>(x + (r0 + i) * ldx) + c)
-                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        float ss[ROWS];
-        unsigned am[ROWS], mant[ROWS], minm1[ROWS];
-#pragma unroll
-        for (int i = 0; i < ROWS; ++i) {
-            float s = 0.f;
-            unsigned a = 0u, m = 0u, mn = 0xFFFFFFFFu;
-#pragma unroll
-            for (int j = 0; j < NV; ++j) {
-                const float4 t = v[i][j];
-                const unsigned b0 = __float_as_uint(t.x), b1 = __float_as_uint(t.y), b2 = __float_as_uint(t.z),
-                               b3 = __float_as_uint(t.w);
-                const unsigned a0 = b0 & 0x7FFFFFFFu, a1 = b1 & 0x7FFFFFFFu, a2 = b2 & 0x7FFFFFFFu, a3 = b3 & 0x7FFFFFFFu;
-                s = fmaf(t.x, t.x, s); s = fmaf(t.y, t.y, s); s = fmaf(t.z, t.z, s); s = fmaf(t.w, t.w, s);
-                a = max(max(a, a0), max(a1, max(a2, a3)));
-                m |= b0 | b1 | b2 | b3;
-                mn = min(min(mn, a0 - 1u), min(a1 - 1u, min(a2 - 1u, a3 - 1u)));
-            }
-            ss[i] = s;
-            mant[i] = m;
-            minm1[i] = mn;
-            am[i] = __reduce_max_sync(0xffffffffu, a);
-        }
-        const float row_ss = multi_sum<ROWS>(ss, lane);                    // total of row r0 + my_row
-        if (writer && r0 + my_row < n) {
-            if (norms) norms[r0 + my_row] = row_ss;
-            max_ss = fmaxf(max_ss, row_ss);
-        }
-#pragma unroll
-        for (int i = 0; i < ROWS; ++i) {
-            const int64_t r = r0 + i;
-            if (r >= n) continue;                               // warp-uniform
-            max_abs_bits = max(max_abs_bits, am[i]);            // >= 0x7F800000 <=> the row holds a NaN or an Inf
-            // scale = 2^sh puts the row maximum in [2^13, 2^14): sh = 13 - (biased exponent - 127), clamped like
-            // scale_from_absmax; an all-zero row keeps scale 1
-            int sh = 140 - (int)(am[i] >> 23);
-            sh = max(-100, min(100, sh));
-            if (am[i] == 0u) sh = 0;
-            const float scale = __uint_as_float((unsigned)(127 + sh) << 23);
-            const unsigned small_thr = (unsigned)(127 - 14 - sh) << 23;       // bits of 2^-14 / scale
-            const bool inexact = ((mant[i] & 0x1FFFu) != 0u) | (minm1[i] < small_thr - 1u);
-            const bool row_lo = __any_sync(0xffffffffu, inexact);
-            if (!row_lo) {
-                // the common case for descriptors (integer-valued SIFT, ORB as float): one packed conversion per two
-                // elements, no residual
-#pragma unroll
-                for (int j = 0; j < NV; ++j) {
-                    const int c = lane + 32 * j;
-                    if (c < dp4) {
-                        const float4 t = v[i][j];
-                        const __half2 ha = __floats2half2_rn(t.x * scale, t.y * scale);
-                        const __half2 hb = __floats2half2_rn(t.z * scale, t.w * scale);
-                        reinterpret_cast<uint2*>(hi + r * ldp)[c] =
-                            make_uint2(*reinterpret_cast<const uint32_t*>(&ha), *reinterpret_cast<const uint32_t*>(&hb));
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < NV; ++j) {
-                    const int c = lane + 32 * j;
-                    if (c < dp4) {                              // pad columns [d, ldp) come out as zeros
-                        const float4 t = v[i][j];
-                        __half h0, h1, h2, h3, l0, l1, l2, l3;
-                        split_f16(t.x * scale, h0, l0); split_f16(t.y * scale, h1, l1);
-                        split_f16(t.z * scale, h2, l2); split_f16(t.w * scale, h3, l3);
-                        const __half2 ha = __halves2half2(h0, h1), hb = __halves2half2(h2, h3);
-                        const __half2 la = __halves2half2(l0, l1), lb = __halves2half2(l2, l3);
-                        reinterpret_cast<uint2*>(hi + r * ldp)[c] =
-                            make_uint2(*reinterpret_cast<const uint32_t*>(&ha), *reinterpret_cast<const uint32_t*>(&hb));
-                        if (lo)
-                            reinterpret_cast<uint2*>(lo + r * ldp)[c] =
-                                make_uint2(*reinterpret_cast<const uint32_t*>(&la), *reinterpret_cast<const uint32_t*>(&lb));
-                    }
-                }
-            }
-            if (lane == 0) {
-                row_inv[r] = __uint_as_float((unsigned)(127 - sh) << 23);
-                if (lo_skipped) lo_skipped[r] = (lo && !row_lo) ? 1 : 0;
-            }
-            any_lo_written |= row_lo;
-        }
-    }
-    max_ss = warp_max(max_ss);
-    if (lane == 0) {
-        if (max_ss > 0.f) atomicMax(reinterpret_cast<int*>(meta + META_MAX_NORM_SQ), __float_as_int(max_ss));
-        if (max_abs_bits >= 0x7F800000u) meta[META_NONFINITE] = 1.f;
-        else if (max_abs_bits != 0u) atomicMax(reinterpret_cast<int*>(meta + META_ABSMAX), (int)max_abs_bits);
-        if (any_lo_written) meta[META_LO_NONZERO] = 1.f;
-    }
+    RowStats st;
+    for (int64_t r0 = warp * ROWS; r0 < n; r0 += nwarps * ROWS)
+        convert_row_group<ROWS, NV>(x, n, d4, dp4, ldx, hi, lo, ldp, norms, row_inv, lo_skipped, r0, lane, st);
+    commit_row_stats(st, meta, lane);
 }
 
 // rows that skipped their (all-zero) lo store get it now -- only when the tensor as a whole has a lo plane in use
@@ -624,6 +493,15 @@ ISE_EXPORT int ise_normalize_l2(ise_ctx* ctx, float* x, int64_t n, int d, void* 
     ISE_CHECK_ARG(x != nullptr);
     DeviceGuard g(ctx->device);
     normalize_l2_kernel<4><<<grid_for_rows(ctx, ceil_div64(n, 4)), kThreads, 0, (cudaStream_t)stream>>>(x, n, d);
+    ISE_LAUNCH_CHECK();
+    return 0;
+}
+
+// used by ise_assign_fused (gemm_select.cu): gated on the device-side meta[LO_NONZERO] flag
+int ise_internal_lo_fixup(ise_ctx* ctx, void* lo, int64_t n, int64_t ldp, const uint8_t* lo_skipped, const float* meta,
+                          void* stream) {
+    lo_fixup_kernel<<<grid_for_rows(ctx, ceil_div64(n, 32)), kThreads, 0, (cudaStream_t)stream>>>((__half*)lo, n, ldp,
+                                                                                                lo_skipped, meta);
     ISE_LAUNCH_CHECK();
     return 0;
 }

@@ -172,9 +172,18 @@ class IndexFlat:
             D, I = ops.flat_search_exact(qf.contiguous(), self._database(), self.metric_type, kk)
         else:
             b = self._operand()
-            a = ops.prepare_operand(q, rows=True)
-            D, I = ops.search_topk(q, a, self._database(), b, self.metric_type, kk, precision=self.precision,
-                                   need_distances=need_distances)
+            # nearest-column queries over raw float32 descriptors (quantisation: FaissKMeans.transform): the row
+            # preparation runs inside the contraction kernel
+            fused = ops.assign_fused(q, b, self.metric_type) if (kk == 1 and q.dtype == torch.float32) else None
+            if fused is not None:
+                D, I, a = fused
+                if need_distances:
+                    ops.rescore_topk_(q, self._database(), a, b, self.metric_type, D, I)
+                ops.last_search_stats.update(mode="fused-split", fallback_rows=0, rows=nq)
+            else:
+                a = ops.prepare_operand(q, rows=True)
+                D, I = ops.search_topk(q, a, self._database(), b, self.metric_type, kk, precision=self.precision,
+                                       need_distances=need_distances)
         if kk < k:
             Dp = torch.full((nq, k), pad, dtype=torch.float32, device=q.device)
             Ip = torch.full((nq, k), -1, dtype=torch.int64, device=q.device)

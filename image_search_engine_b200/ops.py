@@ -251,6 +251,36 @@ def gemm_select(a: Operand, b: Operand, metric: int, topk: int, id_base: int = 0
     return val, idx
 
 
+def assign_fused(x: torch.Tensor, b: Operand, metric: int, id_base: int = 0):
+    """Top-1 of every raw float32 row of ``x`` against the column operand ``b`` with the row preparation fused into
+    the contraction kernel (include/ise.h: ise_assign_fused).  Returns (val [n, 1], idx [n, 1], row operand of x), or
+    None when the shape is not covered by the fused kernel (the caller then prepares the rows separately)."""
+    if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1 or x.shape[1] != b.d or b.n == 0:
+        return None
+    n, d = x.shape
+    if n == 0 or d % 4 != 0 or d > 128:
+        return None
+    dev = _dev(x)
+    lib, ctx = _lib.load(), _lib.ctx(dev)
+    ldp = (d + 7) // 8 * 8
+    hi = torch.empty((n, ldp), dtype=torch.float16, device=x.device)
+    lo = torch.empty((n, ldp), dtype=torch.float16, device=x.device) if b.lo is not None else None
+    norms = torch.empty((n,), dtype=torch.float32, device=x.device)
+    row_inv = torch.empty((n,), dtype=torch.float32, device=x.device)
+    skipped = torch.empty((n,), dtype=torch.uint8, device=x.device) if lo is not None else None
+    meta = torch.empty((8,), dtype=torch.float32, device=x.device)
+    val = torch.empty((n, 1), dtype=torch.float32, device=x.device)
+    idx = torch.empty((n, 1), dtype=torch.int64, device=x.device)
+    rc = lib.ise_assign_fused(ctx, _ptr(x), x.stride(0), n, d, _ptr(hi), _ptr(lo), ldp, _ptr(norms), _ptr(row_inv),
+                              _ptr(skipped), _ptr(meta), _ptr(b.hi), _ptr(b.lo), b.ldp, _ptr(b.meta), _ptr(b.norms), b.n,
+                              int(metric), int(id_base), _ptr(val), _ptr(idx), _stream())
+    if rc == 2:
+        return None
+    _lib.check(rc)
+    _count(3 if lo is not None else 1)
+    return val, idx, Operand(hi, lo, norms, meta, n, d, ldp, row_inv=row_inv)
+
+
 def rescore_topk_(a_raw: torch.Tensor, b_raw: torch.Tensor, a_op: Operand, b_op: Operand, metric: int,
                   val: torch.Tensor, idx: torch.Tensor, id_base: int = 0):
     """Exact FP32 re-score + re-rank (in place) of candidates picked by gemm_select."""

@@ -141,6 +141,23 @@ int ise_gemm_select(ise_ctx* ctx,
                     float* out_val, int64_t* out_idx,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* FUSED ASSIGN (top-1): takes the RAW float32 rows x[m, d] and converts them inside the contraction kernel -- four extra
+ * warps per CTA turn the rows of the CTA's NEXT work item into per-row-scaled FP16 planes (the ise_prepare_rows method)
+ * while the tensor pipe works on the current one, so the HBM-bound preparation pass disappears behind the MMAs.  The
+ * row operand comes out as a by-product (a_hi / a_lo planes with pitch lda, a_norms, a_row_inv, a_meta: the same
+ * contents ise_prepare_rows writes), ready for ise_rescore_topk / ise_kmeans_accumulate_sorted.  Only the hi plane of
+ * A is multiplied in the fused launch; when the rows turn out NOT to be exact in it (a_meta[2] != 0, decided on the
+ * device) the lo plane is completed and the assign repeated with it by two follow-up launches that return at once
+ * otherwise -- keypoint descriptors (integer SIFT, ORB / BRISK as float) are exact.  a_lo may be NULL only when the
+ * caller knows that (no repeat pass then).  Returns 2 and does nothing when the shape is not covered (d % 4 != 0,
+ * d > 128, unaligned rows, or too few rows for an unsplit column range): run ise_prepare_rows + ise_gemm_select then.
+ * Replaces `X.astype(np.float32)` + index.search(X, 1) of FaissKMeans.transform (kmeans_faiss.py:49). */
+int ise_assign_fused(ise_ctx* ctx, const float* x, int64_t ldx, int64_t m, int d,
+                     void* a_hi, void* a_lo, int64_t lda, float* a_norms, float* a_row_inv, uint8_t* a_lo_skipped,
+                     float* a_meta,
+                     const void* b_hi, const void* b_lo, int64_t ldb, const float* b_meta, const float* b_norms,
+                     int64_t n, int metric, int64_t id_base, float* out_val, int64_t* out_idx, void* stream);
+
 /* COLLECT variant of the fused contraction for large k: instead of keeping a bounded list per row, every
  * column whose (coarse) score beats row_seed[row] is appended to the row's buffer cand_*[row, 0..cap)
  * (unsorted; row_count[row] = number of qualifying columns, which may exceed cap = overflow; unused slots

@@ -387,3 +387,62 @@ def test_transform_csr_from_a_python_list_of_arrays():
     assert _pack_list_into(mixed, {}) is None
     assert np.array_equal(bovw.transform_csr(mixed, okapi=ok, n_chunks=4).toarray(),
                           bovw.transform_csr(ints, okapi=ok, n_chunks=4).toarray())
+
+
+@pytest.mark.parametrize("metric_ip", [True, False])
+@pytest.mark.parametrize("m,n,d,kind", [(200_000, 4096, 128, "sift"), (150_001, 1000, 64, "sift"), (120_000, 512, 32, "sift"),
+                                         (160_000, 2048, 128, "float"), (130_000, 777, 128, "mixed")])
+def test_fused_assign_equals_separate_preparation(metric_ip, m, n, d, kind):
+    """ise_assign_fused (row preparation inside the contraction kernel) against ise_prepare_rows + ise_gemm_select: same
+    ids and scores, and the row operand it leaves behind is the one the stand-alone preparation writes.  "float" rows are
+    not exact in one FP16 plane: the device-side flag triggers the follow-up launches with the lo planes; "mixed" has
+    both kinds of rows (skipped lo stores completed by the fix-up)."""
+    from image_search_engine_b200 import ops
+    from image_search_engine_b200._lib import METRIC_IP, METRIC_L2
+    dev = ops.require_cuda()
+    rng = np.random.default_rng(m + n + d)
+    if kind == "sift":
+        x = sift_like(rng, m, d)
+    else:
+        x = (rng.standard_normal((m, d)) * 3).astype(np.float32)
+        if kind == "mixed":
+            x[::3] = sift_like(rng, len(x[::3]), d)
+    c = unit_rows(rng, n, d)
+    xd, cd = torch.from_numpy(x).to(dev), torch.from_numpy(c).to(dev)
+    b = ops.prepare_operand(cd)
+    metric = METRIC_IP if metric_ip else METRIC_L2
+    got = ops.assign_fused(xd, b, metric)
+    assert got is not None, "shape should be covered by the fused kernel"
+    val, idx, a_f = got
+    a_s = ops.prepare_operand(xd, rows=True)
+    val_s, idx_s = ops.gemm_select(a_s, b, metric, 1)
+    assert torch.equal(idx, idx_s) and torch.equal(val, val_s)
+    assert torch.equal(a_f.hi, a_s.hi) and torch.equal(a_f.norms, a_s.norms) and torch.equal(a_f.row_inv, a_s.row_inv)
+    mf, ms = a_f.meta.cpu().numpy(), a_s.meta.cpu().numpy()
+    assert mf[2] == ms[2] == (0.0 if kind == "sift" else 1.0) and mf[0] == 1.0 and mf[4] == ms[4] and mf[7] == 0.0
+    if kind != "sift":
+        assert torch.equal(a_f.lo, a_s.lo)
+    # against the oracle on a sample
+    from oracle import faiss_shim as fs
+    rows = rng.choice(m, 1500, replace=False)
+    Dr, Ir = fs.knn(x[rows], c, 1, fs.METRIC_INNER_PRODUCT if metric_ip else fs.METRIC_L2)
+    assert_topk_parity(idx.cpu().numpy()[rows], Ir, x[rows], c, metric_ip, max_mismatch_frac=0.01)
+    # the public path takes it: FaissKMeans.transform on raw float32 descriptors
+    from image_search_engine_b200 import FaissKMeans, faiss_compat
+    gi = faiss_compat.IndexFlatIP(d) if metric_ip else faiss_compat.IndexFlatL2(d)
+    gi.add(cd)
+    words = FaissKMeans(n, index=gi).transform_device(xd)
+    assert ops.last_search_stats["mode"] == "fused-split" and torch.equal(words, idx.reshape(-1))
+
+
+def test_fused_assign_declines_shapes_it_does_not_cover():
+    from image_search_engine_b200 import ops
+    from image_search_engine_b200._lib import METRIC_IP
+    dev = ops.require_cuda()
+    rng = np.random.default_rng(0)
+    b = ops.prepare_operand(torch.from_numpy(unit_rows(rng, 4096, 128)).to(dev))
+    few = torch.from_numpy(sift_like(rng, 100, 128)).to(dev)                 # one image: the column range is split
+    assert ops.assign_fused(few, b, METRIC_IP) is None
+    b2 = ops.prepare_operand(torch.from_numpy(unit_rows(rng, 300, 256)).to(dev))
+    wide = torch.from_numpy(rng.standard_normal((200_000, 256)).astype(np.float32)).to(dev)
+    assert ops.assign_fused(wide, b2, METRIC_IP) is None                      # d > 128
