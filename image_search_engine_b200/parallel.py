@@ -68,7 +68,8 @@ class DeviceOps:
     def __init__(self):
         self._acc_ws = None       # persistent workspace of the sorted-gather update
         self._stat = None         # 16 device bytes: float64 objective | int32 number of empty clusters
-        self._stat_host = None    # pinned mirror: ONE 16-byte readback per iteration
+        self._stat_slots = None   # two pinned mirrors + events: ONE 16-byte readback per iteration, possibly one iteration late
+        self._slot = 0
 
     def device(self):
         return ops.require_cuda()
@@ -90,7 +91,6 @@ class DeviceOps:
         """(accum [k*d + k] float32 = the all-reduce payload, sums view, counts view, obj float64[1])."""
         accum = torch.empty((k * d + k,), dtype=torch.float32, device=dev)
         self._stat = torch.zeros((16,), dtype=torch.uint8, device=dev)
-        self._stat_host = torch.zeros((16,), dtype=torch.uint8, pin_memory=True)
         return accum, accum[:k * d].view(k, d), accum[k * d:], self._stat[:8].view(torch.float64)
 
     def assign(self, x, a_op, cent, metric, precision="verified"):
@@ -103,20 +103,37 @@ class DeviceOps:
         self._acc_ws = ops.kmeans_accumulate_sorted(x, assign, sums, counts, obj, centroids=cent, metric=metric,
                                                     workspace=self._acc_ws, exact_op=a_op)
 
+    def finalize_begin(self, sums, counts, cent, obj):
+        """mean -> cent, then the 16 statistics bytes (objective, number of empty clusters) start their way to a pinned
+        host slot.  Returns a handle for finalize_read; nothing here waits for the device."""
+        n_empty = self._stat[8:12].view(torch.int32)
+        ops.kmeans_mean(sums, counts, cent, n_empty)
+        if self._stat_slots is None:
+            self._stat_slots = [(torch.zeros((16,), dtype=torch.uint8, pin_memory=True), torch.cuda.Event()) for _ in range(2)]
+        self._slot ^= 1
+        host, ev = self._stat_slots[self._slot]
+        host.copy_(self._stat, non_blocking=True)
+        ev.record()
+        return self._slot
+
+    def finalize_read(self, handle):
+        """(objective, number of empty clusters) of the iteration behind ``handle``; waits for its copy only."""
+        host, ev = self._stat_slots[handle]
+        ev.synchronize()
+        return float(host[:8].view(torch.float64)[0]), int(host[8:12].view(torch.int32)[0])
+
+    def apply_splits(self, counts, cent, n_global):
+        """Faiss's split_clusters: sequential-RNG plan on the host (sparse stream index), applied on the device."""
+        pairs, _ = ops.split_plan(counts.cpu().numpy(), n_global)
+        ops.kmeans_apply_splits(cent, torch.from_numpy(pairs).to(cent.device))
+        return int(pairs.shape[0])
+
     def finalize(self, sums, counts, cent, n_global, spherical, obj):
         """mean -> split empties (host plan, sequential Faiss RNG) -> renorm.  Returns (nsplit, objective): the
         objective and the number of empty clusters come back in ONE 16-byte copy, the only host synchronisation
         of an iteration."""
-        n_empty = self._stat[8:12].view(torch.int32)
-        ops.kmeans_mean(sums, counts, cent, n_empty)
-        self._stat_host.copy_(self._stat, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        o = float(self._stat_host[:8].view(torch.float64)[0])
-        nsplit = 0
-        if int(self._stat_host[8:12].view(torch.int32)[0]) > 0:
-            pairs, _ = ops.split_plan(counts.cpu().numpy(), n_global)
-            nsplit = pairs.shape[0]
-            ops.kmeans_apply_splits(cent, torch.from_numpy(pairs).to(cent.device))
+        o, n_empty = self.finalize_read(self.finalize_begin(sums, counts, cent, obj))
+        nsplit = self.apply_splits(counts, cent, n_global) if n_empty > 0 else 0
         if spherical:
             ops.normalize_l2_(cent)
         return nsplit, o
@@ -176,6 +193,21 @@ def lloyd_train(cp, d, k, x_train, n_train, a_op, lops, *, init_rows, init_centr
     best_cent, best_stats, stats = None, [], []
     timed = x_train.is_cuda
     t_start = time.time()
+    # Speculation (device path, no lock-step trace): an iteration's readback decides only whether empty clusters must be
+    # split before the next assign -- rare once the first iterations are over.  When the previous iteration had no
+    # split, the next assign is launched on the assumption that this one has none either; the 16 bytes are read while
+    # that assign runs, so the host never stalls the device.  A wrong guess restores the saved means, splits,
+    # renormalises and repeats the assign: same results either way (tests/test_gpu_round2.py), one wasted assign at most
+    # per change of regime.
+    import os
+    spec_ok = hasattr(lops, "finalize_begin") and trace is None and timed and not os.environ.get("ISE_KMEANS_NO_SPECULATION")
+    spec_force = bool(os.environ.get("ISE_KMEANS_FORCE_SPECULATION"))      # tests: guess "no split" even after a split
+    cent_bak = torch.empty_like(cent) if spec_ok else None
+
+    def phase_ms(ev):
+        return dict(ms_assign=ev[0].elapsed_time(ev[1]), ms_accumulate=ev[1].elapsed_time(ev[2]),
+                    ms_allreduce=ev[2].elapsed_time(ev[3]))
+
     for redo in range(cp.nredo):
         if n_input:
             cent[:n_input] = torch.from_numpy(ic).to(dev)
@@ -184,11 +216,28 @@ def lloyd_train(cp, d, k, x_train, n_train, a_op, lops, *, init_rows, init_centr
         if cp.spherical:
             lops.normalize(cent)
         o = 0.0
+        pending, prev_nsplit = None, None
         for it in range(cp.niter):
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timed else None
             if timed:
                 ev[0].record()
             dis, assign = lops.assign(x_train, a_op, cent, metric, precision)
+            if pending is not None:
+                # the previous iteration's statistics (its copy finished long ago: the device is busy with the assign above)
+                t_fin = time.time()
+                o_prev, n_empty_prev = lops.finalize_read(pending["handle"])
+                nsplit_prev = 0
+                if n_empty_prev > 0:
+                    cent.copy_(cent_bak)                   # the means, before the renormalisation
+                    nsplit_prev = lops.apply_splits(counts, cent, n_train)      # counts still hold the previous iteration's
+                    if cp.spherical:
+                        lops.normalize(cent)
+                    ev[0].record()
+                    dis, assign = lops.assign(x_train, a_op, cent, metric, precision)
+                st = stats[pending["index"]]
+                st.update(obj=o_prev, nsplit=nsplit_prev, speculated=True, mis_speculated=n_empty_prev > 0,
+                          ms_finalize_host=pending["host_ms"] + (time.time() - t_fin) * 1e3, **phase_ms(pending["ev"]))
+                prev_nsplit, pending = nsplit_prev, None
             if timed:
                 ev[1].record()
             accum.zero_()
@@ -203,19 +252,30 @@ def lloyd_train(cp, d, k, x_train, n_train, a_op, lops, *, init_rows, init_centr
                 allreduce(obj)
             if timed:
                 ev[3].record()
-                torch.cuda.current_stream().synchronize()     # finalize reads the statistics back anyway; this keeps the
-            t_fin = time.time()                               # device phases out of its host wall time
-            nsplit, o = lops.finalize(sums, counts, cent, n_train, cp.spherical, obj)
-            st = dict(obj=o, nsplit=nsplit, time=time.time() - t_start, time_search=0.0, imbalance_factor=float("nan"))
+            st = dict(obj=float("nan"), nsplit=0, time=time.time() - t_start, time_search=0.0, imbalance_factor=float("nan"))
             if cp.verbose:
                 cs = counts.double()
                 st["imbalance_factor"] = float((cs * cs).sum() * k / (cs.sum() ** 2))
+            if spec_ok and (prev_nsplit == 0 or (spec_force and prev_nsplit is not None)) and it < cp.niter - 1:
+                t_fin = time.time()
+                handle = lops.finalize_begin(sums, counts, cent, obj)
+                cent_bak.copy_(cent)
+                if cp.spherical:
+                    lops.normalize(cent)
+                stats.append(st)
+                pending = dict(handle=handle, index=len(stats) - 1, ev=ev, host_ms=(time.time() - t_fin) * 1e3)
+                continue
             if timed:
-                # device time of the three phases of this rank (finalize synchronised the stream) + host wall time of the
-                # finalize (mean, 16-byte readback, Faiss's sequential split_clusters plan when clusters came out empty, renorm)
-                st.update(ms_assign=ev[0].elapsed_time(ev[1]), ms_accumulate=ev[1].elapsed_time(ev[2]),
-                          ms_allreduce=ev[2].elapsed_time(ev[3]), ms_finalize_host=(time.time() - t_fin) * 1e3)
+                torch.cuda.current_stream().synchronize()     # finalize reads the statistics back anyway; this keeps the
+            t_fin = time.time()                               # device phases out of its host wall time
+            nsplit, o = lops.finalize(sums, counts, cent, n_train, cp.spherical, obj)
+            st.update(obj=o, nsplit=nsplit, time=time.time() - t_start)
+            if timed:
+                # device time of the three phases of this rank + host wall time of the finalize (mean, 16-byte readback,
+                # Faiss's sequential split_clusters plan when clusters came out empty, renorm)
+                st.update(ms_finalize_host=(time.time() - t_fin) * 1e3, speculated=False, **phase_ms(ev))
             stats.append(st)
+            prev_nsplit = nsplit
             if trace is not None:
                 trace[-1]["centroids_out"] = cent.clone()
                 trace[-1]["nsplit"] = nsplit

@@ -446,3 +446,35 @@ def test_fused_assign_declines_shapes_it_does_not_cover():
     b2 = ops.prepare_operand(torch.from_numpy(unit_rows(rng, 300, 256)).to(dev))
     wide = torch.from_numpy(rng.standard_normal((200_000, 256)).astype(np.float32)).to(dev)
     assert ops.assign_fused(wide, b2, METRIC_IP) is None                      # d > 128
+
+
+def test_speculative_kmeans_iterations_equal_the_synchronous_loop(monkeypatch):
+    """The Lloyd loop launches the next assign before it has read the previous iteration's statistics back; a wrong
+    guess ("no empty clusters") is rolled back.  Same objectives, same split counts, same centroids as the loop that
+    synchronises every iteration -- including when EVERY guess after a split is forced (and therefore often wrong)."""
+    from image_search_engine_b200 import faiss_compat
+    rng = np.random.default_rng(77)
+    n, d, k = 60000, 64, 256
+    centers = rng.standard_normal((k // 2, d)).astype(np.float32) * 3
+    x = (centers[rng.integers(0, k // 2, n)] + 0.3 * rng.standard_normal((n, d))).astype(np.float32)
+    x[:6000] = x[0]                                     # duplicates: initial centroids coincide -> empty clusters -> splits
+    runs = {}
+    for name, env in (("sync", {"ISE_KMEANS_NO_SPECULATION": "1"}), ("spec", {}), ("forced", {"ISE_KMEANS_FORCE_SPECULATION": "1"})):
+        for key in ("ISE_KMEANS_NO_SPECULATION", "ISE_KMEANS_FORCE_SPECULATION"):
+            monkeypatch.delenv(key, raising=False)
+        for key, v in env.items():
+            monkeypatch.setenv(key, v)
+        km = faiss_compat.Kmeans(d, k, seed=42, niter=12, spherical=True)
+        km.train(x)
+        runs[name] = km
+    ref = runs["sync"]
+    nsplit_ref = [s["nsplit"] for s in ref.iteration_stats]
+    assert sum(nsplit_ref) > 0, "the data set must exercise the split path"
+    assert not any(s.get("speculated") for s in ref.iteration_stats)
+    for name in ("spec", "forced"):
+        km = runs[name]
+        assert [s["nsplit"] for s in km.iteration_stats] == nsplit_ref, name
+        np.testing.assert_allclose(km.obj, ref.obj, rtol=1e-6, err_msg=name)
+        np.testing.assert_allclose(km.centroids, ref.centroids, rtol=1e-4, atol=1e-5, err_msg=name)
+        assert any(s.get("speculated") for s in km.iteration_stats), name
+    assert any(s.get("mis_speculated") for s in runs["forced"].iteration_stats), "the roll-back path was not exercised"
