@@ -1,4 +1,4 @@
-"""Minimal driver for ncu: a few split top-1 gemm_select launches on the C2 shape."""
+"""Minimal driver for ncu: the fused assign (float32 rows converted inside gemm_select, split top-1) on the C2 shape."""
 import sys
 import numpy as np, torch
 sys.path.insert(0, ".")
@@ -10,8 +10,9 @@ rng = np.random.default_rng(2)
 X = torch.from_numpy(sift_like(rng, C2["n_desc"], C2["d"])).to(dev)
 cent = X[torch.randperm(X.shape[0], device=dev)[:C2["k"]]].clone()
 ops.normalize_l2_(cent)
-a = ops.compact_operand(ops.prepare_operand(X)); b = ops.prepare_operand(cent)
+b = ops.prepare_operand(cent)
 for _ in range(4):
-    ops.gemm_select(a, b, METRIC_IP, 1)
+    got = ops.assign_fused(X, b, METRIC_IP)
+assert got is not None
 torch.cuda.synchronize()
 print("ok")

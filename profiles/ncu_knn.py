@@ -13,8 +13,8 @@ for i in range(0, nb, 100_000):
 ops.normalize_l2_(db)
 q = db[torch.randint(0, nb, (nq,), generator=g, device=dev)] + 0.05 * torch.randn((nq, d), generator=g, device=dev)
 ops.normalize_l2_(q)
-b = ops.attach_sample(ops.prepare_operand(db)); a = ops.prepare_operand(q)
-hi = lambda o: ops.Operand(o.hi, None, o.norms, o.meta, o.n, o.d, o.ldp)
+b = ops.attach_sample(ops.prepare_operand(db)); a = ops.prepare_operand(q, rows=True)
+hi = lambda o: o.hi_only()
 seed = ops.gemm_select(hi(a), b.sample, METRIC_IP, 2)[0][:, 1].contiguous()   # launch 1 (+ merge)
 for _ in range(3):                                                             # launches 2..4 of gemm_select
     ops.gemm_select(hi(a), hi(b), METRIC_IP, 32, row_seed=seed)

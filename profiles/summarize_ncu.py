@@ -32,8 +32,12 @@ def short(name):
     return name[:70]
 
 
+traffic_json = None
+args = sys.argv[1:]
+if args and args[0] == "--traffic-json":
+    traffic_json, args = args[1], args[2:]
 seen = {}
-for path in sys.argv[1:]:
+for path in args:
     txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units = rows[0], rows[1]
@@ -60,3 +64,24 @@ for key, (t, r, idx, units, path) in seen.items():
             pass
         cells.append(f"{v} {u}".strip())
     print(f"| `{key}` | " + " | ".join(cells) + " |")
+
+if traffic_json:
+    # per-launch DRAM bytes of the two dominant kernels, read by bench.py (roofline.traffic) -- nothing is hard-coded there
+    import json
+    out = {}
+
+    def grab(key, match, note):
+        for k, (t, r, idx, units, path) in seen.items():
+            if match(k, r[idx["Kernel Name"]]):
+                def val(m):
+                    v, u = float(r[idx[m]].replace(",", "")), units[idx[m]].lower()
+                    return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+                rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
+                out[key] = {"dram_bytes": rd + wr, "dram_read": rd, "dram_write": wr, "kernel": k, "time_us": t,
+                            "source": path.split("/")[-1], "note": note}
+                return
+    grab("assign", lambda k, full: "gemm_select" in k and "assign" in seen[k][4],
+         "fused assign launch at C2 (1M x 4096 x 128), ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum")
+    grab("knn_coarse", lambda k, full: "gemm_select" in k and "knn" in seen[k][4],
+         "coarse seeded top-32 launch at C3 (10k x 1M x 2048), ncu sections, dram__bytes_read.sum + dram__bytes_write.sum")
+    json.dump(out, open(traffic_json, "w"), indent=1)
