@@ -668,7 +668,7 @@ def run_ours(args):
 
     # the node's host -> device ceiling for this step's input, measured the same way: every rank copies its pinned
     # 512 MB at the same time, nothing else running (N >= 4 is bound by this, not by any kernel)
-    h2d_buf = torch.empty_like(X_dev) if False else torch.empty(packed.matrix.shape, dtype=packed.matrix.dtype, device=dev)
+    h2d_buf = torch.empty(packed.matrix.shape, dtype=packed.matrix.dtype, device=dev)
     for _ in range(2):
         h2d_buf.copy_(packed.matrix, non_blocking=True)
     barrier()

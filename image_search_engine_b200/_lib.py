@@ -83,6 +83,11 @@ PROTOTYPES = {
     "ise_okapi_csr": (_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _i64, _f64, _f64, _f64, _f64, _c_void_p, _int,
                              _c_void_p, _c_void_p]),
     "ise_tfidf_finish": (_int, [_c_void_p, _c_void_p, _int, _i64, _int, _c_void_p, _int, _c_void_p]),
+    "ise_comm_init_all": (_int, [_int, _c_void_p, C.POINTER(_c_void_p)]),
+    "ise_comm_destroy": (None, [_c_void_p]),
+    "ise_comm_size": (_int, [_c_void_p]),
+    "ise_allreduce_sum_f32": (_int, [_c_void_p, _c_void_p, _i64, _c_void_p]),
+    "ise_allgather": (_int, [_c_void_p, _c_void_p, _c_void_p, _i64, _c_void_p]),
     "ise_okapi_tf": (_int, [_c_void_p, _c_void_p, _int, _i64, _int, _f64, _f64, _f64, _f64, _c_void_p,
                             _c_void_p]),
 }

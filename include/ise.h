@@ -306,6 +306,21 @@ int ise_ivfpq_scan(ise_ctx* ctx, const float* q, int64_t nq, int d, const float*
                    const int64_t* probes, int nprobe, const float* pq_centroids, int M, int ksub,
                    const uint8_t* codes, const int64_t* list_offsets, int64_t ntotal, float* dist, void* stream);
 
+/* ---- collectives for a single-process multi-GPU host (NCCL over NVLink, resolved with dlopen at run time) ----------
+ * The two exchange steps of the sharded path: the per-iteration all-reduce of the k-means
+ * [k*d sums | k counts] buffer and the all-gather of per-shard top-k lists before ise_topk_merge.  The Python host
+ * uses torch.distributed (one process per GPU) over the same NCCL instead; these are for a host that binds libise
+ * directly and drives all GPUs from one process.  devs = CUDA ordinals (NULL: 0 .. ndev-1); bufs / send / recv /
+ * streams are arrays with one entry per device of the communicator, in communicator order; calls are asynchronous
+ * on the given streams.  The reference has no counterpart (single host process, no GPU). */
+typedef struct ise_comm ise_comm;
+int ise_comm_init_all(int ndev, const int* devs, ise_comm** out);
+void ise_comm_destroy(ise_comm* comm);
+int ise_comm_size(const ise_comm* comm);
+int ise_allreduce_sum_f32(ise_comm* comm, float* const* bufs, int64_t count, void* const* streams);
+int ise_allgather(ise_comm* comm, const void* const* send, void* const* recv, int64_t bytes_per_rank,
+                  void* const* streams);
+
 #ifdef __cplusplus
 }
 #endif
