@@ -77,7 +77,8 @@ if traffic_json:
                     v, u = float(r[idx[m]].replace(",", "")), units[idx[m]].lower()
                     return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
                 rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
-                out[key] = {"dram_bytes": rd + wr, "dram_read": rd, "dram_write": wr, "kernel": k, "time_us": t,
+                out[key] = {"dram_bytes": rd + wr, "dram_read": rd, "dram_write": wr, "kernel": k,
+                            "time": t, "time_unit": units[idx["gpu__time_duration.sum"]],
                             "source": path.split("/")[-1], "note": note}
                 return
     grab("assign", lambda k, full: "gemm_select" in k and "assign" in seen[k][4],
