@@ -117,7 +117,47 @@ struct BlockMT19937 {
         const uint32_t y = (u & 0x80000000u) | (v & 0x7fffffffu);
         return (y >> 1) ^ ((v & 1u) ? 0x9908b0dfu : 0u);
     }
+#if defined(__x86_64__)
+    // the same recurrence, eight words at a time: every vector step reads st[i + 1 .. i + 8] before it writes
+    // st[i .. i + 7], and the second loop's st[i + M - N] were written 227 words earlier -- no hazard inside a vector
+    __attribute__((target("avx2"))) void refill_avx2() {
+        const __m256i upper = _mm256_set1_epi32((int)0x80000000u), lower = _mm256_set1_epi32(0x7fffffff);
+        const __m256i matrix = _mm256_set1_epi32((int)0x9908b0dfu), one = _mm256_set1_epi32(1), zero = _mm256_setzero_si256();
+#define ISE_TWIST8(u, v)                                                                                             \
+    _mm256_xor_si256(_mm256_srli_epi32(_mm256_or_si256(_mm256_and_si256((u), upper), _mm256_and_si256((v), lower)), 1), \
+                     _mm256_and_si256(_mm256_sub_epi32(zero, _mm256_and_si256((v), one)), matrix))
+        int i = 0;
+        for (; i + 8 <= N - M; i += 8) {
+            const __m256i u = _mm256_loadu_si256((const __m256i*)(st + i)), v = _mm256_loadu_si256((const __m256i*)(st + i + 1));
+            const __m256i m = _mm256_loadu_si256((const __m256i*)(st + i + M));
+            _mm256_storeu_si256((__m256i*)(st + i), _mm256_xor_si256(m, ISE_TWIST8(u, v)));
+        }
+        for (; i < N - M; ++i) st[i] = st[i + M] ^ twist(st[i], st[i + 1]);
+        for (; i + 8 <= N - 1; i += 8) {
+            const __m256i u = _mm256_loadu_si256((const __m256i*)(st + i)), v = _mm256_loadu_si256((const __m256i*)(st + i + 1));
+            const __m256i m = _mm256_loadu_si256((const __m256i*)(st + i + M - N));
+            _mm256_storeu_si256((__m256i*)(st + i), _mm256_xor_si256(m, ISE_TWIST8(u, v)));
+        }
+        for (; i < N - 1; ++i) st[i] = st[i + M - N] ^ twist(st[i], st[i + 1]);
+        st[N - 1] = st[M - 1] ^ twist(st[N - 1], st[0]);
+        const __m256i c1 = _mm256_set1_epi32((int)0x9d2c5680u), c2 = _mm256_set1_epi32((int)0xefc60000u);
+        for (i = 0; i + 8 <= N; i += 8) {
+            __m256i y = _mm256_loadu_si256((const __m256i*)(st + i));
+            y = _mm256_xor_si256(y, _mm256_srli_epi32(y, 11));
+            y = _mm256_xor_si256(y, _mm256_and_si256(_mm256_slli_epi32(y, 7), c1));
+            y = _mm256_xor_si256(y, _mm256_and_si256(_mm256_slli_epi32(y, 15), c2));
+            y = _mm256_xor_si256(y, _mm256_srli_epi32(y, 18));
+            _mm256_storeu_si256((__m256i*)(out + i), y);
+        }
+#undef ISE_TWIST8
+        pos = 0;
+    }
+#endif
     void refill() {
+#if defined(__x86_64__)
+        static const bool have_avx2 = __builtin_cpu_supports("avx2");
+        if (have_avx2) { refill_avx2(); return; }
+#endif
         for (int i = 0; i < N - M; ++i) st[i] = st[i + M] ^ twist(st[i], st[i + 1]);
         for (int i = N - M; i < N - 1; ++i) st[i] = st[i + M - N] ^ twist(st[i], st[i + 1]);
         st[N - 1] = st[M - 1] ^ twist(st[N - 1], st[0]);
@@ -155,13 +195,23 @@ struct SplitStreamIndex {
     bool warm_running = false;                            // guarded by mu
     int64_t warm_target = 0;                              // guarded by mu
     std::atomic<bool> stop{false};
+    std::atomic<int> waiters{0};                          // plans waiting for mu: the warm-up thread steps aside for them
     // caller holds mu
     void extend_to(int64_t target) {
         while (generated < target) {
             if (mt.pos == BlockMT19937::N) mt.refill();
             const int take = (int)std::min<int64_t>(BlockMT19937::N - mt.pos, target - generated);
             const uint32_t* o = mt.out + mt.pos;
-            for (int i = 0; i < take; ++i)
+            int i = 0;
+            // 1 draw in 256 is small: test 8 at a time on the OR of their top bytes, look closer only on a hit
+            for (; i + 8 <= take; i += 8) {
+                const uint32_t any = ((o[i] >> 24) == 0) | ((o[i + 1] >> 24) == 0) | ((o[i + 2] >> 24) == 0) | ((o[i + 3] >> 24) == 0) |
+                                     ((o[i + 4] >> 24) == 0) | ((o[i + 5] >> 24) == 0) | ((o[i + 6] >> 24) == 0) | ((o[i + 7] >> 24) == 0);
+                if (any)
+                    for (int j = i; j < i + 8; ++j)
+                        if (o[j] < kSmall) { pos.push_back(generated + j); val.push_back(o[j]); }
+            }
+            for (; i < take; ++i)
                 if (o[i] < kSmall) { pos.push_back(generated + i); val.push_back(o[i]); }
             mt.pos += take;
             generated += take;
@@ -190,6 +240,7 @@ ISE_EXPORT int ise_split_plan_warm(int64_t n_draws) {
     ix.warm = std::thread([]() {
         SplitStreamIndex& s = g_split_stream;
         for (;;) {
+            while (s.waiters.load() > 0 && !s.stop.load()) std::this_thread::yield();   // std::mutex is not fair
             std::lock_guard<std::mutex> g(s.mu);
             if (s.stop.load() || s.generated >= s.warm_target) {
                 s.warm_running = false;
@@ -261,7 +312,9 @@ ISE_EXPORT int ise_split_plan(float* hassign, int64_t k, int64_t n, int32_t* pai
         return split_plan_dense(hassign, k, n, pairs, nsplit);
     if (!(h_max > 1.f)) ISE_FAIL("no cluster has more than one point: split_clusters would never terminate");
     SplitStreamIndex& ix = g_split_stream;
+    ix.waiters.fetch_add(1);
     std::lock_guard<std::mutex> lk(ix.mu);
+    ix.waiters.fetch_sub(1);
     int32_t ns = 0;
     int64_t g = 0;                 // stream position of the next draw
     size_t cur = 0;                // first index entry with pos >= g
