@@ -116,28 +116,32 @@ def test_c5_shard_top100_collect_mode_against_oracle():
     print(f"C5 shard: fallback_rows={stats['fallback_rows']} of {stats['rows']}, near-tie rows in sample={nm}/100")
 
 
-def _adversarial(rng, m, n, d):
+def _adversarial(rng, m, n, d, lo_exp=-16, hi_exp=-9):
     """All-positive operands whose elements sit at the top of the scaled FP16 range (every product has the same
     sign: the truncating tensor-core accumulation errs in one direction and the partial sums are as large as they
     get), and a database of near-duplicates whose exact scores differ by about the coarse error bound."""
     a = rng.uniform(0.90, 1.0, size=(m, d)).astype(np.float32)
     base = rng.uniform(0.90, 1.0, size=(8, d)).astype(np.float32)
     # relative perturbations from 2^-16 to 2^-9 around the 2^-11 FP16 rounding step of the planes
-    scale = np.exp2(rng.uniform(-16, -9, size=(n, 1))).astype(np.float32)
+    scale = np.exp2(rng.uniform(lo_exp, hi_exp, size=(n, 1))).astype(np.float32)
     b = base[rng.integers(0, 8, n)] * (1.0 + scale * rng.standard_normal((n, d)).astype(np.float32))
     b[1::97] = b[0::97][: len(b[1::97])]                 # exact duplicates: lower id must win
     return a, np.ascontiguousarray(b, dtype=np.float32)
 
 
+@pytest.mark.parametrize("spread", ["at_the_bound", "above_the_bound"])
 @pytest.mark.parametrize("metric_ip", [True, False])
-def test_coarse_bound_adversarial_topk(metric_ip):
+def test_coarse_bound_adversarial_topk(metric_ip, spread):
     """d = 2048: every row the proof accepts must equal the FP32-grade split path and the FP64 ground truth (up to
     FP32 near ties); the bound is allowed to be pessimistic (fallback rows), never optimistic."""
     from image_search_engine_b200 import ops
     from image_search_engine_b200._lib import METRIC_IP, METRIC_L2
     rng = np.random.default_rng(2048)
     m, n, d, k = 256, 6000, 2048, 10
-    a, b = _adversarial(rng, m, n, d)
+    # "at_the_bound": perturbations of 2^-16 .. 2^-9 around the 2^-11 rounding step -- nothing can be proven, every row
+    # must fall back; "above_the_bound": 2^-8 .. 2^-4 -- most rows ARE accepted by the proof, and those are the rows an
+    # optimistic bound would get wrong
+    a, b = _adversarial(rng, m, n, d) if spread == "at_the_bound" else _adversarial(rng, m, n, d, -8, -4)
     dev = ops.require_cuda()
     ad, bd = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
     a_op, b_op = ops.prepare_operand(ad), ops.attach_sample(ops.prepare_operand(bd))
@@ -146,7 +150,9 @@ def test_coarse_bound_adversarial_topk(metric_ip):
     sv = dict(ops.last_search_stats)
     Ds, Is = ops.search_topk(ad, a_op, bd, b_op, metric, k, precision="split")
     assert sv["mode"] == "verified"
-    print(f"adversarial top-{k} ({'IP' if metric_ip else 'L2'}): fallback_rows={sv['fallback_rows']} of {m}")
+    print(f"adversarial top-{k} ({'IP' if metric_ip else 'L2'}, {spread}): fallback_rows={sv['fallback_rows']} of {m}")
+    if spread == "above_the_bound":
+        assert sv["fallback_rows"] < m, "no row was accepted by the proof: the accepted-row check below is vacuous"
     # ground truth in float64
     a64, b64 = a.astype(np.float64), b.astype(np.float64)
     s = a64 @ b64.T
