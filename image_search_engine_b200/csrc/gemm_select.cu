@@ -158,22 +158,32 @@ template <> struct SelList<32> { using type = RegList32; };
 //   (re-score, k-means update).  Only the hi plane of A is multiplied: a tensor that turns out NOT to be exact in it
 //   sets meta[LO_NONZERO] and the caller's follow-up launch (Params::skip_if_a_exact) repeats the assign with the lo
 //   planes -- for descriptors (integer SIFT, ORB / BRISK as float) that launch returns at once.
-template <int PA, int PB, bool L2, int KSEL, bool VERIFY, int CG, int MT = 1, bool CONV = false>
+// CL > 1 (CTA pairs only): CL pairs form ONE cluster of 2 CL CTAs on 2 CL adjacent row tiles and share every B tile:
+//   each CTA fetches 1 / CL of its pair's half tile and MULTICASTS it to the CTAs of the same parity in the other pairs,
+//   so a B tile is read from L2 once per cluster instead of once per pair (the large-d coarse pass is bound by the
+//   L2 -> shared-memory feed: A 16 KB + B 16 KB per stage per SM becomes A 16 KB + B 16 / CL KB).  A stage may only be
+//   overwritten when EVERY pair of the cluster has consumed it: each leader's tcgen05.commit of the `empty` barrier is
+//   multicast to all 2 CL CTAs (barrier count CL).
+template <int PA, int PB, bool L2, int KSEL, bool VERIFY, int CG, int MT = 1, bool CONV = false, int CL = 1>
 __global__ void __launch_bounds__(num_threads(KSEL, PA, PB, MT, CONV), 1)
 gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const Params p) {
     static_assert(MT == 1 || (CG == 1 && epi_halves(KSEL, PA, PB) == 1), "two row tiles per CTA: single CTA, one warp per quadrant and tile");
     static_assert(!CONV || (PA == 1 && KSEL == 1 && !VERIFY && MT == 1 && epi_halves(KSEL, PA, PB) == 1), "fused conversion: plain top-1, hi plane of A");
+    static_assert(CL == 1 || (CG == 2 && MT == 1 && !CONV && (CL == 2 || CL == 4)), "multicast clusters are made of CTA pairs");
     // uniform over the whole grid, before any barrier / TMEM state exists
     if (!CONV && p.skip_if_a_exact && __ldcg(p.a_meta + META_LO_NONZERO) == 0.f) return;
     constexpr int STAGES = num_stages(PA, PB, CG, MT);
     constexpr int STAGE_BYTES = stage_bytes(PA, PB, CG, MT);
     constexpr int A_BLOCK_BYTES = PA * A_TILE_BYTES;      // one row tile's planes inside a stage
     constexpr int B_OFFSET = MT * A_BLOCK_BYTES;          // B planes follow the MT row tiles
-    constexpr int GRP = CG * MT;                          // row tiles per work item
+    constexpr int CSIZE = CG * CL;                        // CTAs per cluster
+    constexpr int GRP = CG * MT * CL;                     // row tiles per work item
     constexpr int B_LOAD_BYTES = B_TILE_BYTES / CG;   // this CTA's share of a B tile (one plane)
     constexpr int B_LOAD_ROWS = BLOCK_N / CG;
+    constexpr int B_ISSUE_ROWS = B_LOAD_ROWS / CL;    // ... of which it fetches this many rows itself (CL > 1: multicast)
+    constexpr int B_ISSUE_BYTES = B_LOAD_BYTES / CL;
     constexpr int HALVES = epi_halves(KSEL, PA, PB);
     constexpr int NUM_EPI_THREADS = 128 * HALVES * MT;
     constexpr int COLS_PER_HALF = BLOCK_N / HALVES;
@@ -192,12 +202,18 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         if (PA == 2) ptx::prefetch_tensormap(&tm_a_lo);
         if (PB == 2) ptx::prefetch_tensormap(&tm_b_lo);
     }
-    const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
-    const bool leader = cta_rank == 0;
+    const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;     // rank in the cluster: pair (rank >> 1), CTA of the pair (rank & 1)
+    const uint32_t pair_cta = cta_rank & 1u, pair_idx = cta_rank >> 1, leader_rank = cta_rank & ~1u;
+    const bool leader = pair_cta == 0;
+    const uint16_t pair_mask = (uint16_t)(3u << (2 * pair_idx));                        // both CTAs of this pair
+    const uint16_t cluster_mask = (uint16_t)((1u << CSIZE) - 1u);                       // every CTA of the cluster
+    uint16_t parity_mask = 0;                                                            // this CTA's counterparts in all pairs
+#pragma unroll
+    for (int pp = 0; pp < CL; ++pp) parity_mask |= (uint16_t)(1u << (2 * pp + pair_cta));
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
             ptx::mbar_init(&aux->full[i], CG);      // one arrival per CTA of the pair (+ their TMA bytes)
-            ptx::mbar_init(&aux->empty[i], 1);       // tcgen05.commit (multicast to both CTAs when CG == 2)
+            ptx::mbar_init(&aux->empty[i], CL);      // tcgen05.commit of every pair of the cluster (multicast to all its CTAs)
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&aux->tmem_full[i], 1);
@@ -221,7 +237,7 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     // work items are (column split, group of CG adjacent row tiles); a pair walks them together
     const int n_mgroups = (p.n_mtiles + GRP - 1) / GRP;
     const int total_work = n_mgroups * p.n_splits;
-    const int w_begin = blockIdx.x / CG, w_step = gridDim.x / CG;
+    const int w_begin = blockIdx.x / CSIZE, w_step = gridDim.x / CSIZE;
     // PA / PB are the plane SLOTS of a stage; whether a lo plane is really loaded and multiplied is a
     // run-time property of the data (prepare.cu sets meta[LO_NONZERO]), so callers never have to
     // synchronise with the host to find out that e.g. integer descriptors are exact in one plane.
@@ -245,7 +261,7 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 // this work item's lock-step group: the items of the same split handled in the same round
                 int32_t* cnt = nullptr;
                 int gsize = 0;
-                if (p.sync_cnt != nullptr && leader) {
+                if (p.sync_cnt != nullptr && cta_rank == 0) {
                     const int round = (w - w_begin) / w_step;
                     const int g_lo = max(round * w_step, split * n_mgroups);
                     const int g_hi = min(min((round + 1) * w_step, (split + 1) * n_mgroups), total_work);
@@ -268,7 +284,9 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                         const uint32_t ph = (it / STAGES) & 1;
                         ptx::mbar_wait(&aux->empty[s], ph ^ 1);
                         uint8_t* st = smem + s * STAGE_BYTES;
-                        const int bcol = nt * BLOCK_N + (int)cta_rank * B_LOAD_ROWS;   // this CTA's half of the tile
+                        // this CTA's half of the tile; of that, the 1 / CL it fetches itself
+                        const int bcol = nt * BLOCK_N + (int)pair_cta * B_LOAD_ROWS + (int)pair_idx * B_ISSUE_ROWS;
+                        const int b_sub = (int)pair_idx * B_ISSUE_BYTES;
                         if (CG == 1) {
                             ptx::mbar_arrive_expect_tx(&aux->full[s], tx_bytes);
 #pragma unroll
@@ -286,15 +304,23 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                         } else {
                             // both CTAs' bytes are counted on the LEADER's barrier
                             if (leader) ptx::mbar_arrive_expect_tx(&aux->full[s], 2 * tx_bytes);
-                            else ptx::mbar_arrive_remote(&aux->full[s], 0);
+                            else ptx::mbar_arrive_remote(&aux->full[s], leader_rank);
                             ptx::tma_load_2d_2sm(st, &tm_a_hi, &aux->full[s], kb * BLOCK_K, mt * BLOCK_M);
                             if (use_alo)
                                 ptx::tma_load_2d_2sm(st + A_TILE_BYTES, &tm_a_lo, &aux->full[s], kb * BLOCK_K,
                                                      mt * BLOCK_M);
-                            ptx::tma_load_2d_2sm(st + PA * A_TILE_BYTES, &tm_b_hi, &aux->full[s], kb * BLOCK_K, bcol);
-                            if (use_blo)
-                                ptx::tma_load_2d_2sm(st + PA * A_TILE_BYTES + B_LOAD_BYTES, &tm_b_lo, &aux->full[s],
-                                                     kb * BLOCK_K, bcol);
+                            if (CL == 1) {
+                                ptx::tma_load_2d_2sm(st + PA * A_TILE_BYTES, &tm_b_hi, &aux->full[s], kb * BLOCK_K, bcol);
+                                if (use_blo)
+                                    ptx::tma_load_2d_2sm(st + PA * A_TILE_BYTES + B_LOAD_BYTES, &tm_b_lo, &aux->full[s],
+                                                         kb * BLOCK_K, bcol);
+                            } else {
+                                ptx::tma_load_2d_2sm_mc(st + PA * A_TILE_BYTES + b_sub, &tm_b_hi, &aux->full[s], kb * BLOCK_K,
+                                                        bcol, parity_mask);
+                                if (use_blo)
+                                    ptx::tma_load_2d_2sm_mc(st + PA * A_TILE_BYTES + B_LOAD_BYTES + b_sub, &tm_b_lo,
+                                                            &aux->full[s], kb * BLOCK_K, bcol, parity_mask);
+                            }
                         }
                     }
                 }
@@ -351,11 +377,11 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                         }
                         // frees the smem stage (in both CTAs) when these MMAs retire
                         if (CG == 1) ptx::umma_commit(&aux->empty[s]);
-                        else ptx::umma_commit_2sm(&aux->empty[s]);
+                        else ptx::umma_commit_2sm(&aux->empty[s], CL == 1 ? pair_mask : cluster_mask);
                     }
                     // accumulator complete -> epilogue (of both CTAs)
                     if (CG == 1) ptx::umma_commit(&aux->tmem_full[as]);
-                    else ptx::umma_commit_2sm(&aux->tmem_full[as]);
+                    else ptx::umma_commit_2sm(&aux->tmem_full[as], pair_mask);
                 }
             }
         }
@@ -532,7 +558,7 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 // the MMA issuer (leader CTA) may overwrite this accumulator once every epilogue thread of
                 // the pair has drained it
                 if (CG == 1 || leader) ptx::mbar_arrive(&aux->tmem_empty[as]);
-                else ptx::mbar_arrive_remote(&aux->tmem_empty[as], 0);
+                else ptx::mbar_arrive_remote(&aux->tmem_empty[as], leader_rank);
             }
 
             if (KSEL == 1) {
@@ -754,13 +780,61 @@ static int pick_mt(int64_t m, int d, bool split_products, int topk) {
 // The launch variant (CTAs per MMA, row tiles per CTA) is decided in ONE place: the tensor maps (B box height), the
 // work plan and the kernel instantiation must agree, or a TMA box delivers fewer bytes than the barrier expects.
 struct Variant {
-    int cg, mt;
+    int cg, mt, cl;
 };
-static Variant pick_variant(int64_t m, int d, bool split_products, int topk) {
+// Pairs per multicast cluster (CL) for the coarse top-k / collect pass at large d, where CTA pairs are used and the pass
+// is bound by the L2 -> shared-memory feed: 2 pairs (clusters of 4 CTAs) when there are enough row tiles.
+// ISE_CLUSTER_PAIRS = 1 | 2 | 4 overrides (A/B measurements).
+// Measured on the C3 coarse pass (10 k x 1 M x 2048, ncu, profiles/r02_findings.md): clusters of 2 pairs read 11.7 GB
+// from DRAM instead of 31.9 GB (L2 traffic 263 vs 380 GB) in the same 30.8 ms; 4 pairs 7.0 GB but 3 % slower (only 15
+// clusters of 8 whole-SM CTAs are co-resident: 120 of 148 SMs).  Small column sets (the 1/64 sample pre-pass) keep plain
+// pairs: nothing to share, and the cluster-wide stage hand-shake costs.
+static int pick_cl(int64_t m, int64_t n, int d, bool split_products, int topk, int cg) {
+    if (cg != 2 || split_products || topk == 1) return 1;
+    if (n * (int64_t)d * 2 < (256ll << 20)) return 1;                    // B plane below 256 MB
+    const char* e = getenv("ISE_CLUSTER_PAIRS");
+    int cl = e ? atoi(e) : 2;
+    if (cl != 1 && cl != 2 && cl != 4) cl = 1;
+    while (cl > 1 && ceil_div64(m, BLOCK_M) < 2 * 2 * cl) cl >>= 1;     // at least two clusters' worth of row tiles
+    return cl;
+}
+static Variant pick_variant(int64_t m, int64_t n, int d, bool split_products, int topk) {
     Variant v;
     v.mt = pick_mt(m, d, split_products, topk);
     v.cg = v.mt == 2 ? 1 : pick_cg(m, split_products, d, topk);
+    v.cl = pick_cl(m, n, d, split_products, topk, v.cg);
     return v;
+}
+
+// co-resident clusters of `csize` whole-SM CTAs (clusters of 4 / 8 do not tile every GPC: 33 / 15 on the B200 instead
+// of 37 / 18); the answer is the same for every gemm_select instantiation (one CTA per SM), so one of them is asked once
+static int cluster_slots(const ise_ctx* ctx, int csize) {
+    static int cached[9] = {0};
+    if (csize <= 2) return std::max(1, ctx->sm_count / csize);
+    if (cached[csize] == 0) {
+        int got = 0;
+        if (csize == 4 || csize == 8) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(csize * (ctx->sm_count / csize)));
+            cfg.blockDim = dim3((unsigned)num_threads(32, 1, 1));
+            cfg.dynamicSmemBytes = (size_t)(num_stages(1, 1, 2) * stage_bytes(1, 1, 2) + AUX_BYTES + 1024);
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            if (csize == 4) {
+                auto kern = gemm_select_kernel<1, 1, false, 32, false, 2, 1, false, 2>;
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+                cudaOccupancyMaxActiveClusters(&got, kern, &cfg);
+            } else {
+                auto kern = gemm_select_kernel<1, 1, false, 32, false, 2, 1, false, 4>;
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+                cudaOccupancyMaxActiveClusters(&got, kern, &cfg);
+            }
+        }
+        cached[csize] = got > 0 ? got : std::max(1, ctx->sm_count / csize);
+    }
+    return cached[csize];
 }
 
 static Plan make_plan(const ise_ctx* ctx, int64_t m, int64_t n, int d, int topk, bool single_split = false,
@@ -768,11 +842,11 @@ static Plan make_plan(const ise_ctx* ctx, int64_t m, int64_t n, int d, int topk,
     Plan pl;
     pl.n_mtiles = (int)ceil_div64(m, BLOCK_M);
     pl.n_ntiles = (int)std::max<int64_t>(1, ceil_div64(n, BLOCK_N));
-    const Variant var = pick_variant(m, d, split_products, topk);
-    const int cg = var.cg;
-    const int grp = var.cg * var.mt;
-    const int groups = (pl.n_mtiles + grp - 1) / grp;    // work is scheduled per CTA pair / per two-tile CTA
-    const int slots = std::max(1, ctx->sm_count / cg);
+    const Variant var = pick_variant(m, n, d, split_products, topk);
+    const int cg = var.cg * var.cl;                      // CTAs that walk a work item together (pair / cluster)
+    const int grp = var.cg * var.mt * var.cl;
+    const int groups = (pl.n_mtiles + grp - 1) / grp;    // work is scheduled per CTA pair (cluster) / per two-tile CTA
+    const int slots = cluster_slots(ctx, cg);
     // enough work items for ~4 waves of the persistent grid, but never less than 8 column tiles per
     // item (a fresh item restarts its selection threshold) and at most 256 partial lists per row
     int64_t want = ceil_div64((int64_t)4 * slots, std::max(1, groups));
@@ -809,12 +883,14 @@ static void setup_sync(const ise_ctx* ctx, Params& p, int d, bool split_products
     if (!ctx->sync_buf || (e && e[0] == '0')) return;
     const int64_t tile_bytes = (int64_t)BLOCK_N * ((d + BLOCK_K - 1) / BLOCK_K * BLOCK_K) * 2 * (split_products ? 2 : 1);
     if (tile_bytes * p.tiles_per_split < (24ll << 20) && !(e && e[0] == '1')) return;
-    const int every = (int)std::max<int64_t>(4, (16ll << 20) / tile_bytes);        // ~16 MB of B between check-ins
+    const char* e_mb = getenv("ISE_LOCKSTEP_MB");                                 // A/B: check-in interval in MB of B
+    const int64_t sync_bytes = (int64_t)((e_mb && atoi(e_mb) > 0) ? atoi(e_mb) : 16) << 20;
+    const int every = (int)std::max<int64_t>(1, sync_bytes / tile_bytes);          // ~16 MB of B between check-ins
     const int ncp = (p.tiles_per_split + every - 1) / every;
     const int grp = cg * mt;
     const int n_mgroups = (p.n_mtiles + grp - 1) / grp;
     const int64_t total = (int64_t)n_mgroups * p.n_splits;
-    const int slots = std::max(1, ctx->sm_count / cg);
+    const int slots = cluster_slots(ctx, cg);
     const int64_t rounds = ceil_div64(total, std::min<int64_t>(total, slots));
     const int64_t ints = rounds * p.n_splits * ncp;
     if (ints > kSyncInts) return;
@@ -824,39 +900,48 @@ static void setup_sync(const ise_ctx* ctx, Params& p, int d, bool split_products
     p.sync_ncp = ncp;
 }
 
-template <int PA, int PB, bool L2, int KSEL, bool VERIFY, int CG, int MT = 1, bool CONV = false>
+template <int PA, int PB, bool L2, int KSEL, bool VERIFY, int CG, int MT = 1, bool CONV = false, int CL = 1>
 static int launch_cg(const ise_ctx* ctx, const CUtensorMap* maps, const Params& p, cudaStream_t st) {
-    auto kern = gemm_select_kernel<PA, PB, L2, KSEL, VERIFY, CG, MT, CONV>;
+    auto kern = gemm_select_kernel<PA, PB, L2, KSEL, VERIFY, CG, MT, CONV, CL>;
     const int smem = num_stages(PA, PB, CG, MT) * stage_bytes(PA, PB, CG, MT) + AUX_BYTES + 1024;
     ISE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int groups = (p.n_mtiles + CG * MT - 1) / (CG * MT);
+    constexpr int CSIZE = CG * CL;
+    const int groups = (p.n_mtiles + CSIZE * MT - 1) / (CSIZE * MT);
     const int total = groups * p.n_splits;
     Params pp = p;
-    setup_sync(ctx, pp, p.d, PB == 2, CG, MT, st);
-    const int grid = CG * std::min(total, std::max(1, ctx->sm_count / CG));
+    setup_sync(ctx, pp, p.d, PB == 2, CSIZE, MT, st);
+    int slots = std::max(1, ctx->sm_count / CSIZE);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
+    cfg.gridDim = dim3((unsigned)(CSIZE * slots));
     cfg.blockDim = dim3((unsigned)num_threads(KSEL, PA, PB, MT, CONV));
     cfg.dynamicSmemBytes = (size_t)smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;   // CG == 2: the two CTAs of a pair form a cluster
-    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.x = CG * CL;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    slots = cluster_slots(ctx, CSIZE);
+    const int grid = CSIZE * std::min(total, slots);
+    cfg.gridDim = dim3((unsigned)grid);
     ISE_CUDA(cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], pp));
     return 0;
 }
 
 template <int PA, int PB, bool L2, int KSEL, bool VERIFY = false>
 static int launch(const ise_ctx* ctx, const CUtensorMap* maps, const Params& p, cudaStream_t st) {
-    const Variant var = pick_variant(p.m, p.d, PB == 2, KSEL == 1 ? 1 : 0);
+    const Variant var = pick_variant(p.m, p.n, p.d, PB == 2, KSEL == 1 ? 1 : 0);
     if constexpr (KSEL == 1 && PA == 1 && PB == 1 && epi_halves(KSEL, PA, PB) == 1) {
         if (var.mt == 2) return launch_cg<PA, PB, L2, KSEL, VERIFY, 1, 2>(ctx, maps, p, st);
     }
     if (var.mt != 1) ISE_FAIL("internal: two-row-tile variant picked for a kernel that has none");
+    if constexpr (KSEL != 1 && PA == 1 && PB == 1) {       // coarse top-k / collect: multicast clusters of CTA pairs
+        if (var.cg == 2 && var.cl == 2) return launch_cg<PA, PB, L2, KSEL, VERIFY, 2, 1, false, 2>(ctx, maps, p, st);
+        if (var.cg == 2 && var.cl == 4) return launch_cg<PA, PB, L2, KSEL, VERIFY, 2, 1, false, 4>(ctx, maps, p, st);
+    }
+    if (var.cl != 1) ISE_FAIL("internal: multicast cluster picked for a kernel that has none");
     return var.cg == 2 ? launch_cg<PA, PB, L2, KSEL, VERIFY, 2>(ctx, maps, p, st)
                        : launch_cg<PA, PB, L2, KSEL, VERIFY, 1>(ctx, maps, p, st);
 }
@@ -917,7 +1002,8 @@ ISE_EXPORT int ise_topk_merge(ise_ctx* ctx, const float* val_parts, const int64_
 // shared argument validation + tensor maps
 static int setup_maps(ise_ctx* ctx, const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi,
                       const void* b_lo, int64_t ldb, int64_t m, int64_t n, int d, int topk, CUtensorMap* maps) {
-    const int b_box = gs::BLOCK_N / gs::pick_variant(m, d, b_lo != nullptr, topk).cg;   // a CTA of a pair stages half of every B tile
+    const gs::Variant var = gs::pick_variant(m, n, d, b_lo != nullptr, topk);
+    const int b_box = gs::BLOCK_N / (var.cg * var.cl);   // a CTA of a pair stages half of every B tile (and fetches 1 / CL of that itself)
     ISE_CHECK_ARG(lda >= d && ldb >= d && lda % 8 == 0 && ldb % 8 == 0);
     ISE_CHECK_ARG((reinterpret_cast<uintptr_t>(a_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(b_hi) & 15) == 0);
     if (gs::make_plane_map(ctx, &maps[0], a_hi, m, d, lda, gs::BLOCK_M)) return 1;
@@ -1081,7 +1167,7 @@ ISE_EXPORT int ise_assign_fused(ise_ctx* ctx, const float* x, int64_t ldx, int64
     p.a_norms_w = a_norms; p.a_row_inv_w = a_row_inv; p.a_lo_skipped = a_lo_skipped; p.a_meta_w = a_meta;
     CUtensorMap maps[4];
     if (setup_maps(ctx, a_hi, nullptr, lda, b_hi, b_lo, ldb, m, n, d, 1, maps)) return 1;
-    const int cg = gs::pick_variant(m, d, b_lo != nullptr, 1).cg;
+    const int cg = gs::pick_variant(m, n, d, b_lo != nullptr, 1).cg;
     const bool l2 = metric == ISE_METRIC_L2;
     int rc;
 #define ISE_CONV_LAUNCH(PB, L2V)                                                                                       \

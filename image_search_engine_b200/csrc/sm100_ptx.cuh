@@ -136,6 +136,17 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
         "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1)
         : "memory");
 }
+// the same load, MULTICAST to the CTAs of `cta_mask` (same CTA-relative destination offset in each; the transaction
+// bytes are signalled on the barrier of each destination's pair leader): one L2 read feeds several CTA pairs
+__device__ __forceinline__ void tma_load_2d_2sm_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
+                                                   int32_t c1, uint16_t cta_mask) {
+    const uint32_t leader_bar = smem_u32(bar) & 0xFEFFFFFFu;
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], "
+        "[%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1), "h"(cta_mask)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_slot, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
                  "r"(ncols)
@@ -158,12 +169,13 @@ __device__ __forceinline__ void umma_f16_ss_2sm(uint32_t tmem_d, uint64_t desc_a
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// commit -> arrive on the barrier at this offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+// commit -> arrive on the barrier at this offset in every CTA of `cta_mask` (the two CTAs of the pair; every CTA of the
+// cluster for the stage-free signal of a multicast ring)
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask = 3) {
     asm volatile(
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
             smem_u32(bar)),
-        "h"((uint16_t)3)
+        "h"(cta_mask)
         : "memory");
 }
 

@@ -138,10 +138,17 @@ def test_coarse_bound_adversarial_topk(metric_ip, spread):
     from image_search_engine_b200._lib import METRIC_IP, METRIC_L2
     rng = np.random.default_rng(2048)
     m, n, d, k = 256, 6000, 2048, 10
-    # "at_the_bound": perturbations of 2^-16 .. 2^-9 around the 2^-11 rounding step -- nothing can be proven, every row
-    # must fall back; "above_the_bound": 2^-8 .. 2^-4 -- most rows ARE accepted by the proof, and those are the rows an
-    # optimistic bound would get wrong
-    a, b = _adversarial(rng, m, n, d) if spread == "at_the_bound" else _adversarial(rng, m, n, d, -8, -4)
+    # "at_the_bound": near-duplicate columns (perturbations of 2^-16 .. 2^-9 around the 2^-11 rounding step): nothing can
+    # be proven, every row must fall back
+    a, b = _adversarial(rng, m, n, d)
+    if spread == "above_the_bound":
+        # a head of 40 columns whose scores step down by 1 % of |a||b| (ten times the bound), the rest far below: the
+        # proof accepts these rows -- and they are exactly the rows an optimistic bound would get wrong
+        gain = np.full((n, 1), 0.5, np.float32)
+        head = rng.choice(n, 40, replace=False)
+        gain[head, 0] = 1.0 - 0.01 * np.arange(40, dtype=np.float32)
+        gain[gain[:, 0] == 0.5, 0] *= rng.uniform(0.5, 1.0, size=n - 40).astype(np.float32)
+        b = np.ascontiguousarray(b * gain, dtype=np.float32)
     dev = ops.require_cuda()
     ad, bd = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
     a_op, b_op = ops.prepare_operand(ad), ops.attach_sample(ops.prepare_operand(bd))
