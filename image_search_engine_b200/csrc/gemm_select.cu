@@ -770,7 +770,11 @@ constexpr int64_t kL2BytesPerItem = 0;   // 0 = no cap (see below)
 // profiles/r01_findings.md section 13), so they keep one row tile and double-buffered accumulators.
 // ISE_MT2=0 / 1 overrides (A/B measurements).
 static int pick_mt(int64_t m, int d, bool split_products, int topk) {
-    if (split_products || topk != 1) return 1;
+    if (split_products) return 1;
+    if (topk != 1) {     // A/B only (ISE_MT2_TOPK=1): two row tiles per CTA for the list epilogues, measured slower
+        const char* et = getenv("ISE_MT2_TOPK");
+        return (et && et[0] == '1' && d >= 1024 && ceil_div64(m, BLOCK_M) >= 2) ? 2 : 1;
+    }
     const char* e = getenv("ISE_MT2");
     if (e && e[0] == '0') return 1;
     const bool forced = e && e[0] == '1';
@@ -933,7 +937,7 @@ static int launch_cg(const ise_ctx* ctx, const CUtensorMap* maps, const Params& 
 template <int PA, int PB, bool L2, int KSEL, bool VERIFY = false>
 static int launch(const ise_ctx* ctx, const CUtensorMap* maps, const Params& p, cudaStream_t st) {
     const Variant var = pick_variant(p.m, p.n, p.d, PB == 2, KSEL == 1 ? 1 : 0);
-    if constexpr (KSEL == 1 && PA == 1 && PB == 1 && epi_halves(KSEL, PA, PB) == 1) {
+    if constexpr ((KSEL == 1 || KSEL == 32) && PA == 1 && PB == 1 && epi_halves(KSEL, PA, PB) == 1) {
         if (var.mt == 2) return launch_cg<PA, PB, L2, KSEL, VERIFY, 1, 2>(ctx, maps, p, st);
     }
     if (var.mt != 1) ISE_FAIL("internal: two-row-tile variant picked for a kernel that has none");

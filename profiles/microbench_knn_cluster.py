@@ -24,8 +24,9 @@ def t(fn, n=4):
     return e0.elapsed_time(e1) / n
 ref = None
 for rep in range(2):
-    for cl in ("1", "2", "4"):
-        os.environ["ISE_CLUSTER_PAIRS"] = cl
+    for cl in ("1", "2", "mt2"):
+        os.environ["ISE_CLUSTER_PAIRS"] = "1" if cl == "mt2" else cl
+        os.environ["ISE_MT2_TOPK"] = "1" if cl == "mt2" else "0"
         v, i = ops.gemm_select(a.hi_only(), b.hi_only(), METRIC_IP, 32, row_seed=seed)
         torch.cuda.synchronize()
         if ref is None:
