@@ -170,6 +170,9 @@ def shard_bounds(n: int, world: int) -> np.ndarray:
     return b
 
 
+SPECULATE_MAX_ASSIGN_MS = 10.0      # see lloyd_train: iterations whose assign is longer than this always synchronise
+
+
 def lloyd_train(cp, d, k, x_train, n_train, a_op, lops, *, init_rows, init_centroids=None, allreduce=None,
                 trace=None, precision="verified"):
     """The Lloyd iterations of faiss Clustering::train (SURVEY appendix A.2, steps 4a-4g) over this process's rows;
@@ -216,7 +219,7 @@ def lloyd_train(cp, d, k, x_train, n_train, a_op, lops, *, init_rows, init_centr
         if cp.spherical:
             lops.normalize(cent)
         o = 0.0
-        pending, prev_nsplit = None, None
+        pending, prev_nsplit, last_assign_ms = None, None, None
         for it in range(cp.niter):
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timed else None
             if timed:
@@ -237,7 +240,7 @@ def lloyd_train(cp, d, k, x_train, n_train, a_op, lops, *, init_rows, init_centr
                 st = stats[pending["index"]]
                 st.update(obj=o_prev, nsplit=nsplit_prev, speculated=True, mis_speculated=n_empty_prev > 0,
                           ms_finalize_host=pending["host_ms"] + (time.time() - t_fin) * 1e3, **phase_ms(pending["ev"]))
-                prev_nsplit, pending = nsplit_prev, None
+                prev_nsplit, pending, last_assign_ms = nsplit_prev, None, st["ms_assign"]
             if timed:
                 ev[1].record()
             accum.zero_()
@@ -256,7 +259,10 @@ def lloyd_train(cp, d, k, x_train, n_train, a_op, lops, *, init_rows, init_centr
             if cp.verbose:
                 cs = counts.double()
                 st["imbalance_factor"] = float((cs * cs).sum() * k / (cs.sum() ** 2))
-            if spec_ok and (prev_nsplit == 0 or (spec_force and prev_nsplit is not None)) and it < cp.niter - 1:
+            # worth guessing only where the host latency it hides is a visible share of an iteration: a wrong guess costs
+            # one assign, so long assigns (large codebooks: 28 - 230 ms at C4) always synchronise
+            cheap = last_assign_ms is not None and last_assign_ms < SPECULATE_MAX_ASSIGN_MS
+            if spec_ok and ((prev_nsplit == 0 and cheap) or (spec_force and prev_nsplit is not None)) and it < cp.niter - 1:
                 t_fin = time.time()
                 handle = lops.finalize_begin(sums, counts, cent, obj)
                 cent_bak.copy_(cent)
@@ -276,6 +282,8 @@ def lloyd_train(cp, d, k, x_train, n_train, a_op, lops, *, init_rows, init_centr
                 st.update(ms_finalize_host=(time.time() - t_fin) * 1e3, speculated=False, **phase_ms(ev))
             stats.append(st)
             prev_nsplit = nsplit
+            if timed:
+                last_assign_ms = st["ms_assign"]
             if trace is not None:
                 trace[-1]["centroids_out"] = cent.clone()
                 trace[-1]["nsplit"] = nsplit
