@@ -873,8 +873,9 @@ def run_ours(args):
             "e2e_from_list": {"value": world * C2["n_desc"] / (e2e_list_ms * 1e-3) / 1e6, "unit": "Mdescriptors/s",
                               "ms_per_step": e2e_list_ms, "h2d_bytes_per_step": list_h2d, "d2h_bytes_per_step": d2h,
                               "api": "BOVW.transform_csr(list of 10,000 float32 (100, 128) arrays, okapi=...) -> scipy CSR: the "
-                                     "reference's input contract; list walk + multi-threaded pack into a persistent pinned "
-                                     "buffer (uint8 on the wire when the values allow it) inside the timed region",
+                                     "reference's input contract; list walk + multi-threaded, chunk-ordered pack into a "
+                                     "persistent pinned buffer (uint8 on the wire when the values allow it) inside the timed "
+                                     "region, chunk i + 1 packed while chunk i is copied and quantised",
                               "equals_packed_path": same_as_packed},
             "e2e_dense": {"value": world * C2["n_desc"] / (e2e_dense_ms * 1e-3) / 1e6, "unit": "Mdescriptors/s",
                           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_dense, "ms_per_step": e2e_dense_ms,

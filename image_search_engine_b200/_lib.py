@@ -31,6 +31,10 @@ PROTOTYPES = {
     "ise_split_plan": (_int, [_c_void_p, _i64, _i64, _c_void_p, C.POINTER(C.c_int32)]),
     "ise_split_plan_warm": (_int, [_i64]),
     "ise_pack_rows": (_int, [_c_void_p, _c_void_p, _i64, _i64, _int, _int, _int, _c_void_p, _int, C.POINTER(_int)]),
+    "ise_pack_begin": (_int, [_c_void_p, _c_void_p, _c_void_p, _int, _int, _int, _int, _c_void_p, _int,
+                              C.POINTER(_c_void_p)]),
+    "ise_pack_wait": (_int, [_c_void_p, _int, C.POINTER(_int)]),
+    "ise_pack_end": (_int, [_c_void_p]),
     "ise_prepare_planes": (_int, [_c_void_p, _c_void_p, _int, _i64, _int, _i64, _c_void_p, _c_void_p, _i64,
                                   _c_void_p, _c_void_p, _c_void_p]),
     "ise_prepare_rows": (_int, [_c_void_p, _c_void_p, _int, _i64, _int, _i64, _c_void_p, _c_void_p, _i64,

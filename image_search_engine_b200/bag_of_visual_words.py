@@ -91,67 +91,114 @@ def pack_descriptions(descriptions, pin=False):
     return mat, offsets
 
 
+class _ListPacker:
+    """list[(n_i, d) float32 | uint8 ndarray] -> rows of a PERSISTENT pinned buffer (``bufs`` caches it across calls),
+    copied by ``ise_pack_rows`` on host threads instead of one single-threaded np.concatenate
+    (bag_of_visual_words.py:128) followed by a pin_memory copy.  float32 descriptors whose values are all integers in
+    [0, 255] (OpenCV SIFT, ORB as float) can be narrowed to uint8 on the way: a quarter of the PCIe bytes, and the
+    device widens uint8 for free.  Images are packed range by range (``pack(i0, i1, wire)``), so a caller can overlap
+    the packing of the next chunk with the transfer and the kernels of the previous one.  ``ok`` is False when the
+    list is not a plain list of C-contiguous same-dtype 2-D arrays (the caller then takes the generic path)."""
+
+    def __init__(self, descriptions, bufs: dict, nthreads: int | None = None):
+        import ctypes as C
+        import os
+        from . import _lib
+        self.ok = False
+        n_img = len(descriptions)
+        if n_img == 0:
+            return
+        ptrs = np.empty(n_img, dtype=np.uint64)
+        counts = np.empty(n_img, dtype=np.int64)
+        try:
+            from . import _fastlist                 # C walker (csrc/fastlist.c): ~20 ns per image
+        except ImportError:                          # not built: same checks in the interpreter (~1.6 us per image)
+            _fastlist = None
+        if _fastlist is not None:
+            got = _fastlist.walk(descriptions, ptrs.ctypes.data, counts.ctypes.data)
+            if got is None:
+                return
+            dt, d = (np.dtype(np.float32), got[1]) if got[0] == 0 else (np.dtype(np.uint8), got[1])
+        else:
+            first = descriptions[0]
+            if not isinstance(first, np.ndarray) or first.ndim != 2 or first.dtype not in (np.float32, np.uint8):
+                return
+            dt, d = first.dtype, int(first.shape[1])
+            for i, a in enumerate(descriptions):
+                if not isinstance(a, np.ndarray) or a.dtype != dt or a.ndim != 2 or a.shape[1] != d or not a.flags.c_contiguous:
+                    return
+                ptrs[i] = a.ctypes.data
+                counts[i] = a.shape[0]
+        offsets = np.zeros(n_img + 1, dtype=np.int64)
+        np.cumsum(counts, out=offsets[1:])
+        if int(offsets[-1]) == 0:
+            return
+        self._keep = descriptions                    # the arrays must outlive the raw pointers
+        self.ptrs, self.offsets, self.n_img, self.n_rows, self.d = ptrs, offsets, n_img, int(offsets[-1]), int(d)
+        self.src_u8 = dt == np.uint8
+        self.bufs, self._lib, self._C = bufs, _lib, C
+        self.nthreads = nthreads or min(16, os.cpu_count() or 1)
+        self.ok = True
+
+    def wire_dtypes(self, try_u8: bool = True):
+        """Wire formats to try, in order."""
+        if self.src_u8:
+            return [torch.uint8]
+        return [torch.uint8, torch.float32] if try_u8 else [torch.float32]
+
+    def view(self, wire: torch.dtype) -> torch.Tensor:
+        kind = "u8" if wire == torch.uint8 else "f32"
+        b = self.bufs.get(kind)
+        if b is None or b.numel() < self.n_rows * self.d:
+            b = torch.empty((max(self.n_rows * self.d, 1),), dtype=wire, pin_memory=True)
+            self.bufs[kind] = b
+        return b[: self.n_rows * self.d].view(self.n_rows, self.d)
+
+    def pack(self, i0: int, i1: int, wire: torch.dtype) -> bool:
+        """Copies images [i0, i1) to their rows of view(wire); False = a float32 value does not fit uint8."""
+        C, _lib = self._C, self._lib
+        ok = C.c_int(0)
+        _lib.check(_lib.load().ise_pack_rows(
+            C.c_void_p(self.ptrs.ctypes.data), C.c_void_p(self.offsets.ctypes.data), int(i0), int(i1), self.d,
+            _lib.DTYPE_U8 if self.src_u8 else _lib.DTYPE_F32, _lib.DTYPE_U8 if wire == torch.uint8 else _lib.DTYPE_F32,
+            C.c_void_p(self.view(wire).data_ptr()), self.nthreads, C.byref(ok)))
+        return bool(ok.value)
+
+    def begin(self, image_cuts: np.ndarray, wire: torch.dtype) -> None:
+        """Starts packing the image ranges [image_cuts[c], image_cuts[c + 1]) in the background, in order."""
+        C, _lib = self._C, self._lib
+        self.end()
+        self._cuts = np.ascontiguousarray(image_cuts, dtype=np.int64)
+        job = C.c_void_p()
+        _lib.check(_lib.load().ise_pack_begin(
+            C.c_void_p(self.ptrs.ctypes.data), C.c_void_p(self.offsets.ctypes.data), C.c_void_p(self._cuts.ctypes.data),
+            len(self._cuts) - 1, self.d, _lib.DTYPE_U8 if self.src_u8 else _lib.DTYPE_F32,
+            _lib.DTYPE_U8 if wire == torch.uint8 else _lib.DTYPE_F32, C.c_void_p(self.view(wire).data_ptr()),
+            self.nthreads, C.byref(job)))
+        self._job = job
+
+    def wait(self, chunk: int) -> bool:
+        """Blocks until chunk ``chunk`` is in the pinned buffer; False = a float32 value does not fit uint8."""
+        C, _lib = self._C, self._lib
+        ok = C.c_int(0)
+        _lib.check(_lib.load().ise_pack_wait(self._job, int(chunk), C.byref(ok)))
+        return bool(ok.value)
+
+    def end(self) -> None:
+        job = self.__dict__.pop("_job", None)
+        if job is not None:
+            self._lib.load().ise_pack_end(job)
+
+
 def _pack_list_into(descriptions, bufs: dict, try_u8: bool = True, nthreads: int | None = None):
-    """list[(n_i, d) float32 | uint8 ndarray] -> PackedDescriptions in a PERSISTENT pinned buffer (``bufs`` caches it
-    across calls), copied by ``ise_pack_rows`` on host threads instead of one single-threaded np.concatenate
-    (bag_of_visual_words.py:128) followed by a pin_memory copy.  float32 descriptors whose values are all integers
-    in [0, 255] (OpenCV SIFT, ORB as float) are narrowed to uint8 on the way: a quarter of the PCIe bytes, and the
-    device widens uint8 for free.  Returns None when the list is not a plain list of C-contiguous same-dtype arrays
-    (the caller then takes the generic path)."""
-    import ctypes as C
-    import os
-    from . import _lib
-    if len(descriptions) == 0:
+    """The whole list in one go: PackedDescriptions in the persistent pinned buffer, or None (see _ListPacker)."""
+    pk = _ListPacker(descriptions, bufs, nthreads)
+    if not pk.ok:
         return None
-    n_img = len(descriptions)
-    ptrs = np.empty(n_img, dtype=np.uint64)
-    counts = np.empty(n_img, dtype=np.int64)
-    try:
-        from . import _fastlist                 # C walker (csrc/fastlist.c): ~20 ns per image
-    except ImportError:                          # not built: same checks in the interpreter (~1.6 us per image)
-        _fastlist = None
-    if _fastlist is not None:
-        got = _fastlist.walk(descriptions, ptrs.ctypes.data, counts.ctypes.data)
-        if got is None:
-            return None
-        dt, d = (np.dtype(np.float32), got[1]) if got[0] == 0 else (np.dtype(np.uint8), got[1])
-    else:
-        first = descriptions[0]
-        if not isinstance(first, np.ndarray) or first.ndim != 2 or first.dtype not in (np.float32, np.uint8):
-            return None
-        dt, d = first.dtype, int(first.shape[1])
-        for i, a in enumerate(descriptions):
-            if not isinstance(a, np.ndarray) or a.dtype != dt or a.ndim != 2 or a.shape[1] != d or not a.flags.c_contiguous:
-                return None
-            ptrs[i] = a.ctypes.data
-            counts[i] = a.shape[0]
-    offsets = np.zeros(n_img + 1, dtype=np.int64)
-    np.cumsum(counts, out=offsets[1:])
-    n_rows = int(offsets[-1])
-    if n_rows == 0:
-        return None
-    lib = _lib.load()
-    nthreads = nthreads or min(16, os.cpu_count() or 1)
-    ok = C.c_int(0)
-
-    def buf(kind, torch_dtype):
-        b = bufs.get(kind)
-        if b is None or b.numel() < n_rows * d:
-            b = torch.empty((max(n_rows * d, 1),), dtype=torch_dtype, pin_memory=True)
-            bufs[kind] = b
-        return b[: n_rows * d].view(n_rows, d)
-
-    src_dt = _lib.DTYPE_F32 if dt == np.float32 else _lib.DTYPE_U8
-    if dt == np.uint8 or try_u8:
-        out = buf("u8", torch.uint8)
-        _lib.check(lib.ise_pack_rows(C.c_void_p(ptrs.ctypes.data), C.c_void_p(offsets.ctypes.data), 0, n_img, d, src_dt,
-                                     _lib.DTYPE_U8, C.c_void_p(out.data_ptr()), nthreads, C.byref(ok)))
-        if ok.value:
-            return PackedDescriptions(out, offsets)
-    out = buf("f32", torch.float32)
-    _lib.check(lib.ise_pack_rows(C.c_void_p(ptrs.ctypes.data), C.c_void_p(offsets.ctypes.data), 0, n_img, d, src_dt,
-                                 _lib.DTYPE_F32, C.c_void_p(out.data_ptr()), nthreads, C.byref(ok)))
-    return PackedDescriptions(out, offsets)
+    for wire in pk.wire_dtypes(try_u8):
+        if pk.pack(0, pk.n_img, wire):
+            return PackedDescriptions(pk.view(wire), pk.offsets)
+    return None
 
 
 class BOVW(BaseEstimator):
@@ -311,50 +358,85 @@ class BOVW(BaseEstimator):
             descriptions = describe_dataset(self.describer, X, prediction=True)
         dev = ops.require_cuda()
         k = int(self.n_clusters)
+        packer = None
         if isinstance(descriptions, (list, tuple)) and len(descriptions) >= 2 * n_chunks and k <= ops.CSR_MAX_BINS:
-            # the reference's own input contract (a Python list with one array per image): multi-threaded pack
-            # straight into a persistent pinned buffer, uint8 on the wire when the values allow it
-            packed = _pack_list_into(descriptions, self.__dict__.setdefault("_pack_bufs", {}))
-            if packed is not None:
-                descriptions = packed
+            # the reference's own input contract (a Python list with one array per image): packed chunk by chunk,
+            # on host threads, straight into a persistent pinned buffer (uint8 on the wire when the values allow it);
+            # chunk i + 1 is packed while chunk i is on its way to the device and being quantised
+            packer = _ListPacker(descriptions, self.__dict__.setdefault("_pack_bufs", {}))
+            if not packer.ok:
+                packer = None
         if k > ops.CSR_MAX_BINS:
             # codebooks beyond the shared-memory counter budget: dense kernel, CSR conversion on the host
             H = self.histograms_device(descriptions, okapi=okapi)
             return sp.csr_matrix(H.cpu().numpy())
-        mat, offsets = pack_descriptions(descriptions)
-        if isinstance(mat, np.ndarray):
-            mat = torch.from_numpy(mat)
+        if packer is not None:
+            offsets, wires = packer.offsets, packer.wire_dtypes()
+            mat = packer.view(wires[0])
+        else:
+            mat, offsets = pack_descriptions(descriptions)
+            if isinstance(mat, np.ndarray):
+                mat = torch.from_numpy(mat)
+            wires = [mat.dtype]
         n_img, n_rows = len(offsets) - 1, int(mat.shape[0])
         kw = self._csr_kwargs(okapi)
         off_dev = torch.from_numpy(offsets).to(dev, non_blocking=True)
-        if mat.is_cuda or n_img < 2 * n_chunks or not mat.is_pinned():
+        if packer is None and (mat.is_cuda or n_img < 2 * n_chunks or not mat.is_pinned()):
             words = self.clusterer.transform_device(mat.to(dev, non_blocking=True))
         else:
             # chunked H2D (copy stream) overlapped with the assign of the previous chunk (current stream)
             NB = 3
-            cuts = np.unique(np.linspace(0, n_rows, n_chunks + 1).astype(np.int64))
+            if packer is None:
+                cuts = np.unique(np.linspace(0, n_rows, n_chunks + 1).astype(np.int64))
+                img_cuts = None
+            else:           # whole images per chunk, balanced by rows
+                img_cuts = np.unique(np.searchsorted(offsets, np.linspace(0, n_rows, n_chunks + 1))).astype(np.int64)
+                img_cuts[0], img_cuts[-1] = 0, n_img
+                cuts = offsets[img_cuts]
             max_rows = int(np.diff(cuts).max())
-            key = ("csr", max_rows, int(mat.shape[1]), mat.dtype, str(dev))
-            pc = self.__dict__.get("_csr_cache")
-            if pc is None or pc["key"] != key:
-                pc = dict(key=key, s_in=torch.cuda.Stream(),
-                          xd=[torch.empty((max_rows, mat.shape[1]), dtype=mat.dtype, device=dev) for _ in range(NB)],
-                          ev_in=[torch.cuda.Event() for _ in range(NB)], ev_c=[torch.cuda.Event() for _ in range(NB)])
-                self.__dict__["_csr_cache"] = pc
-            main, s_in = torch.cuda.current_stream(), pc["s_in"]
-            s_in.wait_stream(main)
-            words = torch.empty((n_rows,), dtype=torch.int64, device=dev)
-            for ci, (r0, r1) in enumerate(zip(cuts[:-1], cuts[1:])):
-                b = ci % NB
-                xd = pc["xd"][b][: int(r1 - r0)]
-                with torch.cuda.stream(s_in):
-                    if ci >= NB:
-                        s_in.wait_event(pc["ev_c"][b])
-                    xd.copy_(mat[int(r0):int(r1)], non_blocking=True)
-                    pc["ev_in"][b].record(s_in)
-                main.wait_event(pc["ev_in"][b])
-                words[int(r0):int(r1)] = self.clusterer.transform_device(xd)
-                pc["ev_c"][b].record(main)
+            words = None
+            for wire in wires:
+                if packer is not None:
+                    mat = packer.view(wire)
+                key = ("csr", max_rows, int(mat.shape[1]), mat.dtype, str(dev))
+                pc = self.__dict__.get("_csr_cache")
+                if pc is None or pc["key"] != key:
+                    pc = dict(key=key, s_in=torch.cuda.Stream(),
+                              xd=[torch.empty((max_rows, mat.shape[1]), dtype=mat.dtype, device=dev) for _ in range(NB)],
+                              ev_in=[torch.cuda.Event() for _ in range(NB)], ev_c=[torch.cuda.Event() for _ in range(NB)])
+                    self.__dict__["_csr_cache"] = pc
+                main, s_in = torch.cuda.current_stream(), pc["s_in"]
+                s_in.wait_stream(main)
+                words = torch.empty((n_rows,), dtype=torch.int64, device=dev)
+                fits = True
+                if packer is not None:
+                    packer.begin(img_cuts, wire)
+                try:
+                    for ci, (r0, r1) in enumerate(zip(cuts[:-1], cuts[1:])):
+                        if r1 <= r0:
+                            continue
+                        if packer is not None and not packer.wait(ci):
+                            fits = False      # a value that is not an integer in [0, 255]: start over with float32 on the wire
+                            break
+                        b = ci % NB
+                        xd = pc["xd"][b][: int(r1 - r0)]
+                        with torch.cuda.stream(s_in):
+                            if ci >= NB:
+                                s_in.wait_event(pc["ev_c"][b])
+                            xd.copy_(mat[int(r0):int(r1)], non_blocking=True)
+                            pc["ev_in"][b].record(s_in)
+                        main.wait_event(pc["ev_in"][b])
+                        words[int(r0):int(r1)] = self.clusterer.transform_device(xd)
+                        pc["ev_c"][b].record(main)
+                finally:
+                    if packer is not None:
+                        packer.end()
+                if fits:
+                    break
+                # the pinned rows of the abandoned attempt may still be in flight: let the copies drain before the buffers
+                # are reused / re-packed
+                s_in.synchronize()
+            assert words is not None
         # persistent device + pinned result buffers (indptr | indices | data), grown on demand
         rb = self.__dict__.get("_csr_bufs")
         if rb is None or rb["cap"] < max(n_rows, 1) or rb["n_img"] < n_img or rb["dev"] != str(dev):

@@ -7,6 +7,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <memory>
 #include <mutex>
 #include <random>
 #include <thread>
@@ -401,6 +403,83 @@ inline bool narrow_f32_to_u8(const float* src, uint8_t* dst, int64_t n) {
 }
 }  // namespace
 
+namespace {
+// Thread t's share (of nt) of images [i0, i1): contiguous image ranges balanced by row count.
+void pack_share(const void* const* srcs, const int64_t* offsets, int64_t i0, int64_t i1, int d, int src_dtype,
+                int dst_dtype, void* dst_base, int t, int nt, std::atomic<int>& ok) {
+    const size_t src_elt = src_dtype == ISE_DTYPE_F32 ? 4 : 1, dst_elt = dst_dtype == ISE_DTYPE_F32 ? 4 : 1;
+    const int64_t total_rows = offsets[i1] - offsets[i0];
+    const int64_t r_lo = offsets[i0] + total_rows * t / nt, r_hi = offsets[i0] + total_rows * (t + 1) / nt;
+    int64_t a = std::lower_bound(offsets + i0, offsets + i1, r_lo) - offsets;
+    int64_t b = std::lower_bound(offsets + i0, offsets + i1, r_hi) - offsets;
+    if (t == nt - 1) b = i1;
+    for (int64_t i = a; i < b && ok.load(std::memory_order_relaxed); ++i) {
+        const int64_t rows = offsets[i + 1] - offsets[i];
+        if (rows <= 0) continue;
+        uint8_t* dst = (uint8_t*)dst_base + (size_t)offsets[i] * d * dst_elt;
+        if (src_dtype == dst_dtype) memcpy(dst, srcs[i], (size_t)rows * d * src_elt);
+        else if (!narrow_f32_to_u8((const float*)srcs[i], dst, rows * d)) ok.store(0);
+    }
+}
+
+// One asynchronous packing job: nt threads walk the chunks IN ORDER, each taking its share of every chunk, so chunk 0
+// is complete after ~1/n_chunks of the work and the caller can send it while the rest is still being packed.
+struct PackJob {
+    std::vector<std::thread> threads;
+    std::vector<int64_t> cuts;
+    std::unique_ptr<std::atomic<int>[]> finished;     // per chunk: threads done with it
+    std::atomic<int> ok{1};
+    std::mutex mu;
+    std::condition_variable cv;
+    int nt = 1;
+};
+}  // namespace
+
+ISE_EXPORT int ise_pack_begin(const void* const* srcs, const int64_t* offsets, const int64_t* image_cuts, int n_chunks,
+                              int d, int src_dtype, int dst_dtype, void* dst_base, int nthreads, void** job_out) {
+    ISE_CHECK_ARG(srcs && offsets && image_cuts && dst_base && job_out && d > 0 && n_chunks > 0);
+    ISE_CHECK_ARG(src_dtype == ISE_DTYPE_F32 || src_dtype == ISE_DTYPE_U8);
+    ISE_CHECK_ARG(dst_dtype == ISE_DTYPE_F32 || dst_dtype == ISE_DTYPE_U8);
+    ISE_CHECK_ARG(!(src_dtype == ISE_DTYPE_U8 && dst_dtype == ISE_DTYPE_F32));
+    for (int c = 0; c < n_chunks; ++c) ISE_CHECK_ARG(image_cuts[c] >= 0 && image_cuts[c + 1] >= image_cuts[c]);
+    PackJob* job = new PackJob();
+    job->cuts.assign(image_cuts, image_cuts + n_chunks + 1);
+    job->finished.reset(new std::atomic<int>[n_chunks]);
+    for (int c = 0; c < n_chunks; ++c) job->finished[c].store(0);
+    job->nt = std::max(1, std::min<int>(nthreads, 64));
+    const int nt = job->nt;
+    for (int t = 0; t < nt; ++t)
+        job->threads.emplace_back([=]() {
+            for (int c = 0; c < n_chunks; ++c) {
+                if (job->cuts[c + 1] > job->cuts[c])
+                    pack_share(srcs, offsets, job->cuts[c], job->cuts[c + 1], d, src_dtype, dst_dtype, dst_base, t, nt, job->ok);
+                if (job->finished[c].fetch_add(1) + 1 == nt) {
+                    std::lock_guard<std::mutex> lk(job->mu);
+                    job->cv.notify_all();
+                }
+            }
+        });
+    *job_out = job;
+    return 0;
+}
+
+ISE_EXPORT int ise_pack_wait(void* job_, int chunk, int* ok_out) {
+    PackJob* job = (PackJob*)job_;
+    ISE_CHECK_ARG(job && ok_out && chunk >= 0 && chunk + 1 < (int)job->cuts.size());
+    std::unique_lock<std::mutex> lk(job->mu);
+    job->cv.wait(lk, [&] { return job->finished[chunk].load() == job->nt; });
+    *ok_out = job->ok.load();
+    return 0;
+}
+
+ISE_EXPORT int ise_pack_end(void* job_) {
+    PackJob* job = (PackJob*)job_;
+    if (!job) return 0;
+    for (auto& t : job->threads) t.join();
+    delete job;
+    return 0;
+}
+
 ISE_EXPORT int ise_pack_rows(const void* const* srcs, const int64_t* offsets, int64_t i0, int64_t i1, int d,
                              int src_dtype, int dst_dtype, void* dst_base, int nthreads, int* ok_out) {
     ISE_CHECK_ARG(srcs && offsets && dst_base && ok_out && d > 0 && i0 >= 0 && i1 >= i0);
@@ -409,25 +488,11 @@ ISE_EXPORT int ise_pack_rows(const void* const* srcs, const int64_t* offsets, in
     ISE_CHECK_ARG(!(src_dtype == ISE_DTYPE_U8 && dst_dtype == ISE_DTYPE_F32));     // widening happens on the device
     *ok_out = 1;
     if (i1 == i0) return 0;
-    const size_t src_elt = src_dtype == ISE_DTYPE_F32 ? 4 : 1, dst_elt = dst_dtype == ISE_DTYPE_F32 ? 4 : 1;
     const int64_t total_rows = offsets[i1] - offsets[i0];
     int nt = std::max(1, std::min<int>(nthreads, 64));
     if (total_rows * d < (int64_t)1 << 16) nt = 1;
     std::atomic<int> ok{1};
-    auto work = [&](int t) {
-        // contiguous image ranges balanced by row count
-        const int64_t r_lo = offsets[i0] + total_rows * t / nt, r_hi = offsets[i0] + total_rows * (t + 1) / nt;
-        int64_t a = std::lower_bound(offsets + i0, offsets + i1, r_lo) - offsets;
-        int64_t b = std::lower_bound(offsets + i0, offsets + i1, r_hi) - offsets;
-        if (t == nt - 1) b = i1;
-        for (int64_t i = a; i < b && ok.load(std::memory_order_relaxed); ++i) {
-            const int64_t rows = offsets[i + 1] - offsets[i];
-            if (rows <= 0) continue;
-            uint8_t* dst = (uint8_t*)dst_base + (size_t)offsets[i] * d * dst_elt;
-            if (src_dtype == dst_dtype) memcpy(dst, srcs[i], (size_t)rows * d * src_elt);
-            else if (!narrow_f32_to_u8((const float*)srcs[i], dst, rows * d)) ok.store(0);
-        }
-    };
+    auto work = [&](int t) { pack_share(srcs, offsets, i0, i1, d, src_dtype, dst_dtype, dst_base, t, nt, ok); };
     if (nt == 1) {
         work(0);
     } else {

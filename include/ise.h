@@ -80,6 +80,14 @@ int ise_split_plan_warm(int64_t n_draws);
  * integer in [0, 255] (OpenCV SIFT / ORB-as-float descriptors are): a quarter of the host -> device bytes. */
 int ise_pack_rows(const void* const* srcs_host, const int64_t* offsets_host, int64_t i0, int64_t i1, int d,
                   int src_dtype, int dst_dtype, void* dst_base_host, int nthreads, int* ok);
+/* The same copy as a background job over n_chunks consecutive image ranges [image_cuts[c], image_cuts[c + 1]): the
+ * worker threads finish the chunks IN ORDER, so the caller sends chunk c to the device (ise_pack_wait(job, c, &ok)
+ * returns once its rows are in place; ok = 0: some value did not fit uint8, start over in float32) while chunk c + 1
+ * is still being packed.  srcs / offsets / dst stay valid until ise_pack_end, which joins the threads. */
+int ise_pack_begin(const void* const* srcs_host, const int64_t* offsets_host, const int64_t* image_cuts, int n_chunks,
+                   int d, int src_dtype, int dst_dtype, void* dst_base_host, int nthreads, void** job);
+int ise_pack_wait(void* job, int chunk, int* ok);
+int ise_pack_end(void* job);
 
 /* ---- operand preparation --------------------------------------------------------------
  * The distance contractions run on the tcgen05 tensor cores as FP16 "hi + lo" split

@@ -81,4 +81,13 @@ big = torch.empty((256 << 20,), dtype=torch.float32, device=dev)
 big2 = torch.empty_like(big)
 rec("(reference) torch copy 1 GiB -> 1 GiB", t(lambda: big2.copy_(big)), big.numel() * 8)
 rec("(reference) cudaMemset 1 GiB", t(lambda: big.zero_()), big.numel() * 4)
+# write-only stream of REAL data (not a constant the memory system can compress): the source is a 1 MiB tile that stays in L2
+tile = torch.randn((1 << 18,), device=dev)
+bigv = big.view(-1, 1 << 18)
+rec("(reference) write-only 1 GiB of random data (L2-resident 1 MiB tile broadcast)", t(lambda: bigv.copy_(tile.expand_as(bigv))), big.numel() * 4)
+rec("(reference) read-only 1 GiB (sum)", t(lambda: big.sum()), big.numel() * 4)
+half = torch.empty((big.numel() // 2,), dtype=torch.float16, device=dev)
+rec("(reference) float32 -> float16 cast of 1 GiB (read 4 B, write 2 B per element)", t(lambda: half.copy_(big[: half.numel()])), half.numel() * 6)
+u8big = torch.empty((big.numel() // 2,), dtype=torch.uint8, device=dev)
+rec("(reference) uint8 -> float16 cast (read 1 B, write 2 B per element)", t(lambda: half.copy_(u8big)), half.numel() * 3)
 json.dump(rows, open("gpurun_out/r02_membound.json", "w"), indent=1)

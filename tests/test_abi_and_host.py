@@ -263,3 +263,65 @@ def test_split_plan_sparse_stream_index_equals_dense_scan(monkeypatch):
     assert np.array_equal(p_big, p_big2) and np.array_equal(h_big, h_big2)
     print(f"split plan, k=65536, 400 splits: dense scan {t_dense * 1e3:.1f} ms, cached sparse index {t_warm * 1e3:.2f} ms")
     assert t_warm < t_dense
+
+
+def test_host_packer_whole_and_chunk_ordered_background_job():
+    """ise_pack_rows / ise_pack_begin-wait-end (pure host code): the packed matrix equals np.concatenate
+    (bag_of_visual_words.py:128) for ragged lists with empty images; float32 -> uint8 narrowing is accepted exactly when
+    every value is an integer in [0, 255]; the background job reports a value that does not fit from whichever chunk
+    holds it."""
+    import ctypes as C
+    from image_search_engine_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    d = 32
+    sizes = rng.integers(0, 90, 257)
+    sizes[[0, 100, 256]] = 0
+    imgs = [rng.integers(0, 256, (int(s), d)).astype(np.float32) for s in sizes]
+    want = np.concatenate(imgs)
+    ptrs = np.array([a.ctypes.data for a in imgs], dtype=np.uint64)
+    offsets = np.zeros(len(imgs) + 1, dtype=np.int64)
+    np.cumsum(sizes, out=offsets[1:])
+    p = lambda a: C.c_void_p(a.ctypes.data)
+
+    def whole(dst_dtype, nthreads):
+        dst = np.zeros(want.shape, dtype=np.uint8 if dst_dtype == _lib.DTYPE_U8 else np.float32)
+        ok = C.c_int(-1)
+        _lib.check(lib.ise_pack_rows(p(ptrs), p(offsets), 0, len(imgs), d, _lib.DTYPE_F32, dst_dtype, p(dst), nthreads, C.byref(ok)))
+        return dst, ok.value
+
+    def job(dst_dtype, cuts, nthreads):
+        dst = np.zeros(want.shape, dtype=np.uint8 if dst_dtype == _lib.DTYPE_U8 else np.float32)
+        cuts = np.asarray(cuts, dtype=np.int64)
+        h = C.c_void_p()
+        _lib.check(lib.ise_pack_begin(p(ptrs), p(offsets), p(cuts), len(cuts) - 1, d, _lib.DTYPE_F32, dst_dtype, p(dst),
+                                      nthreads, C.byref(h)))
+        oks = []
+        for c in range(len(cuts) - 1):
+            ok = C.c_int(-1)
+            _lib.check(lib.ise_pack_wait(h, c, C.byref(ok)))
+            if ok.value:                      # chunk c is in place as soon as its wait returns
+                r0, r1 = offsets[cuts[c]], offsets[cuts[c + 1]]
+                assert np.array_equal(dst[r0:r1].astype(np.float32), want[r0:r1])
+            oks.append(ok.value)
+        _lib.check(lib.ise_pack_end(h))
+        return dst, oks
+
+    for nt in (1, 3, 8):
+        for dt in (_lib.DTYPE_F32, _lib.DTYPE_U8):
+            dst, ok = whole(dt, nt)
+            assert ok == 1 and np.array_equal(dst.astype(np.float32), want)
+            dst, oks = job(dt, [0, 1, 1, 60, 200, 257], nt)
+            assert all(oks) and np.array_equal(dst.astype(np.float32), want)
+    # one value of image 230 is not a byte: uint8 refuses (whole call and the job), float32 is unaffected
+    imgs[230][1, 5] = 17.5
+    want = np.concatenate(imgs)
+    assert whole(_lib.DTYPE_U8, 4)[1] == 0
+    assert whole(_lib.DTYPE_F32, 4)[1] == 1
+    _, oks = job(_lib.DTYPE_U8, [0, 64, 128, 192, 257], 4)
+    assert oks[-1] == 0
+    dst, oks = job(_lib.DTYPE_F32, [0, 64, 128, 192, 257], 4)
+    assert all(oks) and np.array_equal(dst, want)
+    for bad in (-1.0, 256.0, np.nan):
+        imgs[230][1, 5] = bad
+        assert whole(_lib.DTYPE_U8, 2)[1] == 0

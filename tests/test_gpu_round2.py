@@ -382,6 +382,14 @@ def test_transform_csr_from_a_python_list_of_arrays():
         assert np.array_equal(got, want)
     assert np.array_equal(bovw.transform_csr(ints, okapi=ok, n_chunks=4).toarray(),
                           bovw.transform_csr(bytes_, okapi=ok, n_chunks=4).toarray())
+    # only an image of the LAST chunk breaks the uint8 narrowing: the chunked packer starts over in float32 after the
+    # first chunks were already sent as uint8
+    late = [a.copy() for a in ints]
+    late[-2][0, 3] += np.float32(0.5)
+    want = bovw.transform_csr(pack_descriptions(late, pin=True), okapi=ok, n_chunks=4).toarray()
+    assert np.array_equal(bovw.transform_csr(late, okapi=ok, n_chunks=4).toarray(), want)
+    assert np.array_equal(bovw.transform_csr(ints, okapi=ok, n_chunks=4).toarray(),        # and uint8 again afterwards
+                          bovw.transform_csr(bytes_, okapi=ok, n_chunks=4).toarray())
     # lists the packer does not understand (mixed dtypes, float64) take the generic path and still work
     mixed = [a.astype(np.float64) if i % 2 else a for i, a in enumerate(ints)]
     assert _pack_list_into(mixed, {}) is None
