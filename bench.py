@@ -404,7 +404,7 @@ def run_c5(args, torch, dist, dev, rank, world, barrier, max_over_ranks, ops, P)
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1) / reps)
-    stats = dict(ops.last_search_stats)
+    stats = ops.search_stats()
     # ---- parity: 128 sampled queries, oracle search of EVERY shard on the host cores of its rank, merged on rank 0 with
     #      the canonical (score, id) order = the unsharded oracle search of the 10 M-row index
     from oracle import faiss_shim as fs
@@ -574,7 +574,18 @@ def run_ours(args):
     ms_step = max_over_ranks(t_start.elapsed_time(t_end) / args.steps)
     # all gemm_select launches of a step (main launch + any fallback re-run) count towards the kernel time
     kern_ms = float(np.sum([a.elapsed_time(b) for a, b in kernel_events]) / args.steps)
-    assign_stats = dict(ops.last_search_stats)
+    assign_stats = ops.search_stats()
+    if assign_stats.get("mode") == "fused-verified":
+        kernel_name = ("gemm_select_kernel<PA=1,PB=1,IP,top-1,VERIFY,CG=2,CONV,ARES>: one tcgen05 product per tile + per-row "
+                       "proof of the winner (float32 -> FP16 plane conversion by converter warps inside the launch, row tile "
+                       "resident in shared memory), then gather + split-product re-run of the flagged rows (all launches timed)")
+        mma_products = 1.0 + 2.0 * assign_stats.get("fallback_rows", 0) / max(1, assign_stats.get("rows", 1))
+    elif assign_stats.get("mode") == "fused-split":
+        kernel_name = ("gemm_select_kernel<PA=1,PB=2,IP,top-1,CG=2,CONV> (fused assign: float32 -> FP16 plane conversion by "
+                       "converter warps inside the launch)")
+        mma_products = 2.0
+    else:
+        kernel_name, mma_products = "gemm_select_kernel<2,2,IP,1>", 2.0
     value = world * C2["n_desc"] / (ms_step * 1e-3) / 1e6
 
     # ---- parity of THIS step's result at full size: 2 000 sampled descriptors re-assigned by the oracle (host) ----
@@ -765,7 +776,7 @@ def run_ours(args):
         knn_ms = max_over_ranks(s.elapsed_time(e) / ksteps)
         # sample pre-pass + coarse main launch + split re-run of unproven rows, all tcgen05 gemm_select launches
         knn_kern_ms = float(np.sum([a.elapsed_time(b) for a, b in kernel_events]) / ksteps)
-        knn_stats = dict(ops.last_search_stats)
+        knn_stats = ops.search_stats()
         sampler.pause()
         # self-check (size independent): every query's best hit is the row it was derived from (rank 0's shard)
         hit = float((I[:, 0] == pick).float().mean().item())
@@ -883,13 +894,13 @@ def run_ours(args):
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": ach, "peak": P["tf_burst"], "unit": "TFLOP/s",
                          "frac": ach / P["tf_burst"], "traffic": traffic, "traffic_source": traffic_src,
-                         "kernel": "gemm_select_kernel<PA=1,PB=2,IP,top-1,CG=2,CONV> (fused assign: float32 -> FP16 plane "
-                                   "conversion by converter warps inside the launch)" if assign_stats.get("mode") == "fused-split"
-                         else "gemm_select_kernel<2,2,IP,1>",
+                         "kernel": kernel_name,
                          "kernel_ms": kern_ms, "search": assign_stats, "kernel_share_of_step": kern_ms / ms_step,
                          "peak_source": P["src"] + ", bf16 burst",
-                         # FP32-grade scores need hi*hi + hi*lo(centroids): 2 tcgen05 products per algorithmic FLOP
-                         "mma_products": 2, "achieved_mma_tflops": 2 * ach, "frac_mma": 2 * ach / P["tf_burst"]},
+                         # tcgen05 products issued per algorithmic FLOP: FP32-grade scores need hi*hi + hi*lo(centroids)
+                         # = 2; the verified pipeline issues 1 for every row + 2 more for the rows it re-runs
+                         "mma_products": mma_products, "achieved_mma_tflops": mma_products * ach,
+                         "frac_mma": mma_products * ach / P["tf_burst"]},
             "parity": step_parity,
             "hbm_kernels": hbm_kernels,
             "cpu_baseline": cpu,

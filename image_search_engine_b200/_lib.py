@@ -49,7 +49,12 @@ PROTOTYPES = {
                                _c_void_p, _c_void_p, _c_void_p, _size, _c_void_p]),
     "ise_assign_fused": (_int, [_c_void_p, _c_void_p, _i64, _i64, _int, _c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p,
                                 _c_void_p, _c_void_p, _c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _i64, _int, _i64,
-                                _c_void_p, _c_void_p, _c_void_p]),
+                                _c_void_p, _c_void_p, _c_void_p, _size, _c_void_p]),
+    "ise_assign_workspace_bytes": (_size, [_c_void_p, _i64, _int]),
+    "ise_assign_verified_covers": (_int, [_c_void_p, _i64, _i64, _int]),
+    "ise_assign_verified": (_int, [_c_void_p, _c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _c_void_p,
+                                   _c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _i64, _i64, _int, _int, _i64,
+                                   _c_void_p, _c_void_p, _c_void_p, _size, _c_void_p]),
     "ise_flat_search_exact_workspace_bytes": (_size, [_c_void_p, _i64, _i64, _int]),
     "ise_flat_search_exact": (_int, [_c_void_p, _c_void_p, _i64, _c_void_p, _i64, _int, _int, _int, _i64,
                                      _c_void_p, _c_void_p, _c_void_p, _size, _c_void_p]),

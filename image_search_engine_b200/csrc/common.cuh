@@ -105,8 +105,8 @@ __device__ __forceinline__ bool cand_better(float va, int64_t ia, float vb, int6
 // 2^-14 round with absolute error <= 2^-25) adds <= 2^-25/scale * sqrt(d) * |other operand|.
 struct CoarseBound {
     float kappa, uf_a, uf_b, nb_max, sq_, ca_;
-    __device__ __forceinline__ void init(const float* a_meta, const float* b_meta, int d) {
-        const float ca = a_meta[META_LO_NONZERO] != 0.f ? 4.8828125e-4f : 0.f;   // 2^-11
+    __device__ __forceinline__ void init(const float* a_meta, const float* b_meta, int d, bool a_exact = false) {
+        const float ca = (!a_exact && a_meta[META_LO_NONZERO] != 0.f) ? 4.8828125e-4f : 0.f;   // 2^-11
         const float cb = b_meta[META_LO_NONZERO] != 0.f ? 4.8828125e-4f : 0.f;
         kappa = 1.02f * (ca + cb) + 2.4e-7f + (float)(d / 16 + 4) * 1.1920929e-7f;
         const float sq = sqrtf((float)d) * 5.9604645e-8f;                         // 2 * 2^-25 * sqrt(d)

@@ -28,9 +28,6 @@
 #define ISE_EPI_PREFETCH 0   // 1 = issue the next chunk's tcgen05.ld before scanning the current one
                              // (measured SLOWER: C2 assign 1.53 vs 1.41 ms split, 1.32 vs 1.01 ms coarse)
 #endif
-#ifndef ISE_EPI_TREE
-#define ISE_EPI_TREE 1       // balanced max tree instead of a 31-deep FMNMX chain
-#endif
 
 namespace gs {
 
@@ -49,13 +46,19 @@ constexpr int EPI_WARP0 = 4;
 #ifndef ISE_EPI_HALVES_COARSE_TOP1
 #define ISE_EPI_HALVES_COARSE_TOP1 1
 #endif
-__host__ __device__ constexpr int epi_halves(int ksel, int pa, int pb) {
-    return (ksel == 1 && pa == 1 && pb == 1) ? ISE_EPI_HALVES_COARSE_TOP1 : 1;
+// The resident-row-tile kernels (ARES: the verified one-product assign at d <= 128) are bound by their epilogue, not by
+// the tensor pipe: a single warp per scheduler runs the dependent max / select chains at ~0.27 IPC (ncu, profiles/
+// r02_findings.md), so they get two warps per quadrant to interleave.
+#ifndef ISE_EPI_HALVES_ARES
+#define ISE_EPI_HALVES_ARES 2
+#endif
+__host__ __device__ constexpr int epi_halves(int ksel, int pa, int pb, bool ares = false) {
+    return ares ? ISE_EPI_HALVES_ARES : ((ksel == 1 && pa == 1 && pb == 1) ? ISE_EPI_HALVES_COARSE_TOP1 : 1);
 }
 // conv: four extra warps that convert the NEXT work item's float32 rows into FP16 planes while the current item is
 // being multiplied (fused assign, see the CONV template parameter)
-__host__ __device__ constexpr int num_threads(int ksel, int pa, int pb, int mt = 1, bool conv = false) {
-    return 128 + 128 * epi_halves(ksel, pa, pb) * mt + (conv ? 128 : 0);
+__host__ __device__ constexpr int num_threads(int ksel, int pa, int pb, int mt = 1, bool conv = false, bool ares = false) {
+    return 128 + 128 * epi_halves(ksel, pa, pb, ares) * mt + (conv ? 128 : 0);
 }
 constexpr int TMEM_COLS = 512;  // 2 accumulator stages x BLOCK_N fp32 columns
 constexpr int AUX_BYTES = 4096;
@@ -69,6 +72,14 @@ __host__ __device__ constexpr int stage_bytes(int pa, int pb, int cg = 1, int mt
 __host__ __device__ constexpr int num_stages(int pa, int pb, int cg = 1, int mt = 1) {
     int s = (SMEM_LIMIT - AUX_BYTES - 1024) / stage_bytes(pa, pb, cg, mt);
     return s > 6 ? 6 : s;
+}
+
+// ARES kernels: two resident A slots of up to two 64-column k-blocks each, stages of B only
+__host__ __device__ constexpr int ares_bytes() { return 2 * 2 * A_TILE_BYTES; }
+__host__ __device__ constexpr int ares_stage_bytes(int pb, int cg) { return pb * (B_TILE_BYTES / cg); }
+__host__ __device__ constexpr int ares_stages(int pb, int cg) {
+    int s = (SMEM_LIMIT - AUX_BYTES - 1024 - ares_bytes()) / ares_stage_bytes(pb, cg);
+    return s > 8 ? 8 : s;
 }
 
 struct Params {
@@ -110,6 +121,10 @@ struct Params {
     // regular kernels: return at once when the A operand turned out exact in its hi plane (meta[LO_NONZERO] == 0); the
     // launch that follows an optimistic hi-only fused assign and repeats it with the lo planes only if they exist
     int skip_if_a_exact;
+    // verified top-1 pipeline (no host synchronisation between its launches):
+    const int32_t* gate;     // optional: the whole launch returns at once unless *gate != 0 (device-side "needed" flag)
+    const int32_t* m_dev;    // optional: the number of rows actually present (<= m, which then is the buffers' capacity)
+    const int32_t* row_map;  // optional [m]: results of row r are written to out_*[row_map[r]] (compacted re-runs)
 };
 
 struct Aux {  // lives after the stage ring in dynamic shared memory
@@ -164,33 +179,49 @@ template <> struct SelList<32> { using type = RegList32; };
 //   L2 -> shared-memory feed: A 16 KB + B 16 KB per stage per SM becomes A 16 KB + B 16 / CL KB).  A stage may only be
 //   overwritten when EVERY pair of the cluster has consumed it: each leader's tcgen05.commit of the `empty` barrier is
 //   multicast to all 2 CL CTAs (barrier count CL).
-template <int PA, int PB, bool L2, int KSEL, bool VERIFY, int CG, int MT = 1, bool CONV = false, int CL = 1>
-__global__ void __launch_bounds__(num_threads(KSEL, PA, PB, MT, CONV), 1)
+// ARES (d <= 128, hi plane of A only): the row tile of a work item stays RESIDENT in shared memory (two slots, loaded with
+//   the item's first stage) instead of being re-fetched with every column tile, and the stage ring carries B only.  The
+//   one-product coarse pass at d = 128 needs 96 KB of operands per 1024 MMA cycles when A travels with every stage --
+//   more than L2 feeds one SM -- and 32 KB (CTA pairs) with A resident.
+template <int PA, int PB, bool L2, int KSEL, bool VERIFY, int CG, int MT = 1, bool CONV = false, int CL = 1, bool ARES = false>
+__global__ void __launch_bounds__(num_threads(KSEL, PA, PB, MT, CONV, ARES), 1)
 gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const Params p) {
-    static_assert(MT == 1 || (CG == 1 && epi_halves(KSEL, PA, PB) == 1), "two row tiles per CTA: single CTA, one warp per quadrant and tile");
-    static_assert(!CONV || (PA == 1 && KSEL == 1 && !VERIFY && MT == 1 && epi_halves(KSEL, PA, PB) == 1), "fused conversion: plain top-1, hi plane of A");
+    static_assert(MT == 1 || (CG == 1 && epi_halves(KSEL, PA, PB, ARES) == 1), "two row tiles per CTA: single CTA, one warp per quadrant and tile");
+    static_assert(!CONV || (PA == 1 && KSEL == 1 && MT == 1), "fused conversion: top-1, hi plane of A");
+    static_assert(epi_halves(KSEL, PA, PB, ARES) <= 2, "the hand-over between column halves is written for two");
+    static_assert(!ARES || (PA == 1 && MT == 1 && CL == 1), "resident row tile: hi plane of A, one row tile per CTA, no multicast");
     static_assert(CL == 1 || (CG == 2 && MT == 1 && !CONV && (CL == 2 || CL == 4)), "multicast clusters are made of CTA pairs");
     // uniform over the whole grid, before any barrier / TMEM state exists
     if (!CONV && p.skip_if_a_exact && __ldcg(p.a_meta + META_LO_NONZERO) == 0.f) return;
-    constexpr int STAGES = num_stages(PA, PB, CG, MT);
-    constexpr int STAGE_BYTES = stage_bytes(PA, PB, CG, MT);
+    if (p.gate != nullptr && __ldcg(p.gate) == 0) return;
+    int64_t m_rows = p.m;
+    int n_mtiles = p.n_mtiles;
+    if (p.m_dev != nullptr) {
+        m_rows = min((int64_t)__ldcg(p.m_dev), p.m);
+        n_mtiles = (int)((m_rows + BLOCK_M - 1) / BLOCK_M);
+    }
+    constexpr int A_RES_BYTES = ARES ? ares_bytes() : 0;
+    constexpr int STAGES = ARES ? ares_stages(PB, CG) : num_stages(PA, PB, CG, MT);
+    constexpr int STAGE_BYTES = ARES ? ares_stage_bytes(PB, CG) : stage_bytes(PA, PB, CG, MT);
     constexpr int A_BLOCK_BYTES = PA * A_TILE_BYTES;      // one row tile's planes inside a stage
-    constexpr int B_OFFSET = MT * A_BLOCK_BYTES;          // B planes follow the MT row tiles
+    constexpr int B_OFFSET = ARES ? 0 : MT * A_BLOCK_BYTES;   // B planes follow the MT row tiles (ARES: the stage is B only)
     constexpr int CSIZE = CG * CL;                        // CTAs per cluster
     constexpr int GRP = CG * MT * CL;                     // row tiles per work item
     constexpr int B_LOAD_BYTES = B_TILE_BYTES / CG;   // this CTA's share of a B tile (one plane)
     constexpr int B_LOAD_ROWS = BLOCK_N / CG;
     constexpr int B_ISSUE_ROWS = B_LOAD_ROWS / CL;    // ... of which it fetches this many rows itself (CL > 1: multicast)
     constexpr int B_ISSUE_BYTES = B_LOAD_BYTES / CL;
-    constexpr int HALVES = epi_halves(KSEL, PA, PB);
+    constexpr int HALVES = epi_halves(KSEL, PA, PB, ARES);
     constexpr int NUM_EPI_THREADS = 128 * HALVES * MT;
     constexpr int COLS_PER_HALF = BLOCK_N / HALVES;
     static_assert(STAGES >= 2 && STAGES <= 8, "pipeline depth");
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_al = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* a_res = smem_al;                         // ARES: 2 slots x 2 k-blocks x 16 KB
+    uint8_t* smem = smem_al + A_RES_BYTES;            // stage ring
     Aux* aux = reinterpret_cast<Aux*>(smem + STAGES * STAGE_BYTES);
 
     const int warp = threadIdx.x >> 5;
@@ -235,7 +266,7 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
 
     const int num_kb = (p.d + BLOCK_K - 1) / BLOCK_K;
     // work items are (column split, group of CG adjacent row tiles); a pair walks them together
-    const int n_mgroups = (p.n_mtiles + GRP - 1) / GRP;
+    const int n_mgroups = (n_mtiles + GRP - 1) / GRP;
     const int total_work = n_mgroups * p.n_splits;
     const int w_begin = blockIdx.x / CSIZE, w_step = gridDim.x / CSIZE;
     // PA / PB are the plane SLOTS of a stage; whether a lo plane is really loaded and multiplied is a
@@ -248,7 +279,7 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t it = 0, item = 0;
-            const uint32_t tx_bytes = MT * A_TILE_BYTES * (1 + (int)use_alo) + B_LOAD_BYTES * (1 + (int)use_blo);
+            const uint32_t tx_bytes = (ARES ? 0 : MT * A_TILE_BYTES * (1 + (int)use_alo)) + B_LOAD_BYTES * (1 + (int)use_blo);
             for (int w = w_begin; w < total_work; w += w_step, ++item) {
                 const int split = w / n_mgroups, mt = (w - split * n_mgroups) * GRP + (int)cta_rank;
                 if (CONV) {
@@ -287,7 +318,28 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                         // this CTA's half of the tile; of that, the 1 / CL it fetches itself
                         const int bcol = nt * BLOCK_N + (int)pair_cta * B_LOAD_ROWS + (int)pair_idx * B_ISSUE_ROWS;
                         const int b_sub = (int)pair_idx * B_ISSUE_BYTES;
-                        if (CG == 1) {
+                        if (ARES) {
+                            // the item's row tile rides on its first stage: all k-blocks into this item's resident slot
+                            const bool first = nt == nt0 && kb == 0;
+                            const uint32_t tx = tx_bytes + (first ? (uint32_t)(num_kb * A_TILE_BYTES) : 0u);
+                            uint8_t* slot = a_res + (item & 1) * (2 * A_TILE_BYTES);
+                            if (CG == 1) {
+                                ptx::mbar_arrive_expect_tx(&aux->full[s], tx);
+                                if (first)
+                                    for (int k2 = 0; k2 < num_kb; ++k2)
+                                        ptx::tma_load_2d(slot + k2 * A_TILE_BYTES, &tm_a_hi, &aux->full[s], k2 * BLOCK_K, mt * BLOCK_M);
+                                ptx::tma_load_2d(st, &tm_b_hi, &aux->full[s], kb * BLOCK_K, bcol);
+                                if (use_blo) ptx::tma_load_2d(st + B_LOAD_BYTES, &tm_b_lo, &aux->full[s], kb * BLOCK_K, bcol);
+                            } else {
+                                if (leader) ptx::mbar_arrive_expect_tx(&aux->full[s], 2 * tx);
+                                else ptx::mbar_arrive_remote(&aux->full[s], leader_rank);
+                                if (first)
+                                    for (int k2 = 0; k2 < num_kb; ++k2)
+                                        ptx::tma_load_2d_2sm(slot + k2 * A_TILE_BYTES, &tm_a_hi, &aux->full[s], k2 * BLOCK_K, mt * BLOCK_M);
+                                ptx::tma_load_2d_2sm(st, &tm_b_hi, &aux->full[s], kb * BLOCK_K, bcol);
+                                if (use_blo) ptx::tma_load_2d_2sm(st + B_LOAD_BYTES, &tm_b_lo, &aux->full[s], kb * BLOCK_K, bcol);
+                            }
+                        } else if (CG == 1) {
                             ptx::mbar_arrive_expect_tx(&aux->full[s], tx_bytes);
 #pragma unroll
                             for (int r = 0; r < MT; ++r) {      // rows past m are zero-filled by TMA
@@ -328,11 +380,12 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0 && leader) {   // CG == 2: only the leader CTA of a pair issues MMAs
+        // the WHOLE warp walks the loops (uniform control flow and operands); one elected lane issues the MMAs / commits
+        if (leader) {   // CG == 2: only the leader CTA of a pair issues MMAs
             constexpr uint32_t idesc = ptx::make_idesc_f16_f32(BLOCK_M * CG, BLOCK_N);
             const uint32_t smem_base = ptx::smem_u32(smem);
-            uint32_t it = 0, tile = 0;
-            for (int w = w_begin; w < total_work; w += w_step) {
+            uint32_t it = 0, tile = 0, item = 0;
+            for (int w = w_begin; w < total_work; w += w_step, ++item) {
                 const int split = w / n_mgroups;
                 const int nt0 = split * p.tiles_per_split;
                 const int nt1 = min(nt0 + p.tiles_per_split, p.n_ntiles);
@@ -348,40 +401,52 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                         const uint32_t ph = (it / STAGES) & 1;
                         ptx::mbar_wait(&aux->full[s], ph);
                         ptx::tc_fence_after();
-                        const uint32_t st = smem_base + s * STAGE_BYTES;
-                        const uint64_t da_hi = ptx::make_smem_desc_sw128(st);
-                        const uint64_t da_lo = ptx::make_smem_desc_sw128(st + A_TILE_BYTES);
-                        const uint64_t db_hi = ptx::make_smem_desc_sw128(st + B_OFFSET);
-                        const uint64_t db_lo = ptx::make_smem_desc_sw128(st + B_OFFSET + B_LOAD_BYTES);
-                        const uint64_t da1_hi = ptx::make_smem_desc_sw128(st + A_BLOCK_BYTES);                  // MT == 2
-                        const uint64_t da1_lo = ptx::make_smem_desc_sw128(st + A_BLOCK_BYTES + A_TILE_BYTES);
+                        // descriptor low words (address >> 4): every operand offset is a multiple of 16 bytes and shared
+                        // memory ends below 2^18, so the 14-bit field never carries
+                        const uint32_t sb = (smem_base + s * STAGE_BYTES) >> 4;
+                        const uint32_t a_hi0 = ARES ? (ptx::smem_u32(a_res) + (item & 1) * (2 * A_TILE_BYTES) + kb * A_TILE_BYTES) >> 4 : sb;
+                        const uint32_t a_lo0 = sb + (A_TILE_BYTES >> 4);
+                        const uint32_t b_hi0 = sb + (B_OFFSET >> 4), b_lo0 = b_hi0 + (B_LOAD_BYTES >> 4);
+                        const uint32_t a1_hi0 = sb + (A_BLOCK_BYTES >> 4), a1_lo0 = a1_hi0 + (A_TILE_BYTES >> 4);   // MT == 2
                         const int rem = p.d - kb * BLOCK_K;
                         const int ksteps = rem >= BLOCK_K ? BLOCK_K / UMMA_K : (rem + UMMA_K - 1) / UMMA_K;
-                        for (int ks = 0; ks < ksteps; ++ks) {
+                        auto issue = [&](int ks) {
                             // advancing 16 fp16 = 32 bytes inside the 128B swizzle span: +2 in the >>4 address
-                            const uint64_t koff = (uint64_t)(ks * ((UMMA_K * 2) >> 4));
+                            const uint32_t koff = (uint32_t)(ks * ((UMMA_K * 2) >> 4));
+                            const uint32_t acc = (uint32_t)((kb | ks) != 0);
                             if (CG == 1) {
-                                ptx::umma_f16_ss(tmem_d, da_hi + koff, db_hi + koff, idesc, (kb | ks) != 0);
-                                if (use_blo) ptx::umma_f16_ss(tmem_d, da_hi + koff, db_lo + koff, idesc, 1);
-                                if (use_alo) ptx::umma_f16_ss(tmem_d, da_lo + koff, db_hi + koff, idesc, 1);
+                                ptx::umma_f16_ss_lo(tmem_d, a_hi0 + koff, b_hi0 + koff, idesc, acc);
+                                if (use_blo) ptx::umma_f16_ss_lo(tmem_d, a_hi0 + koff, b_lo0 + koff, idesc, 1);
+                                if (use_alo) ptx::umma_f16_ss_lo(tmem_d, a_lo0 + koff, b_hi0 + koff, idesc, 1);
                                 if (MT == 2) {      // second row tile, accumulator in TMEM columns [256, 512)
-                                    ptx::umma_f16_ss(tmem_d + BLOCK_N, da1_hi + koff, db_hi + koff, idesc, (kb | ks) != 0);
-                                    if (use_blo) ptx::umma_f16_ss(tmem_d + BLOCK_N, da1_hi + koff, db_lo + koff, idesc, 1);
-                                    if (use_alo) ptx::umma_f16_ss(tmem_d + BLOCK_N, da1_lo + koff, db_hi + koff, idesc, 1);
+                                    ptx::umma_f16_ss_lo(tmem_d + BLOCK_N, a1_hi0 + koff, b_hi0 + koff, idesc, acc);
+                                    if (use_blo) ptx::umma_f16_ss_lo(tmem_d + BLOCK_N, a1_hi0 + koff, b_lo0 + koff, idesc, 1);
+                                    if (use_alo) ptx::umma_f16_ss_lo(tmem_d + BLOCK_N, a1_lo0 + koff, b_hi0 + koff, idesc, 1);
                                 }
                             } else {
-                                ptx::umma_f16_ss_2sm(tmem_d, da_hi + koff, db_hi + koff, idesc, (kb | ks) != 0);
-                                if (use_blo) ptx::umma_f16_ss_2sm(tmem_d, da_hi + koff, db_lo + koff, idesc, 1);
-                                if (use_alo) ptx::umma_f16_ss_2sm(tmem_d, da_lo + koff, db_hi + koff, idesc, 1);
+                                ptx::umma_f16_ss_2sm_lo(tmem_d, a_hi0 + koff, b_hi0 + koff, idesc, acc);
+                                if (use_blo) ptx::umma_f16_ss_2sm_lo(tmem_d, a_hi0 + koff, b_lo0 + koff, idesc, 1);
+                                if (use_alo) ptx::umma_f16_ss_2sm_lo(tmem_d, a_lo0 + koff, b_hi0 + koff, idesc, 1);
+                            }
+                        };
+                        const bool last_kb = kb == num_kb - 1;
+                        if (ptx::elect_one()) {
+                            if (ksteps == BLOCK_K / UMMA_K) {       // a full 64-column block: straight-line issue
+#pragma unroll
+                                for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) issue(ks);
+                            } else {
+                                for (int ks = 0; ks < ksteps; ++ks) issue(ks);
+                            }
+                            // frees the smem stage (in both CTAs) when these MMAs retire
+                            if (CG == 1) ptx::umma_commit(&aux->empty[s]);
+                            else ptx::umma_commit_2sm(&aux->empty[s], CL == 1 ? pair_mask : cluster_mask);
+                            if (last_kb) {      // accumulator complete -> epilogue (of both CTAs)
+                                if (CG == 1) ptx::umma_commit(&aux->tmem_full[as]);
+                                else ptx::umma_commit_2sm(&aux->tmem_full[as], pair_mask);
                             }
                         }
-                        // frees the smem stage (in both CTAs) when these MMAs retire
-                        if (CG == 1) ptx::umma_commit(&aux->empty[s]);
-                        else ptx::umma_commit_2sm(&aux->empty[s], CL == 1 ? pair_mask : cluster_mask);
+                        __syncwarp();
                     }
-                    // accumulator complete -> epilogue (of both CTAs)
-                    if (CG == 1) ptx::umma_commit(&aux->tmem_full[as]);
-                    else ptx::umma_commit_2sm(&aux->tmem_full[as], pair_mask);
                 }
             }
         }
@@ -395,7 +460,7 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         const float b_inv = p.b_meta[META_INV_SCALE];
         const float a_inv_tensor = p.a_meta[META_INV_SCALE];
         CoarseBound bound;
-        if (KSEL == 1 && VERIFY) bound.init(p.a_meta, p.b_meta, p.d);
+        if (KSEL == 1 && VERIFY) bound.init(p.a_meta, p.b_meta, p.d, CONV);   // CONV: a tensor that is not exact in its hi plane is re-run as a whole
         uint32_t tile = 0, item = 0;
         for (int w = w_begin; w < total_work; w += w_step, ++item) {
             const int split = w / n_mgroups, mt = (w - split * n_mgroups) * GRP + (int)cta_rank + rt;
@@ -407,7 +472,7 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             // them and read them with coherent loads (not the read-only path)
             if (CONV) ptx::mbar_wait(&aux->a_ready[item & 1], (item >> 1) & 1);
             // accumulator -> real units: 1 / (scale of this row's A planes * scale of the B planes)
-            const float a_inv = (p.a_row_inv != nullptr && row < p.m)
+            const float a_inv = (p.a_row_inv != nullptr && row < m_rows)
                                     ? (CONV ? __ldcg(p.a_row_inv + row) : __ldg(p.a_row_inv + row)) : a_inv_tensor;
             const float inv = a_inv * b_inv;
             const float two_inv = 2.f * inv;
@@ -420,7 +485,7 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             typename SelList<KSEL>::type list;
             float collect_thr = CUDART_INF_F;   // collect mode: rows beyond m never append
             if (KSEL == 0) {
-                if (row < p.m) {
+                if (row < m_rows) {
                     const float sr = __ldg(p.row_seed + row);
                     collect_thr = L2 ? (__ldg(p.a_norms + row) - sr) : sr / inv;   // scales are powers of two: exact
                 }
@@ -429,7 +494,7 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 // seed = score of a column already known to exist (from a pre-pass over a column sample):
                 // candidates that cannot beat it are never inserted, which removes almost all list traffic
                 float seed = -CUDART_INF_F;
-                if (p.row_seed != nullptr && row < p.m) {
+                if (p.row_seed != nullptr && row < m_rows) {
                     const float sr = __ldg(p.row_seed + row);
                     seed = L2 ? (__ldg(p.a_norms + row) - sr) : sr / inv;           // scales are powers of two: exact
                 }
@@ -478,21 +543,14 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                             for (int j = 0; j < 32; ++j)
                                 if (c + j >= ncols) v[j] = -CUDART_INF_F;
                         }
-                        // balanced max tree (depth 5) instead of a 31-deep dependent chain
-#if ISE_EPI_TREE
-                        float t16[16], t8[8], t4[4];
+                        // four groups of eight (3-input maxima), then the chunk maximum: the group maxima are what the
+                        // rare top-1 update starts from
+                        float g[4];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) t16[j] = fmaxf(v[2 * j], v[2 * j + 1]);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) t8[j] = fmaxf(t16[2 * j], t16[2 * j + 1]);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) t4[j] = fmaxf(t8[2 * j], t8[2 * j + 1]);
-                        const float mx = fmaxf(fmaxf(t4[0], t4[1]), fmaxf(t4[2], t4[3]));
-#else
-                        float mx = v[0];
-#pragma unroll
-                        for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
-#endif
+                        for (int i = 0; i < 4; ++i)
+                            g[i] = fmaxf(fmaxf(fmaxf(v[8 * i], v[8 * i + 1]), fmaxf(v[8 * i + 2], v[8 * i + 3])),
+                                         fmaxf(fmaxf(v[8 * i + 4], v[8 * i + 5]), fmaxf(v[8 * i + 6], v[8 * i + 7])));
+                        const float mx = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
                         if (KSEL == 0) {
                             float cur = mx;
 #pragma unroll 1
@@ -516,17 +574,31 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                             }
                         } else if (KSEL == 1) {
                             if (mx > best) {  // strict: an equal score in a later column never replaces
+                                // a warp takes this branch when ANY of its 32 rows improves (most chunks of a 4096-column
+                                // codebook), so it is kept short: locate the first group holding the maximum, then work
+                                // on that group's eight values only
                                 if (VERIFY) m2 = fmaxf(m2, best);   // the old best's whole chunk is now "other"
                                 best = mx;
-                                int jj = 31;
+                                const bool in01 = (g[0] == mx) || (g[1] == mx);
+                                const bool odd = in01 ? (g[0] != mx) : (g[2] != mx);
+                                const int gi = (in01 ? 0 : 2) + (odd ? 1 : 0);
+                                float w[8];
 #pragma unroll
-                                for (int j = 30; j >= 0; --j)
-                                    if (v[j] == mx) jj = j;  // lowest column among equals
-                                best_id = col0 + c + jj;
+                                for (int e = 0; e < 8; ++e) {
+                                    const float lo = odd ? v[8 + e] : v[e], hi = odd ? v[24 + e] : v[16 + e];
+                                    w[e] = in01 ? lo : hi;
+                                }
+                                int ee = 7;
+#pragma unroll
+                                for (int e = 6; e >= 0; --e)
+                                    if (w[e] == mx) ee = e;  // lowest column among equals
+                                best_id = col0 + c + gi * 8 + ee;
                                 if (VERIFY) {
                                     float s2 = -CUDART_INF_F;
 #pragma unroll
-                                    for (int j = 0; j < 32; ++j) s2 = fmaxf(s2, (j == jj) ? -CUDART_INF_F : v[j]);
+                                    for (int e = 0; e < 8; ++e) s2 = fmaxf(s2, (e == ee) ? -CUDART_INF_F : w[e]);
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) s2 = fmaxf(s2, (i == gi) ? -CUDART_INF_F : g[i]);
                                     sib = s2;
                                 }
                             } else if (VERIFY) {
@@ -580,10 +652,11 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                     }
                     asm volatile("bar.sync 2, %0;" ::"n"(NUM_EPI_THREADS) : "memory");
                 }
-                if (half == 0 && row < p.m) {
+                if (half == 0 && row < m_rows) {
                     const float an = (L2 || VERIFY) ? (CONV ? __ldcg(p.a_norms + row) : __ldg(p.a_norms + row)) : 0.f;
-                    float* ov = p.out_val + ((int64_t)split * p.m + row) * p.topk;
-                    int64_t* oi = p.out_idx + ((int64_t)split * p.m + row) * p.topk;
+                    const int64_t orow = p.row_map != nullptr ? (int64_t)__ldcg(p.row_map + row) : row;
+                    float* ov = p.out_val + ((int64_t)split * p.m + orow) * p.topk;
+                    int64_t* oi = p.out_idx + ((int64_t)split * p.m + orow) * p.topk;
                     if (best_id >= 0) {
                         ov[0] = L2 ? fmaxf(an - best, 0.f) : best * inv;
                         oi[0] = p.id_base + best_id;
@@ -598,7 +671,7 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                         oi[0] = -1;
                     }
                 }
-            } else if (KSEL > 1 && row < p.m) {
+            } else if (KSEL > 1 && row < m_rows) {
                 const float an = L2 ? __ldg(p.a_norms + row) : 0.f;
                 float* ov = p.out_val + ((int64_t)split * p.m + row) * p.topk;
                 int64_t* oi = p.out_idx + ((int64_t)split * p.m + row) * p.topk;
@@ -904,10 +977,11 @@ static void setup_sync(const ise_ctx* ctx, Params& p, int d, bool split_products
     p.sync_ncp = ncp;
 }
 
-template <int PA, int PB, bool L2, int KSEL, bool VERIFY, int CG, int MT = 1, bool CONV = false, int CL = 1>
+template <int PA, int PB, bool L2, int KSEL, bool VERIFY, int CG, int MT = 1, bool CONV = false, int CL = 1, bool ARES = false>
 static int launch_cg(const ise_ctx* ctx, const CUtensorMap* maps, const Params& p, cudaStream_t st) {
-    auto kern = gemm_select_kernel<PA, PB, L2, KSEL, VERIFY, CG, MT, CONV, CL>;
-    const int smem = num_stages(PA, PB, CG, MT) * stage_bytes(PA, PB, CG, MT) + AUX_BYTES + 1024;
+    auto kern = gemm_select_kernel<PA, PB, L2, KSEL, VERIFY, CG, MT, CONV, CL, ARES>;
+    const int smem = (ARES ? ares_bytes() + ares_stages(PB, CG) * ares_stage_bytes(PB, CG)
+                           : num_stages(PA, PB, CG, MT) * stage_bytes(PA, PB, CG, MT)) + AUX_BYTES + 1024;
     ISE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     constexpr int CSIZE = CG * CL;
     const int groups = (p.n_mtiles + CSIZE * MT - 1) / (CSIZE * MT);
@@ -917,7 +991,7 @@ static int launch_cg(const ise_ctx* ctx, const CUtensorMap* maps, const Params& 
     int slots = std::max(1, ctx->sm_count / CSIZE);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(CSIZE * slots));
-    cfg.blockDim = dim3((unsigned)num_threads(KSEL, PA, PB, MT, CONV));
+    cfg.blockDim = dim3((unsigned)num_threads(KSEL, PA, PB, MT, CONV, ARES));
     cfg.dynamicSmemBytes = (size_t)smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -973,6 +1047,7 @@ static int dispatch_metric(const ise_ctx* ctx, const CUtensorMap* maps, const Pa
 static void clear_conv(Params& p) {
     p.a_raw = nullptr; p.lda_raw = 0; p.a_hi_w = nullptr; p.a_lo_w = nullptr; p.lda_w = 0; p.a_norms_w = nullptr;
     p.a_row_inv_w = nullptr; p.a_lo_skipped = nullptr; p.a_meta_w = nullptr; p.skip_if_a_exact = 0;
+    p.gate = nullptr; p.m_dev = nullptr; p.row_map = nullptr;
 }
 
 }  // namespace gs
@@ -1004,9 +1079,16 @@ ISE_EXPORT int ise_topk_merge(ise_ctx* ctx, const float* val_parts, const int64_
 }
 
 // shared argument validation + tensor maps
+static int setup_maps_var(ise_ctx* ctx, const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi,
+                          const void* b_lo, int64_t ldb, int64_t m, int64_t n, int d, gs::Variant var, CUtensorMap* maps);
+
 static int setup_maps(ise_ctx* ctx, const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi,
                       const void* b_lo, int64_t ldb, int64_t m, int64_t n, int d, int topk, CUtensorMap* maps) {
-    const gs::Variant var = gs::pick_variant(m, n, d, b_lo != nullptr, topk);
+    return setup_maps_var(ctx, a_hi, a_lo, lda, b_hi, b_lo, ldb, m, n, d, gs::pick_variant(m, n, d, b_lo != nullptr, topk), maps);
+}
+
+static int setup_maps_var(ise_ctx* ctx, const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi,
+                          const void* b_lo, int64_t ldb, int64_t m, int64_t n, int d, gs::Variant var, CUtensorMap* maps) {
     const int b_box = gs::BLOCK_N / (var.cg * var.cl);   // a CTA of a pair stages half of every B tile (and fetches 1 / CL of that itself)
     ISE_CHECK_ARG(lda >= d && ldb >= d && lda % 8 == 0 && ldb % 8 == 0);
     ISE_CHECK_ARG((reinterpret_cast<uintptr_t>(a_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(b_hi) & 15) == 0);
@@ -1134,13 +1216,196 @@ ISE_EXPORT int ise_gemm_select(ise_ctx* ctx, const void* a_hi, const void* a_lo,
 int ise_internal_lo_fixup(ise_ctx* ctx, void* lo, int64_t n, int64_t ldp, const uint8_t* lo_skipped, const float* meta,
                           void* stream);   // prepare.cu
 
+// ------------------------------------------------------------------------------------------
+// verified top-1 at d <= 128 without a host round trip (quantisation / k-means assign)
+// ------------------------------------------------------------------------------------------
+namespace gs {
+
+// compacts the hi (/ lo) plane rows, norms and scales of the flagged rows; block 0 publishes the row count of the
+// re-run and whether the list overflowed its capacity
+__global__ void gather_flagged_kernel(const int32_t* __restrict__ flag_rows, const int32_t* __restrict__ flag_count, int cap,
+                                      const __half* __restrict__ a_hi, const __half* __restrict__ a_lo, int64_t lda,
+                                      const float* __restrict__ norms, const float* __restrict__ row_inv,
+                                      __half* __restrict__ g_hi, __half* __restrict__ g_lo, float* __restrict__ g_norms,
+                                      float* __restrict__ g_row_inv, int32_t* __restrict__ m_dev, int32_t* __restrict__ overflow) {
+    const int cnt = *flag_count;
+    const int n = min(cnt, cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *m_dev = n;
+        *overflow = cnt > cap ? 1 : 0;
+    }
+    const int vecs = (int)(lda >> 3);                 // 8 halves per 16-byte vector (lda % 8 == 0)
+    // one row per group of `vecs` (<= 16) consecutive threads, grid-stride
+    const int per_block = blockDim.x / vecs;
+    const int sub = threadIdx.x / vecs, c = threadIdx.x - sub * vecs;
+    if (sub >= per_block) return;
+    for (int64_t r = (int64_t)blockIdx.x * per_block + sub; r < n; r += (int64_t)gridDim.x * per_block) {
+        const int64_t src = flag_rows[r];
+        reinterpret_cast<uint4*>(g_hi + r * lda)[c] = __ldg(reinterpret_cast<const uint4*>(a_hi + src * lda) + c);
+        if (a_lo != nullptr) reinterpret_cast<uint4*>(g_lo + r * lda)[c] = __ldg(reinterpret_cast<const uint4*>(a_lo + src * lda) + c);
+        if (c == 0) {
+            g_norms[r] = norms[src];
+            if (row_inv != nullptr) g_row_inv[r] = row_inv[src];
+        }
+    }
+}
+
+struct VerifiedWs {
+    int32_t* ctrl;        // [0] flagged rows, [1] rows of the re-run, [2] overflow
+    int32_t* flag_rows;   // [m]
+    __half* g_hi;
+    __half* g_lo;
+    float* g_norms;
+    float* g_row_inv;
+    int64_t cap;
+    size_t bytes;
+};
+
+static VerifiedWs verified_ws(void* base, int64_t m, int64_t lda) {
+    VerifiedWs w;
+    // a quarter of the rows may be re-run through the compact path; beyond that the whole launch is repeated
+    w.cap = std::min<int64_t>(ceil_div64(m, BLOCK_M) * BLOCK_M, ceil_div64(std::max<int64_t>(m / 4, 1024), BLOCK_M) * BLOCK_M);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return (uint8_t*)base + o; };
+    w.ctrl = (int32_t*)take(16);
+    w.flag_rows = (int32_t*)take((size_t)m * 4);
+    w.g_hi = (__half*)take((size_t)w.cap * lda * 2);
+    w.g_lo = (__half*)take((size_t)w.cap * lda * 2);
+    w.g_norms = (float*)take((size_t)w.cap * 4);
+    w.g_row_inv = (float*)take((size_t)w.cap * 4);
+    w.bytes = off;
+    return w;
+}
+
+// covered: up to two 64-column k-blocks (the resident row tile), enough column tiles to cycle the stage ring within an
+// item, and enough row tiles that one unsplit column range fills the machine
+static bool verified_covers(const ise_ctx* ctx, int64_t m, int64_t n, int d, int64_t lda) {
+    if (getenv("ISE_NO_VERIFIED_ASSIGN")) return false;
+    const int num_kb = (d + BLOCK_K - 1) / BLOCK_K;
+    if (d > 128 || lda > 128 || n < 2) return false;
+    if (ceil_div64(n, BLOCK_N) * num_kb < 8) return false;
+    if (m < (int64_t)2 * BLOCK_M * ctx->sm_count) return false;
+    return make_plan(ctx, m, n, d, 1, false, true).n_splits == 1;
+}
+
+template <bool L2>
+static int verified_launches(ise_ctx* ctx, Params p, const float* x, int64_t ldx, void* a_hi, void* a_lo, int64_t lda,
+                             uint8_t* a_lo_skipped, float* a_meta_w, const void* b_hi, const void* b_lo, int64_t ldb,
+                             const VerifiedWs& w, cudaStream_t st) {
+    const int64_t m = p.m, n = p.n;
+    const int d = p.d;
+    const bool conv = x != nullptr;
+    const bool rerun_lo = !conv && a_lo != nullptr;          // prepared rows that may carry a lo plane
+    const float* a_norms = p.a_norms;
+    const float* a_row_inv = p.a_row_inv;
+    clear_conv(p);                                           // the re-runs are plain launches
+    ISE_CUDA(cudaMemsetAsync(w.ctrl, 0, 16, st));
+    CUtensorMap maps[4];
+    // ---- 1. one product per tile, exact runner-up, rows that are not provably decided are listed
+    {
+        const char* e = getenv("ISE_VERIFIED_CG");
+        Variant var; var.cg = (e && e[0] == '1') ? 1 : 2; var.mt = 1; var.cl = 1;
+        if (setup_maps_var(ctx, a_hi, nullptr, lda, b_hi, nullptr, ldb, m, n, d, var, maps)) return 1;
+        Params q = p;
+        q.flag_rows = w.flag_rows; q.flag_count = w.ctrl;
+        if (conv) {
+            q.a_raw = x; q.lda_raw = ldx; q.a_hi_w = (__half*)a_hi; q.a_lo_w = (__half*)a_lo; q.lda_w = lda;
+            q.a_norms_w = const_cast<float*>(a_norms); q.a_row_inv_w = const_cast<float*>(a_row_inv);
+            q.a_lo_skipped = a_lo_skipped; q.a_meta_w = a_meta_w;
+        }
+        int rc;
+        if (conv) rc = var.cg == 2 ? launch_cg<1, 1, L2, 1, true, 2, 1, true, 1, true>(ctx, maps, q, st)
+                                   : launch_cg<1, 1, L2, 1, true, 1, 1, true, 1, true>(ctx, maps, q, st);
+        else rc = var.cg == 2 ? launch_cg<1, 1, L2, 1, true, 2, 1, false, 1, true>(ctx, maps, q, st)
+                              : launch_cg<1, 1, L2, 1, true, 1, 1, false, 1, true>(ctx, maps, q, st);
+        if (rc) return rc;
+    }
+    // ---- 2. compact the listed rows
+    {
+        gather_flagged_kernel<<<(unsigned)(4 * ctx->sm_count), 256, 0, st>>>(
+            w.flag_rows, w.ctrl, (int)w.cap, (const __half*)a_hi, rerun_lo ? (const __half*)a_lo : nullptr, lda, a_norms,
+            a_row_inv, w.g_hi, w.g_lo, w.g_norms, w.g_row_inv, w.ctrl + 1, w.ctrl + 2);
+        ISE_LAUNCH_CHECK();
+    }
+    Variant pair; pair.cg = 2; pair.mt = 1; pair.cl = 1;
+    // ---- 3. split products over the compacted rows (row count read on the device), results scattered back
+    {
+        Params q = p;
+        q.m = w.cap; q.n_mtiles = (int)ceil_div64(w.cap, BLOCK_M);
+        q.a_norms = w.g_norms; q.a_row_inv = a_row_inv ? w.g_row_inv : nullptr;
+        q.m_dev = w.ctrl + 1; q.row_map = w.flag_rows;
+        if (setup_maps_var(ctx, w.g_hi, rerun_lo ? w.g_lo : nullptr, lda, b_hi, b_lo, ldb, w.cap, n, d, pair, maps)) return 1;
+        const int rc = rerun_lo ? launch_cg<2, 2, L2, 1, false, 2>(ctx, maps, q, st) : launch_cg<1, 2, L2, 1, false, 2>(ctx, maps, q, st);
+        if (rc) return rc;
+    }
+    // ---- 4. more listed rows than the compact buffers hold (degenerate codebooks): everything again, split products
+    {
+        Params q = p;
+        q.gate = w.ctrl + 2;
+        if (setup_maps_var(ctx, a_hi, rerun_lo ? a_lo : nullptr, lda, b_hi, b_lo, ldb, m, n, d, pair, maps)) return 1;
+        const int rc = rerun_lo ? launch_cg<2, 2, L2, 1, false, 2>(ctx, maps, q, st) : launch_cg<1, 2, L2, 1, false, 2>(ctx, maps, q, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+}  // namespace gs
+
+ISE_EXPORT size_t ise_assign_workspace_bytes(ise_ctx* ctx, int64_t m, int d) {
+    if (!ctx || m <= 0 || d <= 0) return 0;
+    return gs::verified_ws(nullptr, m, ((int64_t)d + 7) / 8 * 8).bytes;
+}
+
+ISE_EXPORT int ise_assign_verified_covers(ise_ctx* ctx, int64_t m, int64_t n, int d) {
+    if (!ctx || m <= 0 || n <= 0 || d <= 0) return 0;
+    return gs::verified_covers(ctx, m, n, d, ((int64_t)d + 7) / 8 * 8) ? 1 : 0;
+}
+
+// Verified top-1 over PREPARED row planes (k-means iterations: the rows are prepared once): ids equal the split
+// products'; out_val holds the one-product scores (|error| <= the coarse bound) except for re-run rows.  Returns 2 when
+// the shape is not covered.
+ISE_EXPORT int ise_assign_verified(ise_ctx* ctx, const void* a_hi, const void* a_lo, int64_t lda, const float* a_meta,
+                                   const float* a_norms, const float* a_row_inv, const void* b_hi, const void* b_lo,
+                                   int64_t ldb, const float* b_meta, const float* b_norms, int64_t m, int64_t n, int d,
+                                   int metric, int64_t id_base, float* out_val, int64_t* out_idx, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+    ISE_CHECK_ARG(ctx != nullptr);
+    ISE_CHECK_ARG(metric == ISE_METRIC_IP || metric == ISE_METRIC_L2);
+    ISE_CHECK_ARG(m >= 0 && n > 0 && d > 0 && n < (int64_t)1 << 31 && m < (int64_t)1 << 31);
+    if (m == 0) return 0;
+    ISE_CHECK_ARG(a_hi && a_meta && a_norms && b_hi && b_meta && out_val && out_idx && workspace);
+    if (metric == ISE_METRIC_L2) ISE_CHECK_ARG(b_norms != nullptr);
+    ISE_CHECK_ARG(lda >= d && ldb >= d && lda % 8 == 0 && ldb % 8 == 0);
+    ISE_CHECK_ARG(((reinterpret_cast<uintptr_t>(a_hi) | reinterpret_cast<uintptr_t>(a_lo) | reinterpret_cast<uintptr_t>(b_hi) |
+                    reinterpret_cast<uintptr_t>(b_lo) | reinterpret_cast<uintptr_t>(workspace)) & 15) == 0);
+    if (b_lo == nullptr || !gs::verified_covers(ctx, m, n, d, lda)) return 2;
+    const gs::VerifiedWs w = gs::verified_ws(workspace, m, lda);
+    if (workspace_bytes < w.bytes) ISE_FAIL("workspace too small: need " + std::to_string(w.bytes));
+    DeviceGuard guard(ctx->device);
+    gs::Plan pl = gs::make_plan(ctx, m, n, d, 1, true, false);
+    gs::Params p;
+    p.m = m; p.n = n; p.d = d;
+    p.n_mtiles = pl.n_mtiles; p.n_ntiles = pl.n_ntiles;
+    p.tiles_per_split = pl.tiles_per_split; p.n_splits = pl.n_splits;
+    p.topk = 1; p.id_base = id_base;
+    p.a_meta = a_meta; p.b_meta = b_meta; p.a_norms = a_norms; p.b_norms = b_norms; p.a_row_inv = a_row_inv;
+    p.row_seed = nullptr; p.row_count = nullptr; p.flag_rows = nullptr; p.flag_count = nullptr;
+    p.sync_cnt = nullptr; p.sync_every = 0; p.sync_ncp = 0;
+    p.out_val = out_val; p.out_idx = out_idx;
+    gs::clear_conv(p);
+    return metric == ISE_METRIC_L2
+               ? gs::verified_launches<true>(ctx, p, nullptr, 0, const_cast<void*>(a_hi), const_cast<void*>(a_lo), lda, nullptr, nullptr, b_hi, b_lo, ldb, w, (cudaStream_t)stream)
+               : gs::verified_launches<false>(ctx, p, nullptr, 0, const_cast<void*>(a_hi), const_cast<void*>(a_lo), lda, nullptr, nullptr, b_hi, b_lo, ldb, w, (cudaStream_t)stream);
+}
+
 // Fused assign: raw float32 rows in, nearest column out, with the row operand (planes, norms, per-row scales, meta) as a
 // by-product.  Returns 2 (and does nothing) when the shape is outside what the fused kernel covers -- the caller then
 // runs ise_prepare_rows + ise_gemm_select.
 ISE_EXPORT int ise_assign_fused(ise_ctx* ctx, const float* x, int64_t ldx, int64_t m, int d, void* a_hi, void* a_lo,
                                 int64_t lda, float* a_norms, float* a_row_inv, uint8_t* a_lo_skipped, float* a_meta,
                                 const void* b_hi, const void* b_lo, int64_t ldb, const float* b_meta, const float* b_norms,
-                                int64_t n, int metric, int64_t id_base, float* out_val, int64_t* out_idx, void* stream) {
+                                int64_t n, int metric, int64_t id_base, float* out_val, int64_t* out_idx, void* workspace,
+                                size_t workspace_bytes, void* stream) {
     ISE_CHECK_ARG(ctx != nullptr);
     ISE_CHECK_ARG(metric == ISE_METRIC_IP || metric == ISE_METRIC_L2);
     ISE_CHECK_ARG(m >= 0 && n > 0 && d > 0 && n < (int64_t)1 << 31 && m < (int64_t)1 << 31);
@@ -1169,11 +1434,28 @@ ISE_EXPORT int ise_assign_fused(ise_ctx* ctx, const float* x, int64_t ldx, int64
     gs::clear_conv(p);
     p.a_raw = x; p.lda_raw = ldx; p.a_hi_w = (__half*)a_hi; p.a_lo_w = (__half*)a_lo; p.lda_w = lda;
     p.a_norms_w = a_norms; p.a_row_inv_w = a_row_inv; p.a_lo_skipped = a_lo_skipped; p.a_meta_w = a_meta;
+    const bool l2 = metric == ISE_METRIC_L2;
+    int rc;
+    if (workspace != nullptr && b_lo != nullptr && gs::verified_covers(ctx, m, n, d, lda)) {
+        // ids only need ONE product per tile plus a proof: verified coarse pass, compact split re-run of the few rows
+        // it cannot decide (out_val: one-product scores except for those rows)
+        ISE_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15) == 0);
+        const gs::VerifiedWs w = gs::verified_ws(workspace, m, lda);
+        if (workspace_bytes < w.bytes) ISE_FAIL("workspace too small: need " + std::to_string(w.bytes));
+        p.sync_cnt = nullptr; p.sync_every = 0; p.sync_ncp = 0;
+        rc = l2 ? gs::verified_launches<true>(ctx, p, x, ldx, a_hi, a_lo, lda, a_lo_skipped, a_meta, b_hi, b_lo, ldb, w, st)
+                : gs::verified_launches<false>(ctx, p, x, ldx, a_hi, a_lo, lda, a_lo_skipped, a_meta, b_hi, b_lo, ldb, w, st);
+        if (rc) return rc;
+        if (a_lo) {     // rows that were NOT exact in their hi plane (device-side flag): the split products over all of them
+            if (ise_internal_lo_fixup(ctx, a_lo, m, lda, a_lo_skipped, a_meta, stream)) return 1;
+            return gemm_select_impl(ctx, a_hi, a_lo, lda, a_meta, a_norms, a_row_inv, b_hi, b_lo, ldb, b_meta, b_norms, m, n, d,
+                                    metric, 1, id_base, nullptr, nullptr, nullptr, out_val, out_idx, nullptr, 0, stream, 1);
+        }
+        return 0;
+    }
     CUtensorMap maps[4];
     if (setup_maps(ctx, a_hi, nullptr, lda, b_hi, b_lo, ldb, m, n, d, 1, maps)) return 1;
     const int cg = gs::pick_variant(m, n, d, b_lo != nullptr, 1).cg;
-    const bool l2 = metric == ISE_METRIC_L2;
-    int rc;
 #define ISE_CONV_LAUNCH(PB, L2V)                                                                                       \
     (cg == 2 ? gs::launch_cg<1, PB, L2V, 1, false, 2, 1, true>(ctx, maps, p, st)                                       \
              : gs::launch_cg<1, PB, L2V, 1, false, 1, 1, true>(ctx, maps, p, st))

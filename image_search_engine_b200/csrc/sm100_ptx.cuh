@@ -42,6 +42,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
+// one lane of a CONVERGED warp (the warp keeps running uniformly around the elected lane's work, so the operands of
+// the single-thread instructions it issues stay in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- TMA -------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -167,6 +181,36 @@ __device__ __forceinline__ void umma_f16_ss_2sm(uint32_t tmem_d, uint64_t desc_a
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(tmem_d),
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// The same MMAs with the descriptors given as their LOW words only (start address >> 4; +2 per 16-element k step inside
+// a 128-byte swizzle span): the high word of a SWIZZLE_128B K-major descriptor is a constant, so the issuing thread's
+// per-MMA arithmetic is one 32-bit add per operand instead of 64-bit descriptor updates.
+#define ISE_SW128_DESC_HI "0x40004040"   // SBO = 1024 >> 4 at [32,46), version 1 at bit 46, SWIZZLE_128B (2) at [61,64)
+__device__ __forceinline__ void umma_f16_ss_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, " ISE_SW128_DESC_HI "};\n\t"
+        "mov.b64 db, {%2, " ISE_SW128_DESC_HI "};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss_2sm_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, " ISE_SW128_DESC_HI "};\n\t"
+        "mov.b64 db, {%2, " ISE_SW128_DESC_HI "};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 // commit -> arrive on the barrier at this offset in every CTA of `cta_mask` (the two CTAs of the pair; every CTA of the

@@ -179,7 +179,6 @@ class IndexFlat:
                 D, I, a = fused
                 if need_distances:
                     ops.rescore_topk_(q, self._database(), a, b, self.metric_type, D, I)
-                ops.last_search_stats.update(mode="fused-split", fallback_rows=0, rows=nq)
             else:
                 a = ops.prepare_operand(q, rows=True)
                 D, I = ops.search_topk(q, a, self._database(), b, self.metric_type, kk, precision=self.precision,

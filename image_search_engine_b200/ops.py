@@ -251,10 +251,20 @@ def gemm_select(a: Operand, b: Operand, metric: int, topk: int, id_base: int = 0
     return val, idx
 
 
-def assign_fused(x: torch.Tensor, b: Operand, metric: int, id_base: int = 0):
+def _assign_workspace(n: int, d: int, device) -> torch.Tensor:
+    lib, ctx = _lib.load(), _lib.ctx(device.index if device.index is not None else torch.cuda.current_device())
+    return torch.empty((int(lib.ise_assign_workspace_bytes(ctx, n, d)),), dtype=torch.uint8, device=device)
+
+
+def assign_fused(x: torch.Tensor, b: Operand, metric: int, id_base: int = 0, verified: bool = True):
     """Top-1 of every raw float32 row of ``x`` against the column operand ``b`` with the row preparation fused into
     the contraction kernel (include/ise.h: ise_assign_fused).  Returns (val [n, 1], idx [n, 1], row operand of x), or
-    None when the shape is not covered by the fused kernel (the caller then prepares the rows separately)."""
+    None when the shape is not covered by the fused kernel (the caller then prepares the rows separately).
+
+    verified=True (default): where the shape allows it (d <= 128, enough rows) the ids come from ONE tensor-core product
+    per tile plus a per-row proof, with a compact split-product re-run of the undecided rows (no host round trip); the
+    ids are the split products', ``val`` then holds one-product scores (re-score for distances).
+    ``last_search_stats`` tells which mode ran."""
     if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1 or x.shape[1] != b.d or b.n == 0:
         return None
     n, d = x.shape
@@ -271,14 +281,49 @@ def assign_fused(x: torch.Tensor, b: Operand, metric: int, id_base: int = 0):
     meta = torch.empty((8,), dtype=torch.float32, device=x.device)
     val = torch.empty((n, 1), dtype=torch.float32, device=x.device)
     idx = torch.empty((n, 1), dtype=torch.int64, device=x.device)
+    ws = None
+    if verified and b.lo is not None and lib.ise_assign_verified_covers(ctx, n, b.n, d):
+        ws = _assign_workspace(n, d, x.device)
     rc = lib.ise_assign_fused(ctx, _ptr(x), x.stride(0), n, d, _ptr(hi), _ptr(lo), ldp, _ptr(norms), _ptr(row_inv),
                               _ptr(skipped), _ptr(meta), _ptr(b.hi), _ptr(b.lo), b.ldp, _ptr(b.meta), _ptr(b.norms), b.n,
-                              int(metric), int(id_base), _ptr(val), _ptr(idx), _stream())
+                              int(metric), int(id_base), _ptr(val), _ptr(idx), _ptr(ws), 0 if ws is None else ws.numel(),
+                              _stream())
     if rc == 2:
         return None
     _lib.check(rc)
-    _count(3 if lo is not None else 1)
+    if ws is not None:
+        ctrl = ws[:16].view(torch.int32)
+        last_search_stats.update(mode="fused-verified", fallback_rows=ctrl[0], rows=n, overflow=ctrl[2])
+        _count(6 if lo is not None else 4)
+    else:
+        last_search_stats.update(mode="fused-split", fallback_rows=0, rows=n)
+        _count(3 if lo is not None else 1)
     return val, idx, Operand(hi, lo, norms, meta, n, d, ldp, row_inv=row_inv)
+
+
+def assign_verified(a: Operand, b: Operand, metric: int, id_base: int = 0):
+    """Verified top-1 over PREPARED row planes (include/ise.h: ise_assign_verified): one product per tile + proof +
+    compact split re-run, no host round trip.  Returns (val [n, 1] one-product scores, idx [n, 1]) or None when the shape
+    is not covered."""
+    if b.lo is None or a.d > 128 or a.n == 0 or b.n < 2:
+        return None
+    dev = _dev(a.hi)
+    lib, ctx = _lib.load(), _lib.ctx(dev)
+    if not lib.ise_assign_verified_covers(ctx, a.n, b.n, a.d):
+        return None
+    val = torch.empty((a.n, 1), dtype=torch.float32, device=a.hi.device)
+    idx = torch.empty((a.n, 1), dtype=torch.int64, device=a.hi.device)
+    ws = _assign_workspace(a.n, a.d, a.hi.device)
+    rc = lib.ise_assign_verified(ctx, _ptr(a.hi), _ptr(a.lo), a.ldp, _ptr(a.meta), _ptr(a.norms), _ptr(a.row_inv),
+                                 _ptr(b.hi), _ptr(b.lo), b.ldp, _ptr(b.meta), _ptr(b.norms), a.n, b.n, a.d, int(metric),
+                                 int(id_base), _ptr(val), _ptr(idx), _ptr(ws), ws.numel(), _stream())
+    if rc == 2:
+        return None
+    _lib.check(rc)
+    ctrl = ws[:16].view(torch.int32)
+    last_search_stats.update(mode="verified-resident", fallback_rows=ctrl[0], rows=a.n, overflow=ctrl[2])
+    _count(4)
+    return val, idx
 
 
 def rescore_topk_(a_raw: torch.Tensor, b_raw: torch.Tensor, a_op: Operand, b_op: Operand, metric: int,
@@ -347,7 +392,26 @@ COARSE_TOP1_MIN_D = int(os.environ.get("ISE_COARSE_TOP1_MIN_D", "512"))
 VERIFIED_MAX_K = 100   # coarse candidates: 32 per query for k <= 16, 128 for k <= 100
 
 # statistics of the last search_topk call on this process (bench.py / tests read them)
-last_search_stats = {"mode": None, "fallback_rows": 0, "rows": 0}
+class _SearchStats(dict):
+    """Counters of the sync-free pipelines stay on the device until somebody asks for them."""
+
+    def __getitem__(self, key):
+        v = dict.__getitem__(self, key)
+        if isinstance(v, torch.Tensor):
+            v = int(v.item())
+            dict.__setitem__(self, key, v)
+        return v
+
+    def resolved(self) -> dict:
+        return {k: self[k] for k in list(self.keys())}
+
+
+last_search_stats = _SearchStats(mode=None, fallback_rows=0, rows=0)
+
+
+def search_stats() -> dict:
+    """last_search_stats with device-side counters read back (one small synchronising copy each)."""
+    return last_search_stats.resolved()
 
 
 def search_topk(q_raw: torch.Tensor, a_op: Operand, db_raw: torch.Tensor, b_op: Operand, metric: int, k: int,
@@ -381,6 +445,14 @@ def search_topk(q_raw: torch.Tensor, a_op: Operand, db_raw: torch.Tensor, b_op: 
             I.index_copy_(0, sel, I2)
         return nflag
 
+    if precision == "verified" and k == 1 and nb > 1 and a_op.d <= 128:
+        # resident-row-tile pipeline: one product + proof + compact re-run, nothing read back
+        got = assign_verified(a_op, b_op, metric, id_base)
+        if got is not None:
+            D, I = got
+            if need_distances:
+                rescore_topk_(q_raw, db_raw, a_op, b_op, metric, D, I, id_base)
+            return D, I
     if precision == "verified" and k == 1 and nb > 1 and a_op.d >= COARSE_TOP1_MIN_D:
         # the verifying kernel keeps one runner-up per row, i.e. does not split the column range over
         # CTAs: only worth it when the rows alone give every SM a few 128-row tiles

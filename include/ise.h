@@ -164,7 +164,32 @@ int ise_assign_fused(ise_ctx* ctx, const float* x, int64_t ldx, int64_t m, int d
                      void* a_hi, void* a_lo, int64_t lda, float* a_norms, float* a_row_inv, uint8_t* a_lo_skipped,
                      float* a_meta,
                      const void* b_hi, const void* b_lo, int64_t ldb, const float* b_meta, const float* b_norms,
-                     int64_t n, int metric, int64_t id_base, float* out_val, int64_t* out_idx, void* stream);
+                     int64_t n, int metric, int64_t id_base, float* out_val, int64_t* out_idx,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* VERIFIED ASSIGN (d <= 128): quantisation and the k-means assign need the nearest column's ID, and an id only needs
+ * ONE tensor-core product per tile plus a proof.  With workspace != NULL (ise_assign_workspace_bytes) ise_assign_fused
+ * -- and ise_assign_verified, the same pipeline over PREPARED row planes (k-means iterations prepare the rows once) --
+ * runs: (1) a one-product pass (hi planes) whose epilogue tracks the exact runner-up of every row and lists the rows
+ * whose winner is not separated from it by more than twice the rigorous error bound of the neglected lo-plane /
+ * accumulation terms; the 128-row tile of a work item stays resident in shared memory and only B streams; (2) a
+ * compaction of the listed rows' planes; (3) the split products over the compacted rows, row count read on the device,
+ * results scattered back; (4) a launch that repeats everything with the split products and returns at once unless the
+ * list overflowed its capacity (a quarter of the rows).  No host synchronisation anywhere.  Ids are those of the split
+ * products; out_val holds one-product scores (|error| <= the bound) for the rows decided in (1) -- callers that need
+ * distances pass workspace = NULL or re-score (ise_rescore_topk).  workspace[0..2] (int32) afterwards: listed rows, rows
+ * re-run, overflow flag.  Both return 2 (nothing done; ise_assign_fused falls back to its plain mode by itself) when
+ * the shape is not covered: d > 128, fewer than 8 stages of B per row tile, or too few rows to fill the machine with an
+ * unsplit column range.  Replaces index.search(X, 1) of FaissKMeans.transform (kmeans_faiss.py:49) and the assign of
+ * faiss.Kmeans.train (kmeans_faiss.py:41). */
+size_t ise_assign_workspace_bytes(ise_ctx* ctx, int64_t m, int d);
+int ise_assign_verified_covers(ise_ctx* ctx, int64_t m, int64_t n, int d);   /* 1 = the verified pipeline takes this shape */
+int ise_assign_verified(ise_ctx* ctx,
+                        const void* a_hi, const void* a_lo, int64_t lda, const float* a_meta, const float* a_norms,
+                        const float* a_row_inv,
+                        const void* b_hi, const void* b_lo, int64_t ldb, const float* b_meta, const float* b_norms,
+                        int64_t m, int64_t n, int d, int metric, int64_t id_base,
+                        float* out_val, int64_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
 
 /* COLLECT variant of the fused contraction for large k: instead of keeping a bounded list per row, every
  * column whose (coarse) score beats row_seed[row] is appended to the row's buffer cand_*[row, 0..cap)

@@ -74,7 +74,7 @@ dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 sorted_ok = bool((D[:, :-1] >= D[:, 1:]).all())
 out["c5"] = {"nb": nb_local * world, "d": dq, "nq": nq, "topk": topk, "ms_per_batch": float(ms.item()),
              "qps": nq / float(ms.item()) * 1e3, "sorted": sorted_ok, "top1_score_mean": float(D[:, 0].mean()),
-             "search_stats_rank0": dict(ops.last_search_stats)}
+             "search_stats_rank0": ops.search_stats()}
 if rank == 0:
     print(json.dumps(out), flush=True)
 dist.destroy_process_group()

@@ -35,7 +35,7 @@ def test_c2_full_size_assign_against_oracle():
     idx = faiss_compat.IndexFlatIP(d)
     idx.add(cent)
     dis, words = idx.search(x, 1)
-    stats = dict(ops.last_search_stats)
+    stats = ops.search_stats()
     rows = torch.randperm(n, generator=gen, device=dev)[:2000]
     xs, cs = x[rows].cpu().numpy(), cent.cpu().numpy()
     Dr, Ir = fs.knn(xs, cs, 1, fs.METRIC_INNER_PRODUCT)
@@ -79,7 +79,7 @@ def test_c3_full_size_search_against_oracle():
     idx = faiss_compat.IndexFlatIP(2048)
     idx.add(db)
     D, I = idx.search(q, 10)
-    stats = dict(ops.last_search_stats)
+    stats = ops.search_stats()
     assert stats["mode"] == "verified"
     assert float((I[:, 0] == pick).float().mean()) > 0.999
     g = torch.Generator(device=dev)
@@ -102,7 +102,7 @@ def test_c5_shard_top100_collect_mode_against_oracle():
     idx = faiss_compat.IndexFlatIP(512)
     idx.add(db)
     D, I = idx.search(q, 100)
-    stats = dict(ops.last_search_stats)
+    stats = ops.search_stats()
     assert stats["mode"] == "verified-collect"
     assert float((I[:, 0] == pick).float().mean()) > 0.999
     assert bool((D[:, :-1] >= D[:, 1:]).all()) and bool((I >= 0).all())
@@ -154,7 +154,7 @@ def test_coarse_bound_adversarial_topk(metric_ip, spread):
     a_op, b_op = ops.prepare_operand(ad), ops.attach_sample(ops.prepare_operand(bd))
     metric = METRIC_IP if metric_ip else METRIC_L2
     Dv, Iv = ops.search_topk(ad, a_op, bd, b_op, metric, k, precision="verified")
-    sv = dict(ops.last_search_stats)
+    sv = ops.search_stats()
     Ds, Is = ops.search_topk(ad, a_op, bd, b_op, metric, k, precision="split")
     assert sv["mode"] == "verified"
     print(f"adversarial top-{k} ({'IP' if metric_ip else 'L2'}, {spread}): fallback_rows={sv['fallback_rows']} of {m}")
@@ -199,7 +199,7 @@ def test_coarse_bound_adversarial_top1_verification():
     bd = torch.from_numpy(b).to(dev)
     a_op, b_op = ops.prepare_operand(ad), ops.prepare_operand(bd)
     Dv, Iv = ops.search_topk(ad, a_op, bd, b_op, METRIC_IP, 1, precision="verified")
-    sv = dict(ops.last_search_stats)
+    sv = ops.search_stats()
     assert sv["mode"] == "verified" and sv["rows"] == m
     print(f"adversarial top-1: fallback_rows={sv['fallback_rows']} of {m}")
     Ds, Is = ops.search_topk(ad, a_op, bd, b_op, METRIC_IP, 1, precision="split")

@@ -318,7 +318,7 @@ def test_verified_assign_flags_ties_and_near_ties(dev):
     xd, cd = torch.from_numpy(x).to(dev), torch.from_numpy(c).to(dev)
     a, b = ops.prepare_operand(xd), ops.prepare_operand(cd)
     D, I = ops.search_topk(xd, a, cd, b, METRIC_IP, 1)
-    st = dict(ops.last_search_stats)
+    st = ops.search_stats()
     assert st["mode"] == "verified" and 100 <= st["fallback_rows"] < n // 4, st
     Do, Io = _oracle_knn(x, c, 1, True)
     assert (I.cpu().numpy()[:50, 0] == 7).all() and (I.cpu().numpy()[50:100, 0] == 301).all()

@@ -419,8 +419,9 @@ def test_fused_assign_equals_separate_preparation(metric_ip, m, n, d, kind):
     xd, cd = torch.from_numpy(x).to(dev), torch.from_numpy(c).to(dev)
     b = ops.prepare_operand(cd)
     metric = METRIC_IP if metric_ip else METRIC_L2
-    got = ops.assign_fused(xd, b, metric)
+    got = ops.assign_fused(xd, b, metric, verified=False)
     assert got is not None, "shape should be covered by the fused kernel"
+    assert ops.last_search_stats["mode"] == "fused-split"
     val, idx, a_f = got
     a_s = ops.prepare_operand(xd, rows=True)
     val_s, idx_s = ops.gemm_select(a_s, b, metric, 1)
@@ -440,7 +441,68 @@ def test_fused_assign_equals_separate_preparation(metric_ip, m, n, d, kind):
     gi = faiss_compat.IndexFlatIP(d) if metric_ip else faiss_compat.IndexFlatL2(d)
     gi.add(cd)
     words = FaissKMeans(n, index=gi).transform_device(xd)
-    assert ops.last_search_stats["mode"] == "fused-split" and torch.equal(words, idx.reshape(-1))
+    assert ops.last_search_stats["mode"] in ("fused-split", "fused-verified") and torch.equal(words, idx.reshape(-1))
+
+
+@pytest.mark.parametrize("metric_ip", [True, False])
+@pytest.mark.parametrize("m,n,d,kind", [(200_000, 4096, 128, "sift"), (150_001, 3000, 64, "sift"), (120_000, 2048, 32, "sift"),
+                                         (160_000, 2048, 128, "float"), (130_000, 1777, 128, "mixed"),
+                                         (140_000, 2048, 128, "duplicates")])
+def test_verified_assign_equals_the_split_products(metric_ip, m, n, d, kind):
+    """The verified pipeline (one product per tile with the row tile resident in shared memory, per-row proof, compact
+    split-product re-run of the undecided rows, no host round trip) returns exactly the ids of the split products --
+    through the fused entry point (raw float32 rows) and through ise_assign_verified (prepared planes); its scores are
+    within the coarse bound; "duplicates": every column exists twice, so NO row can be decided and the overflow launch
+    must repeat everything."""
+    from image_search_engine_b200 import ops
+    from image_search_engine_b200._lib import METRIC_IP, METRIC_L2
+    dev = ops.require_cuda()
+    rng = np.random.default_rng(m + n + d + 1)
+    if kind in ("sift", "duplicates"):
+        x = sift_like(rng, m, d)
+    else:
+        x = (rng.standard_normal((m, d)) * 3).astype(np.float32)
+        if kind == "mixed":
+            x[::3] = sift_like(rng, len(x[::3]), d)
+    c = unit_rows(rng, n, d)
+    if kind == "duplicates":
+        c[n // 2:] = c[:n // 2]
+    xd, cd = torch.from_numpy(x).to(dev), torch.from_numpy(c).to(dev)
+    b = ops.prepare_operand(cd)
+    metric = METRIC_IP if metric_ip else METRIC_L2
+    a_s = ops.prepare_operand(xd, rows=True)
+    val_s, idx_s = ops.gemm_select(a_s, b, metric, 1)
+    # fused entry point
+    val, idx, a_f = ops.assign_fused(xd, b, metric)
+    st = ops.search_stats()
+    assert st["mode"] == "fused-verified", st
+    assert torch.equal(idx, idx_s)
+    assert torch.equal(a_f.hi, a_s.hi) and torch.equal(a_f.norms, a_s.norms) and torch.equal(a_f.row_inv, a_s.row_inv)
+    if kind == "duplicates":
+        assert st["fallback_rows"] == m and st["overflow"] == 1, st
+    elif kind == "sift":
+        assert 0 < st["fallback_rows"] < m // 4 and st["overflow"] == 0, st
+    print(f"verified assign {kind} d={d} n={n}: {st['fallback_rows']} of {m} rows re-run")
+    xn = torch.linalg.vector_norm(xd, dim=1, keepdim=True)
+    tol = (2e-3 if metric_ip else 4e-3) * xn * float(np.linalg.norm(c, axis=1).max()) + 1e-6
+    assert bool(((val - val_s).abs() <= tol).all())
+    # prepared planes
+    got = ops.assign_verified(a_s, b, metric)
+    assert got is not None
+    st2 = ops.search_stats()
+    assert st2["mode"] == "verified-resident" and torch.equal(got[1], idx_s)
+    if kind == "sift":
+        assert st2["fallback_rows"] == st["fallback_rows"]
+    # ids-only public paths: quantisation and one k-means assign
+    from image_search_engine_b200 import FaissKMeans, faiss_compat
+    gi = faiss_compat.IndexFlatIP(d) if metric_ip else faiss_compat.IndexFlatL2(d)
+    gi.add(cd)
+    assert torch.equal(FaissKMeans(n, index=gi).transform_device(xd), idx_s.reshape(-1))
+    # distances through the search API stay exact FP32 (re-scored)
+    D, I = gi._search_device(xd[:50_000], 1)
+    De, Ie = ops.flat_search_exact(xd[:64].contiguous(), cd, metric, 1)
+    assert torch.equal(I[:64], Ie) or kind == "duplicates"
+    assert torch.allclose(D[:64], De, rtol=2e-6, atol=1e-3 if not metric_ip else 1e-4)
 
 
 def test_fused_assign_declines_shapes_it_does_not_cover():
