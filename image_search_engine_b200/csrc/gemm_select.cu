@@ -61,7 +61,7 @@ __host__ __device__ constexpr int num_threads(int ksel, int pa, int pb, int mt =
     return 128 + 128 * epi_halves(ksel, pa, pb, ares) * mt + (conv ? 128 : 0);
 }
 constexpr int TMEM_COLS = 512;  // 2 accumulator stages x BLOCK_N fp32 columns
-constexpr int AUX_BYTES = 4096;
+constexpr int AUX_BYTES = 8192;
 constexpr int SMEM_LIMIT = 232448;  // 227 KiB opt-in per CTA on sm_100
 
 // cg = CTAs per MMA (cta_group): with 2, each CTA of the pair stages only half of every B tile
@@ -137,9 +137,9 @@ struct Aux {  // lives after the stage ring in dynamic shared memory
     uint32_t tmem_base;
     uint32_t pad_[3];
     float bnorm[2][BLOCK_N];
-    float xbest[BLOCK_M];   // half-1 -> half-0 hand-over of the top-1 state at the end of a work item
-    float xrun[BLOCK_M];
-    int xid[BLOCK_M];
+    float xbest[3][BLOCK_M];   // column slices 1.. -> slice 0 hand-over of the top-1 state at the end of a work item
+    float xrun[3][BLOCK_M];
+    int xid[3][BLOCK_M];
 };
 static_assert(sizeof(Aux) <= AUX_BYTES, "aux area too small");
 
@@ -190,7 +190,7 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                    const Params p) {
     static_assert(MT == 1 || (CG == 1 && epi_halves(KSEL, PA, PB, ARES) == 1), "two row tiles per CTA: single CTA, one warp per quadrant and tile");
     static_assert(!CONV || (PA == 1 && KSEL == 1 && MT == 1), "fused conversion: top-1, hi plane of A");
-    static_assert(epi_halves(KSEL, PA, PB, ARES) <= 2, "the hand-over between column halves is written for two");
+    static_assert(epi_halves(KSEL, PA, PB, ARES) == 1 || epi_halves(KSEL, PA, PB, ARES) == 2 || epi_halves(KSEL, PA, PB, ARES) == 4, "column slices per tile");
     static_assert(!ARES || (PA == 1 && MT == 1 && CL == 1), "resident row tile: hi plane of A, one row tile per CTA, no multicast");
     static_assert(CL == 1 || (CG == 2 && MT == 1 && !CONV && (CL == 2 || CL == 4)), "multicast clusters are made of CTA pairs");
     // uniform over the whole grid, before any barrier / TMEM state exists
@@ -636,19 +636,22 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             if (KSEL == 1) {
                 // combine the two column halves of this row (half 1 hands its state to half 0)
                 float runner = fmaxf(sib, m2);
-                if (HALVES == 2) {
-                    if (half == 1) {
-                        aux->xbest[row_in_tile] = best;
-                        aux->xrun[row_in_tile] = runner;
-                        aux->xid[row_in_tile] = best_id;
+                if (HALVES > 1) {
+                    if (half > 0) {
+                        aux->xbest[half - 1][row_in_tile] = best;
+                        aux->xrun[half - 1][row_in_tile] = runner;
+                        aux->xid[half - 1][row_in_tile] = best_id;
                     }
                     asm volatile("bar.sync 2, %0;" ::"n"(NUM_EPI_THREADS) : "memory");
                     if (half == 0) {
-                        const float ob = aux->xbest[row_in_tile], orun = aux->xrun[row_in_tile];
-                        const int oid = aux->xid[row_in_tile];
-                        const bool other_wins = (oid >= 0) && (best_id < 0 || ob > best || (ob == best && oid < best_id));
-                        runner = fmaxf(fmaxf(runner, orun), other_wins ? best : ob);
-                        if (other_wins) { best = ob; best_id = oid; }
+#pragma unroll
+                        for (int h = 0; h < HALVES - 1; ++h) {      // in column order: an equal score further right never wins
+                            const float ob = aux->xbest[h][row_in_tile], orun = aux->xrun[h][row_in_tile];
+                            const int oid = aux->xid[h][row_in_tile];
+                            const bool other_wins = (oid >= 0) && (best_id < 0 || ob > best || (ob == best && oid < best_id));
+                            runner = fmaxf(fmaxf(runner, orun), other_wins ? best : ob);
+                            if (other_wins) { best = ob; best_id = oid; }
+                        }
                     }
                     asm volatile("bar.sync 2, %0;" ::"n"(NUM_EPI_THREADS) : "memory");
                 }

@@ -94,6 +94,16 @@ __device__ __forceinline__ float load_as_f32<float>(const float* p) { return __l
 template <>
 __device__ __forceinline__ float load_as_f32<uint8_t>(const uint8_t* p) { return (float)__ldg(p); }
 
+// meta[LO_NONZERO] doubles as the largest squared norm of a row's hi-plane residual |x - hi / scale|^2 (real units):
+// 0 = the lo plane is all zeros; any other value says it is not, and a value other than the plain flag 1.0 lets the
+// coarse-pass error bound use the MEASURED residual instead of the worst case 2^-11 |x| (CoarseBound, common.cuh).
+__device__ __forceinline__ void publish_lo_residual(float* meta, bool any_lo, float max_rs_scaled, float scale, int lane) {
+    if (!any_lo || lane != 0) return;
+    const float inv = 1.f / scale;
+    const float v = fmaxf(max_rs_scaled * inv * inv * 1.0001f, 1.17549435e-38f);     // never reads as "no lo plane"
+    atomicMax(reinterpret_cast<int*>(meta + META_LO_NONZERO), __float_as_int(v));
+}
+
 template <typename T>
 __global__ void prepare_planes_kernel(const T* __restrict__ x, int64_t n, int d, int64_t ldx,
                                       __half* __restrict__ hi, __half* __restrict__ lo, int64_t ldp,
@@ -108,13 +118,13 @@ __global__ void prepare_planes_kernel(const T* __restrict__ x, int64_t n, int d,
         if (fixed_unit_scale) meta[META_ABSMAX] = 255.f;
     }
     bool any_lo = false;
-    float max_ss = 0.f;
+    float max_ss = 0.f, max_rs = 0.f;
     const int dp = (int)ldp;
     for (int64_t r = warp; r < n; r += nwarps) {
         const T* row = x + r * ldx;
         __half* hrow = hi + r * ldp;
         __half* lrow = lo ? lo + r * ldp : nullptr;
-        float ss = 0.f;
+        float ss = 0.f, rs = 0.f;
         // two columns per lane per step so the plane stores are 32-bit
         for (int c = lane * 2; c < dp; c += 64) {
             float v0 = (c < d) ? load_as_f32<T>(row + c) : 0.f;
@@ -123,8 +133,11 @@ __global__ void prepare_planes_kernel(const T* __restrict__ x, int64_t n, int d,
             ss = fmaf(v1, v1, ss);
             float s0 = v0 * scale, s1 = v1 * scale;
             __half h0 = __float2half_rn(s0), h1 = __float2half_rn(s1);
-            __half l0 = __float2half_rn(s0 - __half2float(h0));
-            __half l1 = __float2half_rn(s1 - __half2float(h1));
+            const float e0 = s0 - __half2float(h0), e1 = s1 - __half2float(h1);    // exact residuals of the hi plane
+            rs = fmaf(e0, e0, rs);
+            rs = fmaf(e1, e1, rs);
+            __half l0 = __float2half_rn(e0);
+            __half l1 = __float2half_rn(e1);
             *reinterpret_cast<__half2*>(hrow + c) = __halves2half2(h0, h1);
             if (lrow) *reinterpret_cast<__half2*>(lrow + c) = __halves2half2(l0, l1);
             any_lo |= (__half2float(l0) != 0.f) | (__half2float(l1) != 0.f);
@@ -132,11 +145,12 @@ __global__ void prepare_planes_kernel(const T* __restrict__ x, int64_t n, int d,
         ss = warp_sum(ss);
         if (norms && lane == 0) norms[r] = ss;
         max_ss = fmaxf(max_ss, ss);
+        if (__any_sync(0xffffffffu, rs != 0.f)) max_rs = fmaxf(max_rs, warp_sum(rs));
     }
     // largest row norm^2 (non-negative floats order like ints; one atomic per warp): the coarse-pass
     // error bound of ise_rescore_select needs it
     if (lane == 0 && max_ss > 0.f) atomicMax(reinterpret_cast<int*>(meta + META_MAX_NORM_SQ), __float_as_int(max_ss));
-    if (__any_sync(0xffffffffu, any_lo) && lane == 0) meta[META_LO_NONZERO] = 1.f;
+    publish_lo_residual(meta, __any_sync(0xffffffffu, any_lo), max_rs, scale, lane);
 }
 
 // Fast path, float32 rows with d % 4 == 0 (16-byte aligned rows and planes): a lane converts four consecutive
@@ -167,12 +181,14 @@ __global__ void __launch_bounds__(kThreads, EXACT ? 5 : 3) prepare_planes_f32x4_
     if (exact != EXACT) return;
     if (EXACT) lo = nullptr;
     bool any_lo = false;
-    float max_ss = 0.f;
+    float max_ss = 0.f, max_rs = 0.f;
     const int d4 = d >> 2, dp4 = (int)(ldp >> 2);
     for (int64_t r0 = warp * ROWS; r0 < n; r0 += nwarps * ROWS) {
-        float ss[ROWS];
+        float ss[ROWS], rs[EXACT ? 1 : ROWS];
 #pragma unroll
         for (int i = 0; i < ROWS; ++i) ss[i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < (EXACT ? 1 : ROWS); ++i) rs[i] = 0.f;
         for (int c = lane; c < dp4; c += 32) {
             float4 v[ROWS];
 #pragma unroll
@@ -200,6 +216,12 @@ __global__ void __launch_bounds__(kThreads, EXACT ? 5 : 3) prepare_planes_f32x4_
                 __half h0, h1, h2, h3, l0, l1, l2, l3;
                 split_f16(v[i].x * scale, h0, l0); split_f16(v[i].y * scale, h1, l1);
                 split_f16(v[i].z * scale, h2, l2); split_f16(v[i].w * scale, h3, l3);
+                if (!EXACT) {   // exact residuals of the hi plane (what the coarse pass neglects)
+                    const float e0 = v[i].x * scale - __half2float(h0), e1 = v[i].y * scale - __half2float(h1);
+                    const float e2 = v[i].z * scale - __half2float(h2), e3 = v[i].w * scale - __half2float(h3);
+                    rs[i] = fmaf(e0, e0, rs[i]); rs[i] = fmaf(e1, e1, rs[i]);
+                    rs[i] = fmaf(e2, e2, rs[i]); rs[i] = fmaf(e3, e3, rs[i]);
+                }
                 const __half2 ha = __halves2half2(h0, h1), hb = __halves2half2(h2, h3);
                 const __half2 la = __halves2half2(l0, l1), lb = __halves2half2(l2, l3);
                 uint2 hv, lv;
@@ -217,10 +239,11 @@ __global__ void __launch_bounds__(kThreads, EXACT ? 5 : 3) prepare_planes_f32x4_
                 if (norms && lane == 0) norms[r0 + i] = t;
                 max_ss = fmaxf(max_ss, t);
             }
+            if (!EXACT) max_rs = fmaxf(max_rs, warp_sum(rs[EXACT ? 0 : i]));
         }
     }
     if (lane == 0 && max_ss > 0.f) atomicMax(reinterpret_cast<int*>(meta + META_MAX_NORM_SQ), __float_as_int(max_ss));
-    if (__any_sync(0xffffffffu, any_lo) && lane == 0) meta[META_LO_NONZERO] = 1.f;
+    if (!EXACT) publish_lo_residual(meta, __any_sync(0xffffffffu, any_lo), max_rs, scale, lane);
 }
 
 // ---- single-pass preparation of ROW operands (descriptors / queries) ------------------------------------------------

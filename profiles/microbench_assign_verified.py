@@ -16,7 +16,8 @@ ks = [int(a) for a in sys.argv[1:]] or [4096, 65536]
 
 
 def timed(fn, reps=5):
-    fn(); fn()
+    for _ in range(4):
+        fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

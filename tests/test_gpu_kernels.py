@@ -418,7 +418,11 @@ def test_exact_inputs_skip_the_lo_plane_and_nobody_reads_it(dev):
     # non-exact data still gets its lo plane
     y = torch.randn((5000, 128), device=dev)
     ay = ops.prepare_operand(y)
-    assert float(ay.meta[2]) == 1.0 and not bool(torch.isnan(ay.lo.float()).any())
+    assert float(ay.meta[2]) != 0.0 and not bool(torch.isnan(ay.lo.float()).any())
+    # ... and meta[2] carries the largest squared hi-plane residual of a row, which the coarse error bound uses
+    sc = float(ay.meta[0])
+    res = (y.double() - ay.hi[:, :128].double() / sc).pow(2).sum(1).max().item()
+    assert res <= float(ay.meta[2]) <= res * 1.001 + 1e-30
     # a value far below the maximum leaves FP16's normal range once scaled: the input no longer counts as exact and
     # the lo plane is written again (zeros here: such a value underflows in both planes, which the coarse error
     # bound accounts for)

@@ -205,7 +205,7 @@ def test_prepare_rows_single_pass(d):
     assert (np.abs(rec - x) <= ref_mag * 2.0 ** -21 + 1e-30).all()
     assert (op.hi.cpu().numpy()[:, d:] == 0).all()
     np.testing.assert_allclose(op.norms.cpu().numpy(), (x.astype(np.float64) ** 2).sum(1), rtol=2e-6)
-    assert float(op.meta[2]) == 1.0 and float(op.meta[7]) == 0.0
+    assert float(op.meta[2]) != 0.0 and float(op.meta[7]) == 0.0
     np.testing.assert_allclose(float(op.meta[4]), (x.astype(np.float64) ** 2).sum(1).max(), rtol=2e-6)
     for bad in (np.nan, np.inf, -np.inf):
         y = x.copy()
