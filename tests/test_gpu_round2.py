@@ -447,7 +447,8 @@ def test_fused_assign_equals_separate_preparation(metric_ip, m, n, d, kind):
 @pytest.mark.parametrize("metric_ip", [True, False])
 @pytest.mark.parametrize("m,n,d,kind", [(200_000, 4096, 128, "sift"), (150_001, 3000, 64, "sift"), (120_000, 2048, 32, "sift"),
                                          (160_000, 2048, 128, "float"), (130_000, 1777, 128, "mixed"),
-                                         (140_000, 2048, 128, "duplicates")])
+                                         (140_000, 2048, 128, "duplicates"), (100_000, 1500, 100, "sift"),
+                                         (90_000, 1100, 96, "mixed")])
 def test_verified_assign_equals_the_split_products(metric_ip, m, n, d, kind):
     """The verified pipeline (one product per tile with the row tile resident in shared memory, per-row proof, compact
     split-product re-run of the undecided rows, no host round trip) returns exactly the ids of the split products --
@@ -503,6 +504,34 @@ def test_verified_assign_equals_the_split_products(metric_ip, m, n, d, kind):
     De, Ie = ops.flat_search_exact(xd[:64].contiguous(), cd, metric, 1)
     assert torch.equal(I[:64], Ie) or kind == "duplicates"
     assert torch.allclose(D[:64], De, rtol=2e-6, atol=1e-3 if not metric_ip else 1e-4)
+
+
+def test_verified_assign_with_no_undecided_row():
+    """Well separated columns: the one-product pass decides every row, the compact re-run launch finds a row count of zero
+    on the device and the overflow launch returns at once -- results still equal the exact search."""
+    from image_search_engine_b200 import ops
+    from image_search_engine_b200._lib import METRIC_IP, METRIC_L2
+    dev = ops.require_cuda()
+    d, n, m = 128, 1024, 80_000
+    j = np.arange(n)
+    c = np.zeros((n, d), dtype=np.float32)
+    c[j, j % d] = 1.0
+    c[j, (j // d + j % d + 1) % d] += 0.5
+    c /= np.linalg.norm(c, axis=1, keepdims=True)
+    rng = np.random.default_rng(9)
+    pick = rng.integers(0, n, m)
+    x = np.zeros((m, d), dtype=np.float32)
+    x[np.arange(m), pick % d] = 200.0
+    x[np.arange(m), (pick // d + pick % d + 1) % d] += 100.0
+    xd, cd = torch.from_numpy(x).to(dev), torch.from_numpy(c).to(dev)
+    b = ops.prepare_operand(cd)
+    for metric in (METRIC_IP, METRIC_L2):
+        val, idx, _ = ops.assign_fused(xd, b, metric)
+        st = ops.search_stats()
+        assert st["mode"] == "fused-verified" and st["fallback_rows"] == 0 and st["overflow"] == 0, st
+        assert np.array_equal(idx.cpu().numpy().reshape(-1), pick)
+        got = ops.assign_verified(ops.prepare_operand(xd, rows=True), b, metric)
+        assert ops.search_stats()["fallback_rows"] == 0 and np.array_equal(got[1].cpu().numpy().reshape(-1), pick)
 
 
 def test_fused_assign_declines_shapes_it_does_not_cover():
