@@ -548,9 +548,10 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                         float g[4];
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            g[i] = fmaxf(fmaxf(fmaxf(v[8 * i], v[8 * i + 1]), fmaxf(v[8 * i + 2], v[8 * i + 3])),
-                                         fmaxf(fmaxf(v[8 * i + 4], v[8 * i + 5]), fmaxf(v[8 * i + 6], v[8 * i + 7])));
-                        const float mx = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+                            g[i] = ptx::fmax3(ptx::fmax3(v[8 * i], v[8 * i + 1], v[8 * i + 2]),
+                                              ptx::fmax3(v[8 * i + 3], v[8 * i + 4], v[8 * i + 5]), fmaxf(v[8 * i + 6], v[8 * i + 7]));
+                        const float t01 = fmaxf(g[0], g[1]), t23 = fmaxf(g[2], g[3]);
+                        const float mx = fmaxf(t01, t23);
                         if (KSEL == 0) {
                             float cur = mx;
 #pragma unroll 1
@@ -574,32 +575,57 @@ gemm_select_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                             }
                         } else if (KSEL == 1) {
                             if (mx > best) {  // strict: an equal score in a later column never replaces
-                                // a warp takes this branch when ANY of its 32 rows improves (most chunks of a 4096-column
-                                // codebook), so it is kept short: locate the first group holding the maximum, then work
-                                // on that group's eight values only
-                                if (VERIFY) m2 = fmaxf(m2, best);   // the old best's whole chunk is now "other"
-                                best = mx;
-                                const bool in01 = (g[0] == mx) || (g[1] == mx);
-                                const bool odd = in01 ? (g[0] != mx) : (g[2] != mx);
-                                const int gi = (in01 ? 0 : 2) + (odd ? 1 : 0);
-                                float w[8];
+                                // a warp takes this branch when ANY of its 32 rows improves (two thirds of the chunks of a
+                                // 4096-column codebook), and the epilogue is bound by the half-rate ALU pipe (max / compare /
+                                // select): the update is written for few ALU instructions
+                                if constexpr (VERIFY) {
+                                    // Position and runner-up from maxima over BIT PARTITIONS of the index: the maximum sits
+                                    // where the partition maximum equals it, and the second largest value is the largest
+                                    // min(side 0, side 1) over the bits (the top two differ in at least one bit).  A duplicated
+                                    // maximum gives runner-up == maximum (and an arbitrary position): such a row is never
+                                    // accepted by the proof, the split re-run decides it with the exact tie rule.
+                                    m2 = fmaxf(m2, best);   // the old best's whole chunk is now "other"
+                                    best = mx;
+                                    const float u02 = fmaxf(g[0], g[2]), u13 = fmaxf(g[1], g[3]);
+                                    const int gi = (t01 != mx ? 2 : 0) + (u02 != mx ? 1 : 0);
+                                    const float sib_g = fmaxf(fminf(t01, t23), fminf(u02, u13));
+                                    // the winning group's eight values (a trip through local memory instead of these 24
+                                    // selects was measured slower: 1.46 vs 1.02 ms at the C2 shape)
+                                    const bool ghi = t01 != mx, godd = u02 != mx;
+                                    float w[8];
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) {
-                                    const float lo = odd ? v[8 + e] : v[e], hi = odd ? v[24 + e] : v[16 + e];
-                                    w[e] = in01 ? lo : hi;
-                                }
-                                int ee = 7;
+                                    for (int e = 0; e < 8; ++e) {
+                                        const float lo = godd ? v[8 + e] : v[e], hi = godd ? v[24 + e] : v[16 + e];
+                                        w[e] = ghi ? hi : lo;
+                                    }
+                                    float4 wa, wb;
+                                    wa.x = w[0]; wa.y = w[1]; wa.z = w[2]; wa.w = w[3];
+                                    wb.x = w[4]; wb.y = w[5]; wb.z = w[6]; wb.w = w[7];
+                                    const float p01 = fmaxf(wa.x, wa.y), p23 = fmaxf(wa.z, wa.w);
+                                    const float p45 = fmaxf(wb.x, wb.y), p67 = fmaxf(wb.z, wb.w);
+                                    const float a2 = fmaxf(p01, p23), b2 = fmaxf(p45, p67);                 // bit 2: 0..3 | 4..7
+                                    const float a1 = fmaxf(p01, p45), b1 = fmaxf(p23, p67);                 // bit 1
+                                    const float a0 = ptx::fmax3(wa.x, wa.z, fmaxf(wb.x, wb.z));             // bit 0: even | odd
+                                    const float b0 = ptx::fmax3(wa.y, wa.w, fmaxf(wb.y, wb.w));
+                                    const int ee = (a2 != mx ? 4 : 0) + (a1 != mx ? 2 : 0) + (a0 != mx ? 1 : 0);
+                                    sib = fmaxf(ptx::fmax3(fminf(a2, b2), fminf(a1, b1), fminf(a0, b0)), sib_g);
+                                    best_id = col0 + c + gi * 8 + ee;
+                                } else {
+                                    best = mx;
+                                    const bool in01 = (g[0] == mx) || (g[1] == mx);
+                                    const bool odd = in01 ? (g[0] != mx) : (g[2] != mx);
+                                    const int gi = (in01 ? 0 : 2) + (odd ? 1 : 0);
+                                    float w[8];
 #pragma unroll
-                                for (int e = 6; e >= 0; --e)
-                                    if (w[e] == mx) ee = e;  // lowest column among equals
-                                best_id = col0 + c + gi * 8 + ee;
-                                if (VERIFY) {
-                                    float s2 = -CUDART_INF_F;
+                                    for (int e = 0; e < 8; ++e) {
+                                        const float lo = odd ? v[8 + e] : v[e], hi = odd ? v[24 + e] : v[16 + e];
+                                        w[e] = in01 ? lo : hi;
+                                    }
+                                    int ee = 7;
 #pragma unroll
-                                    for (int e = 0; e < 8; ++e) s2 = fmaxf(s2, (e == ee) ? -CUDART_INF_F : w[e]);
-#pragma unroll
-                                    for (int i = 0; i < 4; ++i) s2 = fmaxf(s2, (i == gi) ? -CUDART_INF_F : g[i]);
-                                    sib = s2;
+                                    for (int e = 6; e >= 0; --e)
+                                        if (w[e] == mx) ee = e;  // lowest column among equals
+                                    best_id = col0 + c + gi * 8 + ee;
                                 }
                             } else if (VERIFY) {
                                 m2 = fmaxf(m2, mx);

@@ -42,6 +42,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
+// three-input maximum (one FMNMX3)
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
 // one lane of a CONVERGED warp (the warp keeps running uniformly around the elected lane's work, so the operands of
 // the single-thread instructions it issues stay in uniform registers)
 __device__ __forceinline__ bool elect_one() {
