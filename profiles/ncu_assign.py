@@ -1,4 +1,5 @@
-"""Minimal driver for ncu: the fused assign (float32 rows converted inside gemm_select, split top-1) on the C2 shape."""
+"""Minimal driver for ncu: the verified fused assign (float32 rows converted inside gemm_select, one-product pass +
+compact split re-run) on the C2 shape."""
 import sys
 import numpy as np, torch
 sys.path.insert(0, ".")

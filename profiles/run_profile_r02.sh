@@ -8,8 +8,10 @@ CMD="python bench.py --steps 2 --warmup 3 --no-cpu --no-c4 --no-c5"
 timeout 300 $CMD > gpurun_out/r02_plain_a.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r02_launches.csv $CMD > gpurun_out/r02_ncu_a.log 2>&1
 echo "launch-list rc=$?"
+# four gemm_select launches per verified fused assign (one-product pass, compact split re-run, two gated launches that
+# return at once): skip two calls, capture the third call's pass and re-run
 timeout 120 python profiles/ncu_assign.py > gpurun_out/r02_plain_b.log 2>&1 &&
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm_select -s 2 -c 1 -f -o gpurun_out/r02_assign python profiles/ncu_assign.py > gpurun_out/r02_ncu_b.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm_select -s 8 -c 2 -f -o gpurun_out/r02_assign python profiles/ncu_assign.py > gpurun_out/r02_ncu_b.log 2>&1
 echo "assign capture rc=$?"
 timeout 120 python profiles/ncu_knn.py > gpurun_out/r02_plain_c.log 2>&1 &&
 timeout 400 ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section MemoryWorkloadAnalysis_Tables --section LaunchStats --section Occupancy --section WarpStateStats --section ComputeWorkloadAnalysis --clock-control none -k regex:gemm_select -s 3 -c 1 -f -o gpurun_out/r02_knn python profiles/ncu_knn.py > gpurun_out/r02_ncu_c.log 2>&1
