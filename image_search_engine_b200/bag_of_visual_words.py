@@ -137,7 +137,15 @@ class _ListPacker:
         self.ptrs, self.offsets, self.n_img, self.n_rows, self.d = ptrs, offsets, n_img, int(offsets[-1]), int(d)
         self.src_u8 = dt == np.uint8
         self.bufs, self._lib, self._C = bufs, _lib, C
-        self.nthreads = nthreads or min(16, os.cpu_count() or 1)
+        if nthreads is None:
+            # the host cores this process may use, shared with the other ranks of the node (torchrun: LOCAL_WORLD_SIZE)
+            try:
+                cores = len(os.sched_getaffinity(0))
+            except (AttributeError, OSError):
+                cores = os.cpu_count() or 1
+            ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+            nthreads = max(2, min(16, cores // ranks))
+        self.nthreads = nthreads
         self.ok = True
 
     def wire_dtypes(self, try_u8: bool = True):
