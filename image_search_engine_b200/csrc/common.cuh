@@ -100,27 +100,29 @@ __device__ __forceinline__ bool cand_better(float va, int64_t ia, float vb, int6
 
 // Rigorous bound on |coarse - exact| for an inner product computed from the FP16 hi planes only.
 // With a = hi_a + lo_a, |lo_a| <= 2^-11 |a| (round-to-nearest FP16; 0 when the plane is exact) the
-// neglected terms are <= (c_a + c_b + c_a c_b) sum|a_i b_i| <= (c_a + c_b + 2^-22) |a||b| (Cauchy-Schwarz) -- for B the
-// MEASURED residual max_j |b_j - hi_j| replaces c_b |b| when the preparation pass published it (typically 2-3x smaller);
+// neglected terms are <= (c_a + c_b + c_a c_b) |a||b| (Cauchy-Schwarz) -- c_a, c_b are the MEASURED relative residuals
+// max_rows |x - hi| / |x| when the preparation pass published them (typically 2-3x below 2^-11);
 // the truncating FP32 accumulation adds <= (d/16 + 4) 2^-23 |a||b|; FP16 underflow (scaled elements below
 // 2^-14 round with absolute error <= 2^-25) adds <= 2^-25/scale * sqrt(d) * |other operand|.
 struct CoarseBound {
     float kappa, uf_a, uf_b, nb_max, sq_, ca_, rb_;
     // a_exact: the caller knows the A planes are exact in hi (or re-runs the whole tensor when they are not)
+    // meta[LO_NONZERO]: 0 = exact in the hi plane; 1.0 = inexact, residual unknown (worst case 2^-11 |x|); any other
+    // value = the largest measured |x - hi|^2 / |x|^2 of a row (rows_convert.cuh: publish_lo_residual)
+    __device__ __forceinline__ static float rel_residual(float flag) {
+        if (flag == 0.f) return 0.f;
+        return flag == 1.f ? 4.8828125e-4f : fminf(1.0001f * sqrtf(flag), 4.8828125e-4f);
+    }
     __device__ __forceinline__ void init(const float* a_meta, const float* b_meta, int d, bool a_exact = false) {
-        const float ca = (!a_exact && a_meta[META_LO_NONZERO] != 0.f) ? 4.8828125e-4f : 0.f;   // 2^-11
-        // B: the column preparation publishes the largest measured |b - b_hi|^2 of a column in meta[LO_NONZERO]
-        // (prepare.cu: publish_lo_residual); the plain flag 1.0 (other writers) means "unknown": worst case 2^-11 |b|
-        const float lob = b_meta[META_LO_NONZERO];
-        const bool measured = lob != 0.f && lob != 1.f;
-        const float cb = (lob != 0.f && !measured) ? 4.8828125e-4f : 0.f;
-        rb_ = measured ? 1.0001f * (1.f + ca) * sqrtf(lob) : 0.f;                  // |<a_hi, b - b_hi>| <= (1 + ca) |a| rb
+        const float ca = a_exact ? 0.f : rel_residual(a_meta[META_LO_NONZERO]);
+        const float cb = rel_residual(b_meta[META_LO_NONZERO]);
+        rb_ = 0.f;
         kappa = 1.02f * (ca + cb) + 2.4e-7f + (float)(d / 16 + 4) * 1.1920929e-7f;
         const float sq = sqrtf((float)d) * 5.9604645e-8f;                         // 2 * 2^-25 * sqrt(d)
         sq_ = sq;
         ca_ = ca;
         uf_a = ca != 0.f ? sq * a_meta[META_INV_SCALE] : 0.f;                     // times |b|
-        uf_b = lob != 0.f ? sq * b_meta[META_INV_SCALE] : 0.f;                    // times |a|
+        uf_b = cb != 0.f ? sq * b_meta[META_INV_SCALE] : 0.f;                     // times |a|
         nb_max = sqrtf(b_meta[META_MAX_NORM_SQ]);
     }
     // row operands prepared with a per-row scale (ise_prepare_rows): the FP16-underflow term of the A planes follows

@@ -94,15 +94,7 @@ __device__ __forceinline__ float load_as_f32<float>(const float* p) { return __l
 template <>
 __device__ __forceinline__ float load_as_f32<uint8_t>(const uint8_t* p) { return (float)__ldg(p); }
 
-// meta[LO_NONZERO] doubles as the largest squared norm of a row's hi-plane residual |x - hi / scale|^2 (real units):
-// 0 = the lo plane is all zeros; any other value says it is not, and a value other than the plain flag 1.0 lets the
-// coarse-pass error bound use the MEASURED residual instead of the worst case 2^-11 |x| (CoarseBound, common.cuh).
-__device__ __forceinline__ void publish_lo_residual(float* meta, bool any_lo, float max_rs_scaled, float scale, int lane) {
-    if (!any_lo || lane != 0) return;
-    const float inv = 1.f / scale;
-    const float v = fmaxf(max_rs_scaled * inv * inv * 1.0001f, 1.17549435e-38f);     // never reads as "no lo plane"
-    atomicMax(reinterpret_cast<int*>(meta + META_LO_NONZERO), __float_as_int(v));
-}
+// (publish_lo_residual: rows_convert.cuh)
 
 template <typename T>
 __global__ void prepare_planes_kernel(const T* __restrict__ x, int64_t n, int d, int64_t ldx,
@@ -145,12 +137,12 @@ __global__ void prepare_planes_kernel(const T* __restrict__ x, int64_t n, int d,
         ss = warp_sum(ss);
         if (norms && lane == 0) norms[r] = ss;
         max_ss = fmaxf(max_ss, ss);
-        if (__any_sync(0xffffffffu, rs != 0.f)) max_rs = fmaxf(max_rs, warp_sum(rs));
+        if (__any_sync(0xffffffffu, rs != 0.f)) max_rs = fmaxf(max_rs, warp_sum(rs) / (scale * scale * ss));   // relative
     }
     // largest row norm^2 (non-negative floats order like ints; one atomic per warp): the coarse-pass
     // error bound of ise_rescore_select needs it
     if (lane == 0 && max_ss > 0.f) atomicMax(reinterpret_cast<int*>(meta + META_MAX_NORM_SQ), __float_as_int(max_ss));
-    publish_lo_residual(meta, __any_sync(0xffffffffu, any_lo), max_rs, scale, lane);
+    publish_lo_residual(meta, __any_sync(0xffffffffu, any_lo), max_rs, lane);
 }
 
 // Fast path, float32 rows with d % 4 == 0 (16-byte aligned rows and planes): a lane converts four consecutive
@@ -239,11 +231,11 @@ __global__ void __launch_bounds__(kThreads, EXACT ? 5 : 3) prepare_planes_f32x4_
                 if (norms && lane == 0) norms[r0 + i] = t;
                 max_ss = fmaxf(max_ss, t);
             }
-            if (!EXACT) max_rs = fmaxf(max_rs, warp_sum(rs[EXACT ? 0 : i]));
+            if (!EXACT && r0 + i < n && t > 0.f) max_rs = fmaxf(max_rs, warp_sum(rs[EXACT ? 0 : i]) / (scale * scale * t));
         }
     }
     if (lane == 0 && max_ss > 0.f) atomicMax(reinterpret_cast<int*>(meta + META_MAX_NORM_SQ), __float_as_int(max_ss));
-    if (!EXACT) publish_lo_residual(meta, __any_sync(0xffffffffu, any_lo), max_rs, scale, lane);
+    if (!EXACT) publish_lo_residual(meta, __any_sync(0xffffffffu, any_lo), max_rs, lane);
 }
 
 // ---- single-pass preparation of ROW operands (descriptors / queries) ------------------------------------------------

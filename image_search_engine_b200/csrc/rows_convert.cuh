@@ -50,8 +50,29 @@ __device__ __forceinline__ int multi_row(int lane) {
 struct RowStats {            // per-lane accumulators, committed to meta[] once at the end
     bool any_lo = false;
     float max_ss = 0.f;
+    float max_res = 0.f;     // largest |x - hi / scale|^2 / |x|^2 of a row that needed its lo plane
     unsigned max_abs_bits = 0u;
 };
+
+// meta[LO_NONZERO] doubles as the largest RELATIVE squared hi-plane residual |x - hi / scale|^2 / |x|^2 of a row:
+// 0 = the lo plane is all zeros; any other value says it is not, and a value other than the plain flag 1.0 lets the
+// coarse-pass error bound use the MEASURED residual instead of the worst case (2^-11)^2 (CoarseBound, common.cuh).
+__device__ __forceinline__ void publish_lo_residual(float* meta, bool any_lo, float max_rel_sq, int lane) {
+    if (!any_lo || lane != 0) return;
+    const float v = fmaxf(max_rel_sq * 1.0002f, 1.17549435e-38f);     // never reads as "no lo plane"
+    atomicMax(reinterpret_cast<int*>(meta + META_LO_NONZERO), __float_as_int(v));
+}
+
+// the lane that holds the total of row i after multi_sum<R>
+template <int R>
+__device__ __forceinline__ int multi_lane_of_row(int i) {
+    int l = 0, width = 16;
+#pragma unroll
+    for (int n = R; n > 1; n >>= 1, width >>= 1) {
+        if (i >= n / 2) { l += width; i -= n / 2; }
+    }
+    return l;
+}
 
 // One warp converts the ROWS rows [r0, r0 + ROWS) (those below n): see prepare_rows_f32_kernel for the method.
 template <int ROWS, int NV>
@@ -126,6 +147,7 @@ __device__ __forceinline__ void convert_row_group(const float* __restrict__ x, i
                 }
             }
         } else {
+            float rs = 0.f;                                 // squared residual of the hi plane (scaled units)
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
                 const int c = lane + 32 * j;
@@ -134,6 +156,9 @@ __device__ __forceinline__ void convert_row_group(const float* __restrict__ x, i
                     __half h0, h1, h2, h3, l0, l1, l2, l3;
                     split_f16(t.x * scale, h0, l0); split_f16(t.y * scale, h1, l1);
                     split_f16(t.z * scale, h2, l2); split_f16(t.w * scale, h3, l3);
+                    const float e0 = t.x * scale - __half2float(h0), e1 = t.y * scale - __half2float(h1);
+                    const float e2 = t.z * scale - __half2float(h2), e3 = t.w * scale - __half2float(h3);
+                    rs = fmaf(e0, e0, rs); rs = fmaf(e1, e1, rs); rs = fmaf(e2, e2, rs); rs = fmaf(e3, e3, rs);
                     const __half2 ha = __halves2half2(h0, h1), hb = __halves2half2(h2, h3);
                     const __half2 la = __halves2half2(l0, l1), lb = __halves2half2(l2, l3);
                     reinterpret_cast<uint2*>(hi + r * ldp)[c] =
@@ -143,6 +168,11 @@ __device__ __forceinline__ void convert_row_group(const float* __restrict__ x, i
                             make_uint2(*reinterpret_cast<const uint32_t*>(&la), *reinterpret_cast<const uint32_t*>(&lb));
                 }
             }
+            // relative to the row's squared norm (held by the lane that owns row i after multi_sum)
+            rs = warp_sum(rs);
+            const float ss_i = __shfl_sync(0xffffffffu, row_ss, multi_lane_of_row<ROWS>(i));
+            const float inv_s = __uint_as_float((unsigned)(127 - sh) << 23);
+            if (ss_i > 0.f) st.max_res = fmaxf(st.max_res, rs * inv_s * inv_s / ss_i);
         }
         if (lane == 0) {
             row_inv[r] = __uint_as_float((unsigned)(127 - sh) << 23);
@@ -159,6 +189,6 @@ __device__ __forceinline__ void commit_row_stats(RowStats& st, float* meta, int 
         if (st.max_ss > 0.f) atomicMax(reinterpret_cast<int*>(meta + META_MAX_NORM_SQ), __float_as_int(st.max_ss));
         if (st.max_abs_bits >= 0x7F800000u) meta[META_NONFINITE] = 1.f;
         else if (st.max_abs_bits != 0u) atomicMax(reinterpret_cast<int*>(meta + META_ABSMAX), (int)st.max_abs_bits);
-        if (st.any_lo) meta[META_LO_NONZERO] = 1.f;
     }
+    publish_lo_residual(meta, __any_sync(0xffffffffu, st.any_lo), warp_max(st.max_res), lane);
 }

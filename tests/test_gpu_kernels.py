@@ -419,10 +419,15 @@ def test_exact_inputs_skip_the_lo_plane_and_nobody_reads_it(dev):
     y = torch.randn((5000, 128), device=dev)
     ay = ops.prepare_operand(y)
     assert float(ay.meta[2]) != 0.0 and not bool(torch.isnan(ay.lo.float()).any())
-    # ... and meta[2] carries the largest squared hi-plane residual of a row, which the coarse error bound uses
+    # ... and meta[2] carries the largest RELATIVE squared hi-plane residual of a row, which the coarse error bound uses
     sc = float(ay.meta[0])
-    res = (y.double() - ay.hi[:, :128].double() / sc).pow(2).sum(1).max().item()
-    assert res <= float(ay.meta[2]) <= res * 1.001 + 1e-30
+    res = ((y.double() - ay.hi[:, :128].double() / sc).pow(2).sum(1) / y.double().pow(2).sum(1)).max().item()
+    assert res <= float(ay.meta[2]) <= res * 1.001 and float(ay.meta[2]) < 2.0 ** -22
+    # the single-pass row preparation publishes the same quantity (per-row scales)
+    ar = ops.prepare_operand(y, rows=True)
+    hr = ar.hi[:, :128].double() * ar.row_inv.double()[:, None]
+    res_r = ((y.double() - hr).pow(2).sum(1) / y.double().pow(2).sum(1)).max().item()
+    assert res_r <= float(ar.meta[2]) <= res_r * 1.001 and float(ar.meta[2]) < 2.0 ** -22
     # a value far below the maximum leaves FP16's normal range once scaled: the input no longer counts as exact and
     # the lo plane is written again (zeros here: such a value underflows in both planes, which the coarse error
     # bound accounts for)

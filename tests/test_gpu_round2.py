@@ -235,7 +235,7 @@ def test_prepare_rows_exact_rows_skip_their_lo_store():
         poison = torch.full((20000, 128), float("nan"), dtype=torch.float16, device=dev)
         del poison
         om = ops.prepare_operand(torch.from_numpy(mixed).to(dev), rows=True)
-    assert float(om.meta[2]) == 1.0
+    assert 0.0 < float(om.meta[2]) < 2.0 ** -22          # inexact rows exist; the value is their largest relative residual^2
     lo = om.lo.float().cpu().numpy()
     assert not np.isnan(lo).any()
     exact_rows = np.ones(20000, bool)
@@ -428,7 +428,8 @@ def test_fused_assign_equals_separate_preparation(metric_ip, m, n, d, kind):
     assert torch.equal(idx, idx_s) and torch.equal(val, val_s)
     assert torch.equal(a_f.hi, a_s.hi) and torch.equal(a_f.norms, a_s.norms) and torch.equal(a_f.row_inv, a_s.row_inv)
     mf, ms = a_f.meta.cpu().numpy(), a_s.meta.cpu().numpy()
-    assert mf[2] == ms[2] == (0.0 if kind == "sift" else 1.0) and mf[0] == 1.0 and mf[4] == ms[4] and mf[7] == 0.0
+    assert mf[2] == ms[2] and (mf[2] == 0.0 if kind == "sift" else 0.0 < mf[2] < 2.0 ** -22)
+    assert mf[0] == 1.0 and mf[4] == ms[4] and mf[7] == 0.0
     if kind != "sift":
         assert torch.equal(a_f.lo, a_s.lo)
     # against the oracle on a sample
