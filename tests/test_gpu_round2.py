@@ -535,6 +535,29 @@ def test_verified_assign_with_no_undecided_row():
         assert ops.search_stats()["fallback_rows"] == 0 and np.array_equal(got[1].cpu().numpy().reshape(-1), pick)
 
 
+def test_verified_assign_takes_uint8_descriptors():
+    """ORB / BRISK style uint8 descriptors are widened on the device (per-tensor scale, no per-row scales): the
+    verified pipeline over their prepared planes gives the ids of the float32 copy of the same values."""
+    from image_search_engine_b200 import FaissKMeans, faiss_compat, ops
+    dev = ops.require_cuda()
+    rng = np.random.default_rng(21)
+    m, n, d = 120_000, 2048, 64
+    xb = rng.integers(0, 256, (m, d), dtype=np.uint8)
+    c = unit_rows(rng, n, d)
+    gi = faiss_compat.IndexFlatIP(d)
+    gi.add(c)
+    km = FaissKMeans(n, index=gi)
+    w8 = km.transform_device(torch.from_numpy(xb).to(dev))
+    st = ops.search_stats()
+    assert st["mode"] == "verified-resident", st
+    wf = km.transform_device(torch.from_numpy(xb.astype(np.float32)).to(dev))
+    assert ops.search_stats()["mode"] == "fused-verified" and torch.equal(w8, wf)
+    from oracle import faiss_shim as fs
+    rows = rng.choice(m, 1000, replace=False)
+    _, Ir = fs.knn(xb[rows].astype(np.float32), c, 1, fs.METRIC_INNER_PRODUCT)
+    assert_topk_parity(w8.cpu().numpy()[rows].reshape(-1, 1), Ir, xb[rows].astype(np.float32), c, True, max_mismatch_frac=0.01)
+
+
 def test_fused_assign_declines_shapes_it_does_not_cover():
     from image_search_engine_b200 import ops
     from image_search_engine_b200._lib import METRIC_IP
