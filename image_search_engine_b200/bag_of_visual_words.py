@@ -133,20 +133,43 @@ class _ListPacker:
         np.cumsum(counts, out=offsets[1:])
         if int(offsets[-1]) == 0:
             return
-        self._keep = descriptions                    # the arrays must outlive the raw pointers
-        self.ptrs, self.offsets, self.n_img, self.n_rows, self.d = ptrs, offsets, n_img, int(offsets[-1]), int(d)
-        self.src_u8 = dt == np.uint8
+        self._finish(descriptions, ptrs, offsets, int(d), dt == np.uint8, bufs, nthreads)
+
+    def _finish(self, keep, ptrs, offsets, d, src_u8, bufs, nthreads):
+        import ctypes as C
+        from . import _lib
+        self._keep = keep                            # the arrays must outlive the raw pointers
+        self.ptrs, self.offsets, self.n_img, self.n_rows, self.d = ptrs, offsets, len(offsets) - 1, int(offsets[-1]), d
+        self.src_u8 = src_u8
         self.bufs, self._lib, self._C = bufs, _lib, C
-        if nthreads is None:
-            # the host cores this process may use, shared with the other ranks of the node (torchrun: LOCAL_WORLD_SIZE)
-            try:
-                cores = len(os.sched_getaffinity(0))
-            except (AttributeError, OSError):
-                cores = os.cpu_count() or 1
-            ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
-            nthreads = max(2, min(16, cores // ranks))
-        self.nthreads = nthreads
+        self.nthreads = nthreads or self.default_threads()
         self.ok = True
+
+    @staticmethod
+    def default_threads() -> int:
+        """The host cores this process may use, shared with the other ranks of the node (torchrun: LOCAL_WORLD_SIZE)."""
+        import os
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except (AttributeError, OSError):
+            cores = os.cpu_count() or 1
+        ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+        return max(2, min(16, cores // ranks))
+
+    @classmethod
+    def from_matrix(cls, mat: torch.Tensor, bufs: dict, block_rows: int = 4096, nthreads: int | None = None):
+        """The same packer over an already packed float32 host matrix, cut into blocks of rows (its "images"): used to
+        NARROW integer-valued descriptors to uint8 on the way to the device when the host has the cores for it."""
+        self = cls.__new__(cls)
+        self.ok = False
+        n, d = int(mat.shape[0]), int(mat.shape[1])
+        if n == 0 or mat.dtype != torch.float32 or mat.is_cuda or not mat.is_contiguous():
+            return self
+        starts = np.arange(0, n, block_rows, dtype=np.int64)
+        offsets = np.append(starts, np.int64(n))
+        ptrs = (np.uint64(mat.data_ptr()) + starts.astype(np.uint64) * np.uint64(d * 4)).astype(np.uint64)
+        self._finish(mat, ptrs, offsets, d, False, bufs, nthreads)
+        return self
 
     def wire_dtypes(self, try_u8: bool = True):
         """Wire formats to try, in order."""
@@ -209,6 +232,22 @@ def _pack_list_into(descriptions, bufs: dict, try_u8: bool = True, nthreads: int
     return None
 
 
+def _narrow_on_the_wire(mat, n_chunks: int) -> bool:
+    """Whether a packed float32 host matrix is worth narrowing to uint8 for the host -> device copy: the narrowing pass
+    reads the matrix once on host threads, so it only pays when this process has cores (and memory bandwidth) to spare
+    -- measured: 1 - 2 ranks per node yes; 8 ranks sharing the host no (profiles/r02_findings.md section 3).
+    ISE_NARROW_PINNED=0 / 1 overrides."""
+    import os
+    if not isinstance(mat, torch.Tensor) or mat.is_cuda or mat.dtype != torch.float32 or not mat.is_pinned():
+        return False
+    if not mat.is_contiguous() or mat.shape[0] < 8192 * n_chunks:
+        return False
+    env = os.environ.get("ISE_NARROW_PINNED")
+    if env is not None:
+        return env == "1"
+    return _ListPacker.default_threads() >= 8
+
+
 class BOVW(BaseEstimator):
     """Bag of Visual Words: describe -> cluster (codebook) -> quantise -> per-image histogram."""
 
@@ -221,7 +260,7 @@ class BOVW(BaseEstimator):
         # copy first: on Python >= 3.11 BaseEstimator.__getstate__ hands back the LIVE __dict__, and popping from it
         # would drop the caches of the estimator being pickled
         state = dict(super().__getstate__())
-        for key in ("_pipe_cache", "_csr_cache", "_csr_bufs", "_pipe_lock", "_pack_bufs"):   # CUDA streams / events / staging buffers / locks are not persisted
+        for key in ("_pipe_cache", "_csr_cache", "_csr_bufs", "_pipe_lock", "_pack_bufs", "_last_transfer"):   # CUDA streams / events / staging buffers / locks are not persisted
             state.pop(key, None)
         return state
 
@@ -378,14 +417,23 @@ class BOVW(BaseEstimator):
             # codebooks beyond the shared-memory counter budget: dense kernel, CSR conversion on the host
             H = self.histograms_device(descriptions, okapi=okapi)
             return sp.csr_matrix(H.cpu().numpy())
+        # attempts, in order: (packer or None, wire dtype or None = "send `mat` as it is")
         if packer is not None:
-            offsets, wires = packer.offsets, packer.wire_dtypes()
-            mat = packer.view(wires[0])
+            offsets = packer.offsets
+            mat = packer.view(packer.wire_dtypes()[0])
+            attempts = [(packer, w) for w in packer.wire_dtypes()]
         else:
             mat, offsets = pack_descriptions(descriptions)
             if isinstance(mat, np.ndarray):
                 mat = torch.from_numpy(mat)
-            wires = [mat.dtype]
+            attempts = [(None, None)]
+            if _narrow_on_the_wire(mat, n_chunks):
+                # pinned float32 matrix on a host with cores to spare: integer-valued descriptors (OpenCV SIFT, ORB as
+                # float) cross PCIe as uint8 -- a quarter of the bytes, narrowed block by block on host threads while
+                # the previous chunk is copied and quantised; any other value makes the first block refuse at once
+                npk = _ListPacker.from_matrix(mat, self.__dict__.setdefault("_pack_bufs", {}))
+                if npk.ok:
+                    attempts = [(npk, torch.uint8), (None, None)]
         n_img, n_rows = len(offsets) - 1, int(mat.shape[0])
         kw = self._csr_kwargs(okapi)
         off_dev = torch.from_numpy(offsets).to(dev, non_blocking=True)
@@ -394,18 +442,19 @@ class BOVW(BaseEstimator):
         else:
             # chunked H2D (copy stream) overlapped with the assign of the previous chunk (current stream)
             NB = 3
-            if packer is None:
-                cuts = np.unique(np.linspace(0, n_rows, n_chunks + 1).astype(np.int64))
-                img_cuts = None
-            else:           # whole images per chunk, balanced by rows
-                img_cuts = np.unique(np.searchsorted(offsets, np.linspace(0, n_rows, n_chunks + 1))).astype(np.int64)
-                img_cuts[0], img_cuts[-1] = 0, n_img
-                cuts = offsets[img_cuts]
-            max_rows = int(np.diff(cuts).max())
+            src_mat = mat
             words = None
-            for wire in wires:
-                if packer is not None:
-                    mat = packer.view(wire)
+            for pk, wire in attempts:
+                if pk is None:
+                    mat = src_mat
+                    cuts = np.unique(np.linspace(0, n_rows, n_chunks + 1).astype(np.int64))
+                    unit_cuts = None
+                else:           # whole packer units (images / row blocks) per chunk, balanced by rows
+                    mat = pk.view(wire)
+                    unit_cuts = np.unique(np.searchsorted(pk.offsets, np.linspace(0, n_rows, n_chunks + 1))).astype(np.int64)
+                    unit_cuts[0], unit_cuts[-1] = 0, pk.n_img
+                    cuts = pk.offsets[unit_cuts]
+                max_rows = int(np.diff(cuts).max())
                 key = ("csr", max_rows, int(mat.shape[1]), mat.dtype, str(dev))
                 pc = self.__dict__.get("_csr_cache")
                 if pc is None or pc["key"] != key:
@@ -417,13 +466,13 @@ class BOVW(BaseEstimator):
                 s_in.wait_stream(main)
                 words = torch.empty((n_rows,), dtype=torch.int64, device=dev)
                 fits = True
-                if packer is not None:
-                    packer.begin(img_cuts, wire)
+                if pk is not None:
+                    pk.begin(unit_cuts, wire)
                 try:
                     for ci, (r0, r1) in enumerate(zip(cuts[:-1], cuts[1:])):
                         if r1 <= r0:
                             continue
-                        if packer is not None and not packer.wait(ci):
+                        if pk is not None and not pk.wait(ci):
                             fits = False      # a value that is not an integer in [0, 255]: start over with float32 on the wire
                             break
                         b = ci % NB
@@ -437,14 +486,17 @@ class BOVW(BaseEstimator):
                         words[int(r0):int(r1)] = self.clusterer.transform_device(xd)
                         pc["ev_c"][b].record(main)
                 finally:
-                    if packer is not None:
-                        packer.end()
+                    if pk is not None:
+                        pk.end()
                 if fits:
                     break
                 # the pinned rows of the abandoned attempt may still be in flight: let the copies drain before the buffers
                 # are reused / re-packed
                 s_in.synchronize()
             assert words is not None
+        # what crossed PCIe on the way in (bench.py reports it)
+        self.__dict__["_last_transfer"] = dict(h2d_bytes=int(mat.numel() * mat.element_size() + offsets.nbytes),
+                                               wire=str(mat.dtype).replace("torch.", ""), rows=n_rows)
         # persistent device + pinned result buffers (indptr | indices | data), grown on demand
         rb = self.__dict__.get("_csr_bufs")
         if rb is None or rb["cap"] < max(n_rows, 1) or rb["n_img"] < n_img or rb["dev"] != str(dev):

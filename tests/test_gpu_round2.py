@@ -397,6 +397,41 @@ def test_transform_csr_from_a_python_list_of_arrays():
                           bovw.transform_csr(ints, okapi=ok, n_chunks=4).toarray())
 
 
+def test_pinned_float_matrix_is_narrowed_on_the_wire(monkeypatch):
+    """A pinned float32 PackedDescriptions whose values are integers in [0, 255] crosses PCIe as uint8 (narrowed block by
+    block on host threads inside transform_csr) and gives exactly the float32-wire result; a single non-integer value
+    anywhere makes the call fall back to float32 on the wire."""
+    from image_search_engine_b200 import BOVW, FaissKMeans, OkapiTransformer, faiss_compat
+    from image_search_engine_b200.bag_of_visual_words import PackedDescriptions
+    rng = np.random.default_rng(31)
+    k, d, n_img = 512, 128, 700
+    gi = faiss_compat.IndexFlatIP(d)
+    gi.add(unit_rows(rng, k, d))
+    bovw = BOVW(None, n_clusters=k)
+    bovw.clusterer = FaissKMeans(k, index=gi)
+    ok = OkapiTransformer()
+    sizes = rng.integers(150, 260, n_img)
+    offsets = np.zeros(n_img + 1, dtype=np.int64)
+    np.cumsum(sizes, out=offsets[1:])
+    x = sift_like(rng, int(offsets[-1]), d)
+    packed = PackedDescriptions(torch.from_numpy(x.copy()), offsets).pin()
+    monkeypatch.setenv("ISE_NARROW_PINNED", "0")
+    want = bovw.transform_csr(packed, okapi=ok, n_chunks=4).toarray()
+    assert bovw._last_transfer["wire"] == "float32"
+    monkeypatch.setenv("ISE_NARROW_PINNED", "1")
+    got = bovw.transform_csr(packed, okapi=ok, n_chunks=4).toarray()
+    assert bovw._last_transfer["wire"] == "uint8" and bovw._last_transfer["h2d_bytes"] < x.nbytes // 3
+    assert np.array_equal(got, want)
+    # a non-integer value in the LAST block: the uint8 attempt is abandoned mid-way, float32 is sent instead
+    y = x.copy()
+    y[-3, 7] += 0.25
+    packed_y = PackedDescriptions(torch.from_numpy(y), offsets).pin()
+    got_y = bovw.transform_csr(packed_y, okapi=ok, n_chunks=4).toarray()
+    assert bovw._last_transfer["wire"] == "float32"
+    monkeypatch.setenv("ISE_NARROW_PINNED", "0")
+    assert np.array_equal(got_y, bovw.transform_csr(packed_y, okapi=ok, n_chunks=4).toarray())
+
+
 @pytest.mark.parametrize("metric_ip", [True, False])
 @pytest.mark.parametrize("m,n,d,kind", [(200_000, 4096, 128, "sift"), (150_001, 1000, 64, "sift"), (120_000, 512, 32, "sift"),
                                          (160_000, 2048, 128, "float"), (130_000, 777, 128, "mixed")])
