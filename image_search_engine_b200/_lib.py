@@ -34,6 +34,8 @@ PROTOTYPES = {
     "ise_pack_begin": (_int, [_c_void_p, _c_void_p, _c_void_p, _int, _int, _int, _int, _c_void_p, _int,
                               C.POINTER(_c_void_p)]),
     "ise_pack_wait": (_int, [_c_void_p, _int, C.POINTER(_int)]),
+    "ise_pack_poll": (_int, [_c_void_p, _int, C.POINTER(_int), C.POINTER(_int)]),
+    "ise_pack_claim": (_int, [_c_void_p, _int, C.POINTER(_int)]),
     "ise_pack_end": (_int, [_c_void_p]),
     "ise_prepare_planes": (_int, [_c_void_p, _c_void_p, _int, _i64, _int, _i64, _c_void_p, _c_void_p, _i64,
                                   _c_void_p, _c_void_p, _c_void_p]),

@@ -12,7 +12,9 @@ gives the intended word-id histogram.  ``transform`` ignores X when ``self.descr
 """
 from __future__ import annotations
 
+import os
 import threading
+import time
 from pathlib import Path
 
 import joblib
@@ -154,7 +156,11 @@ class _ListPacker:
         except (AttributeError, OSError):
             cores = os.cpu_count() or 1
         ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
-        return max(2, min(16, cores // ranks))
+        env = os.environ.get("ISE_PACK_THREADS")
+        if env:
+            return max(1, int(env))
+        # two cores stay free for the calling thread (it feeds the copy engine and launches the kernels) and the driver
+        return max(2, min(16, cores // ranks - 2))
 
     @classmethod
     def from_matrix(cls, mat: torch.Tensor, bufs: dict, block_rows: int = 4096, nthreads: int | None = None):
@@ -215,6 +221,20 @@ class _ListPacker:
         _lib.check(_lib.load().ise_pack_wait(self._job, int(chunk), C.byref(ok)))
         return bool(ok.value)
 
+    def poll(self, chunk: int):
+        """(done, ok) without blocking: done = the workers have finished the chunk; ok = no value refused so far."""
+        C, _lib = self._C, self._lib
+        done, ok = C.c_int(0), C.c_int(0)
+        _lib.check(_lib.load().ise_pack_poll(self._job, int(chunk), C.byref(done), C.byref(ok)))
+        return bool(done.value), bool(ok.value)
+
+    def claim(self, chunk: int) -> bool:
+        """Takes a chunk the workers have not started away from them (the caller sends it in its source format)."""
+        C, _lib = self._C, self._lib
+        got = C.c_int(0)
+        _lib.check(_lib.load().ise_pack_claim(self._job, int(chunk), C.byref(got)))
+        return bool(got.value)
+
     def end(self) -> None:
         job = self.__dict__.pop("_job", None)
         if job is not None:
@@ -245,7 +265,7 @@ def _narrow_on_the_wire(mat, n_chunks: int) -> bool:
     env = os.environ.get("ISE_NARROW_PINNED")
     if env is not None:
         return env == "1"
-    return _ListPacker.default_threads() >= 8
+    return _ListPacker.default_threads() >= 6
 
 
 class BOVW(BaseEstimator):
@@ -437,66 +457,142 @@ class BOVW(BaseEstimator):
         n_img, n_rows = len(offsets) - 1, int(mat.shape[0])
         kw = self._csr_kwargs(okapi)
         off_dev = torch.from_numpy(offsets).to(dev, non_blocking=True)
+        sent_bytes, wire_name = int(mat.numel() * mat.element_size()), str(mat.dtype).replace("torch.", "")
         if packer is None and (mat.is_cuda or n_img < 2 * n_chunks or not mat.is_pinned()):
             words = self.clusterer.transform_device(mat.to(dev, non_blocking=True))
         else:
-            # chunked H2D (copy stream) overlapped with the assign of the previous chunk (current stream)
+            # chunked H2D (copy stream) overlapped with the assign of the previous chunk (current stream); staging
+            # buffers per wire dtype, NB deep
             NB = 3
+            caches = self.__dict__.get("_csr_cache")
+            if caches is None or caches.get("dev") != str(dev):
+                caches = {"dev": str(dev), "s_in": torch.cuda.Stream()}
+                self.__dict__["_csr_cache"] = caches
+            main, s_in = torch.cuda.current_stream(), caches["s_in"]
+            s_in.wait_stream(main)
+            ncol = int(mat.shape[1])
             src_mat = mat
-            words = None
+            words = torch.empty((n_rows,), dtype=torch.int64, device=dev)
+
+            def pool(max_rows, dtype, depth=NB):
+                key = (max_rows, ncol, dtype, depth)
+                pc = caches.get(key)
+                if pc is None:
+                    for old in [q for q in caches if isinstance(q, tuple) and q[:2] != key[:2]]:
+                        del caches[old]          # staging buffers of another batch shape
+                    pc = dict(xd=[torch.empty((max_rows, ncol), dtype=dtype, device=dev) for _ in range(depth)],
+                              ev_in=[torch.cuda.Event() for _ in range(depth)], ev_c=[torch.cuda.Event() for _ in range(depth)],
+                              depth=depth)
+                    caches[key] = pc
+                pc["used"] = 0
+                return pc
+
+            def send(pc, rows, r0, r1):
+                """rows (pinned host) -> staging buffer -> words[r0:r1]; returns the event of the copy"""
+                i = pc["used"]
+                pc["used"] = i + 1
+                b = i % pc["depth"]
+                xd = pc["xd"][b][: int(r1 - r0)]
+                with torch.cuda.stream(s_in):
+                    if i >= pc["depth"]:
+                        s_in.wait_event(pc["ev_c"][b])
+                    xd.copy_(rows, non_blocking=True)
+                    pc["ev_in"][b].record(s_in)
+                main.wait_event(pc["ev_in"][b])
+                words[int(r0):int(r1)] = self.clusterer.transform_device(xd)
+                pc["ev_c"][b].record(main)
+                return pc["ev_in"][b]
+
+            def unit_chunks(pk):
+                """whole packer units (images / row blocks) per chunk, balanced by rows"""
+                uc = np.unique(np.searchsorted(pk.offsets, np.linspace(0, n_rows, n_chunks + 1))).astype(np.int64)
+                uc[0], uc[-1] = 0, pk.n_img
+                return uc, pk.offsets[uc]
+
             for pk, wire in attempts:
-                if pk is None:
-                    mat = src_mat
-                    cuts = np.unique(np.linspace(0, n_rows, n_chunks + 1).astype(np.int64))
-                    unit_cuts = None
-                else:           # whole packer units (images / row blocks) per chunk, balanced by rows
-                    mat = pk.view(wire)
-                    unit_cuts = np.unique(np.searchsorted(pk.offsets, np.linspace(0, n_rows, n_chunks + 1))).astype(np.int64)
-                    unit_cuts[0], unit_cuts[-1] = 0, pk.n_img
-                    cuts = pk.offsets[unit_cuts]
-                max_rows = int(np.diff(cuts).max())
-                key = ("csr", max_rows, int(mat.shape[1]), mat.dtype, str(dev))
-                pc = self.__dict__.get("_csr_cache")
-                if pc is None or pc["key"] != key:
-                    pc = dict(key=key, s_in=torch.cuda.Stream(),
-                              xd=[torch.empty((max_rows, mat.shape[1]), dtype=mat.dtype, device=dev) for _ in range(NB)],
-                              ev_in=[torch.cuda.Event() for _ in range(NB)], ev_c=[torch.cuda.Event() for _ in range(NB)])
-                    self.__dict__["_csr_cache"] = pc
-                main, s_in = torch.cuda.current_stream(), pc["s_in"]
-                s_in.wait_stream(main)
-                words = torch.empty((n_rows,), dtype=torch.int64, device=dev)
                 fits = True
-                if pk is not None:
-                    pk.begin(unit_cuts, wire)
-                try:
-                    for ci, (r0, r1) in enumerate(zip(cuts[:-1], cuts[1:])):
-                        if r1 <= r0:
-                            continue
-                        if pk is not None and not pk.wait(ci):
-                            fits = False      # a value that is not an integer in [0, 255]: start over with float32 on the wire
-                            break
-                        b = ci % NB
-                        xd = pc["xd"][b][: int(r1 - r0)]
-                        with torch.cuda.stream(s_in):
-                            if ci >= NB:
-                                s_in.wait_event(pc["ev_c"][b])
-                            xd.copy_(mat[int(r0):int(r1)], non_blocking=True)
-                            pc["ev_in"][b].record(s_in)
-                        main.wait_event(pc["ev_in"][b])
-                        words[int(r0):int(r1)] = self.clusterer.transform_device(xd)
-                        pc["ev_c"][b].record(main)
-                finally:
-                    if pk is not None:
+                if pk is None:
+                    # the matrix as it is, in order
+                    cuts = np.unique(np.linspace(0, n_rows, n_chunks + 1).astype(np.int64))
+                    pc = pool(int(np.diff(cuts).max()), src_mat.dtype)
+                    for r0, r1 in zip(cuts[:-1], cuts[1:]):
+                        send(pc, src_mat[int(r0):int(r1)], r0, r1)
+                    sent_bytes, wire_name = int(src_mat.numel() * src_mat.element_size()), str(src_mat.dtype).replace("torch.", "")
+                elif pk is packer:
+                    # list input: chunk c is sent once the background job has packed it; a value that is not an integer
+                    # in [0, 255] makes the uint8 attempt start over with float32 on the wire
+                    uc, cuts = unit_chunks(pk)
+                    buf = pk.view(wire)
+                    pc = pool(int(np.diff(cuts).max()), buf.dtype)
+                    pk.begin(uc, wire)
+                    try:
+                        for ci, (r0, r1) in enumerate(zip(cuts[:-1], cuts[1:])):
+                            if r1 <= r0:
+                                continue
+                            if not pk.wait(ci):
+                                fits = False
+                                break
+                            send(pc, buf[int(r0):int(r1)], r0, r1)
+                    finally:
                         pk.end()
+                    sent_bytes, wire_name = int(buf.numel() * buf.element_size()), str(buf.dtype).replace("torch.", "")
+                else:
+                    # pinned float32 matrix, two-ended: the workers narrow chunks to uint8 from the FRONT; whenever the copy
+                    # engine has room and no narrowed chunk is ready, a chunk is claimed from the BACK and sent as float32
+                    # -- the two meet where the host's and PCIe's bandwidth balance.  A value that does not fit uint8 stops
+                    # the narrowing; the chunks already sent stay valid, the rest goes as float32.
+                    uc, cuts = unit_chunks(pk)
+                    buf = pk.view(torch.uint8)
+                    max_rows = int(np.diff(cuts).max())
+                    pu, pf = pool(max_rows, torch.uint8), pool(max_rows, torch.float32, depth=4)
+                    front, back, narrowing, inflight, sent_bytes, n_u8 = 0, len(cuts) - 2, True, [], 0, 0
+                    trace = [] if os.environ.get("ISE_TRACE_WIRE") else None
+                    t_begin = time.perf_counter()
+                    pk.begin(uc, torch.uint8)
+                    try:
+                        while front <= back:
+                            if not narrowing:
+                                r0, r1 = int(cuts[front]), int(cuts[front + 1])
+                                send(pf, src_mat[r0:r1], r0, r1)
+                                sent_bytes += (r1 - r0) * ncol * 4
+                                front += 1
+                                continue
+                            done, ok = pk.poll(front)
+                            if not ok:
+                                narrowing = False
+                                continue
+                            if done:
+                                r0, r1 = int(cuts[front]), int(cuts[front + 1])
+                                send(pu, buf[r0:r1], r0, r1)
+                                if trace is not None:
+                                    trace.append(("u8", front, round((time.perf_counter() - t_begin) * 1e3, 2)))
+                                sent_bytes += (r1 - r0) * ncol
+                                n_u8 += 1
+                                front += 1
+                                continue
+                            inflight = [e for e in inflight if not e.query()]
+                            if len(inflight) < 3 and back > front and pk.claim(back):
+                                r0, r1 = int(cuts[back]), int(cuts[back + 1])
+                                inflight.append(send(pf, src_mat[r0:r1], r0, r1))
+                                if trace is not None:
+                                    trace.append(("f32", back, round((time.perf_counter() - t_begin) * 1e3, 2)))
+                                sent_bytes += (r1 - r0) * ncol * 4
+                                back -= 1
+                                continue
+                            time.sleep(2e-5)
+                    finally:
+                        pk.end()
+                    n_all = len(cuts) - 1
+                    if trace is not None:
+                        print("wire trace (kind, chunk, ms):", trace, flush=True)
+                    wire_name = "uint8" if n_u8 == n_all else ("float32" if n_u8 == 0 else f"uint8 ({n_u8} of {n_all} chunks) + float32")
                 if fits:
                     break
                 # the pinned rows of the abandoned attempt may still be in flight: let the copies drain before the buffers
                 # are reused / re-packed
                 s_in.synchronize()
-            assert words is not None
         # what crossed PCIe on the way in (bench.py reports it)
-        self.__dict__["_last_transfer"] = dict(h2d_bytes=int(mat.numel() * mat.element_size() + offsets.nbytes),
-                                               wire=str(mat.dtype).replace("torch.", ""), rows=n_rows)
+        self.__dict__["_last_transfer"] = dict(h2d_bytes=int(sent_bytes + offsets.nbytes), wire=wire_name, rows=n_rows)
         # persistent device + pinned result buffers (indptr | indices | data), grown on demand
         rb = self.__dict__.get("_csr_bufs")
         if rb is None or rb["cap"] < max(n_rows, 1) or rb["n_img"] < n_img or rb["dev"] != str(dev):

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <memory>
 #include <mutex>
@@ -422,16 +423,33 @@ void pack_share(const void* const* srcs, const int64_t* offsets, int64_t i0, int
     }
 }
 
-// One asynchronous packing job: nt threads walk the chunks IN ORDER, each taking its share of every chunk, so chunk 0
-// is complete after ~1/n_chunks of the work and the caller can send it while the rest is still being packed.
+// One unit (image / row block) into its place of the packed matrix.
+inline void pack_unit(const void* const* srcs, const int64_t* offsets, int64_t i, int d, int src_dtype, int dst_dtype,
+                      void* dst_base, std::atomic<int>& ok) {
+    const int64_t rows = offsets[i + 1] - offsets[i];
+    if (rows <= 0 || !ok.load(std::memory_order_relaxed)) return;
+    const size_t src_elt = src_dtype == ISE_DTYPE_F32 ? 4 : 1, dst_elt = dst_dtype == ISE_DTYPE_F32 ? 4 : 1;
+    uint8_t* dst = (uint8_t*)dst_base + (size_t)offsets[i] * d * dst_elt;
+    if (src_dtype == dst_dtype) memcpy(dst, srcs[i], (size_t)rows * d * src_elt);
+    else if (!narrow_f32_to_u8((const float*)srcs[i], dst, rows * d)) ok.store(0);
+}
+
+// One asynchronous packing job: nt threads walk the chunks IN ORDER and take the units of a chunk from a shared counter
+// (a thread that starts late or shares its core does not hold a chunk back), so chunk 0 is complete after ~1/n_chunks of
+// the work and the caller can send it while the rest is still being packed.
 struct PackJob {
     std::vector<std::thread> threads;
     std::vector<int64_t> cuts;
-    std::unique_ptr<std::atomic<int>[]> finished;     // per chunk: threads done with it
+    std::unique_ptr<std::atomic<int64_t>[]> next;     // per chunk: next unit to hand out (relative)
+    std::unique_ptr<std::atomic<int64_t>[]> done;     // per chunk: units completed
+    std::unique_ptr<std::atomic<int>[]> owner;        // per chunk: 0 = nobody yet, 1 = the workers, 2 = the caller took it
     std::atomic<int> ok{1};
     std::mutex mu;
     std::condition_variable cv;
     int nt = 1;
+    bool finished(int c) const {
+        return owner[c].load() == 2 || done[c].load() >= cuts[c + 1] - cuts[c];
+    }
 };
 }  // namespace
 
@@ -444,18 +462,27 @@ ISE_EXPORT int ise_pack_begin(const void* const* srcs, const int64_t* offsets, c
     for (int c = 0; c < n_chunks; ++c) ISE_CHECK_ARG(image_cuts[c] >= 0 && image_cuts[c + 1] >= image_cuts[c]);
     PackJob* job = new PackJob();
     job->cuts.assign(image_cuts, image_cuts + n_chunks + 1);
-    job->finished.reset(new std::atomic<int>[n_chunks]);
-    for (int c = 0; c < n_chunks; ++c) job->finished[c].store(0);
+    job->next.reset(new std::atomic<int64_t>[n_chunks]);
+    job->done.reset(new std::atomic<int64_t>[n_chunks]);
+    job->owner.reset(new std::atomic<int>[n_chunks]);
+    for (int c = 0; c < n_chunks; ++c) { job->next[c].store(0); job->done[c].store(0); job->owner[c].store(0); }
     job->nt = std::max(1, std::min<int>(nthreads, 64));
     const int nt = job->nt;
     for (int t = 0; t < nt; ++t)
         job->threads.emplace_back([=]() {
             for (int c = 0; c < n_chunks; ++c) {
-                if (job->cuts[c + 1] > job->cuts[c])
-                    pack_share(srcs, offsets, job->cuts[c], job->cuts[c + 1], d, src_dtype, dst_dtype, dst_base, t, nt, job->ok);
-                if (job->finished[c].fetch_add(1) + 1 == nt) {
-                    std::lock_guard<std::mutex> lk(job->mu);
-                    job->cv.notify_all();
+                int who = 0;
+                job->owner[c].compare_exchange_strong(who, 1);      // the first worker to arrive takes the chunk ...
+                if (job->owner[c].load() != 1) continue;            // ... unless the caller claimed it (ise_pack_claim)
+                const int64_t u0 = job->cuts[c], n_units = job->cuts[c + 1] - u0;
+                for (;;) {
+                    const int64_t u = job->next[c].fetch_add(1);
+                    if (u >= n_units) break;
+                    pack_unit(srcs, offsets, u0 + u, d, src_dtype, dst_dtype, dst_base, job->ok);
+                    if (job->done[c].fetch_add(1) + 1 == n_units) {
+                        std::lock_guard<std::mutex> lk(job->mu);
+                        job->cv.notify_all();
+                    }
                 }
             }
         });
@@ -467,8 +494,26 @@ ISE_EXPORT int ise_pack_wait(void* job_, int chunk, int* ok_out) {
     PackJob* job = (PackJob*)job_;
     ISE_CHECK_ARG(job && ok_out && chunk >= 0 && chunk + 1 < (int)job->cuts.size());
     std::unique_lock<std::mutex> lk(job->mu);
-    job->cv.wait(lk, [&] { return job->finished[chunk].load() == job->nt; });
+    // (re-checked every 200 us: a chunk without units completes without a notification)
+    while (!job->finished(chunk)) job->cv.wait_for(lk, std::chrono::microseconds(200));
     *ok_out = job->ok.load();
+    return 0;
+}
+
+ISE_EXPORT int ise_pack_poll(void* job_, int chunk, int* done_out, int* ok_out) {
+    PackJob* job = (PackJob*)job_;
+    ISE_CHECK_ARG(job && done_out && ok_out && chunk >= 0 && chunk + 1 < (int)job->cuts.size());
+    const bool done = job->owner[chunk].load() != 2 && job->done[chunk].load() >= job->cuts[chunk + 1] - job->cuts[chunk];
+    *ok_out = job->ok.load();      // read AFTER the count: ok == 1 now means no unit of the chunk was skipped
+    *done_out = done ? 1 : 0;
+    return 0;
+}
+
+ISE_EXPORT int ise_pack_claim(void* job_, int chunk, int* claimed_out) {
+    PackJob* job = (PackJob*)job_;
+    ISE_CHECK_ARG(job && claimed_out && chunk >= 0 && chunk + 1 < (int)job->cuts.size());
+    int who = 0;
+    *claimed_out = job->owner[chunk].compare_exchange_strong(who, 2) ? 1 : 0;
     return 0;
 }
 

@@ -87,6 +87,12 @@ int ise_pack_rows(const void* const* srcs_host, const int64_t* offsets_host, int
 int ise_pack_begin(const void* const* srcs_host, const int64_t* offsets_host, const int64_t* image_cuts, int n_chunks,
                    int d, int src_dtype, int dst_dtype, void* dst_base_host, int nthreads, void** job);
 int ise_pack_wait(void* job, int chunk, int* ok);
+/* Two-ended use (a caller that can also send a chunk in its source format): ise_pack_poll is the non-blocking form of
+ * ise_pack_wait (done = 1: the workers have finished the chunk); ise_pack_claim takes a chunk the workers have not
+ * started away from them (claimed = 1: they will skip it) -- the workers walk the chunks from the front, the caller
+ * claims from the back whenever its copy engine is idle, and the two meet where host and PCIe bandwidth balance. */
+int ise_pack_poll(void* job, int chunk, int* done, int* ok);
+int ise_pack_claim(void* job, int chunk, int* claimed);
 int ise_pack_end(void* job);
 
 /* ---- operand preparation --------------------------------------------------------------

@@ -420,14 +420,15 @@ def test_pinned_float_matrix_is_narrowed_on_the_wire(monkeypatch):
     assert bovw._last_transfer["wire"] == "float32"
     monkeypatch.setenv("ISE_NARROW_PINNED", "1")
     got = bovw.transform_csr(packed, okapi=ok, n_chunks=4).toarray()
-    assert bovw._last_transfer["wire"] == "uint8" and bovw._last_transfer["h2d_bytes"] < x.nbytes // 3
+    # two-ended: host threads narrow chunks from the front while idle PCIe time sends chunks from the back as float32
+    assert bovw._last_transfer["wire"].startswith("uint8") and bovw._last_transfer["h2d_bytes"] < 0.9 * x.nbytes
     assert np.array_equal(got, want)
     # a non-integer value in the LAST block: the uint8 attempt is abandoned mid-way, float32 is sent instead
     y = x.copy()
     y[-3, 7] += 0.25
     packed_y = PackedDescriptions(torch.from_numpy(y), offsets).pin()
     got_y = bovw.transform_csr(packed_y, okapi=ok, n_chunks=4).toarray()
-    assert bovw._last_transfer["wire"] == "float32"
+    assert "float32" in bovw._last_transfer["wire"]
     monkeypatch.setenv("ISE_NARROW_PINNED", "0")
     assert np.array_equal(got_y, bovw.transform_csr(packed_y, okapi=ok, n_chunks=4).toarray())
 
