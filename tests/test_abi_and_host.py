@@ -325,3 +325,30 @@ def test_host_packer_whole_and_chunk_ordered_background_job():
     for bad in (-1.0, 256.0, np.nan):
         imgs[230][1, 5] = bad
         assert whole(_lib.DTYPE_U8, 2)[1] == 0
+    # two-ended use: a chunk the caller claims is skipped by the workers (its rows stay untouched), every other chunk is
+    # packed; polling reports completion without blocking
+    imgs[230][1, 5] = 3.0
+    want = np.concatenate(imgs)
+    cuts = np.asarray([0, 64, 128, 192, 257], dtype=np.int64)
+    dst = np.full(want.shape, 255, dtype=np.uint8)
+    h = C.c_void_p()
+    _lib.check(lib.ise_pack_begin(p(ptrs), p(offsets), p(cuts), 4, d, _lib.DTYPE_F32, _lib.DTYPE_U8, p(dst), 2, C.byref(h)))
+    got = C.c_int(-1)
+    _lib.check(lib.ise_pack_claim(h, 3, C.byref(got)))
+    claimed = bool(got.value)
+    for c in range(4):
+        ok = C.c_int(-1)
+        _lib.check(lib.ise_pack_wait(h, c, C.byref(ok)))
+        assert ok.value == 1
+        done, ok2 = C.c_int(-1), C.c_int(-1)
+        _lib.check(lib.ise_pack_poll(h, c, C.byref(done), C.byref(ok2)))
+        assert ok2.value == 1 and bool(done.value) == (not (claimed and c == 3))
+    _lib.check(lib.ise_pack_claim(h, 0, C.byref(got)))
+    assert got.value == 0                                    # the workers had it: too late to claim
+    _lib.check(lib.ise_pack_end(h))
+    r3 = offsets[cuts[3]]
+    assert np.array_equal(dst[:r3].astype(np.float32), want[:r3])
+    if claimed:
+        assert (dst[r3:] == 255).all()
+    else:
+        assert np.array_equal(dst[r3:].astype(np.float32), want[r3:])
