@@ -105,7 +105,7 @@ __device__ __forceinline__ bool cand_better(float va, int64_t ia, float vb, int6
 // the truncating FP32 accumulation adds <= (d/16 + 4) 2^-23 |a||b|; FP16 underflow (scaled elements below
 // 2^-14 round with absolute error <= 2^-25) adds <= 2^-25/scale * sqrt(d) * |other operand|.
 struct CoarseBound {
-    float kappa, uf_a, uf_b, nb_max, sq_, ca_, rb_;
+    float kappa, uf_a, uf_b, nb_max, sq_, ca_;
     // a_exact: the caller knows the A planes are exact in hi (or re-runs the whole tensor when they are not)
     // meta[LO_NONZERO]: 0 = exact in the hi plane; 1.0 = inexact, residual unknown (worst case 2^-11 |x|); any other
     // value = the largest measured |x - hi|^2 / |x|^2 of a row (rows_convert.cuh: publish_lo_residual)
@@ -116,7 +116,6 @@ struct CoarseBound {
     __device__ __forceinline__ void init(const float* a_meta, const float* b_meta, int d, bool a_exact = false) {
         const float ca = a_exact ? 0.f : rel_residual(a_meta[META_LO_NONZERO]);
         const float cb = rel_residual(b_meta[META_LO_NONZERO]);
-        rb_ = 0.f;
         kappa = 1.02f * (ca + cb) + 2.4e-7f + (float)(d / 16 + 4) * 1.1920929e-7f;
         const float sq = sqrtf((float)d) * 5.9604645e-8f;                         // 2 * 2^-25 * sqrt(d)
         sq_ = sq;
@@ -133,7 +132,7 @@ struct CoarseBound {
     // every coarse inner product of a row with squared norm `an` is within eps(an) of the exact one
     __device__ __forceinline__ float eps(float an) const {
         const float na = sqrtf(an);
-        return (kappa * nb_max + rb_) * na + uf_a * nb_max + uf_b * na;
+        return kappa * nb_max * na + uf_a * nb_max + uf_b * na;
     }
 };
 
