@@ -235,7 +235,8 @@ def lloyd_train(cp, d, k, x_train, n_train, a_op, lops, *, init_rows, init_centr
                     nsplit_prev = lops.apply_splits(counts, cent, n_train)      # counts still hold the previous iteration's
                     if cp.spherical:
                         lops.normalize(cent)
-                    ev[0].record()
+                    if timed:
+                        ev[0].record()
                     dis, assign = lops.assign(x_train, a_op, cent, metric, precision)
                 st = stats[pending["index"]]
                 st.update(obj=o_prev, nsplit=nsplit_prev, speculated=True, mis_speculated=n_empty_prev > 0,
